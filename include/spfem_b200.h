@@ -1,0 +1,121 @@
+/* spfem_b200 -- C ABI of the B200-native element-assembly path.
+ *
+ * The reference (kinnala/sp.fem) is pure Python: it has no FFI.  This header
+ * is the boundary a maintainer would bind from `spfem/assembly.py` (ctypes
+ * stub in INTEGRATION.md) to replace the bodies of
+ *
+ *   AssemblerElement.iasm   spfem/assembly.py:919-1006
+ *   AssemblerElement.fasm   spfem/assembly.py:1011-1183
+ *   coo_matrix(...).tocsr() spfem/assembly.py:985-986, 1158-1159 (SciPy)
+ *   coo_matrix(...).toarray().T[0]         :1005-1006, 1182-1183
+ *
+ * Conventions: every function returns 0 on success and a non-zero code on
+ * failure; `spfem_last_error()` then returns a thread-local message.  All
+ * `d_*` pointers are DEVICE pointers owned by the caller (PyTorch tensors in
+ * the Python host layer); `h_*` are host pointers.  `stream` is a
+ * `cudaStream_t` passed as `void*` (NULL = legacy default stream).  No entry
+ * point allocates device memory behind the caller's back except the `*_host`
+ * convenience call, which says so.  Re-entrant per stream.
+ */
+#ifndef SPFEM_B200_H
+#define SPFEM_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SPFEM_ABI_VERSION 1
+
+/* Argument block of every generated kernel (see spfem_b200/codegen.py; the
+ * generated source declares the identical struct). */
+typedef struct SpfemArgs {
+    long long n;             /* elements / facets to process                    */
+    long long ldo;           /* leading dimension of the entry-major output      */
+    const int *sel;          /* optional element subset (`tind`) or NULL          */
+    const int *t;            /* vertex connectivity t[k*ldt + e]                  */
+    long long ldt;
+    const double *p;         /* vertex coordinates p[k*ldp + v]                   */
+    long long ldp;
+    const int *tdof_u;       /* trial DOF table (interp only) [j*ldd + e]         */
+    long long ldd;
+    const double *interp[8]; /* interpolated solution vectors (`w`)               */
+    const int *fv;           /* facet kernels: facet vertex ids fv[k*n + f]       */
+    const int *e1;           /* facet kernels: first / second adjacent element    */
+    const int *e2;
+    const int *lf1;          /* facet kernels: local facet index inside e1        */
+    double *out;             /* local entries out[entry*ldo + k]                  */
+} SpfemArgs;
+
+int         spfem_abi_version(void);
+const char *spfem_last_error(void);
+/* number of visible CUDA devices (0 without a driver); never fails */
+int         spfem_device_count(void);
+
+/* ---- run-time compilation (NVRTC, --gpu-architecture=sm_100a) -------------
+ * Compiles `src` to a cubin.  `*image` is malloc'ed (release with spfem_free),
+ * `*log` likewise (may be NULL on success).  Works without a GPU.            */
+int  spfem_nvrtc_compile(const char *src, const char *arch, char **image,
+                         size_t *image_size, char **log);
+void spfem_free(void *ptr);
+
+/* ---- module handling / launch ------------------------------------------- */
+int spfem_module_load(const void *image, size_t image_size, void **module);
+int spfem_module_unload(void *module);
+int spfem_module_get_kernel(void *module, const char *name, void **kernel);
+/* Launches a generated kernel: one thread per item, `block` threads per CTA. */
+int spfem_launch(void *kernel, const SpfemArgs *args, int block, void *stream);
+
+/* ---- sparsity pattern: COO (row, col) pairs -> CSR + contribution lists ----
+ * Replaces SciPy's coo_tocsr + sum_duplicates structure pass.  Entry ids are
+ * `id = (j*nloc_v + i)*n + k` for item k, local trial j, local test i
+ * (the reference's COO block order, spfem/assembly.py:977); entry `id` has
+ * row = d_rowdof[i*ldr + k], col = d_coldof[j*ldc + k] (col = 0 if
+ * d_coldof == NULL: linear forms).
+ *
+ * spfem_pattern_sort : sorts all entries by (row, col) [stable radix sort on
+ *    64-bit keys], flags the first entry of every distinct (row, col) and
+ *    returns their number in *h_nnz (synchronises `stream`).
+ * spfem_pattern_fill : writes indptr (nrows+1), indices (nnz), cptr (nnz+1)
+ *    and contrib (n_entries): CSR slot s sums the local entries
+ *    contrib[cptr[s] .. cptr[s+1]) in that (ascending entry id) order.
+ *    Optional d_rowstart (nrows+1): position in `contrib` where the entries
+ *    of each row start -- with it spfem_reduce(cptr = rowstart, nslots =
+ *    nrows) yields the dense load vector of a linear form (toarray()).
+ *    d_indptr / d_indices / d_cptr may be NULL when only rowstart is wanted.
+ * `index_bytes` is 4 or 8 (SciPy's rule: int64 iff max(n_entries, nrows,
+ * ncols) > 2^31-1).                                                           */
+size_t spfem_pattern_ws_bytes(long long n_entries);
+int spfem_pattern_sort(const int *d_rowdof, long long ldr,
+                       const int *d_coldof, long long ldc,
+                       long long n, int nloc_v, int nloc_u,
+                       long long nrows, long long ncols,
+                       void *d_ws, size_t ws_bytes, long long *h_nnz,
+                       void *stream);
+int spfem_pattern_fill(const void *d_ws, long long n_entries,
+                       long long nrows, long long ncols, long long nnz,
+                       int index_bytes, void *d_indptr, void *d_indices,
+                       int *d_cptr, int *d_contrib, int *d_rowstart,
+                       void *stream);
+
+/* ---- deterministic duplicate summation ------------------------------------
+ * d_values[s] = sum_{k = cptr[s]}^{cptr[s+1]-1} d_local[contrib[k]], added in
+ * ascending k with plain fp64 adds (fixed order => bitwise reproducible).    */
+int spfem_reduce(const double *d_local, const int *d_cptr,
+                 const int *d_contrib, long long nslots, double *d_values,
+                 void *stream);
+
+/* ---- element ordering -------------------------------------------------------
+ * Morton (Z-order) permutation of the elements by centroid: d_perm[k] = index
+ * of the k-th element along the curve.  ws: spfem_morton_ws_bytes(nt).        */
+size_t spfem_morton_ws_bytes(long long nt);
+int spfem_morton_order(const double *d_p, long long ldp, int dim,
+                       const int *d_t, long long ldt, int nve, long long nt,
+                       const double *h_lo, const double *h_hi, /* bounding box */
+                       int *d_perm, void *d_ws, size_t ws_bytes, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPFEM_B200_H */

@@ -1,0 +1,138 @@
+# -*- coding: utf-8 -*-
+"""ctypes binding of the C-ABI library ``csrc/libspfem_b200.so``
+(declared in ``include/spfem_b200.h``).
+
+The library is built in-tree by :func:`build` (``nvcc`` for sm_100a) and is the
+only way the package touches the GPU besides PyTorch tensor ownership.  A
+missing library is an error -- there is no CPU fallback."""
+import ctypes as C
+import os
+import subprocess
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB_PATH = os.path.join(CSRC, "libspfem_b200.so")
+INCLUDE = os.path.join(os.path.dirname(HERE), "include")
+
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3",
+              "-std=c++17", "-shared", "-Xcompiler", "-fPIC", "-cudart", "static"]
+
+
+class SpfemArgs(C.Structure):
+    """Mirror of ``struct SpfemArgs`` (include/spfem_b200.h)."""
+    _fields_ = [
+        ("n", C.c_longlong), ("ldo", C.c_longlong),
+        ("sel", C.c_void_p),
+        ("t", C.c_void_p), ("ldt", C.c_longlong),
+        ("p", C.c_void_p), ("ldp", C.c_longlong),
+        ("tdof_u", C.c_void_p), ("ldd", C.c_longlong),
+        ("interp", C.c_void_p * 8),
+        ("fv", C.c_void_p), ("e1", C.c_void_p), ("e2", C.c_void_p),
+        ("lf1", C.c_void_p),
+        ("out", C.c_void_p),
+    ]
+
+
+SYMBOLS = {
+    # name: (restype, argtypes)
+    "spfem_abi_version": (C.c_int, []),
+    "spfem_last_error": (C.c_char_p, []),
+    "spfem_device_count": (C.c_int, []),
+    "spfem_nvrtc_compile": (C.c_int, [C.c_char_p, C.c_char_p,
+                                      C.POINTER(C.c_void_p),
+                                      C.POINTER(C.c_size_t),
+                                      C.POINTER(C.c_void_p)]),
+    "spfem_free": (None, [C.c_void_p]),
+    "spfem_module_load": (C.c_int, [C.c_void_p, C.c_size_t,
+                                    C.POINTER(C.c_void_p)]),
+    "spfem_module_unload": (C.c_int, [C.c_void_p]),
+    "spfem_module_get_kernel": (C.c_int, [C.c_void_p, C.c_char_p,
+                                          C.POINTER(C.c_void_p)]),
+    "spfem_launch": (C.c_int, [C.c_void_p, C.POINTER(SpfemArgs), C.c_int,
+                               C.c_void_p]),
+    "spfem_pattern_ws_bytes": (C.c_size_t, [C.c_longlong]),
+    "spfem_pattern_sort": (C.c_int, [C.c_void_p, C.c_longlong, C.c_void_p,
+                                     C.c_longlong, C.c_longlong, C.c_int,
+                                     C.c_int, C.c_longlong, C.c_longlong,
+                                     C.c_void_p, C.c_size_t,
+                                     C.POINTER(C.c_longlong), C.c_void_p]),
+    "spfem_pattern_fill": (C.c_int, [C.c_void_p, C.c_longlong, C.c_longlong,
+                                     C.c_longlong, C.c_longlong, C.c_int,
+                                     C.c_void_p, C.c_void_p, C.c_void_p,
+                                     C.c_void_p, C.c_void_p, C.c_void_p]),
+    "spfem_reduce": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p,
+                               C.c_longlong, C.c_void_p, C.c_void_p]),
+    "spfem_morton_ws_bytes": (C.c_size_t, [C.c_longlong]),
+    "spfem_morton_order": (C.c_int, [C.c_void_p, C.c_longlong, C.c_int,
+                                     C.c_void_p, C.c_longlong, C.c_int,
+                                     C.c_longlong, C.POINTER(C.c_double),
+                                     C.POINTER(C.c_double), C.c_void_p,
+                                     C.c_void_p, C.c_size_t, C.c_void_p]),
+}
+
+_lib = None
+
+
+class SpfemError(RuntimeError):
+    """An entry point of libspfem_b200 returned a non-zero status."""
+
+
+def build(force=False, verbose=False):
+    """Compile ``csrc/spfem_b200.cu`` into ``csrc/libspfem_b200.so``."""
+    src = os.path.join(CSRC, "spfem_b200.cu")
+    hdr = os.path.join(INCLUDE, "spfem_b200.h")
+    if (not force and os.path.exists(LIB_PATH)
+            and os.path.getmtime(LIB_PATH) >= max(os.path.getmtime(src),
+                                                  os.path.getmtime(hdr))):
+        return LIB_PATH
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    cmd = [nvcc] + NVCC_FLAGS + ["-o", LIB_PATH, src, "-lnvrtc", "-Xlinker",
+                                 "-rpath", "-Xlinker", "/usr/local/cuda/lib64"]
+    if verbose:
+        print(" ".join(cmd))
+    subprocess.check_call(cmd)
+    return LIB_PATH
+
+
+def load():
+    """Load the library (raises if it has not been built)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise SpfemError("libspfem_b200.so is not built: run "
+                         "`python -c 'import __graft_entry__ as g; g.build()'` "
+                         "(nvcc, sm_100a). There is no CPU fallback.")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SYMBOLS.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    if lib.spfem_abi_version() != 1:
+        raise SpfemError("libspfem_b200.so ABI version mismatch; rebuild")
+    _lib = lib
+    return lib
+
+
+def check(status):
+    if status != 0:
+        raise SpfemError(load().spfem_last_error().decode("utf-8", "replace"))
+
+
+def nvrtc_compile(source, arch="sm_100a"):
+    """CUDA C -> cubin bytes through ``spfem_nvrtc_compile``."""
+    lib = load()
+    image = C.c_void_p()
+    size = C.c_size_t()
+    log = C.c_void_p()
+    st = lib.spfem_nvrtc_compile(source.encode("utf-8"), arch.encode("ascii"),
+                                 C.byref(image), C.byref(size), C.byref(log))
+    try:
+        if st != 0:
+            raise SpfemError(lib.spfem_last_error().decode("utf-8", "replace"))
+        return C.string_at(image.value, size.value)
+    finally:
+        if image.value:
+            lib.spfem_free(image)
+        if log.value:
+            lib.spfem_free(log)

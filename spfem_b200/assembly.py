@@ -1,0 +1,341 @@
+# -*- coding: utf-8 -*-
+"""Element / facet assembly on the GPU behind the sp.fem API.
+
+Drop-in for the hot path of spfem/assembly.py: ``AssemblerElement.__init__``
+(:813-837), ``.iasm`` (:839-1006), ``.fasm`` (:1008-1183) and ``Dofnum``
+(:1487-1566).  The call signatures, return types (``scipy.sparse.csr_matrix``
+with rows = test DOFs, columns = trial DOFs, explicit zeros kept, sorted
+indices; or a 1-D ``ndarray`` for linear forms) and the exceptions are the
+reference's.  What happens inside is not:
+
+1. the user's form is *traced* with proxy arguments (``tracer.py``),
+2. CUDA C for one fused kernel is generated (``codegen.py``) and compiled with
+   NVRTC for sm_100a through the C-ABI library (``_lib.py`` ->
+   ``csrc/spfem_b200.cu``),
+3. the sparsity pattern -- CSR ``indptr``/``indices`` plus the map from CSR
+   slots to the local-matrix entries that are summed into them -- is built on
+   the device once per assembler (radix sort + run-length encoding),
+4. the kernel writes the local matrices, and a deterministic, fixed-order
+   gather-reduction sums them into the CSR values (no floating point atomics).
+
+There is no CPU fallback: without the CUDA library / a GPU the calls raise.
+"""
+import inspect
+import numpy as np
+from scipy.sparse import csr_matrix
+
+from . import mesh as _mesh
+from . import element as _element
+from .quadrature import get_quadrature
+from .tracer import (Coef, Form, TraceError, basis_args, zero_like, call_form)
+from . import codegen
+
+__all__ = ["Assembler", "AssemblerElement", "Dofnum", "TraceError"]
+
+
+class Dofnum(object):
+    """Global degree-of-freedom numbering (spfem/assembly.py:1487-1566):
+    vertex DOFs ``v*n_dofs + k`` first, then edge DOFs (3-D meshes), facet
+    DOFs, interior DOFs; ``t_dof`` lists, per element, the vertex DOFs of
+    each local vertex, then local edges, local facets and interior DOFs."""
+
+    def __init__(self, mesh, element):
+        nv = mesh.p.shape[1]
+        nt = mesh.t.shape[1]
+        self.n_dof = np.arange(element.n_dofs * nv, dtype=np.int64).reshape(
+            (element.n_dofs, nv), order='F')
+        offset = element.n_dofs * nv
+        self.e_dof = np.array([])
+        self.f_dof = np.array([])
+        has_edges = hasattr(mesh, 'edges')
+        has_facets = hasattr(mesh, 'facets')
+        if has_edges:
+            ne = mesh.edges.shape[1]
+            self.e_dof = np.arange(element.e_dofs * ne, dtype=np.int64).reshape(
+                (element.e_dofs, ne), order='F') + offset
+            offset += element.e_dofs * ne
+        if has_facets:
+            nf = mesh.facets.shape[1]
+            self.f_dof = np.arange(element.f_dofs * nf, dtype=np.int64).reshape(
+                (element.f_dofs, nf), order='F') + offset
+            offset += element.f_dofs * nf
+        self.i_dof = np.arange(element.i_dofs * nt, dtype=np.int64).reshape(
+            (element.i_dofs, nt), order='F') + offset
+        rows = [self.n_dof[:, mesh.t[k, :]] for k in range(mesh.t.shape[0])]
+        if has_edges:
+            rows += [self.e_dof[:, mesh.t2e[k, :]] for k in range(mesh.t2e.shape[0])]
+        if has_facets:
+            rows += [self.f_dof[:, mesh.t2f[k, :]] for k in range(mesh.t2f.shape[0])]
+        rows.append(self.i_dof)
+        self.t_dof = np.vstack(rows).astype(np.int64)
+        self.N = int(np.max(self.t_dof)) + 1
+
+    def getdofs(self, N=None, F=None, E=None, T=None):
+        """Global DOF numbers of the given nodes / facets / edges / elements."""
+        dofs = np.zeros(0, dtype=np.int64)
+        if N is not None:
+            dofs = np.hstack((dofs, self.n_dof[:, N].flatten()))
+        if F is not None:
+            dofs = np.hstack((dofs, self.f_dof[:, F].flatten()))
+        if E is not None:
+            dofs = np.hstack((dofs, self.e_dof[:, E].flatten()))
+        if T is not None:
+            dofs = np.hstack((dofs, self.i_dof[:, T].flatten()))
+        return dofs.flatten()
+
+
+class Assembler(object):
+    """Base class (spfem/assembly.py:31-254)."""
+
+    def __init__(self):
+        raise NotImplementedError("Assembler constructor not implemented!")
+
+
+def _argnames(form):
+    return list(inspect.getfullargspec(form).args)
+
+
+class _Plan(object):
+    """A traced + generated kernel, independent of any device."""
+
+    def __init__(self, kind, spec, source, name, bilinear, wkeys):
+        self.kind, self.spec, self.source, self.name = kind, spec, source, name
+        self.bilinear, self.wkeys = bilinear, wkeys
+
+
+class AssemblerElement(Assembler):
+    """Finite element assembler for elements defined through reference basis
+    functions (spfem/assembly.py:789-837)."""
+
+    def __init__(self, mesh, elem_u, elem_v=None, mapping=None):
+        if not isinstance(mesh, _mesh.Mesh):
+            raise Exception("First parameter must be an instance of "
+                            "spfem.mesh.Mesh!")
+        if not isinstance(elem_u, _element.Element):
+            raise Exception("Second parameter must be an instance of "
+                            "spfem.element.Element!")
+        self.mapping = mesh.mapping() if mapping is None else mapping
+        self.mesh = mesh
+        self.elem_u = elem_u
+        self.dofnum_u = Dofnum(mesh, elem_u)
+        if elem_v is None:
+            self.elem_v = elem_u
+            self.dofnum_v = self.dofnum_u
+        else:
+            self.elem_v = elem_v
+            self.dofnum_v = Dofnum(mesh, elem_v)
+        self._engine = None        # device state, created on first assembly
+        self.last_stats = {}
+
+    # ------------------------------------------------------------------
+    # tracing
+    # ------------------------------------------------------------------
+    def _elem_info(self):
+        bu, ncu = _element.scalar_parent(self.elem_u)
+        bv, ncv = _element.scalar_parent(self.elem_v)
+        return bu, ncu, bv, ncv
+
+    def _check_interp(self, interp):
+        if interp is None:
+            return []
+        if not isinstance(interp, dict):
+            raise Exception("The input solution vector(s) must be in a "
+                            "dictionary! Pass e.g. {0:u} instead of u.")
+        keys = list(interp.keys())
+        if len(keys) > 8:
+            raise NotImplementedError("at most 8 interpolated fields")
+        return keys
+
+    def plan_iasm(self, form, intorder=None, interp=None):
+        """Trace ``form`` and generate the interior kernel (no device work)."""
+        mesh = self.mesh
+        if intorder is None:
+            intorder = self.elem_u.maxdeg + self.elem_v.maxdeg
+        names = _argnames(form)
+        bilinear = ('u' in names) or ('du' in names)
+        wkeys = self._check_interp(interp)
+        X, W = get_quadrature(mesh.refdom, intorder)
+        dim = mesh.p.shape[0]
+        bu, ncu, bv, ncv = self._elem_info()
+        if not (hasattr(bu, "polys") and hasattr(bv, "polys")):
+            raise NotImplementedError("element type without reference "
+                                      "polynomials is not supported on the "
+                                      "device path")
+        quad = mesh.refdom == "quad"
+        if mesh.refdom not in ("tri", "tet", "quad"):
+            raise NotImplementedError("iasm: unsupported reference domain %r"
+                                      % (mesh.refdom,))
+        if quad:
+            invdf = {l: {k: Coef.sym("iJ%d%d" % (l, k), True) for k in range(dim)}
+                     for l in range(dim)}
+            absdet = Coef.sym("absdetq", True)
+            h = Form.coef(Coef.sym("hq", True))
+        else:
+            invdf = {l: {k: Coef.sym("iA%d%d" % (l, k)) for k in range(dim)}
+                     for l in range(dim)}
+            absdet = Coef.sym("absdet")
+            h = Form.coef(Coef.sym("h"))
+        x = {k: Form.coef(Coef.sym("x%d" % k, True)) for k in range(dim)}
+        w = {key: Form.coef(Coef.sym("w%d" % s, True))
+             for s, key in enumerate(wkeys)}
+        blocks = {}
+        for cu in range(ncu if bilinear else 1):
+            for cv in range(ncv):
+                v, dv = basis_args(ncv, cv, 1, dim, invdf)
+                avail = {'v': v, 'dv': dv, 'x': x, 'w': w, 'h': h}
+                if bilinear:
+                    u, du = basis_args(ncu, cu, 0, dim, invdf)
+                    avail['u'] = u
+                    avail['du'] = du
+                f = call_form(form, names, avail)
+                # the Jacobian factor |detDF| of spfem/assembly.py:980-981
+                blocks[(cu, cv)] = f * Form.coef(absdet)
+        tab_u = self._tables(bu, X)
+        tab_v = self._tables(bv, X)
+        spec = codegen.InteriorSpec(mesh.refdom, dim, bilinear,
+                                    bu.nbfun_ref(), bv.nbfun_ref(), ncu, ncv,
+                                    blocks, X, W, tab_u, tab_v, nw=len(wkeys))
+        src = codegen.generate_interior(spec, "spfem_elem")
+        return _Plan("interior", spec, src, "spfem_elem", bilinear, wkeys)
+
+    @staticmethod
+    def _tables(base, X):
+        phi, dphi = _element.tabulate(base, X)
+        dim = X.shape[0]
+        return [phi] + [dphi[:, l, :] for l in range(dim)]
+
+    def plan_fasm(self, form, interior=False, intorder=None, normals=True,
+                  interp=None):
+        """Trace ``form`` and generate the facet kernel (no device work)."""
+        mesh = self.mesh
+        if intorder is None:
+            intorder = self.elem_u.maxdeg + self.elem_v.maxdeg
+        names = _argnames(form)
+        if interior:
+            bilinear = ('u1' in names) or ('du1' in names)
+        else:
+            bilinear = ('u' in names) or ('du' in names)
+        wkeys = self._check_interp(interp)
+        if not bilinear and interior:
+            raise Exception("No interior support in linear facet form.")
+        X, W = get_quadrature(mesh.brefdom, intorder)
+        X = np.atleast_2d(X)
+        dim = mesh.p.shape[0]
+        if mesh.refdom not in ("tri", "tet", "quad"):
+            raise NotImplementedError("fasm: unsupported reference domain %r"
+                                      % (mesh.refdom,))
+        if mesh.refdom == "quad" and (interior or normals):
+            raise NotImplementedError("MappingQ1 has no normals / interior "
+                                      "facet support (pass normals=False)")
+        bu, ncu, bv, ncv = self._elem_info()
+        inv = {s: {l: {k: Coef.sym("iA%d_%d%d" % (s, l, k), True)
+                       for k in range(dim)} for l in range(dim)}
+               for s in (1, 2)}
+        x = {k: Form.coef(Coef.sym("x%d" % k, True)) for k in range(dim)}
+        h = Form.coef(Coef.sym("hf", True))
+        n = ({k: Form.coef(Coef.sym("n%d" % k, True)) for k in range(dim)}
+             if normals else {})
+        w = {key: Form.coef(Coef.sym("w%d" % s, True))
+             for s, key in enumerate(wkeys)}
+        dw = {key: {a: Form.coef(Coef.sym("dw%d_%d" % (s, a), True))
+                    for a in range(dim)} for s, key in enumerate(wkeys)}
+        sides = [(1, 1), (2, 2), (2, 1), (1, 2)] if interior else [(1, 1)]
+        blocks = []
+        for (su, sv) in sides:
+            blk = {}
+            for cu in range(ncu if bilinear else 1):
+                for cv in range(ncv):
+                    avail = {'x': x, 'h': h, 'n': n, 'w': w, 'dw': dw}
+                    if interior:
+                        zu, dzu = zero_like(ncu, dim)
+                        zv, dzv = zero_like(ncv, dim)
+                        ub, dub = basis_args(ncu, cu, 0, dim, inv[su])
+                        vb, dvb = basis_args(ncv, cv, 1, dim, inv[sv])
+                        avail.update({
+                            'u1': ub if su == 1 else zu, 'u2': ub if su == 2 else zu,
+                            'du1': dub if su == 1 else dzu, 'du2': dub if su == 2 else dzu,
+                            'v1': vb if sv == 1 else zv, 'v2': vb if sv == 2 else zv,
+                            'dv1': dvb if sv == 1 else dzv, 'dv2': dvb if sv == 2 else dzv})
+                    else:
+                        v, dv = basis_args(ncv, cv, 1, dim, inv[1])
+                        avail.update({'v': v, 'dv': dv})
+                        if bilinear:
+                            u, du = basis_args(ncu, cu, 0, dim, inv[1])
+                            avail.update({'u': u, 'du': du})
+                    blk[(cu, cv)] = call_form(form, names, avail)
+            blocks.append(blk)
+        spec = codegen.FacetSpec(mesh.refdom, dim, bilinear, interior,
+                                 bu.nbfun_ref(), bv.nbfun_ref(), ncu, ncv,
+                                 blocks, sides, X, W, bu.polys(), bv.polys(),
+                                 normals=normals, nw=len(wkeys))
+        src = codegen.generate_facet(spec, "spfem_facet")
+        return _Plan("facet", spec, src, "spfem_facet", bilinear, wkeys)
+
+    # ------------------------------------------------------------------
+    # index tables shared by the device path and the tests
+    # ------------------------------------------------------------------
+    def facet_tables(self, find):
+        """``(fv, e1, e2, lf1)`` for the facets ``find``: facet vertex ids,
+        the two neighbouring elements (``f2t``, second = -1 on the boundary)
+        and the local index of the facet inside the first element (used for
+        the reference normal, spfem/mapping.py:494-497)."""
+        mesh = self.mesh
+        find = np.asarray(find, dtype=np.int64)
+        fv = mesh.facets[:, find]
+        e1 = mesh.f2t[0, find]
+        e2 = mesh.f2t[1, find]
+        lf1 = np.zeros(find.shape[0], dtype=np.int64)
+        for itr in range(mesh.t2f.shape[0]):
+            lf1[mesh.t2f[itr, e1] == find] = itr
+        return fv, e1, e2, lf1
+
+    def facet_dofs(self, find, interior):
+        """Row / column DOF tables of the facet COO blocks
+        (spfem/assembly.py:1131-1156)."""
+        e1 = self.mesh.f2t[0, find]
+        if not interior:
+            return self.dofnum_v.t_dof[:, e1], self.dofnum_u.t_dof[:, e1]
+        e2 = self.mesh.f2t[1, find]
+        tv, tu = self.dofnum_v.t_dof, self.dofnum_u.t_dof
+        rows = np.hstack((tv[:, e1], tv[:, e2], tv[:, e1], tv[:, e2]))
+        cols = np.hstack((tu[:, e1], tu[:, e2], tu[:, e2], tu[:, e1]))
+        return rows, cols
+
+    # ------------------------------------------------------------------
+    # public API
+    # ------------------------------------------------------------------
+    def _get_engine(self):
+        if self._engine is None:
+            from .engine import Engine
+            self._engine = Engine(self)
+        return self._engine
+
+    def iasm(self, form, intorder=None, tind=None, interp=None):
+        """Assemble a bilinear or linear form over element interiors.
+
+        Same contract as spfem/assembly.py:839-1006: the form's argument names
+        select among ``u, v, du, dv, x, w, h``; bilinear iff it names ``u`` or
+        ``du``.  Returns a CSR matrix of shape ``(dofnum_v.N, dofnum_u.N)`` or
+        a vector of length ``dofnum_v.N``."""
+        plan = self.plan_iasm(form, intorder=intorder, interp=interp)
+        return self._get_engine().run_interior(plan, tind, interp)
+
+    def iasm_device(self, form, intorder=None, tind=None, interp=None):
+        """Like :meth:`iasm` but leaves the result on the GPU
+        (:class:`engine.DeviceCSR` or a device tensor for linear forms)."""
+        plan = self.plan_iasm(form, intorder=intorder, interp=interp)
+        return self._get_engine().run_interior(plan, tind, interp, to_host=False)
+
+    def fasm(self, form, find=None, interior=False, intorder=None,
+             normals=True, interp=None):
+        """Assemble a bilinear or linear form over facets
+        (spfem/assembly.py:1008-1183): boundary facets by default, interior
+        facets (two-sided ``u1, u2, v1, v2, du1, ...`` forms) with
+        ``interior=True``."""
+        if find is None:
+            find = (self.mesh.interior_facets() if interior
+                    else self.mesh.boundary_facets())
+        plan = self.plan_fasm(form, interior=interior, intorder=intorder,
+                              normals=normals, interp=interp)
+        return self._get_engine().run_facet(plan, np.asarray(find), interior,
+                                            interp)

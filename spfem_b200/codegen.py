@@ -1,0 +1,725 @@
+# -*- coding: utf-8 -*-
+"""CUDA C generation for the element / facet kernels.
+
+Input: the traced normal form of a weak form (``tracer.Form`` per pair of
+vector components) plus the reference element tables.  Output: the source of
+one ``extern "C" __global__`` kernel for sm_100a, compiled by NVRTC through
+the C-ABI (``spfem_nvrtc_compile``).
+
+Interior kernels (``AssemblerElement.iasm``, spfem/assembly.py:919-1006)
+----------------------------------------------------------------------
+One thread per element.  The thread loads the element's vertex ids and
+coordinates, rebuilds the affine geometry of ``MappingAffine``
+(spfem/mapping.py:207-302; same operation order, ``__dmul_rn/__dadd_rn`` so no
+FMA contraction changes ``x`` -- forms compare coordinates with ``==``) and
+evaluates the few coefficient expressions ``G^{ab}`` of the traced form.  Every
+local matrix entry is then a short dot product
+
+    A_loc[j, i] = sum_terms  K_term(j, i) * G_term
+
+with *compile-time* constants ``K``: for element-constant coefficients the sum
+over quadrature points is folded on the host into the reference tensors
+``K^{ab}_{ji} = sum_q W_q psi^a_j(X_q) psi^b_i(X_q)``; coefficients that vary
+from point to point (``x``, ``w``, bilinear ``MappingQ1`` Jacobians) keep one
+term per quadrature point.  Entries whose constants are all zero are known at
+generation time and cost nothing.
+
+Facet kernels (``fasm``, spfem/assembly.py:1011-1183) evaluate the basis
+polynomials at run time at the per-facet reference points
+``Y = invF(G(X))`` and loop over points and basis pairs; there are O(sqrt(nt))
+boundary facets, so that kernel is written for generality, not speed.
+
+The element body is a ``SPFEM_DEVICE`` function so the identical text can be
+compiled for the host (``-DSPFEM_HOST``, tests only) to check generated code
+against the oracle without a GPU.
+"""
+import hashlib
+import numpy as np
+from .tracer import Coef, NONE
+
+PRELUDE = r"""
+#ifdef SPFEM_HOST
+#include <math.h>
+#define SPFEM_DEVICE static inline
+#define __dmul_rn(a, b) ((a) * (b))
+#define __dadd_rn(a, b) ((a) + (b))
+#define __dsub_rn(a, b) ((a) - (b))
+#define __ddiv_rn(a, b) ((a) / (b))
+#define __restrict__
+#else
+#define SPFEM_DEVICE static __device__ __forceinline__
+#endif
+struct SpfemArgs {
+    long long n;              /* number of elements / facets to process        */
+    long long ldo;            /* leading dimension of the entry-major output    */
+    const int *sel;           /* optional element subset (tind) or null         */
+    const int *t;             /* vertex connectivity, t[k*ldt + e]              */
+    long long ldt;
+    const double *p;          /* vertex coordinates, p[k*ldp + v]               */
+    long long ldp;
+    const int *tdof_u;        /* trial DOF table (interp only), [j*ldd + e]     */
+    long long ldd;
+    const double *interp[8];  /* interpolated solution vectors (w)              */
+    const int *fv;            /* facet kernels: facet vertex ids fv[k*n + f]    */
+    const int *e1;            /* facet kernels: first / second element          */
+    const int *e2;
+    const int *lf1;           /* facet kernels: local facet index inside e1     */
+    double *out;              /* out[entry*ldo + k]                             */
+};
+"""
+
+
+def lit(x):
+    """Exact C literal of a double."""
+    x = float(x)
+    if x != x:
+        return "(0.0/0.0)"
+    if x in (float("inf"), float("-inf")):
+        return "(1.0/0.0)" if x > 0 else "(-1.0/0.0)"
+    if x == int(x) and abs(x) < 1e15:
+        return "%d.0" % int(x) if x >= 0 else "(-%d.0)" % int(-x)
+    h = x.hex()
+    return h if x >= 0 else "(%s)" % h
+
+
+_FUN1 = {"abs": "fabs", "sin": "sin", "cos": "cos", "tan": "tan", "exp": "exp",
+         "log": "log", "sqrt": "sqrt", "arcsin": "asin", "arccos": "acos",
+         "arctan": "atan", "sinh": "sinh", "cosh": "cosh", "tanh": "tanh",
+         "log10": "log10", "log2": "log2", "floor": "floor", "ceil": "ceil"}
+_CMP = {"lt": "<", "le": "<=", "gt": ">", "ge": ">=", "eq": "==", "ne": "!="}
+
+
+class Emitter(object):
+    """Emits the coefficient DAG as straight-line C; ``scope`` separates the
+    copies of point-dependent nodes (one per quadrature point)."""
+
+    def __init__(self):
+        self.lines = []
+        self.done = {}
+
+    def emit(self, s):
+        self.lines.append("    " + s)
+
+    def name(self, node, scope, symname):
+        if node.kind == "const":
+            return lit(node.value)
+        sc = scope if node.qdep else ""
+        key = (node.uid, sc)
+        nm = self.done.get(key)
+        if nm is not None:
+            return nm
+        if node.kind == "sym":
+            nm = symname(node.value, sc)
+            self.done[key] = nm
+            return nm
+        a = [self.name(x, scope, symname) for x in node.args]
+        k = node.kind
+        if k == "add":
+            e = "%s + %s" % (a[0], a[1])
+        elif k == "sub":
+            e = "%s - %s" % (a[0], a[1])
+        elif k == "mul":
+            e = "%s * %s" % (a[0], a[1])
+        elif k == "div":
+            e = "%s / %s" % (a[0], a[1])
+        elif k == "neg":
+            e = "-%s" % a[0]
+        elif k == "pow":
+            e = "pow(%s, %s)" % (a[0], a[1])
+        elif k in _FUN1:
+            e = "%s(%s)" % (_FUN1[k], a[0])
+        elif k in _CMP:
+            e = "((%s %s %s) ? 1.0 : 0.0)" % (a[0], _CMP[k], a[1])
+        elif k == "and":
+            e = "((%s != 0.0 && %s != 0.0) ? 1.0 : 0.0)" % (a[0], a[1])
+        elif k == "or":
+            e = "((%s != 0.0 || %s != 0.0) ? 1.0 : 0.0)" % (a[0], a[1])
+        elif k == "not":
+            e = "((%s != 0.0) ? 0.0 : 1.0)" % a[0]
+        elif k == "max":
+            e = "fmax(%s, %s)" % (a[0], a[1])
+        elif k == "min":
+            e = "fmin(%s, %s)" % (a[0], a[1])
+        elif k == "arctan2":
+            e = "atan2(%s, %s)" % (a[0], a[1])
+        elif k == "sign":
+            e = "((%s > 0.0) ? 1.0 : ((%s < 0.0) ? -1.0 : 0.0))" % (a[0], a[0])
+        else:
+            raise NotImplementedError("codegen: operator %s" % k)
+        nm = "c%d%s" % (node.uid, ("_" + sc) if sc else "")
+        self.emit("const double %s = %s;" % (nm, e))
+        self.done[key] = nm
+        return nm
+
+
+def collect_syms(forms):
+    """Names of all symbols used by the coefficient DAGs of ``forms``."""
+    seen, syms = set(), set()
+    stack = [c for f in forms for c in f.terms.values()]
+    while stack:
+        n = stack.pop()
+        if n.uid in seen:
+            continue
+        seen.add(n.uid)
+        if n.kind == "sym":
+            syms.add(n.value)
+        stack.extend(n.args)
+    return syms
+
+
+# ---------------------------------------------------------------------------
+# geometry text
+# ---------------------------------------------------------------------------
+def _mul(a, b):
+    return "__dmul_rn(%s, %s)" % (a, b)
+
+
+def _add(a, b):
+    return "__dadd_rn(%s, %s)" % (a, b)
+
+
+def _sub(a, b):
+    return "__dsub_rn(%s, %s)" % (a, b)
+
+
+def _div(a, b):
+    return "__ddiv_rn(%s, %s)" % (a, b)
+
+
+def _neg(a):
+    return "(-%s)" % a
+
+
+def affine_geometry(dim, sfx="", elem="e"):
+    """C statements computing ``A, b, detA, invA`` of element ``elem`` with
+    the operation order of spfem/mapping.py:207-229 (tri) / 244-279 (tet).
+    Variables carry the suffix ``sfx`` (facet kernels have two elements)."""
+    L = []
+    nve = dim + 1
+    for k in range(nve):
+        L.append("const int vtx%s_%d = P.t[%d * P.ldt + %s];" % (sfx, k, k, elem))
+    for i in range(dim):
+        L.append("const double b%s_%d = P.p[%d * P.ldp + vtx%s_0];" % (sfx, i, i, sfx))
+        for j in range(dim):
+            L.append("const double A%s_%d%d = %s;" % (
+                sfx, i, j, _sub("P.p[%d * P.ldp + vtx%s_%d]" % (i, sfx, j + 1),
+                                "b%s_%d" % (sfx, i))))
+    A = lambda i, j: "A%s_%d%d" % (sfx, i, j)
+    if dim == 2:
+        L.append("const double detA%s = %s;" % (
+            sfx, _sub(_mul(A(0, 0), A(1, 1)), _mul(A(0, 1), A(1, 0)))))
+        inv = {(0, 0): A(1, 1), (0, 1): _neg(A(0, 1)),
+               (1, 0): _neg(A(1, 0)), (1, 1): A(0, 0)}
+    else:
+        def m2(a, b, c, d):   # a*b - c*d
+            return _sub(_mul(a, b), _mul(c, d))
+        # detA = A00*(A11*A22 - A12*A21) - A01*(A10*A22 - A12*A20)
+        #      + A02*(A10*A21 - A11*A20)          (spfem/mapping.py:265-267)
+        t0 = _mul(A(0, 0), m2(A(1, 1), A(2, 2), A(1, 2), A(2, 1)))
+        t1 = _mul(A(0, 1), m2(A(1, 0), A(2, 2), A(1, 2), A(2, 0)))
+        t2 = _mul(A(0, 2), m2(A(1, 0), A(2, 1), A(1, 1), A(2, 0)))
+        L.append("const double detA%s = %s;" % (sfx, _add(_sub(t0, t1), t2)))
+
+        def cof(a, b, c, d):  # (-a*b + c*d)   (spfem/mapping.py:271-279)
+            return _add(_mul(_neg(a), b), _mul(c, d))
+        inv = {
+            (0, 0): cof(A(1, 2), A(2, 1), A(1, 1), A(2, 2)),
+            (1, 0): m2(A(1, 2), A(2, 0), A(1, 0), A(2, 2)),
+            (2, 0): cof(A(1, 1), A(2, 0), A(1, 0), A(2, 1)),
+            (0, 1): m2(A(0, 2), A(2, 1), A(0, 1), A(2, 2)),
+            (1, 1): cof(A(0, 2), A(2, 0), A(0, 0), A(2, 2)),
+            (2, 1): m2(A(0, 1), A(2, 0), A(0, 0), A(2, 1)),
+            (0, 2): cof(A(0, 2), A(1, 1), A(0, 1), A(1, 2)),
+            (1, 2): m2(A(0, 2), A(1, 0), A(0, 0), A(1, 2)),
+            (2, 2): cof(A(0, 1), A(1, 0), A(0, 0), A(1, 1)),
+        }
+    for (i, j), e in sorted(inv.items()):
+        L.append("const double iA%s_%d%d = %s;" % (sfx, i, j,
+                                                  _div(e, "detA%s" % sfx)))
+    L.append("const double absdet%s = fabs(detA%s);" % (sfx, sfx))
+    return L
+
+
+def q1_geometry_q(tag, xq, yq):
+    """Jacobian of the bilinear map at the reference point ``(xq, yq)``
+    (spfem/mapping.py:58-74, 142-171); the corner coordinates ``Q{i}_{k}``
+    must be in scope.  ``xq``/``yq`` are floats (folded into literals);
+    variables get the suffix ``tag``."""
+    L = []
+    one_m_y, one_p_y = lit(1.0 - yq), lit(1.0 + yq)
+    one_m_x, one_p_x = lit(1.0 - xq), lit(1.0 + xq)
+    q = tag
+    for i in range(2):
+        P = ["Q%d_%d" % (i, k) for k in range(4)]
+        # 0.25*(-P0*(1-y) + P1*(1-y) + P2*(1+y) - P3*(1+y))
+        e0 = _sub(_add(_add(_mul(_neg(P[0]), one_m_y), _mul(P[1], one_m_y)),
+                       _mul(P[2], one_p_y)), _mul(P[3], one_p_y))
+        # 0.25*(-P0*(1-x) - P1*(1+x) + P2*(1+x) + P3*(1-x))
+        e1 = _add(_add(_sub(_mul(_neg(P[0]), one_m_x), _mul(P[1], one_p_x)),
+                       _mul(P[2], one_p_x)), _mul(P[3], one_m_x))
+        L.append("const double J%d0_%s = %s;" % (i, q, _mul("0.25", e0)))
+        L.append("const double J%d1_%s = %s;" % (i, q, _mul("0.25", e1)))
+    L.append("const double detJ_%s = %s;" % (
+        q, _sub(_mul("J00_%s" % q, "J11_%s" % q), _mul("J01_%s" % q, "J10_%s" % q))))
+    L.append("const double iJ_00_%s = %s;" % (q, _div("J11_%s" % q, "detJ_%s" % q)))
+    L.append("const double iJ_01_%s = %s;" % (q, _div(_neg("J01_%s" % q), "detJ_%s" % q)))
+    L.append("const double iJ_10_%s = %s;" % (q, _div(_neg("J10_%s" % q), "detJ_%s" % q)))
+    L.append("const double iJ_11_%s = %s;" % (q, _div("J00_%s" % q, "detJ_%s" % q)))
+    L.append("const double absdetq_%s = fabs(detJ_%s);" % (q, q))
+    return L
+
+
+def _q1_basis(x, y, k):
+    sx = (-1, 1, 1, -1)[k]
+    sy = (-1, -1, 1, 1)[k]
+    return 0.25 * (1 + sx * x) * (1 + sy * y)
+
+
+# ---------------------------------------------------------------------------
+# interior kernels
+# ---------------------------------------------------------------------------
+class InteriorSpec(object):
+    """Everything the generator needs for one ``iasm`` kernel.
+
+    ``blocks``: ``{(cu, cv): Form}``; ``tab_u`` / ``tab_v``: reference tables
+    ``psi[a][j][q]`` with ``a = 0`` the value and ``1 + l`` the l-th reference
+    derivative of the *scalar* parent element."""
+
+    def __init__(self, refdom, dim, bilinear, nbu, nbv, ncu, ncv, blocks,
+                 X, W, tab_u, tab_v, nw=0):
+        self.refdom, self.dim, self.bilinear = refdom, dim, bilinear
+        self.nbu, self.nbv, self.ncu, self.ncv = nbu, nbv, ncu, ncv
+        self.blocks, self.X, self.W = blocks, X, W
+        self.tab_u, self.tab_v, self.nw = tab_u, tab_v, nw
+
+    @property
+    def n_rows(self):
+        return self.nbv * self.ncv
+
+    @property
+    def n_cols(self):
+        return self.nbu * self.ncu if self.bilinear else 1
+
+    @property
+    def n_entries(self):
+        return self.n_rows * self.n_cols
+
+
+def _psi(tab, a, j, q):
+    return 1.0 if a == NONE else tab[a][j][q]
+
+
+def interior_terms(spec, drop_tol=1e-15):
+    """For every local entry the list ``[(constant, coef_node, scope)]``.
+
+    Returns ``(entries, coef_uses)`` where ``entries[idx]`` follows the
+    reference's COO block numbering ``idx = Nbfun_v*j + i``
+    (spfem/assembly.py:977) and ``coef_uses`` is the ordered list of
+    ``(node, scope)`` that must be evaluated."""
+    nq = len(spec.W)
+    entries = [[] for _ in range(spec.n_entries)]
+    uses, seen = [], set()
+    nbu = spec.nbu if spec.bilinear else 1
+    for (cu, cv), form in sorted(spec.blocks.items()):
+        for (a, b), coef in sorted(form.terms.items(),
+                                   key=lambda kv: kv[0]):
+            if a != NONE and not spec.bilinear:
+                raise ValueError("trial function in a linear form")
+            # K[j, i, q] = W_q psi^a_j(q) psi^b_i(q)
+            K = np.empty((nbu, spec.nbv, nq))
+            for j in range(nbu):
+                for i in range(spec.nbv):
+                    for q in range(nq):
+                        K[j, i, q] = (spec.W[q] * _psi(spec.tab_u, a, j, q)
+                                      * _psi(spec.tab_v, b, i, q))
+            if coef.qdep:
+                scale = np.max(np.abs(K)) if K.size else 0.0
+                for q in range(nq):
+                    used = False
+                    for j in range(nbu):
+                        for i in range(spec.nbv):
+                            if abs(K[j, i, q]) > drop_tol * scale:
+                                idx = ((j * spec.ncu + cu) * spec.n_rows
+                                       + (i * spec.ncv + cv))
+                                entries[idx].append((K[j, i, q], coef, "%d" % q))
+                                used = True
+                    if used and (coef.uid, q) not in seen:
+                        seen.add((coef.uid, q))
+                        uses.append((coef, "%d" % q))
+            else:
+                # exactly rounded sum over the points (math.fsum)
+                import math
+                Ks = np.array([[math.fsum(K[j, i, :]) for i in range(spec.nbv)]
+                               for j in range(nbu)])
+                mag = np.array([[math.fsum(np.abs(K[j, i, :]))
+                                 for i in range(spec.nbv)] for j in range(nbu)])
+                scale = np.max(mag) if mag.size else 0.0
+                used = False
+                for j in range(nbu):
+                    for i in range(spec.nbv):
+                        if abs(Ks[j, i]) > drop_tol * scale:
+                            idx = ((j * spec.ncu + cu) * spec.n_rows
+                                   + (i * spec.ncv + cv))
+                            entries[idx].append((Ks[j, i], coef, ""))
+                            used = True
+                if used and (coef.uid, "") not in seen:
+                    seen.add((coef.uid, ""))
+                    uses.append((coef, ""))
+    return entries, uses
+
+
+def generate_interior(spec, name="spfem_elem"):
+    """Source text of the interior element kernel for ``spec``."""
+    dim, nq = spec.dim, len(spec.W)
+    entries, uses = interior_terms(spec)
+    syms = collect_syms(list(spec.blocks.values()))
+    em = Emitter()
+    quad = spec.refdom == "quad"
+
+    body = []
+    if quad:
+        for k in range(4):
+            body.append("const int vtx_%d = P.t[%d * P.ldt + e];" % (k, k))
+        for i in range(2):
+            for k in range(4):
+                body.append("const double Q%d_%d = P.p[%d * P.ldp + vtx_%d];"
+                            % (i, k, i, k))
+        for q in range(nq):
+            body += q1_geometry_q("%d" % q, spec.X[0, q], spec.X[1, q])
+            if "hq" in syms:
+                body.append("const double hq_%d = pow(absdetq_%d, %s);"
+                            % (q, q, lit(1.0 / dim)))
+    else:
+        body += affine_geometry(dim)
+        if "h" in syms:
+            body.append("const double h = pow(absdet, %s);" % lit(1.0 / dim))
+    # global coordinates of the quadrature points (only if the form uses x)
+    for k in range(dim):
+        if ("x%d" % k) not in syms:
+            continue
+        for q in range(nq):
+            if quad:
+                # sum_k P_k * N_k(X_q)                (spfem/mapping.py:104-110)
+                acc = _mul("Q%d_0" % k, lit(_q1_basis(spec.X[0, q], spec.X[1, q], 0)))
+                for c in range(1, 4):
+                    acc = _add(acc, _mul("Q%d_%d" % (k, c), lit(
+                        _q1_basis(spec.X[0, q], spec.X[1, q], c))))
+                body.append("const double x%d_%d = %s;" % (k, q, acc))
+            else:
+                # outer(A_k0, X0) + outer(A_k1, X1) (+ ...) + b_k
+                #                                    (spfem/mapping.py:318-319)
+                acc = _mul("A_%d0" % k, lit(spec.X[0, q]))
+                for l in range(1, dim):
+                    acc = _add(acc, _mul("A_%d%d" % (k, l), lit(spec.X[l, q])))
+                body.append("const double x%d_%d = %s;" % (k, q, _add(acc, "b_%d" % k)))
+    # interpolated fields w[k] = sum_j interp[k][t_dof_u[j, e]] phi_j(X_q)
+    #                                          (spfem/assembly.py:955-959)
+    for s in range(spec.nw):
+        if not any(("w%d" % s) == nm for nm in syms):
+            continue
+        for j in range(spec.nbu):
+            body.append("const double wc%d_%d = P.interp[%d][P.tdof_u[%d * P.ldd + e]];"
+                        % (s, j, s, j))
+        for q in range(nq):
+            terms = ["wc%d_%d * %s" % (s, j, lit(spec.tab_u[0][j][q]))
+                     for j in range(spec.nbu)]
+            body.append("const double w%d_%d = 0.0 + %s;" % (s, q, " + ".join(terms)))
+
+    def symname(nm, scope):
+        if nm.startswith("iA"):
+            return "iA_" + nm[2:]
+        if nm.startswith("iJ"):
+            return "iJ_%s_%s" % (nm[2:], scope)
+        if scope:
+            return "%s_%s" % (nm, scope)
+        return nm
+
+    names = {}
+    for node, scope in uses:
+        names[(node.uid, scope)] = em.name(node, scope, symname)
+    body += [ln.strip() for ln in em.lines]
+
+    for idx, terms in enumerate(entries):
+        # merge terms that multiply the same coefficient (e.g. G^{12} == G^{21})
+        merged, order = {}, []
+        for K, node, scope in terms:
+            key = (node.uid, scope)
+            if key in merged:
+                merged[key] = (merged[key][0] + K, node, scope)
+            else:
+                merged[key] = (K, node, scope)
+                order.append(key)
+        terms = [merged[k] for k in order if merged[k][0] != 0.0]
+        if not terms:
+            body.append("SPFEM_STORE(%d, 0.0);" % idx)
+            continue
+        expr = " + ".join("%s * %s" % (lit(K), names[(node.uid, scope)])
+                          for K, node, scope in terms)
+        body.append("SPFEM_STORE(%d, %s);" % (idx, expr))
+
+    src = [PRELUDE]
+    src.append("#define SPFEM_NENTRIES %d" % spec.n_entries)
+    src.append("#ifndef SPFEM_STORE")
+    src.append("#define SPFEM_STORE(idx, val) P.out[(long long)(idx) * P.ldo + k] = (val)")
+    src.append("#endif")
+    src.append("SPFEM_DEVICE void %s_body(const SpfemArgs &P, const long long k)\n{" % name)
+    src.append("    const long long e = P.sel ? (long long)P.sel[k] : k;")
+    src += ["    " + ln for ln in body]
+    src.append("}")
+    src.append("#ifndef SPFEM_HOST")
+    src.append('extern "C" __global__ void __launch_bounds__(128) %s(const SpfemArgs P)\n{' % name)
+    src.append("    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;")
+    src.append("    if (k < P.n) %s_body(P, k);" % name)
+    src.append("}")
+    src.append("#else")
+    src.append('extern "C" void %s_host(const SpfemArgs *P)\n{' % name)
+    src.append("    for (long long k = 0; k < P->n; ++k) %s_body(*P, k);" % name)
+    src.append("}")
+    src.append("#endif")
+    return "\n".join(src) + "\n"
+
+
+# ---------------------------------------------------------------------------
+# facet kernels
+# ---------------------------------------------------------------------------
+class FacetSpec(object):
+    """``fasm`` kernel description.  ``blocks``: list over the facet blocks --
+    one for boundary facets, four ((1,1),(2,2),(2,1),(1,2) = (side_u, side_v),
+    spfem/assembly.py:1131-1149) for interior facets -- of
+    ``{(cu, cv): Form}``."""
+
+    def __init__(self, refdom, dim, bilinear, interior, nbu, nbv, ncu, ncv,
+                 blocks, sides, X, W, polys_u, polys_v, normals=True, nw=0):
+        self.refdom, self.dim, self.bilinear = refdom, dim, bilinear
+        self.interior = interior
+        self.nbu, self.nbv, self.ncu, self.ncv = nbu, nbv, ncu, ncv
+        self.blocks, self.sides, self.X, self.W = blocks, sides, X, W
+        self.polys_u, self.polys_v = polys_u, polys_v
+        self.normals, self.nw = normals, nw
+
+    @property
+    def n_rows(self):
+        return self.nbv * self.ncv
+
+    @property
+    def n_cols(self):
+        return self.nbu * self.ncu if self.bilinear else 1
+
+    @property
+    def n_entries(self):
+        return self.n_rows * self.n_cols
+
+
+_NREF = {2: ((0.0, -1.0), (1.0, 1.0), (-1.0, 0.0)),
+         3: ((0.0, 0.0, -1.0), (0.0, -1.0, 0.0), (-1.0, 0.0, 0.0),
+             (1.0, 1.0, 1.0))}
+
+
+def generate_facet(spec, name="spfem_facet"):
+    """Source text of the facet kernel: one thread per facet, run-time loops
+    over quadrature points and basis functions."""
+    dim, nq = spec.dim, len(spec.W)
+    bd = dim - 1                       # dimension of the reference facet
+    quad = spec.refdom == "quad"
+    all_forms = [f for blk in spec.blocks for f in blk.values()]
+    syms = collect_syms(all_forms)
+    nsides = 2 if spec.interior else 1
+    NA = 1 + dim
+    L = []
+    A = L.append
+    A("const long long f = k;")
+    for s in range(1, nsides + 1):
+        A("const long long el%d = P.e%d[f];" % (s, s))
+    # facet geometry: B, c, detB            (spfem/mapping.py:234-242, 284-302)
+    for i in range(dim):
+        A("const double c_%d = P.p[%d * P.ldp + P.fv[f]];" % (i, i))
+        for j in range(bd):
+            A("const double B_%d%d = %s;" % (
+                i, j, _sub("P.p[%d * P.ldp + P.fv[%d * P.n + f]]" % (i, j + 1),
+                           "c_%d" % i)))
+    if dim == 2:
+        A("const double detB = sqrt(%s);" % _add(_mul("B_00", "B_00"),
+                                                 _mul("B_10", "B_10")))
+    else:
+        A("const double cr0 = %s;" % _sub(_mul("B_10", "B_21"), _mul("B_20", "B_11")))
+        A("const double cr1 = %s;" % _add(_mul(_neg("B_00"), "B_21"), _mul("B_20", "B_01")))
+        A("const double cr2 = %s;" % _sub(_mul("B_00", "B_11"), _mul("B_10", "B_01")))
+        A("const double detB = sqrt(%s);" % _add(_add(_mul("cr0", "cr0"),
+                                                      _mul("cr1", "cr1")),
+                                                 _mul("cr2", "cr2")))
+    A("const double absdetB = fabs(detB);")
+    A("const double hf = pow(absdetB, %s);" % lit(1.0 / (dim - 1.0)))
+    # element geometry on each side
+    for s in range(1, nsides + 1):
+        if quad:
+            # MappingQ1.invF = one Newton step from the origin
+            #                                   (spfem/mapping.py:124-139)
+            for kk in range(4):
+                A("const int vq%d_%d = P.t[%d * P.ldt + el%d];" % (s, kk, kk, s))
+            for i in range(2):
+                for kk in range(4):
+                    A("const double Q%d_%d = P.p[%d * P.ldp + vq%d_%d];"
+                      % (i, kk, i, s, kk))
+            for ln in q1_geometry_q("c%d" % s, 0.0, 0.0):
+                A(ln)
+            for i in range(2):
+                acc = _mul("Q%d_0" % i, lit(_q1_basis(0.0, 0.0, 0)))
+                for c in range(1, 4):
+                    acc = _add(acc, _mul("Q%d_%d" % (i, c), lit(_q1_basis(0.0, 0.0, c))))
+                A("const double F0%d_%d = %s;" % (s, i, acc))
+        else:
+            for ln in affine_geometry(dim, sfx=str(s), elem="el%d" % s):
+                A(ln)
+    # outward normal of side 1           (spfem/mapping.py:474-524)
+    if spec.normals and not quad:
+        A("const int lf = P.lf1[f];")
+        for k in range(dim):
+            sel = "0.0"
+            for itr in range(len(_NREF[dim]) - 1, -1, -1):
+                sel = "(lf == %d ? %s : %s)" % (itr, lit(_NREF[dim][itr][k]), sel)
+            A("const double nr_%d = %s;" % (k, sel))
+        for k in range(dim):
+            acc = _mul("iA1_0%d" % k, "nr_0")
+            for l in range(1, dim):
+                acc = _add(acc, _mul("iA1_%d%d" % (l, k), "nr_%d" % l))
+            A("const double nn_%d = %s;" % (k, acc))
+        acc = _mul("nn_0", "nn_0")
+        for k in range(1, dim):
+            acc = _add(acc, _mul("nn_%d" % k, "nn_%d" % k))
+        A("const double nlen = sqrt(%s);" % acc)
+        for k in range(dim):
+            A("const double n%d = %s;" % (k, _div("nn_%d" % k, "nlen")))
+    A("double acc[%d];" % (len(spec.blocks) * spec.n_entries))
+    A("for (int z = 0; z < %d; ++z) acc[z] = 0.0;" % (len(spec.blocks) * spec.n_entries))
+    A("const double XQ[%d][%d] = {%s};" % (
+        max(bd, 1), nq, ", ".join("{" + ", ".join(lit(spec.X[r, q]) for q in range(nq)) + "}"
+                                  for r in range(bd))))
+    A("const double WQ[%d] = {%s};" % (nq, ", ".join(lit(w) for w in spec.W)))
+    A("#pragma unroll 1")
+    A("for (int q = 0; q < %d; ++q) {" % nq)
+    # x = G(X)                               (spfem/mapping.py:389-415)
+    for i in range(dim):
+        acc = _mul("B_%d0" % i, "XQ[0][q]")
+        for j in range(1, bd):
+            acc = _add(acc, _mul("B_%d%d" % (i, j), "XQ[%d][q]" % j))
+        A("  const double x%d = %s;" % (i, _add(acc, "c_%d" % i)))
+    A("  const double wdet = WQ[q] * absdetB;")
+    for s in range(1, nsides + 1):
+        # Y = invF(x)                         (spfem/mapping.py:350-387)
+        if quad:
+            for i in range(2):
+                A("  const double g%d_%d = %s;" % (s, i, _sub("x%d" % i, "F0%d_%d" % (s, i))))
+            for i in range(2):
+                A("  const double Y%d_%d = %s;" % (s, i, _add(_add("0.0", _mul(
+                    "iJ_%d0_c%d" % (i, s), "g%d_0" % s)), _mul("iJ_%d1_c%d" % (i, s), "g%d_1" % s))))
+        else:
+            for i in range(dim):
+                A("  const double g%d_%d = %s;" % (s, i, _sub("x%d" % i, "b%d_%d" % (s, i))))
+            for i in range(dim):
+                acc = _mul("iA%d_%d0" % (s, i), "g%d_0" % s)
+                for j in range(1, dim):
+                    acc = _add(acc, _mul("iA%d_%d%d" % (s, i, j), "g%d_%d" % (s, j)))
+                A("  const double Y%d_%d = %s;" % (s, i, acc))
+        ynames = ["Y%d_%d" % (s, i) for i in range(dim)]
+        if quad:
+            # per-point inverse Jacobian at Y (gbasis -> invDF(Y), element.py:474)
+            A("  double iJ%d[2][2];" % s)
+            A("  {")
+            xq, yq = ynames
+            for i in range(2):
+                P_ = ["Q%d_%d" % (i, kk) for kk in range(4)]
+                if s == 2:
+                    pass
+                e0 = _sub(_add(_add(_mul(_neg(P_[0]), _sub("1.0", yq)), _mul(P_[1], _sub("1.0", yq))),
+                               _mul(P_[2], _add("1.0", yq))), _mul(P_[3], _add("1.0", yq)))
+                e1 = _add(_add(_sub(_mul(_neg(P_[0]), _sub("1.0", xq)), _mul(P_[1], _add("1.0", xq))),
+                               _mul(P_[2], _add("1.0", xq))), _mul(P_[3], _sub("1.0", xq)))
+                A("    const double j%d0 = %s;" % (i, _mul("0.25", e0)))
+                A("    const double j%d1 = %s;" % (i, _mul("0.25", e1)))
+            A("    const double dj = %s;" % _sub(_mul("j00", "j11"), _mul("j01", "j10")))
+            A("    iJ%d[0][0] = j11 / dj; iJ%d[0][1] = -j01 / dj;" % (s, s))
+            A("    iJ%d[1][0] = -j10 / dj; iJ%d[1][1] = j00 / dj;" % (s, s))
+            A("  }")
+        for side, (polys, nb, tag) in enumerate(((spec.polys_u, spec.nbu, "pu"),
+                                                 (spec.polys_v, spec.nbv, "pv"))):
+            if side == 0 and not spec.bilinear and spec.nw == 0:
+                continue
+            P_, dP_ = polys
+            A("  double %s%d[%d][%d];" % (tag, s, NA, nb))
+            for j in range(nb):
+                A("  %s%d[0][%d] = %s;" % (tag, s, j, P_[j].c_expr(ynames)))
+                for l in range(dim):
+                    A("  %s%d[%d][%d] = %s;" % (tag, s, 1 + l, j,
+                                                dP_[j][l].c_expr(ynames)))
+    # interpolated w / dw on side 1           (spfem/assembly.py:1076-1089)
+    for sl in range(spec.nw):
+        if ("w%d" % sl) in syms or any(("dw%d_%d" % (sl, a)) in syms for a in range(dim)):
+            A("  double w%d = 0.0;" % sl)
+            for a in range(dim):
+                A("  double dw%d_%d = 0.0;" % (sl, a))
+            A("  for (int j = 0; j < %d; ++j) {" % spec.nbu)
+            A("    const double cf = P.interp[%d][P.tdof_u[j * P.ldd + el1]];" % sl)
+            A("    w%d += cf * pu1[0][j];" % sl)
+            for a in range(dim):
+                if quad:
+                    g = " + ".join("iJ1[%d][%d] * pu1[%d][j]" % (l, a, 1 + l) for l in range(dim))
+                else:
+                    g = " + ".join("iA1_%d%d * pu1[%d][j]" % (l, a, 1 + l) for l in range(dim))
+                A("    dw%d_%d += cf * (%s);" % (sl, a, g))
+            A("  }")
+
+    def symname(nm, scope):
+        # iA1_lk / iA2_lk : inverse Jacobians of side 1 / 2
+        if quad and nm.startswith("iA"):
+            return "iJ%s[%s][%s]" % (nm[2], nm[4], nm[5])
+        return nm
+
+    em = Emitter()
+    em_lines_start = len(L)
+    for bi, blk in enumerate(spec.blocks):
+        su, sv = spec.sides[bi]
+        for (cu, cv), form in sorted(blk.items()):
+            for (a, b), coef in sorted(form.terms.items(), key=lambda kv: kv[0]):
+                for node in (coef,):
+                    # q-dependence is irrelevant inside the run-time loop
+                    pass
+                before = len(em.lines)
+                g = em.name(coef, "", symname)
+                for ln in em.lines[before:]:
+                    A("  " + ln.strip())
+                del em.lines[before:]
+                pu = "1.0" if a == NONE else "pu%d[%d][j]" % (su, a)
+                pv = "1.0" if b == NONE else "pv%d[%d][i]" % (sv, b)
+                nbu = spec.nbu if spec.bilinear else 1
+                A("  for (int j = 0; j < %d; ++j)" % nbu)
+                A("    for (int i = 0; i < %d; ++i)" % spec.nbv)
+                A("      acc[%d + (j * %d + %d) * %d + (i * %d + %d)] += wdet * (%s) * %s * %s;"
+                  % (bi * spec.n_entries, spec.ncu if spec.bilinear else 1, cu,
+                     spec.n_rows, spec.ncv, cv, g, pu, pv))
+    A("}")
+    nblk = len(spec.blocks)
+    A("for (int b = 0; b < %d; ++b)" % nblk)
+    A("  for (int z = 0; z < %d; ++z)" % spec.n_entries)
+    A("    P.out[(long long)z * P.ldo + (long long)b * P.n + k] = acc[b * %d + z];"
+      % spec.n_entries)
+
+    src = [PRELUDE]
+    src.append("#define SPFEM_NENTRIES %d" % spec.n_entries)
+    src.append("SPFEM_DEVICE void %s_body(const SpfemArgs &P, const long long k)\n{" % name)
+    src += ["    " + ln for ln in L]
+    src.append("}")
+    src.append("#ifndef SPFEM_HOST")
+    src.append('extern "C" __global__ void __launch_bounds__(64) %s(const SpfemArgs P)\n{' % name)
+    src.append("    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;")
+    src.append("    if (k < P.n) %s_body(P, k);" % name)
+    src.append("}")
+    src.append("#else")
+    src.append('extern "C" void %s_host(const SpfemArgs *P)\n{' % name)
+    src.append("    for (long long k = 0; k < P->n; ++k) %s_body(*P, k);" % name)
+    src.append("}")
+    src.append("#endif")
+    return "\n".join(src) + "\n"
+
+
+def source_key(src):
+    return hashlib.sha256(src.encode("utf-8")).hexdigest()[:24]

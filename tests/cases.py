@@ -1,0 +1,229 @@
+# -*- coding: utf-8 -*-
+"""Shared parity cases: the same (mesh, element pair, form, options) tuples are
+run through the patched reference (``tests/golden/make_golden.py`` -> golden
+``.npz``), the oracle, the host emulation of the generated kernels and the
+CUDA path.  Forms are the idioms of the reference's own tests
+(SURVEY.md appendix B): spfem/test_asm.py, test_mapping.py, test_module.py,
+README.md and learning/Example 1."""
+import numpy as np
+
+GAMMA = 100.0
+
+
+def lap2(du, dv):
+    return du[0] * dv[0] + du[1] * dv[1]
+
+
+def lap3(du, dv):
+    return du[0] * dv[0] + du[1] * dv[1] + du[2] * dv[2]
+
+
+def mass(u, v):
+    return u * v
+
+
+def load1(v):
+    return 1.0 * v
+
+
+def load_sin_h(v, x, h):
+    return h * np.sin(np.pi * x[0]) * np.sin(np.pi * x[1]) * v
+
+
+def mass_x2(u, v, x):
+    return x[0] ** 2 * u * v
+
+
+def load_masks(v, x):
+    # boolean masks as in spfem/test_asm.py:200-201, test_module.py:284-288
+    return ((x[0] >= 0.4) & (x[0] <= 0.6) & (x[1] == 1.0)) * v + (x[0] == 1) * 1.0 * v
+
+
+def mass_w(u, v, w):
+    return w[0] * u * v
+
+
+def load_w2(v, w):
+    return w[7] * w[7] * v
+
+
+def _eps(dw):
+    return [[dw[0][0], 0.5 * (dw[0][1] + dw[1][0])],
+            [0.5 * (dw[0][1] + dw[1][0]), dw[1][1]]]
+
+
+def elasticity(du, dv):
+    # 2 mu eps(u):eps(v) + lambda tr eps(u) tr eps(v), lambda = mu = 1
+    eu, ev = _eps(du), _eps(dv)
+    return (2.0 * sum(eu[i][j] * ev[i][j] for i in range(2) for j in range(2))
+            + 1.0 * (eu[0][0] + eu[1][1]) * (ev[0][0] + ev[1][1]))
+
+
+def stokes_b(du, v):
+    return (du[0][0] + du[1][1]) * v
+
+
+def vec3_mixed(u, v, du, dv):
+    return (u[0] * v[0] + u[1] * v[1] + u[2] * v[2] + du[0][1] * dv[1][0]
+            + du[2][2] * dv[0][0])
+
+
+def q_load(v, x, h):
+    return h * np.exp(x[0]) * x[1] * v
+
+
+def bnd_mass(u, v):
+    return u * v
+
+
+def nitsche(u, v, du, dv, x, h, n):
+    # spfem/test_module.py:498-501
+    return (GAMMA * 1 / h * u * v - du[0] * n[0] * v - du[1] * n[1] * v
+            - u * dv[0] * n[0] - u * dv[1] * n[1])
+
+
+def bnd_lin(v, dv, x, h, n):
+    return GAMMA / h * np.sin(x[0]) * v - dv[0] * n[0] * x[1]
+
+
+def normal0(v, n):
+    return n[0] * v
+
+
+def normal2(v, n):
+    return n[2] * v
+
+
+def sipg(u1, u2, v1, v2, du1, du2, dv1, dv2, h, n):
+    # spfem/test_asm.py:38-44 style interior penalty terms
+    # (signs chosen so that the terms do not cancel for continuous elements)
+    return (10 / h * (u1 + 2 * u2) * (v1 - 3 * v2)
+            - 0.5 * ((du1[0] + du2[0]) * n[0] + (du1[1] + du2[1]) * n[1]) * (v1 + v2))
+
+
+def facet_w(v, w, dw, n):
+    return w[0] * v + (dw[0][0] * n[0] + dw[0][1] * n[1]) * v
+
+
+def vec_nitsche(u, v, du, dv, h, n):
+    return (GAMMA / h * (u[0] * v[0] + u[1] * v[1])
+            - sum(du[i][j] * n[j] * v[i] for i in range(2) for j in range(2))
+            - sum(dv[i][j] * n[j] * u[i] for i in range(2) for j in range(2)))
+
+
+def tet_bnd(u, v, du, dv, x, h, n):
+    return (1 / h * u * v - (du[0] * n[0] + du[1] * n[1] + du[2] * n[2]) * v
+            + x[2] * u * v)
+
+
+def jump(u1, u2, v1, v2, h):
+    return 1 / h * (u1 + 2 * u2) * (v1 - 3 * v2)
+
+
+def q_bnd(u, v, x, h):
+    return 1 / h * u * v * x[0]
+
+
+def q_bnd_lin(v, dv, x):
+    return x[1] * v + dv[0]
+
+
+def _interp_vec(n, seed=0):
+    return np.random.default_rng(seed).standard_normal(n)
+
+
+class Case(object):
+    def __init__(self, name, mesh, refine, eu, form, kind="iasm", ncu=1,
+                 ev=None, ncv=1, interp_key=None, tind_step=None,
+                 find_step=None, **kw):
+        self.name, self.mesh, self.refine = name, mesh, refine
+        self.eu, self.ev, self.ncu, self.ncv = eu, ev, ncu, ncv
+        self.form, self.kind, self.kw = form, kind, kw
+        self.interp_key, self.tind_step, self.find_step = interp_key, tind_step, find_step
+
+
+CASES = [
+    Case("trip1_lap", "MeshTri", 4, "TriP1", lap2),
+    Case("trip1_mass", "MeshTri", 4, "TriP1", mass),
+    Case("trip1_lap_r6", "MeshTri", 6, "TriP1", lap2),
+    Case("trip2_lap", "MeshTri", 3, "TriP2", lap2),
+    Case("trip2_mass", "MeshTri", 3, "TriP2", mass),
+    Case("tetp1_lap", "MeshTet", 2, "TetP1", lap3),
+    Case("tetp2_lap", "MeshTet", 2, "TetP2", lap3),
+    Case("tetp2_mass", "MeshTet", 2, "TetP2", mass),
+    Case("q1_lap", "MeshQuad", 3, "Q1", lap2),
+    Case("q2_lap", "MeshQuad", 3, "Q2", lap2),
+    Case("q2_mass", "MeshQuad", 3, "Q2", mass),
+    Case("trip1_load", "MeshTri", 4, "TriP1", load1),
+    Case("trip1_load_sin_h", "MeshTri", 4, "TriP1", load_sin_h),
+    Case("trip1_mass_x2", "MeshTri", 4, "TriP1", mass_x2),
+    Case("trip1_masks", "MeshTri", 4, "TriP1", load_masks),
+    Case("trip1_interp_mass", "MeshTri", 4, "TriP1", mass_w, interp_key=0),
+    Case("trip1_interp_load", "MeshTri", 4, "TriP1", load_w2, interp_key=7),
+    Case("trip1_tind", "MeshTri", 4, "TriP1", lap2, tind_step=3),
+    Case("trip1_lap_order5", "MeshTri", 3, "TriP1", lap2, intorder=5),
+    Case("vecp2_elasticity", "MeshTri", 3, "TriP2", elasticity, ncu=2, ncv=2),
+    Case("stokes_b", "MeshTri", 3, "TriP2", stokes_b, ncu=2, ev="TriP1", ncv=1),
+    Case("vectetp1_mixed", "MeshTet", 2, "TetP1", vec3_mixed, ncu=3, ncv=3),
+    Case("q1_load", "MeshQuad", 3, "Q1", q_load),
+    # facets
+    Case("f_trip1_mass", "MeshTri", 3, "TriP1", bnd_mass, kind="fasm"),
+    Case("f_trip1_nitsche", "MeshTri", 3, "TriP1", nitsche, kind="fasm"),
+    Case("f_trip1_lin", "MeshTri", 3, "TriP1", bnd_lin, kind="fasm"),
+    Case("f_trip1_n0", "MeshTri", 3, "TriP1", normal0, kind="fasm"),
+    Case("f_trip1_sipg", "MeshTri", 3, "TriP1", sipg, kind="fasm", interior=True),
+    Case("f_trip1_subset", "MeshTri", 3, "TriP1", bnd_mass, kind="fasm", find_step=2),
+    Case("f_trip1_interp", "MeshTri", 3, "TriP1", facet_w, kind="fasm", interp_key=0),
+    Case("f_trip2_nitsche", "MeshTri", 3, "TriP2", nitsche, kind="fasm"),
+    Case("f_vecp2_nitsche", "MeshTri", 2, "TriP2", vec_nitsche, kind="fasm", ncu=2, ncv=2),
+    Case("f_tetp1_n2", "MeshTet", 2, "TetP1", normal2, kind="fasm"),
+    Case("f_tetp1_bnd", "MeshTet", 2, "TetP1", tet_bnd, kind="fasm"),
+    Case("f_tetp2_bnd", "MeshTet", 1, "TetP2", tet_bnd, kind="fasm"),
+    Case("f_tetp2_jump", "MeshTet", 1, "TetP2", jump, kind="fasm", interior=True),
+    Case("f_q1_bnd", "MeshQuad", 3, "Q1", q_bnd, kind="fasm", normals=False),
+    Case("f_q2_lin", "MeshQuad", 2, "Q2", q_bnd_lin, kind="fasm", normals=False),
+]
+BY_NAME = {c.name: c for c in CASES}
+
+
+def case_inputs(case, mesh, ndofs_u):
+    """Keyword arguments (interp / tind / find) of a case for a given mesh."""
+    kw = dict(case.kw)
+    if case.interp_key is not None:
+        kw["interp"] = {case.interp_key: _interp_vec(ndofs_u)}
+    if case.tind_step:
+        kw["tind"] = np.arange(0, mesh.t.shape[1], case.tind_step)
+    if case.find_step:
+        bnd = np.nonzero(mesh.f2t[1] == -1)[0]
+        kw["find"] = bnd[::case.find_step]
+    return kw
+
+
+def compare_csr(A, B, rtol=1e-12):
+    """Parity metric of SURVEY.md 8(c): identical pattern; per stored entry
+    ``|a-b| <= rtol * max(|a|, |b|, s_row)`` with ``s_row`` the largest
+    magnitude in the oracle row -- plus an absolute floor of
+    ``1e-3 * rtol * max|A|`` for rows that are pure cancellation noise
+    (e.g. jump terms of a continuous element)."""
+    assert A.shape == B.shape, (A.shape, B.shape)
+    assert A.indptr.dtype == B.indptr.dtype and A.indices.dtype == B.indices.dtype, \
+        (A.indptr.dtype, B.indptr.dtype)
+    assert np.array_equal(A.indptr, B.indptr), "indptr differs"
+    assert np.array_equal(A.indices, B.indices), "indices differ"
+    if A.nnz == 0:
+        return 0.0
+    rows = np.repeat(np.arange(A.shape[0]), np.diff(A.indptr))
+    srow = np.zeros(A.shape[0])
+    np.maximum.at(srow, rows, np.abs(B.data))
+    scale = np.maximum(np.maximum(np.abs(A.data), np.abs(B.data)), srow[rows])
+    scale = np.maximum(scale, 1e-3 * np.abs(B.data).max())
+    err = np.abs(A.data - B.data) / np.maximum(scale, 1e-300)
+    assert err.max() <= rtol, "max relative error %.3e" % err.max()
+    return float(err.max())
+
+
+def compare_vec(a, b, rtol=1e-12):
+    assert a.shape == b.shape
+    err = np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300)
+    assert err <= rtol, "max relative error %.3e" % err
+    return float(err)

@@ -1,0 +1,68 @@
+#!/usr/bin/env python
+"""Generate the golden fixtures ``tests/golden/<case>.npz`` by running the
+REFERENCE ITSELF (``/root/reference/spfem``, mechanically Python-3 patched by
+``oracle/make_ref.py`` into ``oracle/_ref``) on the cases of ``tests/cases.py``.
+
+Run in the build container only (needs ``/root/reference``):
+    python tests/golden/make_golden.py
+Each fixture stores the reference's CSR ``indptr / indices / data`` (or the
+load vector) plus the mesh size; the GPU box never needs the reference."""
+import os
+import sys
+import warnings
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+warnings.simplefilter("ignore")
+import make_ref  # noqa: E402
+
+make_ref.build(quiet=True)
+spfem = make_ref.import_ref()
+import spfem.mesh as rmesh  # noqa: E402
+import spfem.element as relem  # noqa: E402
+import spfem.assembly as rasm  # noqa: E402
+import cases  # noqa: E402
+
+
+def ref_element(name, ncomp):
+    e = getattr(relem, "Element" + name)()
+    return relem.ElementH1Vec(e) if ncomp > 1 else e
+
+
+def main():
+    for c in cases.CASES:
+        m = getattr(rmesh, c.mesh)()
+        m.refine(c.refine)
+        eu = ref_element(c.eu, c.ncu)
+        if c.ev is None and c.ncv == c.ncu:
+            a = rasm.AssemblerElement(m, eu)
+        else:
+            a = rasm.AssemblerElement(m, eu, ref_element(c.ev or c.eu, c.ncv))
+        kw = cases.case_inputs(c, m, a.dofnum_u.N)
+        out = a.iasm(c.form, **kw) if c.kind == "iasm" else a.fasm(c.form, **kw)
+        path = os.path.join(HERE, c.name + ".npz")
+        if hasattr(out, "indptr"):
+            np.savez_compressed(path, kind="csr", shape=np.array(out.shape),
+                                indptr=out.indptr, indices=out.indices,
+                                data=out.data, nt=m.t.shape[1])
+            print("%-22s csr %s nnz %d %s" % (c.name, out.shape, out.nnz, out.indices.dtype))
+        else:
+            np.savez_compressed(path, kind="vec", data=out, nt=m.t.shape[1])
+            print("%-22s vec %d" % (c.name, out.shape[0]))
+    # known answer of the reference's own test (spfem/test_asm.py:145-163)
+    m = rmesh.MeshTri()
+    m.refine(5)
+    a = rasm.AssemblerElement(m, relem.ElementTriP1())
+    A = a.iasm(cases.lap2)
+    b = a.iasm(cases.load1)
+    import spfem.utils as rutils
+    x = rutils.direct(A, b, I=m.interior_nodes())
+    print("test_asm.py:163 max(x) =", repr(np.max(x)), "(reference pins 0.073614737354524146)")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,113 @@
+# -*- coding: utf-8 -*-
+"""GPU parity tests proper: the product API (``AssemblerElement.iasm/fasm`` ->
+C-ABI -> generated sm_100a kernels) against the reference's golden outputs,
+the oracle, and size-independent properties at larger sizes."""
+import numpy as np
+import pytest
+import scipy.sparse.linalg as spl
+
+import cases
+import util
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(case):
+    asm = util.assembler_for(case)
+    kw = cases.case_inputs(case, asm.mesh, asm.dofnum_u.N)
+    fn = asm.iasm if case.kind == "iasm" else asm.fasm
+    return fn(case.form, **kw)
+
+
+@pytest.mark.parametrize("case", cases.CASES, ids=lambda c: c.name)
+def test_cuda_matches_reference_golden(case):
+    util.check(_run(case), util.golden(case))
+
+
+@pytest.mark.parametrize("name", ["trip1_lap_r6", "vecp2_elasticity", "tetp2_lap",
+                                  "f_trip2_nitsche", "trip1_load_sin_h"])
+def test_cuda_matches_oracle(name):
+    case = cases.BY_NAME[name]
+    util.check(_run(case), util.oracle_run(case))
+
+
+def test_native_library_loaded():
+    """The CUDA path must be the one that ran: the C-ABI library is mapped
+    into this process and at least one generated module is resident."""
+    from spfem_b200 import engine, _lib
+    _run(cases.BY_NAME["trip1_lap"])
+    assert _lib._lib is not None
+    assert len(engine._MODULES) > 0
+    with open("/proc/self/maps") as fh:
+        assert "libspfem_b200.so" in fh.read()
+
+
+def test_bitwise_reproducible():
+    """No floating point atomics: two runs give identical bits."""
+    case = cases.BY_NAME["vecp2_elasticity"]
+    A, B = _run(case), _run(case)
+    assert np.array_equal(A.data.view(np.int64), B.data.view(np.int64))
+    case = cases.BY_NAME["trip1_load_sin_h"]
+    a, b = _run(case), _run(case)
+    assert np.array_equal(a.view(np.int64), b.view(np.int64))
+
+
+def test_readme_example_config1():
+    """BASELINE config 1 (README.md:30-48): refine(6) P1 Poisson, direct solve;
+    max(x) of the patched reference is 0.07365718549079245."""
+    import spfem_b200 as sp
+    from spfem_b200.assembly import AssemblerElement
+    m = sp.MeshTri()
+    m.refine(6)
+    a = AssemblerElement(m, sp.ElementTriP1())
+    A = a.iasm(lambda du, dv: du[0] * dv[0] + du[1] * dv[1])
+    b = a.iasm(lambda v: 1.0 * v)
+    assert A.shape == (4225, 4225) and A.nnz == 29057
+    assert A.indices.dtype == np.int32 and A.has_sorted_indices
+    x = sp.direct(A, b, I=m.interior_nodes())
+    assert abs(np.max(x) - 0.07365718549079245) < 1e-12
+
+
+def test_known_answer_test_asm_163():
+    import spfem_b200 as sp
+    from spfem_b200.assembly import AssemblerElement
+    m = sp.MeshTri()
+    m.refine(5)
+    a = AssemblerElement(m, sp.ElementTriP1())
+    A = a.iasm(cases.lap2)
+    b = a.iasm(cases.load1)
+    x = sp.direct(A, b, I=m.interior_nodes())
+    assert abs(np.max(x) - 0.073614737354524146) < 1e-7
+
+
+def test_large_mesh_properties():
+    """refine(9) (524 288 triangles): properties that do not need the oracle --
+    stiffness rows sum to zero, mass sums to the area, both symmetric, pattern
+    nnz = nv + 2*ne, and subset assemblies add up to the whole
+    (spfem/test_asm.py:274-310)."""
+    import spfem_b200 as sp
+    from spfem_b200.assembly import AssemblerElement
+    m = sp.MeshTri()
+    m.refine(9)
+    a = AssemblerElement(m, sp.ElementTriP1())
+    K = a.iasm(cases.lap2)
+    M = a.iasm(cases.mass)
+    nv, ne = m.p.shape[1], m.facets.shape[1]
+    assert K.nnz == nv + 2 * ne == M.nnz
+    assert np.max(np.abs(K.dot(np.ones(nv)))) < 1e-10
+    assert abs(M.sum() - 1.0) < 1e-12
+    assert abs(K - K.T).max() < 1e-12 and abs(M - M.T).max() < 1e-15
+    nt = m.t.shape[1]
+    K1 = a.iasm(cases.lap2, tind=np.arange(0, nt // 2))
+    K2 = a.iasm(cases.lap2, tind=np.arange(nt // 2, nt))
+    assert abs((K1 + K2) - K).max() < 1e-10
+    f = a.iasm(cases.load1)
+    assert abs(f.sum() - 1.0) < 1e-12
+
+
+def test_device_resident_result():
+    case = cases.BY_NAME["trip2_lap"]
+    asm = util.assembler_for(case)
+    d = asm.iasm_device(case.form)
+    assert d.values.is_cuda and d.nnz == util.golden(case).nnz
+    util.check(d.to_scipy(), util.golden(case))

@@ -1,0 +1,125 @@
+# -*- coding: utf-8 -*-
+"""Host logic without a GPU: API surface / error behaviour of the reference,
+tracer rules, NVRTC compilation for sm_100a, and the C-ABI exports."""
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+import spfem_b200 as sp
+from spfem_b200 import _lib
+from spfem_b200.assembly import AssemblerElement, Dofnum
+from spfem_b200.tracer import TraceError
+from spfem_b200.engine import scipy_index_dtype
+import cases
+import util
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    _lib.build()
+    return _lib.load()
+
+
+def test_c_abi_exports_every_declared_symbol(lib):
+    hdr = open(os.path.join(ROOT, "include", "spfem_b200.h")).read()
+    declared = set(re.findall(r"\b(spfem_[a-z_0-9]+)\s*\(", hdr))
+    assert declared, "no declarations found"
+    out = subprocess.check_output(["nm", "-D", "--defined-only", _lib.LIB_PATH]).decode()
+    exported = set(re.findall(r"\bT (spfem_[a-z_0-9]+)", out))
+    assert declared <= exported, declared - exported
+    assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
+    assert lib.spfem_abi_version() == 1
+    assert lib.spfem_device_count() >= 0
+
+
+def test_nvrtc_compiles_generated_kernels_for_sm100a(lib):
+    for name in ("trip1_lap", "vecp2_elasticity", "q2_lap", "f_vecp2_nitsche",
+                 "f_trip1_sipg", "trip1_interp_mass"):
+        case = cases.BY_NAME[name]
+        asm = util.assembler_for(case)
+        kw = cases.case_inputs(case, asm.mesh, asm.dofnum_u.N)
+        kw.pop("tind", None)
+        kw.pop("find", None)
+        plan = (asm.plan_iasm(case.form, **kw) if case.kind == "iasm"
+                else asm.plan_fasm(case.form, **kw))
+        image = _lib.nvrtc_compile(plan.source)
+        assert image[:4] == b"\x7fELF" and len(image) > 1000
+
+
+def test_nvrtc_error_is_reported(lib):
+    with pytest.raises(_lib.SpfemError):
+        _lib.nvrtc_compile("this is not CUDA")
+
+
+def test_constructor_errors():
+    m = sp.MeshTri()
+    with pytest.raises(Exception, match="First parameter must be an instance"):
+        AssemblerElement("mesh", sp.ElementTriP1())
+    with pytest.raises(Exception, match="Second parameter must be an instance"):
+        AssemblerElement(m, "elem")
+
+
+def test_interp_must_be_dict_and_unknown_argument():
+    m = sp.MeshTri()
+    m.refine(1)
+    a = AssemblerElement(m, sp.ElementTriP1())
+    with pytest.raises(Exception, match="must be in a dictionary"):
+        a.plan_iasm(lambda v, w: w[0] * v, interp=np.zeros(3))
+    with pytest.raises(IndexError):
+        a.plan_iasm(lambda v, foo: v)
+    with pytest.raises(Exception, match="No interior support"):
+        a.plan_fasm(lambda v1, v2: v1, interior=True)
+
+
+def test_nonlinear_forms_are_rejected():
+    m = sp.MeshTri()
+    a = AssemblerElement(m, sp.ElementTriP1())
+    with pytest.raises(TraceError):
+        a.plan_iasm(lambda u, v: u * u * v)
+    with pytest.raises(TraceError):
+        a.plan_iasm(lambda u, v: np.sin(u) * v)
+    with pytest.raises(TraceError):
+        a.plan_iasm(lambda v, x: v if x[0] > 0 else 0 * v)
+
+
+def test_dofnum_matches_oracle():
+    import asm_oracle
+    for mesh, ref, el, nc in (("MeshTri", 3, "TriP2", 1), ("MeshTri", 2, "TriP2", 2),
+                              ("MeshTet", 1, "TetP2", 1), ("MeshQuad", 2, "Q2", 1),
+                              ("MeshTet", 1, "TetP1", 3)):
+        m = getattr(sp, mesh)()
+        m.refine(ref)
+        d = Dofnum(m, util.element(el, nc))
+        t_dof, N = asm_oracle.dofnum(m, el, nc)
+        assert d.N == N and np.array_equal(d.t_dof, t_dof)
+
+
+def test_scipy_index_width_rule():
+    assert scipy_index_dtype(10, 5, 5) == np.int32
+    assert scipy_index_dtype(2 ** 31 - 1, 5, 5) == np.int32
+    assert scipy_index_dtype(2 ** 31, 5, 5) == np.int64
+    assert scipy_index_dtype(10, 2 ** 31, 5) == np.int64
+
+
+def test_no_cpu_fallback_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    m = sp.MeshTri()
+    a = AssemblerElement(m, sp.ElementTriP1())
+    with pytest.raises(_lib.SpfemError, match="no CPU fallback"):
+        a.iasm(cases.mass)
+
+
+def test_tensor_mode_precontracts_quadrature():
+    """Element-constant coefficients fold the quadrature sum into constants:
+    the P1 Laplace kernel has no per-point code at all."""
+    m = sp.MeshTri()
+    a = AssemblerElement(m, sp.ElementTriP1())
+    src = a.plan_iasm(cases.lap2).source
+    assert "x0_" not in src and src.count("SPFEM_STORE(") == 9 + 1
