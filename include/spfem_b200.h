@@ -66,6 +66,12 @@ int spfem_module_unload(void *module);
 int spfem_module_get_kernel(void *module, const char *name, void **kernel);
 /* Launches a generated kernel: one thread per item, `block` threads per CTA. */
 int spfem_launch(void *kernel, const SpfemArgs *args, int block, void *stream);
+/* Launches the fused tile kernel `<name>_tile` of a generated module: `args`
+ * points to a SpfemTileArgs block (declared in the generated source and in
+ * spfem_b200/_lib.py), one CTA per tile, `smem_bytes` of dynamic shared memory
+ * (opt-in above 48 KB is handled here).                                       */
+int spfem_launch_tiled(void *kernel, const void *args, unsigned grid, unsigned block,
+                       size_t smem_bytes, void *stream);
 
 /* ---- sparsity pattern: COO (row, col) pairs -> CSR + contribution lists ----
  * Replaces SciPy's coo_tocsr + sum_duplicates structure pass.  Entry ids are

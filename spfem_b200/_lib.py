@@ -33,6 +33,16 @@ class SpfemArgs(C.Structure):
     ]
 
 
+class SpfemTileArgs(C.Structure):
+    """Mirror of ``struct SpfemTileArgs`` (generated source, codegen.TILE_KERNEL)."""
+    _fields_ = [
+        ("base", SpfemArgs),
+        ("tiles", C.c_void_p), ("elems", C.c_void_p), ("cptr", C.c_void_p),
+        ("contrib", C.c_void_p), ("rowbase", C.c_void_p), ("gdelta", C.c_void_p),
+        ("values", C.c_void_p), ("ldl", C.c_int),
+    ]
+
+
 SYMBOLS = {
     # name: (restype, argtypes)
     "spfem_abi_version": (C.c_int, []),
@@ -50,6 +60,8 @@ SYMBOLS = {
                                           C.POINTER(C.c_void_p)]),
     "spfem_launch": (C.c_int, [C.c_void_p, C.POINTER(SpfemArgs), C.c_int,
                                C.c_void_p]),
+    "spfem_launch_tiled": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint, C.c_uint,
+                                     C.c_size_t, C.c_void_p]),
     "spfem_pattern_ws_bytes": (C.c_size_t, [C.c_longlong]),
     "spfem_pattern_sort": (C.c_int, [C.c_void_p, C.c_longlong, C.c_void_p,
                                      C.c_longlong, C.c_longlong, C.c_int,

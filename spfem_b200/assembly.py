@@ -326,6 +326,13 @@ class AssemblerElement(Assembler):
         plan = self.plan_iasm(form, intorder=intorder, interp=interp)
         return self._get_engine().run_interior(plan, tind, interp, to_host=False)
 
+    def prepare_iasm(self, form, intorder=None, tind=None, interp=None):
+        """Trace, compile and stage ``form`` once; the returned handle's
+        ``launch()`` re-runs the assembly on the device (time stepping,
+        benchmarks) and ``result()`` fetches it like :meth:`iasm`."""
+        plan = self.plan_iasm(form, intorder=intorder, interp=interp)
+        return self._get_engine().prepare_interior(plan, tind, interp)
+
     def fasm(self, form, find=None, interior=False, intorder=None,
              normals=True, interp=None):
         """Assemble a bilinear or linear form over facets

@@ -68,6 +68,54 @@ struct SpfemArgs {
 };
 """
 
+# Fused tile kernel: one CTA per tile of (Morton-contiguous) elements plus the
+# halo elements that touch rows the tile owns.  Phase A: every thread computes
+# local matrices into shared memory (entry-major, sL[idx*ldl + el]).  Phase B:
+# one thread per CSR slot owned by the tile sums its contributions from shared
+# memory in a fixed order (tile-local contribution lists, 16-bit) and writes
+# the CSR value exactly once -- no atomics, no partial sums in HBM.
+TILE_KERNEL = r"""
+struct SpfemTileDesc { int e0, ne, cp0, ns, c0, r0, rb0, pad; };
+struct SpfemTileArgs {
+    SpfemArgs base;
+    const SpfemTileDesc *tiles;     /* one descriptor per CTA                     */
+    const int *elems;               /* tile element lists (device element order)  */
+    const unsigned short *cptr;     /* per tile ns+1 offsets; bit 15 = row head   */
+    const unsigned short *contrib;  /* shared-memory index idx*ldl + el           */
+    const unsigned short *rowbase;  /* rows before every 32nd slot of the tile    */
+    const int *gdelta;              /* per tile row: CSR start - tile slot start  */
+    double *values;                 /* CSR values                                  */
+    int ldl;                        /* leading dimension of the smem tile         */
+};
+extern "C" __global__ void __launch_bounds__(256) @NAME@_tile(const SpfemTileArgs T)
+{
+    extern __shared__ double sL[];
+    const SpfemTileDesc d = T.tiles[blockIdx.x];
+    const int ldl = T.ldl;
+    for (int el = threadIdx.x; el < d.ne; el += blockDim.x)
+        @NAME@_body(T.base, (long long)T.elems[d.e0 + el], sL, (long long)ldl, (long long)el);
+    __syncthreads();
+    const unsigned short *cp = T.cptr + d.cp0;
+    const unsigned short *cb = T.contrib + d.c0;
+    const unsigned lane = threadIdx.x & 31u;
+    const int nsp = (d.ns + 31) & ~31;
+    for (int s = threadIdx.x; s < nsp; s += blockDim.x) {
+        unsigned c0 = 0, c1 = 0;
+        if (s < d.ns) { c0 = cp[s]; c1 = cp[s + 1]; }
+        const unsigned head = c0 >> 15;
+        const unsigned heads = __ballot_sync(0xffffffffu, head != 0u);
+        double acc = 0.0;
+        const unsigned b = c0 & 0x7fffu, e = c1 & 0x7fffu;
+        for (unsigned k = b; k < e; ++k) acc += sL[cb[k]];
+        if (s < d.ns) {
+            const int row = (int)T.rowbase[d.rb0 + (s >> 5)]
+                          + __popc(heads & (0xffffffffu >> (31u - lane))) - 1;
+            T.values[T.gdelta[d.r0 + row] + s] = acc;
+        }
+    }
+}
+"""
+
 
 def lit(x):
     """Exact C literal of a double."""
@@ -459,21 +507,24 @@ def generate_interior(spec, name="spfem_elem"):
 
     src = [PRELUDE]
     src.append("#define SPFEM_NENTRIES %d" % spec.n_entries)
-    src.append("#ifndef SPFEM_STORE")
-    src.append("#define SPFEM_STORE(idx, val) P.out[(long long)(idx) * P.ldo + k] = (val)")
-    src.append("#endif")
-    src.append("SPFEM_DEVICE void %s_body(const SpfemArgs &P, const long long k)\n{" % name)
-    src.append("    const long long e = P.sel ? (long long)P.sel[k] : k;")
+    src.append("#define SPFEM_STORE(idx, val) out[(long long)(idx) * ldo + k] = (val)")
+    # body(P, e, out, ldo, k): local matrix of element e -> out[idx*ldo + k]
+    src.append("template <typename OUT>")
+    src.append("SPFEM_DEVICE void %s_body(const SpfemArgs &P, const long long e, "
+               "OUT *__restrict__ out, const long long ldo, const long long k)\n{" % name)
     src += ["    " + ln for ln in body]
     src.append("}")
     src.append("#ifndef SPFEM_HOST")
     src.append('extern "C" __global__ void __launch_bounds__(128) %s(const SpfemArgs P)\n{' % name)
     src.append("    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;")
-    src.append("    if (k < P.n) %s_body(P, k);" % name)
+    src.append("    if (k < P.n) %s_body(P, P.sel ? (long long)P.sel[k] : k, P.out, P.ldo, k);" % name)
     src.append("}")
+    if spec.bilinear:
+        src.append(TILE_KERNEL.replace("@NAME@", name))
     src.append("#else")
     src.append('extern "C" void %s_host(const SpfemArgs *P)\n{' % name)
-    src.append("    for (long long k = 0; k < P->n; ++k) %s_body(*P, k);" % name)
+    src.append("    for (long long k = 0; k < P->n; ++k)")
+    src.append("        %s_body(*P, P->sel ? (long long)P->sel[k] : k, P->out, P->ldo, k);" % name)
     src.append("}")
     src.append("#endif")
     return "\n".join(src) + "\n"

@@ -321,6 +321,24 @@ int spfem_launch(void *kernel, const SpfemArgs *args, int block, void *stream)
     return 0;
 }
 
+int spfem_launch_tiled(void *kernel, const void *args, unsigned grid, unsigned block,
+                       size_t smem_bytes, void *stream)
+{
+    if (!kernel || !args) return fail("spfem_launch_tiled: null argument");
+    if (grid == 0) return 0;
+    if (smem_bytes > 48 * 1024) {
+        int dev = 0;
+        CUDA_TRY(cudaGetDevice(&dev));
+        CUDA_TRY(cudaKernelSetAttributeForDevice((cudaKernel_t)kernel,
+                                                 cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                 (int)smem_bytes, dev));
+    }
+    void *params[] = {(void *)args};
+    CUDA_TRY(cudaLaunchKernel((const void *)kernel, dim3(grid), dim3(block), params,
+                              smem_bytes, (cudaStream_t)stream));
+    return 0;
+}
+
 size_t spfem_pattern_ws_bytes(long long n_entries)
 {
     if (n_entries <= 0) n_entries = 1;

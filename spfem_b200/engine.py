@@ -58,19 +58,22 @@ def compile_cached(source):
 
 
 def get_kernel(source, name):
+    """Kernel handle ``name`` of the module generated from ``source``."""
     key = source_key(source)
     hit = _MODULES.get(key)
-    if hit is not None:
-        return hit[1]
     lib = _lib.load()
-    key, image = compile_cached(source)
-    module = C.c_void_p()
-    buf = C.create_string_buffer(image, len(image))
-    _lib.check(lib.spfem_module_load(buf, len(image), C.byref(module)))
-    kernel = C.c_void_p()
-    _lib.check(lib.spfem_module_get_kernel(module, name.encode(), C.byref(kernel)))
-    _MODULES[key] = (module, kernel, buf)
-    return kernel
+    if hit is None:
+        key, image = compile_cached(source)
+        module = C.c_void_p()
+        buf = C.create_string_buffer(image, len(image))
+        _lib.check(lib.spfem_module_load(buf, len(image), C.byref(module)))
+        hit = _MODULES[key] = (module, {}, buf)
+    kernels = hit[1]
+    if name not in kernels:
+        kernel = C.c_void_p()
+        _lib.check(lib.spfem_module_get_kernel(hit[0], name.encode(), C.byref(kernel)))
+        kernels[name] = kernel
+    return kernels[name]
 
 
 def scipy_index_dtype(n_entries, nrows, ncols):
@@ -120,6 +123,81 @@ class DeviceCSR(object):
         return A
 
 
+class Prepared(object):
+    """A ready-to-launch assembly: ``launch()`` enqueues the generated element
+    kernel and the fixed-order reduction on the current stream and returns the
+    (device) values tensor -- no host synchronisation, no allocation."""
+
+    def __init__(self, engine, plan, kernel, args, block, local, pattern, keep=()):
+        self.engine, self.plan, self.kernel = engine, plan, kernel
+        self.args, self.block, self.local, self.pattern = args, block, local, pattern
+        self._keep = keep
+        torch = engine.torch
+        n = pattern.nnz if plan.bilinear else pattern.nrows
+        self.values = engine._empty(max(n, 1), torch.float64)[:n]
+        self.n_launches = 2
+
+    def launch_element_kernel(self):
+        e = self.engine
+        a = self.args
+        a.t, a.ldt = e.t.data_ptr(), e.t.shape[1]
+        a.p, a.ldp = e.p.data_ptr(), e.p.shape[1]
+        _lib.check(e.lib.spfem_launch(self.kernel, C.byref(a), self.block, e._stream()))
+
+    def launch_reduce(self):
+        e, pat = self.engine, self.pattern
+        if self.plan.bilinear:
+            cptr, nslots = pat.cptr, pat.nnz
+        else:
+            cptr, nslots = pat.rowstart, pat.nrows
+        _lib.check(e.lib.spfem_reduce(e._ptr(self.local), e._ptr(cptr),
+                                      e._ptr(pat.contrib), nslots,
+                                      e._ptr(self.values), e._stream()))
+
+    def launch(self):
+        self.launch_element_kernel()
+        self.launch_reduce()
+        return self.values
+
+    def result(self, to_host=True):
+        """The assembled matrix / vector of the last ``launch()``."""
+        return self.engine._finish(self.values, self.pattern,
+                                   self.plan.bilinear, to_host)
+
+
+class TiledPrepared(Prepared):
+    """Fused variant: one launch of ``<name>_tile`` (codegen.TILE_KERNEL) --
+    local matrices stay in shared memory and every CSR value is written once."""
+
+    def __init__(self, engine, plan, kernel, tile_kernel, args, local, pattern,
+                 tp, keep=()):
+        Prepared.__init__(self, engine, plan, kernel, args, 128, local, pattern, keep)
+        self.tile_kernel, self.tp = tile_kernel, tp
+        ta = _lib.SpfemTileArgs()
+        ta.tiles = tp["desc"].data_ptr()
+        ta.elems = tp["elems"].data_ptr()
+        ta.cptr = tp["cptr"].data_ptr()
+        ta.contrib = tp["contrib"].data_ptr()
+        ta.rowbase = tp["rowbase"].data_ptr()
+        ta.gdelta = tp["gdelta"].data_ptr()
+        ta.values = self.values.data_ptr()
+        ta.ldl = tp["ldl"]
+        self.targs = ta
+        self.smem = 8 * plan.spec.n_entries * tp["ldl"]
+        self.n_launches = 1
+
+    def launch(self):
+        e = self.engine
+        a = self.args
+        a.t, a.ldt = e.t.data_ptr(), e.t.shape[1]
+        a.p, a.ldp = e.p.data_ptr(), e.p.shape[1]
+        self.targs.base = a
+        _lib.check(e.lib.spfem_launch_tiled(self.tile_kernel, C.byref(self.targs),
+                                            self.tp["ntiles"], 256, self.smem,
+                                            e._stream()))
+        return self.values
+
+
 class Engine(object):
     def __init__(self, asm, device=None, morton=True):
         self.torch = torch = _torch()
@@ -129,6 +207,7 @@ class Engine(object):
                                    if device is None else device)
         self.patterns = {}
         self.stats = {}
+        self.fused = os.environ.get("SPFEM_FUSED", "1") != "0"
         mesh = asm.mesh
         self.nt = mesh.t.shape[1]
         self.nv = mesh.p.shape[1]
@@ -265,22 +344,11 @@ class Engine(object):
             out.append(self._dev(np.asarray(interp[key]), np.float64))
         return out
 
-    def _reduce(self, local, pat, bilinear):
-        torch, lib = self.torch, self.lib
-        if bilinear:
-            values = self._empty(max(pat.nnz, 1), torch.float64)[:pat.nnz]
-            _lib.check(lib.spfem_reduce(self._ptr(local), self._ptr(pat.cptr),
-                                        self._ptr(pat.contrib), pat.nnz,
-                                        self._ptr(values), self._stream()))
-        else:
-            values = self._empty(pat.nrows, torch.float64)
-            _lib.check(lib.spfem_reduce(self._ptr(local), self._ptr(pat.rowstart),
-                                        self._ptr(pat.contrib), pat.nrows,
-                                        self._ptr(values), self._stream()))
-        return values
-
-    def run_interior(self, plan, tind=None, interp=None, to_host=True):
-        torch, lib, asm = self.torch, self.lib, self.asm
+    def prepare_interior(self, plan, tind=None, interp=None):
+        """Everything up to the launch: compiled kernel, pattern, scratch and
+        output tensors, argument block.  Returns a :class:`Prepared` whose
+        ``launch()`` only enqueues the two kernels on the current stream."""
+        torch, asm = self.torch, self.asm
         spec = plan.spec
         kernel = get_kernel(plan.source, plan.name)
         if tind is None:
@@ -302,20 +370,58 @@ class Engine(object):
             coldof = self.tdof_u.index_select(1, pos) if plan.bilinear else None
             pat = self.build_pattern(rowdof, coldof, asm.dofnum_v.N,
                                      asm.dofnum_u.N if plan.bilinear else 1)
-        local = self._empty(max(spec.n_entries * n, 1), torch.float64)
         wt = self._interp_tensors(plan, interp)
         a = _lib.SpfemArgs()
         a.n, a.ldo = n, n
         a.sel = sel.data_ptr() if sel is not None else None
-        a.t, a.ldt = self.t.data_ptr(), self.t.shape[1]
-        a.p, a.ldp = self.p.data_ptr(), self.p.shape[1]
         a.tdof_u, a.ldd = self.tdof_u.data_ptr(), self.tdof_u.shape[1]
         for s, w in enumerate(wt):
             a.interp[s] = w.data_ptr()
+        tp = None
+        if tind is None and plan.bilinear and self.fused:
+            tp = self.tile_plan(pat, n, spec.n_entries)
+        if tp is not None:
+            tk = get_kernel(plan.source, plan.name + "_tile")
+            return TiledPrepared(self, plan, kernel, tk, a, None, pat, tp, keep=(wt,))
+        local = self._empty(max(spec.n_entries * n, 1), torch.float64)
         a.out = local.data_ptr()
-        _lib.check(lib.spfem_launch(kernel, C.byref(a), 128, self._stream()))
-        values = self._reduce(local, pat, plan.bilinear)
-        return self._finish(values, pat, plan.bilinear, to_host)
+        return Prepared(self, plan, kernel, a, 128, local, pat, keep=(sel, wt))
+
+    def tile_plan(self, pat, n, nent):
+        """Tile plan of the fused kernel for ``pat`` (cached on the pattern);
+        ``None`` if a tile does not fit in shared memory / 16-bit indices."""
+        cache = getattr(pat, "_tile_plans", None)
+        if cache is None:
+            cache = pat._tile_plans = {}
+        if nent in cache:
+            return cache[nent]
+        from .tileplan import build_tile_plan
+        E = int(os.environ.get("SPFEM_TILE_E", "0"))
+        if E <= 0:
+            budget = int(os.environ.get("SPFEM_TILE_SMEM", str(96 * 1024)))
+            E = budget // (8 * nent)
+            E = int(E / 1.15) // 32 * 32
+        tp = None
+        t0 = time.perf_counter()
+        while E >= 32:
+            try:
+                tp = build_tile_plan(self.torch, pat.indptr, pat.cptr, pat.contrib,
+                                     n, nent, E)
+            except ValueError:
+                tp = None
+            if tp is not None and 8 * nent * tp["ldl"] <= 200 * 1024:
+                break
+            tp = None
+            E //= 2
+        self.torch.cuda.synchronize(self.device)
+        self.stats["tile_plan_s"] = time.perf_counter() - t0
+        cache[nent] = tp
+        return tp
+
+    def run_interior(self, plan, tind=None, interp=None, to_host=True):
+        prep = self.prepare_interior(plan, tind, interp)
+        values = prep.launch()
+        return self._finish(values, prep.pattern, plan.bilinear, to_host)
 
     def run_facet(self, plan, find, interior, interp=None, to_host=True):
         torch, lib, asm = self.torch, self.lib, self.asm
@@ -340,16 +446,15 @@ class Engine(object):
         wt = self._interp_tensors(plan, interp)
         a = _lib.SpfemArgs()
         a.n, a.ldo = n, nblk * n
-        a.t, a.ldt = self.t.data_ptr(), self.t.shape[1]
-        a.p, a.ldp = self.p.data_ptr(), self.p.shape[1]
         a.tdof_u, a.ldd = self.tdof_u.data_ptr(), self.tdof_u.shape[1]
         for s, w in enumerate(wt):
             a.interp[s] = w.data_ptr()
         a.fv, a.e1, a.e2, a.lf1 = (fv_d.data_ptr(), e1_d.data_ptr(),
                                    e2_d.data_ptr(), lf_d.data_ptr())
         a.out = local.data_ptr()
-        _lib.check(lib.spfem_launch(kernel, C.byref(a), 64, self._stream()))
-        values = self._reduce(local, pat, plan.bilinear)
+        prep = Prepared(self, plan, kernel, a, 64, local, pat,
+                        keep=(fv_d, e1_d, e2_d, lf_d, wt))
+        values = prep.launch()
         return self._finish(values, pat, plan.bilinear, to_host)
 
     def _finish(self, values, pat, bilinear, to_host):

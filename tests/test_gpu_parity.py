@@ -111,3 +111,24 @@ def test_device_resident_result():
     d = asm.iasm_device(case.form)
     assert d.values.is_cuda and d.nnz == util.golden(case).nnz
     util.check(d.to_scipy(), util.golden(case))
+
+
+@pytest.mark.parametrize("name", ["trip1_lap_r6", "trip2_lap", "vecp2_elasticity",
+                                  "stokes_b", "tetp2_lap", "q2_lap",
+                                  "trip1_interp_mass", "trip1_mass_x2"])
+@pytest.mark.parametrize("mode", ["unfused", "small_tiles"])
+def test_both_assembly_paths(name, mode, monkeypatch):
+    """The two-kernel path (local matrices in HBM + gather reduction) and the
+    fused tile kernel with many small tiles (exercises halos and row ownership)
+    both reproduce the reference."""
+    if mode == "unfused":
+        monkeypatch.setenv("SPFEM_FUSED", "0")
+    else:
+        monkeypatch.setenv("SPFEM_TILE_E", "32")
+    case = cases.BY_NAME[name]
+    asm = util.assembler_for(case)
+    kw = cases.case_inputs(case, asm.mesh, asm.dofnum_u.N)
+    prep = asm.prepare_iasm(case.form, **kw)
+    assert prep.n_launches == (2 if mode == "unfused" else 1)
+    prep.launch()
+    util.check(prep.result(), util.golden(case))
