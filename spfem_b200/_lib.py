@@ -37,9 +37,9 @@ class SpfemTileArgs(C.Structure):
     """Mirror of ``struct SpfemTileArgs`` (generated source, codegen.TILE_KERNEL)."""
     _fields_ = [
         ("base", SpfemArgs),
-        ("tiles", C.c_void_p), ("elems", C.c_void_p), ("cptr", C.c_void_p),
-        ("contrib", C.c_void_p), ("rowbase", C.c_void_p), ("gdelta", C.c_void_p),
-        ("values", C.c_void_p), ("ldl", C.c_int),
+        ("desc", C.c_void_p), ("blob", C.c_void_p), ("values", C.c_void_p),
+        ("ldl", C.c_int), ("max_a", C.c_int), ("max_b", C.c_int),
+        ("max_ns", C.c_int), ("max_nr", C.c_int),
     ]
 
 

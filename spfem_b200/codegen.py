@@ -34,6 +34,7 @@ compiled for the host (``-DSPFEM_HOST``, tests only) to check generated code
 against the oracle without a GPU.
 """
 import hashlib
+import os
 import numpy as np
 from .tracer import Coef, NONE
 
@@ -69,50 +70,112 @@ struct SpfemArgs {
 """
 
 # Fused tile kernel: one CTA per tile of (Morton-contiguous) elements plus the
-# halo elements that touch rows the tile owns.  Phase A: every thread computes
-# local matrices into shared memory (entry-major, sL[idx*ldl + el]).  Phase B:
-# one thread per CSR slot owned by the tile sums its contributions from shared
-# memory in a fixed order (tile-local contribution lists, 16-bit) and writes
-# the CSR value exactly once -- no atomics, no partial sums in HBM.
+# halo elements that touch rows the tile owns (tileplan.py).  The per-tile blob
+# (vertex ids, contribution lists, CSR offsets) is brought into shared memory by
+# two TMA bulk copies (cp.async.bulk + mbarrier, SASS UBLKCP).  Phase A: every
+# thread computes one local matrix into shared memory (entry-major,
+# sL[idx*ldl + el]).  Phase B: one thread per CSR slot owned by the tile sums
+# its contributions from shared memory in a fixed order and writes the CSR value
+# exactly once -- no atomics, no partial sums in HBM.
+TILE_THREADS = int(os.environ.get("SPFEM_TILE_T", "512"))
 TILE_KERNEL = r"""
-struct SpfemTileDesc { int e0, ne, cp0, ns, c0, r0, rb0, pad; };
 struct SpfemTileArgs {
     SpfemArgs base;
-    const SpfemTileDesc *tiles;     /* one descriptor per CTA                     */
-    const int *elems;               /* tile element lists (device element order)  */
-    const unsigned short *cptr;     /* per tile ns+1 offsets; bit 15 = row head   */
-    const unsigned short *contrib;  /* shared-memory index idx*ldl + el           */
-    const unsigned short *rowbase;  /* rows before every 32nd slot of the tile    */
-    const int *gdelta;              /* per tile row: CSR start - tile slot start  */
-    double *values;                 /* CSR values                                  */
-    int ldl;                        /* leading dimension of the smem tile         */
+    const int *desc;              /* 16 ints per tile (tileplan.py)              */
+    const unsigned char *blob;    /* packed per-tile data, 16-byte aligned       */
+    double *values;               /* CSR values                                   */
+    int ldl;                      /* leading dimension of the smem tile           */
+    int max_a, max_b;             /* smem bytes reserved for blob sections A / B  */
+    int max_ns, max_nr;           /* largest slot / row count of a tile           */
 };
-extern "C" __global__ void __launch_bounds__(256) @NAME@_tile(const SpfemTileArgs T)
+static __device__ __forceinline__ unsigned spfem_smem(const void *p)
 {
-    extern __shared__ double sL[];
-    const SpfemTileDesc d = T.tiles[blockIdx.x];
+    return (unsigned)__cvta_generic_to_shared(p);
+}
+static __device__ __forceinline__ void spfem_mbar_init(void *bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(spfem_smem(bar)), "r"(count));
+}
+static __device__ __forceinline__ void spfem_bulk_load(void *dst, const void *src,
+                                                       unsigned bytes, void *bar)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
+                 ::"r"(spfem_smem(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(spfem_smem(dst)), "l"(src), "r"(bytes), "r"(spfem_smem(bar)) : "memory");
+}
+static __device__ __forceinline__ void spfem_mbar_wait(void *bar, unsigned parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "SPFEM_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra SPFEM_DONE;\n"
+        "bra SPFEM_WAIT;\n"
+        "SPFEM_DONE:\n"
+        "}\n" ::"r"(spfem_smem(bar)), "r"(parity) : "memory");
+}
+extern "C" __global__ void __launch_bounds__(@THREADS@) @NAME@_tile(const SpfemTileArgs T)
+{
+    extern __shared__ __align__(128) unsigned char spfem_smem_raw[];
     const int ldl = T.ldl;
-    for (int el = threadIdx.x; el < d.ne; el += blockDim.x)
-        @NAME@_body(T.base, (long long)T.elems[d.e0 + el], sL, (long long)ldl, (long long)el);
+    double *sL = (double *)spfem_smem_raw;
+    unsigned char *sA = spfem_smem_raw + (((size_t)8 * SPFEM_NENTRIES * ldl + 15) & ~(size_t)15);
+    unsigned char *sB = sA + T.max_a;
+    double *sV = (double *)(sB + T.max_b);
+    unsigned long long *bars = (unsigned long long *)(sV + T.max_ns);
+    int *sG = (int *)(bars + 2);
+    const int *d = T.desc + 16 * (size_t)blockIdx.x;
+    const int bytes_a = d[1], bytes_b = d[2], ne = d[3], ne_pad = d[4], ns = d[5], nr = d[9];
+    if (ne == 0 || ns == 0) return;
+    if (threadIdx.x == 0) {
+        spfem_mbar_init(&bars[0], 1);
+        spfem_mbar_init(&bars[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        const unsigned char *src = T.blob + (size_t)(unsigned)d[0] * 16;
+        spfem_bulk_load(sA, src, (unsigned)bytes_a, &bars[0]);
+        spfem_bulk_load(sB, src + bytes_a, (unsigned)bytes_b, &bars[1]);
+    }
     __syncthreads();
-    const unsigned short *cp = T.cptr + d.cp0;
-    const unsigned short *cb = T.contrib + d.c0;
-    const unsigned lane = threadIdx.x & 31u;
-    const int nsp = (d.ns + 31) & ~31;
-    for (int s = threadIdx.x; s < nsp; s += blockDim.x) {
-        unsigned c0 = 0, c1 = 0;
-        if (s < d.ns) { c0 = cp[s]; c1 = cp[s + 1]; }
-        const unsigned head = c0 >> 15;
-        const unsigned heads = __ballot_sync(0xffffffffu, head != 0u);
+    /* phase A: local matrices -> sL */
+    spfem_mbar_wait(&bars[0], 0);
+    const unsigned short *vt = (const unsigned short *)sA;   /* tile-local vertex ids */
+    const double *pc = (const double *)(sA + d[12]);          /* tile-local coordinates */
+    const long long ldpc = d[11];
+    for (int el = threadIdx.x; el < ne; el += blockDim.x)
+        @NAME@_body(T.base, @ELEM@, vt, (long long)ne_pad, (long long)el, pc, ldpc,
+                    sL, (long long)ldl, (long long)el);
+    /* phase B1: one thread per owned row walks the row's contribution list
+       (bit 15 of an entry = last contribution of a CSR slot) and adds in list
+       order -- fixed order => bitwise reproducible.  The finished slot value
+       and its CSR position are staged in shared memory.                       */
+    spfem_mbar_wait(&bars[1], 0);
+    const int2 *rinfo = (const int2 *)sB;      /* {gdelta, s_start | k_start<<16} */
+    const unsigned short *cb = (const unsigned short *)(sB + d[8]);
+    __syncthreads();
+    for (int row = threadIdx.x; row < nr; row += blockDim.x) {
+        const int2 ri = rinfo[row];
+        const unsigned kend = ((unsigned)rinfo[row + 1].y) >> 16;
+        unsigned s = (unsigned)ri.y & 0xffffu;
+        int g = ri.x + (int)s;
         double acc = 0.0;
-        const unsigned b = c0 & 0x7fffu, e = c1 & 0x7fffu;
-        for (unsigned k = b; k < e; ++k) acc += sL[cb[k]];
-        if (s < d.ns) {
-            const int row = (int)T.rowbase[d.rb0 + (s >> 5)]
-                          + __popc(heads & (0xffffffffu >> (31u - lane))) - 1;
-            T.values[T.gdelta[d.r0 + row] + s] = acc;
+        for (unsigned k = ((unsigned)ri.y) >> 16; k < kend; ++k) {
+            const unsigned c = cb[k];
+            acc += sL[c & 0x7fffu];
+            if (c & 0x8000u) {
+                sV[s] = acc;
+                sG[s] = g;
+                acc = 0.0;
+                ++s;
+                ++g;
+            }
         }
     }
+    __syncthreads();
+    /* phase B2: coalesced store of the tile's CSR values */
+    for (int s = threadIdx.x; s < ns; s += blockDim.x)
+        T.values[sG[s]] = sV[s];
 }
 """
 
@@ -238,19 +301,20 @@ def _neg(a):
     return "(-%s)" % a
 
 
-def affine_geometry(dim, sfx="", elem="e"):
+def affine_geometry(dim, sfx="", elem="e", vt="P.t", ldv="P.ldt",
+                    fast_inverse=False, pc="P.p", ldpc="P.ldp"):
     """C statements computing ``A, b, detA, invA`` of element ``elem`` with
     the operation order of spfem/mapping.py:207-229 (tri) / 244-279 (tet).
     Variables carry the suffix ``sfx`` (facet kernels have two elements)."""
     L = []
     nve = dim + 1
     for k in range(nve):
-        L.append("const int vtx%s_%d = P.t[%d * P.ldt + %s];" % (sfx, k, k, elem))
+        L.append("const int vtx%s_%d = %s[%d * %s + %s];" % (sfx, k, vt, k, ldv, elem))
     for i in range(dim):
-        L.append("const double b%s_%d = P.p[%d * P.ldp + vtx%s_0];" % (sfx, i, i, sfx))
+        L.append("const double b%s_%d = %s[%d * %s + vtx%s_0];" % (sfx, i, pc, i, ldpc, sfx))
         for j in range(dim):
             L.append("const double A%s_%d%d = %s;" % (
-                sfx, i, j, _sub("P.p[%d * P.ldp + vtx%s_%d]" % (i, sfx, j + 1),
+                sfx, i, j, _sub("%s[%d * %s + vtx%s_%d]" % (pc, i, ldpc, sfx, j + 1),
                                 "b%s_%d" % (sfx, i))))
     A = lambda i, j: "A%s_%d%d" % (sfx, i, j)
     if dim == 2:
@@ -281,9 +345,15 @@ def affine_geometry(dim, sfx="", elem="e"):
             (1, 2): m2(A(0, 2), A(1, 0), A(0, 0), A(1, 2)),
             (2, 2): cof(A(0, 1), A(1, 0), A(0, 0), A(1, 1)),
         }
-    for (i, j), e in sorted(inv.items()):
-        L.append("const double iA%s_%d%d = %s;" % (sfx, i, j,
-                                                  _div(e, "detA%s" % sfx)))
+    if fast_inverse:
+        # one division: adj * (1/det) instead of adj / det (<= 1 ulp apart)
+        L.append("const double rdetA%s = 1.0 / detA%s;" % (sfx, sfx))
+        for (i, j), e in sorted(inv.items()):
+            L.append("const double iA%s_%d%d = %s * rdetA%s;" % (sfx, i, j, e, sfx))
+    else:
+        for (i, j), e in sorted(inv.items()):
+            L.append("const double iA%s_%d%d = %s;" % (sfx, i, j,
+                                                      _div(e, "detA%s" % sfx)))
     L.append("const double absdet%s = fabs(detA%s);" % (sfx, sfx))
     return L
 
@@ -427,10 +497,10 @@ def generate_interior(spec, name="spfem_elem"):
     body = []
     if quad:
         for k in range(4):
-            body.append("const int vtx_%d = P.t[%d * P.ldt + e];" % (k, k))
+            body.append("const int vtx_%d = vt[%d * ldv + ev];" % (k, k))
         for i in range(2):
             for k in range(4):
-                body.append("const double Q%d_%d = P.p[%d * P.ldp + vtx_%d];"
+                body.append("const double Q%d_%d = pc[%d * ldpc + vtx_%d];"
                             % (i, k, i, k))
         for q in range(nq):
             body += q1_geometry_q("%d" % q, spec.X[0, q], spec.X[1, q])
@@ -438,7 +508,8 @@ def generate_interior(spec, name="spfem_elem"):
                 body.append("const double hq_%d = pow(absdetq_%d, %s);"
                             % (q, q, lit(1.0 / dim)))
     else:
-        body += affine_geometry(dim)
+        body += affine_geometry(dim, vt="vt", ldv="ldv", elem="ev", fast_inverse=True,
+                                pc="pc", ldpc="ldpc")
         if "h" in syms:
             body.append("const double h = pow(absdet, %s);" % lit(1.0 / dim))
     # global coordinates of the quadrature points (only if the form uses x)
@@ -508,23 +579,34 @@ def generate_interior(spec, name="spfem_elem"):
     src = [PRELUDE]
     src.append("#define SPFEM_NENTRIES %d" % spec.n_entries)
     src.append("#define SPFEM_STORE(idx, val) out[(long long)(idx) * ldo + k] = (val)")
-    # body(P, e, out, ldo, k): local matrix of element e -> out[idx*ldo + k]
-    src.append("template <typename OUT>")
+    # body(P, e, vt, ldv, ev, out, ldo, k): local matrix of element e whose
+    # vertex ids are vt[r*ldv + ev]  ->  out[idx*ldo + k]
+    src.append("template <typename VT, typename OUT>")
     src.append("SPFEM_DEVICE void %s_body(const SpfemArgs &P, const long long e, "
+               "const VT *__restrict__ vt, const long long ldv, const long long ev, "
+               "const double *__restrict__ pc, const long long ldpc, "
                "OUT *__restrict__ out, const long long ldo, const long long k)\n{" % name)
     src += ["    " + ln for ln in body]
     src.append("}")
     src.append("#ifndef SPFEM_HOST")
     src.append('extern "C" __global__ void __launch_bounds__(128) %s(const SpfemArgs P)\n{' % name)
     src.append("    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;")
-    src.append("    if (k < P.n) %s_body(P, P.sel ? (long long)P.sel[k] : k, P.out, P.ldo, k);" % name)
+    src.append("    if (k >= P.n) return;")
+    src.append("    const long long e = P.sel ? (long long)P.sel[k] : k;")
+    src.append("    %s_body(P, e, P.t, P.ldt, e, P.p, P.ldp, P.out, P.ldo, k);" % name)
     src.append("}")
     if spec.bilinear:
-        src.append(TILE_KERNEL.replace("@NAME@", name))
+        nve = 4 if quad else dim + 1
+        # element id (only needed for the interp gathers through P.tdof_u)
+        elem = "(long long)((const int *)(sA + d[13]))[el]" if spec.nw > 0 else "0LL"
+        src.append(TILE_KERNEL.replace("@NAME@", name).replace("@ELEM@", elem)
+                   .replace("@THREADS@", str(TILE_THREADS)))
     src.append("#else")
     src.append('extern "C" void %s_host(const SpfemArgs *P)\n{' % name)
-    src.append("    for (long long k = 0; k < P->n; ++k)")
-    src.append("        %s_body(*P, P->sel ? (long long)P->sel[k] : k, P->out, P->ldo, k);" % name)
+    src.append("    for (long long k = 0; k < P->n; ++k) {")
+    src.append("        const long long e = P->sel ? (long long)P->sel[k] : k;")
+    src.append("        %s_body(*P, e, P->t, P->ldt, e, P->p, P->ldp, P->out, P->ldo, k);" % name)
+    src.append("    }")
     src.append("}")
     src.append("#endif")
     return "\n".join(src) + "\n"

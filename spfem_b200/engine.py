@@ -26,6 +26,18 @@ from scipy.sparse import csr_matrix
 from . import _lib
 from .codegen import source_key
 
+
+def tile_smem_bytes(nent, tp):
+    """Dynamic shared memory of the tile kernel (layout in codegen.TILE_KERNEL)."""
+    sl = (8 * nent * tp["ldl"] + 15) // 16 * 16
+    return (sl + tp["max_bytes_a"] + tp["max_bytes_b"] + 8 * tp["max_ns"] + 16
+            + 4 * tp["max_ns"] + 16)
+
+
+def codegen_tile_threads():
+    from . import codegen
+    return codegen.TILE_THREADS
+
 _KCACHE_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_kcache")
 _MODULES = {}     # source hash -> (module handle, kernel handle, image bytes)
 
@@ -174,16 +186,17 @@ class TiledPrepared(Prepared):
         Prepared.__init__(self, engine, plan, kernel, args, 128, local, pattern, keep)
         self.tile_kernel, self.tp = tile_kernel, tp
         ta = _lib.SpfemTileArgs()
-        ta.tiles = tp["desc"].data_ptr()
-        ta.elems = tp["elems"].data_ptr()
-        ta.cptr = tp["cptr"].data_ptr()
-        ta.contrib = tp["contrib"].data_ptr()
-        ta.rowbase = tp["rowbase"].data_ptr()
-        ta.gdelta = tp["gdelta"].data_ptr()
+        ta.desc = tp["desc"].data_ptr()
+        ta.blob = tp["blob"].data_ptr()
         ta.values = self.values.data_ptr()
         ta.ldl = tp["ldl"]
+        ta.max_a = tp["max_bytes_a"]
+        ta.max_b = tp["max_bytes_b"]
+        ta.max_ns = tp["max_ns"]
+        ta.max_nr = tp["max_nr"]
         self.targs = ta
-        self.smem = 8 * plan.spec.n_entries * tp["ldl"]
+        self.smem = tile_smem_bytes(plan.spec.n_entries, tp)
+        self.threads = codegen_tile_threads()
         self.n_launches = 1
 
     def launch(self):
@@ -193,8 +206,8 @@ class TiledPrepared(Prepared):
         a.p, a.ldp = e.p.data_ptr(), e.p.shape[1]
         self.targs.base = a
         _lib.check(e.lib.spfem_launch_tiled(self.tile_kernel, C.byref(self.targs),
-                                            self.tp["ntiles"], 256, self.smem,
-                                            e._stream()))
+                                            self.tp["ntiles"], self.threads,
+                                            self.smem, e._stream()))
         return self.values
 
 
@@ -207,6 +220,8 @@ class Engine(object):
                                    if device is None else device)
         self.patterns = {}
         self.stats = {}
+        self._tile_plans = []
+        self.p_version = 0
         self.fused = os.environ.get("SPFEM_FUSED", "1") != "0"
         mesh = asm.mesh
         self.nt = mesh.t.shape[1]
@@ -256,6 +271,13 @@ class Engine(object):
                 tdv = self._dev(asm.dofnum_v.t_dof, np.int32)
                 self.tdof_v = tdv if self.perm is None else tdv.index_select(1, self.perm_l)
         self.t = t32 if self.perm is None else t32.index_select(1, self.perm_l).contiguous()
+        if not first:
+            # the fused kernel reads tile-private copies of the coordinates
+            from .tileplan import fill_coordinates
+            self.p_version += 1
+            for tp in self._tile_plans:
+                fill_coordinates(tp, self.p)
+                tp["p_version"] = self.p_version
 
     def _morton_perm(self, t32):
         torch = self.torch
@@ -379,7 +401,7 @@ class Engine(object):
             a.interp[s] = w.data_ptr()
         tp = None
         if tind is None and plan.bilinear and self.fused:
-            tp = self.tile_plan(pat, n, spec.n_entries)
+            tp = self.tile_plan(pat, n, spec.n_entries, spec.nw > 0)
         if tp is not None:
             tk = get_kernel(plan.source, plan.name + "_tile")
             return TiledPrepared(self, plan, kernel, tk, a, None, pat, tp, keep=(wt,))
@@ -387,35 +409,44 @@ class Engine(object):
         a.out = local.data_ptr()
         return Prepared(self, plan, kernel, a, 128, local, pat, keep=(sel, wt))
 
-    def tile_plan(self, pat, n, nent):
+    def tile_plan(self, pat, n, nent, with_el=False):
         """Tile plan of the fused kernel for ``pat`` (cached on the pattern);
         ``None`` if a tile does not fit in shared memory / 16-bit indices."""
         cache = getattr(pat, "_tile_plans", None)
         if cache is None:
             cache = pat._tile_plans = {}
-        if nent in cache:
-            return cache[nent]
+        ckey = (nent, with_el)
+        if ckey in cache:
+            return cache[ckey]
         from .tileplan import build_tile_plan
+        threads = codegen_tile_threads()
         E = int(os.environ.get("SPFEM_TILE_E", "0"))
         if E <= 0:
-            budget = int(os.environ.get("SPFEM_TILE_SMEM", str(96 * 1024)))
-            E = budget // (8 * nent)
-            E = int(E / 1.15) // 32 * 32
+            # about one element per thread, and the local matrices of a tile
+            # within ~64 KB of shared memory
+            E = min(int(threads / 1.15), (64 * 1024) // (8 * nent)) // 32 * 32
+            E = max(E, 32)
         tp = None
         t0 = time.perf_counter()
-        while E >= 32:
+        while E >= 16:
             try:
                 tp = build_tile_plan(self.torch, pat.indptr, pat.cptr, pat.contrib,
-                                     n, nent, E)
+                                     n, nent, E, self.t, with_el=with_el,
+                                     dim=self.p.shape[0])
             except ValueError:
                 tp = None
-            if tp is not None and 8 * nent * tp["ldl"] <= 200 * 1024:
+            if tp is not None and tile_smem_bytes(nent, tp) <= 220 * 1024:
                 break
             tp = None
             E //= 2
+        if tp is not None:
+            from .tileplan import fill_coordinates
+            fill_coordinates(tp, self.p)
+            tp["p_version"] = self.p_version
+            self._tile_plans.append(tp)
         self.torch.cuda.synchronize(self.device)
         self.stats["tile_plan_s"] = time.perf_counter() - t0
-        cache[nent] = tp
+        cache[ckey] = tp
         return tp
 
     def run_interior(self, plan, tind=None, interp=None, to_host=True):

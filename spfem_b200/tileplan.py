@@ -14,28 +14,48 @@ Built once per sparsity pattern from the global contribution lists
 on the device (set-up plumbing; the tensors work on the CPU too, which is how
 ``tests/test_tileplan.py`` checks the plan without a GPU).
 
-Per tile (descriptor ``e0, ne, cp0, ns, c0, r0, rb0``):
-  elems[e0 : e0+ne]        element ids whose local matrices the CTA computes
-  cptr[cp0 : cp0+ns+1]     uint16 start of each owned slot's contribution list
-                           (relative to c0), bit 15 marks the first slot of a row
-  contrib[c0 : ...]        uint16 shared-memory index ``idx*ldl + el``
-  rowbase[rb0 + s//32]     number of owned rows that start before slot 32*(s//32)
-  gdelta[r0 + row]         CSR position of the row's first slot minus its tile
-                           slot index
+Everything a CTA needs besides the vertex coordinates is packed into ONE
+contiguous, 16-byte aligned byte blob per tile so that it can be brought into
+shared memory with two TMA bulk copies (``cp.async.bulk``):
+
+  section A (needed to compute local matrices)
+    vt     uint16 [nve][ne_pad]   TILE-LOCAL vertex ids of the tile's elements
+    el     int32  [ne_pad]        element ids (optional; interp gathers only)
+    pc     f64    [dim][nvt_pad]  coordinates of the tile's vertices (a private
+                                  copy, refreshed by ``fill_coordinates`` whenever
+                                  the mesh coordinates are uploaded)
+  section B (needed to sum and store)
+    rinfo  int32x2 [nr+1] per owned row: {CSR position of the row's first slot
+                         minus its tile slot index, tile slot index of the first
+                         slot | start of the row's contribution list << 16}
+    contrib uint16 [nc]  shared-memory index ``idx*ldl + el`` of a contribution;
+                         bit 15 marks the last contribution of a CSR slot
+
+Descriptor (int32 x 16 per tile):
+  0 blob offset / 16   1 bytes A   2 bytes B   3 ne   4 ne_pad   5 ns
+  6 unused   7 unused   8 byte offset of contrib in B   9 nr  10 nc
+  11 nvt_pad  12 byte offset of pc in A  13 byte offset of el in A  14 nvt  15 0
 """
 import numpy as np
 
 
-def build_tile_plan(torch, indptr, cptr, contrib, n, nent, E):
-    """All arguments are tensors on one device; returns a dict of tensors."""
+def _pad(x, m):
+    return (x + m - 1) // m * m
+
+
+def build_tile_plan(torch, indptr, cptr, contrib, n, nent, E, vt, with_el=True, dim=2):
+    """All tensor arguments live on one device.  ``vt``: int32 ``(nve, n)``
+    vertex table in device element order.  Returns a dict of tensors/ints."""
     dev = indptr.device
     i64 = torch.int64
     N = indptr.numel() - 1
     nnz = cptr.numel() - 1
+    nve = vt.shape[0]
     indptr = indptr.to(i64)
     cptr = cptr.to(i64)
     contrib = contrib.to(i64)
     ntiles = (n + E - 1) // E
+    ar_t = torch.arange(ntiles, device=dev)
     counts = cptr[1:] - cptr[:-1]
     ar_nnz = torch.arange(nnz, device=dev)
     slot_of_c = torch.repeat_interleave(ar_nnz, counts)
@@ -58,18 +78,19 @@ def build_tile_plan(torch, indptr, cptr, contrib, n, nent, E):
     _, c_order = torch.sort(cpos, stable=True)
     k_s, ij_s = k[c_order], ij[c_order]
     tile_c = tile_of_slot[slot_of_c][c_order]
+    del cpos, slot_of_c, row_of_c
     # tile element lists = unique (tile, element) pairs, sorted by element
     ukey, inv = torch.unique(tile_c * n + k_s, return_inverse=True)
     tile_of_u = ukey // n
-    elems = (ukey % n).to(torch.int32)
+    elems = ukey % n
     ne = torch.bincount(tile_of_u, minlength=ntiles)[:ntiles]
     e0 = torch.cumsum(ne, 0) - ne
     eloc = inv - e0[tile_c]
-    ldl = int(ne.max().item())
-    ldl = (ldl + 31) // 32 * 32 + 1          # odd multiple: spreads banks across idx
+    ne_max = int(ne.max().item())
+    ldl = _pad(ne_max, 32) + 1           # odd: consecutive idx rows shift banks
     if nent * ldl > 65535:
         raise ValueError("tile too large for 16-bit shared-memory indices")
-    contrib16 = (ij_s * ldl + eloc).to(torch.int32)
+    contrib16 = ij_s * ldl + eloc
     # per-slot contribution list starts (relative to the tile's base)
     counts_s = counts[slot_order]
     cstart = torch.cumsum(counts_s, 0) - counts_s
@@ -83,69 +104,166 @@ def build_tile_plan(torch, indptr, cptr, contrib, n, nent, E):
     head = torch.ones(nnz, dtype=i64, device=dev)
     if nnz > 1:
         head[1:] = ((rows_s[1:] != rows_s[:-1]) | (tile_sorted[1:] != tile_sorted[:-1])).to(i64)
-    cptr16 = torch.empty(nnz + ntiles, dtype=torch.int32, device=dev)
-    cptr16[ar_nnz + tile_sorted] = (lstart + (head << 15)).to(torch.int32)
-    cp0 = s0 + torch.arange(ntiles, device=dev)
-    cptr16[cp0 + ns] = nc.to(torch.int32)
-    # rows
     heads_cum = torch.cumsum(head, 0)
     nr = torch.zeros(ntiles, dtype=i64, device=dev)
     nr.scatter_add_(0, tile_sorted, head)
     r0 = torch.cumsum(nr, 0) - nr
     hidx = torch.nonzero(head).squeeze(1)
-    gdelta = (slot_order[hidx] - (hidx - s0[tile_sorted[hidx]])).to(torch.int32)
-    # rowbase: heads strictly before every 32nd slot of each tile
+    gdelta = slot_order[hidx] - (hidx - s0[tile_sorted[hidx]])
     nchunk = (ns + 31) // 32
     rb0 = torch.cumsum(nchunk, 0) - nchunk
     tot_chunks = int(nchunk.sum().item())
-    chunk_tile = torch.repeat_interleave(torch.arange(ntiles, device=dev), nchunk)
+    chunk_tile = torch.repeat_interleave(ar_t, nchunk)
     chunk_idx = torch.arange(tot_chunks, device=dev) - rb0[chunk_tile]
     spos = s0[chunk_tile] + 32 * chunk_idx
-    before = heads_cum[spos] - head[spos] - r0[chunk_tile]
-    rowbase = before.to(torch.int32)
-    desc = torch.stack([e0, ne, cp0, ns, c0, r0, rb0, torch.zeros_like(e0)], 1)
+    rowbase = heads_cum[spos] - head[spos] - r0[chunk_tile]
+
+    # ---- tile-local vertex numbering ----------------------------------------
+    nv_glob = int(vt.max().item()) + 1
+    vt_e = vt.to(i64)[:, elems]                      # (nve, total tile elements)
+    vkey = (tile_of_u * nv_glob).unsqueeze(0) + vt_e
+    uv, vinv = torch.unique(vkey.reshape(-1), return_inverse=True)
+    tile_of_v = uv // nv_glob
+    vid = uv % nv_glob                               # global id of every tile vertex
+    nvt = torch.bincount(tile_of_v, minlength=ntiles)[:ntiles]
+    v0 = torch.cumsum(nvt, 0) - nvt
+    vloc = vinv.reshape(nve, -1) - v0[tile_of_u].unsqueeze(0)
+    if int(nvt.max().item()) > 65535:
+        raise ValueError("more than 65535 vertices in one tile")
+    # ---- pack the per-tile blobs ------------------------------------------
+    ne_pad = (ne + 7) // 8 * 8
+    nvt_pad = (nvt + 1) // 2 * 2
+    off_el = nve * ne_pad * 2
+    off_pc = off_el + (ne_pad * 4 if with_el else 0)
+    bytes_a = off_pc + dim * nvt_pad * 8
+    off_cptr = torch.zeros_like(nr)
+    off_rowbase = torch.zeros_like(nr)
+    off_contrib = ((nr + 1) * 8 + 15) // 16 * 16
+    bytes_b = off_contrib + (nc * 2 + 15) // 16 * 16
+    tile_bytes = bytes_a + bytes_b
+    blob_off = torch.cumsum(tile_bytes, 0) - tile_bytes
+    total = int(tile_bytes.sum().item())
+    if int((blob_off // 16).max().item()) > 2 ** 31 - 1:
+        raise ValueError("tile blob exceeds 32 GB")
+    blob = torch.zeros(total, dtype=torch.uint8, device=dev)
+    b32 = blob.view(torch.int32)
+    b16 = blob.view(torch.int16)
+    # section A: local vertex table, optional element ids
+    el_local = torch.arange(elems.numel(), device=dev) - e0[tile_of_u]
+    base16 = (blob_off // 2)[tile_of_u]
+    npad_u = ne_pad[tile_of_u]
+    for r in range(nve):
+        b16[base16 + r * npad_u + el_local] = vloc[r].to(torch.int16)
+    if with_el:
+        b32[((blob_off + off_el) // 4)[tile_of_u] + el_local] = elems.to(torch.int32)
+    # destination (in float64 units) of coordinate d of every tile vertex:
+    # pc_index + d * pc_stride
+    v_local = torch.arange(vid.numel(), device=dev) - v0[tile_of_v]
+    pc_index = ((blob_off + off_pc) // 8)[tile_of_v] + v_local
+    pc_stride = nvt_pad[tile_of_v]
+    # section B
+    if nent * ldl > 32767:
+        raise ValueError("tile too large for 15-bit shared-memory indices")
+    bbase = blob_off + bytes_a
+    hrow_local = heads_cum[hidx] - 1 - r0[tile_sorted[hidx]]
+    slot_local = ar_nnz - s0[tile_sorted]
+    ri_base = (bbase // 4)[tile_sorted[hidx]] + 2 * hrow_local
+    b32[ri_base] = gdelta.to(torch.int32)
+    packed = slot_local[hidx] + (lstart[hidx] << 16)
+    b32[ri_base + 1] = torch.where(packed >= 2 ** 31, packed - 2 ** 32, packed).to(torch.int32)
+    # terminating entry of every tile: {0, ns | nc << 16}
+    endp = ns + (nc << 16)
+    b32[(bbase // 4) + 2 * nr + 1] = torch.where(endp >= 2 ** 31, endp - 2 ** 32, endp).to(torch.int32)
+    c_local = torch.arange(contrib16.numel(), device=dev) - c0[tile_c]
+    # last contribution of every slot: the next contribution starts a new slot
+    cend = torch.cumsum(counts_s, 0) - 1          # global position of each slot's last entry
+    last = torch.zeros(contrib16.numel(), dtype=i64, device=dev)
+    last[cend[counts_s > 0]] = 1
+    b16[((bbase + off_contrib) // 2)[tile_c] + c_local] = (contrib16 + (last << 15)).to(torch.int16)
+    z = torch.zeros_like(ne)
+    desc = torch.stack([blob_off // 16, bytes_a, bytes_b, ne, ne_pad, ns, off_cptr,
+                        off_rowbase, off_contrib, nr, nc, nvt_pad, off_pc,
+                        off_el if with_el else z - 1, nvt, z], 1)
     if int(desc.max().item()) > 2 ** 31 - 1:
         raise ValueError("tile plan offsets exceed 32 bits")
     return {
-        "ntiles": ntiles, "ldl": ldl, "E": E,
+        "ntiles": ntiles, "ldl": ldl, "E": E, "nve": nve,
         "desc": desc.to(torch.int32).contiguous(),
-        "elems": elems.contiguous(),
-        "cptr": cptr16.to(torch.int16).contiguous(),
-        "contrib": contrib16.to(torch.int16).contiguous(),
-        "rowbase": rowbase.to(torch.int16).contiguous(),
-        "gdelta": gdelta.contiguous(),
+        "blob": blob,
+        "max_bytes_a": int(bytes_a.max().item()),
+        "max_bytes_b": int(bytes_b.max().item()),
+        "max_ns": int(ns.max().item()), "max_nr": int(nr.max().item()),
+        "tile_elems": (elems, e0, ne),
+        "vid": vid, "pc_index": pc_index, "pc_stride": pc_stride, "dim": dim,
+        "tile_vertices": float(nvt.sum().item()),
         "halo_factor": float(ne.sum().item()) / float(n),
-        "bytes": None,
+        "blob_bytes": total,
     }
 
 
-def emulate(plan, local, n, nnz):
+def emulate(plan, local, nnz):
     """NumPy emulation of phase B of the tile kernel (tests only): ``local`` is
-    the entry-major ``(nent, n)`` array of local matrices."""
-    desc = plan["desc"].cpu().numpy()
-    elems = plan["elems"].cpu().numpy()
-    cptr = plan["cptr"].cpu().numpy().view(np.uint16).astype(np.int64)
-    contrib = plan["contrib"].cpu().numpy().view(np.uint16).astype(np.int64)
-    rowbase = plan["rowbase"].cpu().numpy().view(np.uint16).astype(np.int64)
-    gdelta = plan["gdelta"].cpu().numpy().astype(np.int64)
-    ldl = plan["ldl"]
+    the entry-major ``(nent, n)`` array of local matrices.  Reads only the
+    packed blob, exactly like the kernel."""
+    desc = plan["desc"].cpu().numpy().astype(np.int64)
+    blob = plan["blob"].cpu().numpy()
+    ldl, nve = plan["ldl"], plan["nve"]
     nent = local.shape[0]
     values = np.full(nnz, np.nan)
     written = np.zeros(nnz, dtype=np.int64)
-    for (e0, ne, cp0, ns, c0, r0, rb0, _) in desc:
+    all_elems = plan["tile_elems"][0].cpu().numpy()
+    e0s = plan["tile_elems"][1].cpu().numpy()
+    for ti, (off16, ba, bb, ne, ne_pad, ns, o_cp, o_rb, o_cb, nr, nc, *_r) in enumerate(desc):
+        B = blob[off16 * 16 + ba: off16 * 16 + ba + bb]
+        elems = all_elems[e0s[ti]: e0s[ti] + ne]
+        rinfo = B[:(nr + 1) * 8].view(np.int32).astype(np.int64).reshape(nr + 1, 2)
+        contrib = B[o_cb:o_cb + 2 * nc].view(np.uint16).astype(np.int64)
         sL = np.zeros(nent * ldl)
         for idx in range(nent):
-            sL[idx * ldl: idx * ldl + ne] = local[idx, elems[e0:e0 + ne]]
-        cp = cptr[cp0:cp0 + ns + 1]
-        heads = (cp[:ns] >> 15) & 1
-        starts = np.concatenate((cp[:ns] & 0x7fff, [cp[ns] & 0x7fff]))
-        for s in range(ns):
-            chunk = s >> 5
-            row = rowbase[rb0 + chunk] + int(heads[32 * chunk: s + 1].sum()) - 1
+            sL[idx * ldl: idx * ldl + ne] = local[idx, elems]
+        for row in range(nr):
+            packed = rinfo[row, 1] & 0xffffffff
+            kend = (rinfo[row + 1, 1] & 0xffffffff) >> 16
+            s = packed & 0xffff
+            g = rinfo[row, 0] + s
             acc = 0.0
-            for kk in range(starts[s], starts[s + 1]):
-                acc += sL[contrib[c0 + kk]]
-            g = gdelta[r0 + row] + s
-            values[g] = acc
-            written[g] += 1
+            for kk in range(packed >> 16, kend):
+                c = contrib[kk]
+                acc += sL[c & 0x7fff]
+                if c & 0x8000:
+                    values[g] = acc
+                    written[g] += 1
+                    acc = 0.0
+                    s += 1
+                    g += 1
     return values, written
+
+
+def fill_coordinates(plan, p):
+    """Copy the vertex coordinates ``p`` (dim, nv) into the tiles' private
+    coordinate sections (device-side gather; call after every change of p)."""
+    b64 = plan["blob"].view(p.dtype)
+    for d in range(plan["dim"]):
+        b64[plan["pc_index"] + d * plan["pc_stride"]] = p[d][plan["vid"]]
+
+
+def check_vertex_table(plan, vt, p):
+    """Tests only: section A of every blob holds, through the tile-local vertex
+    ids, the coordinates of the vertices of the tile's elements."""
+    desc = plan["desc"].cpu().numpy().astype(np.int64)
+    blob = plan["blob"].cpu().numpy()
+    nve, dim = plan["nve"], plan["dim"]
+    vt = np.asarray(vt)
+    all_elems = plan["tile_elems"][0].cpu().numpy()
+    e0s = plan["tile_elems"][1].cpu().numpy()
+    for ti, d in enumerate(desc):
+        off16, ba, ne, ne_pad, nvt_pad, off_pc = d[0], d[1], d[3], d[4], d[11], d[12]
+        A = blob[off16 * 16: off16 * 16 + ba]
+        loc = A[:nve * ne_pad * 2].view(np.uint16).reshape(nve, ne_pad)[:, :ne]
+        pc = A[off_pc: off_pc + dim * nvt_pad * 8].view(np.float64).reshape(dim, nvt_pad)
+        elems = all_elems[e0s[ti]: e0s[ti] + ne]
+        for r in range(nve):
+            for k in range(dim):
+                if not np.array_equal(pc[k, loc[r]], p[k, vt[r, elems]]):
+                    return False
+    return True

@@ -9,7 +9,8 @@ import torch
 import cases
 import util
 import hostemu
-from spfem_b200.tileplan import build_tile_plan, emulate
+from spfem_b200.tileplan import (build_tile_plan, emulate, check_vertex_table,
+                                 fill_coordinates)
 
 
 def _morton(mesh):
@@ -56,9 +57,13 @@ def test_tile_plan_reproduces_assembly(name, E):
     nnz = len(ukeys)
     rows = ukeys // asm.dofnum_u.N
     indptr = np.searchsorted(rows, np.arange(asm.dofnum_v.N + 1))
+    vt = np.ascontiguousarray(asm.mesh.t[:, perm], dtype=np.int32)
     tp = build_tile_plan(torch, torch.from_numpy(indptr), torch.from_numpy(cptr),
-                         torch.from_numpy(contrib), n, plan.spec.n_entries, E)
-    values, written = emulate(tp, local, n, nnz)
+                         torch.from_numpy(contrib), n, plan.spec.n_entries, E,
+                         torch.from_numpy(vt), dim=asm.mesh.p.shape[0])
+    fill_coordinates(tp, torch.from_numpy(np.ascontiguousarray(asm.mesh.p)))
+    assert check_vertex_table(tp, vt, asm.mesh.p)
+    values, written = emulate(tp, local, nnz)
     assert np.all(written == 1)
     ref = util.golden(case)
     assert nnz == ref.nnz
