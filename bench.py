@@ -203,14 +203,25 @@ def run_gpu_arm(args):
     import spfem_b200 as sp
     from spfem_b200.assembly import AssemblerElement
 
-    # every rank assembles its own refine(R) mesh shard-sized workload (weak
-    # scaling: per-GPU work fixed); see DESIGN.md "Multi-GPU"
+    # N = 1: the BASELINE configs[1] mesh itself.  N > 1 (weak scaling, fixed
+    # work per GPU): a strip of N such unit-square meshes glued along x; rank r
+    # assembles copy r plus the halo elements that touch rows it owns
+    # (spfem_b200/distributed.py) -- no data-path collective.
     t0 = time.perf_counter()
-    m = sp.MeshTri()
-    m.refine(args.refine)
+    if world == 1:
+        m = sp.MeshTri()
+        m.refine(args.refine)
+        a = AssemblerElement(m, sp.ElementTriP1())
+        nt = m.t.shape[1]
+    else:
+        from spfem_b200.distributed import DistributedAssembler, strip_part
+        part = strip_part(rank, world, args.refine)
+        da = DistributedAssembler(None, sp.ElementTriP1(), part=part, rank=rank, world=world)
+        a = da.local
+        m = part.mesh
+        nt = part.n_own_elements
     t_mesh = time.perf_counter() - t0
-    nt, nv = m.t.shape[1], m.p.shape[1]
-    a = AssemblerElement(m, sp.ElementTriP1())
+    nv = m.p.shape[1]
     t0 = time.perf_counter()
     preps = [a.prepare_iasm(f) for _, f in FORMS]
     torch.cuda.synchronize()
@@ -276,13 +287,17 @@ def run_gpu_arm(args):
     barrier()
     t0 = time.perf_counter()
     d2h = 0
+    t_up = 0.0
     for _ in range(e2e_steps):
+        tu = time.perf_counter()
         eng.upload_mesh()                       # H2D of p and t (host inputs)
+        t_up += time.perf_counter() - tu
         for _, f in FORMS:
             A = a.iasm(f)                       # scipy CSR on the host
             d2h += A.data.nbytes
     barrier()
     dt = time.perf_counter() - t0
+    e2e_upload_ms = 1e3 * t_up / e2e_steps
     if world > 1:
         tt = torch.tensor([dt], device="cuda", dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -331,7 +346,10 @@ def run_gpu_arm(args):
         "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "MeshTri.refine(%d) ElementTriP1 Laplace+mass iasm" % args.refine,
+        "config": {"workload": ("MeshTri.refine(%d) ElementTriP1 Laplace+mass iasm" % args.refine)
+                               + ("" if world == 1 else
+                                  " x %d (strip of unit squares, one per GPU, halo "
+                                  "recompute, no data-path collective)" % world),
                    "nt_per_gpu": nt, "nv": nv, "nnz": nnz,
                    "elements_per_step": elems_per_step,
                    "l2": "inputs+outputs per step (%.0f MB) exceed the 126 MB L2"
@@ -348,6 +366,7 @@ def run_gpu_arm(args):
                      "algorithmic_bytes_per_assembly": balg},
         "cpu_baseline": cpu,
         "e2e": {"value": e2e_value, "unit": UNIT, "steps": e2e_steps,
+                "ms_per_step": 1e3 * dt / e2e_steps, "upload_ms": e2e_upload_ms,
                 "h2d_bytes_per_step": int(eng.h2d_bytes),
                 "d2h_bytes_per_step": int(d2h // e2e_steps)},
         "gpu_launches": int(args.steps * sum(p.n_launches for p in preps)),

@@ -116,7 +116,7 @@ static __device__ __forceinline__ void spfem_mbar_wait(void *bar, unsigned parit
         "SPFEM_DONE:\n"
         "}\n" ::"r"(spfem_smem(bar)), "r"(parity) : "memory");
 }
-extern "C" __global__ void __launch_bounds__(@THREADS@) @NAME@_tile(const SpfemTileArgs T)
+extern "C" __global__ void __launch_bounds__(@THREADS@, @MINB@) @NAME@_tile(const SpfemTileArgs T)
 {
     extern __shared__ __align__(128) unsigned char spfem_smem_raw[];
     const int ldl = T.ldl;
@@ -600,7 +600,8 @@ def generate_interior(spec, name="spfem_elem"):
         # element id (only needed for the interp gathers through P.tdof_u)
         elem = "(long long)((const int *)(sA + d[13]))[el]" if spec.nw > 0 else "0LL"
         src.append(TILE_KERNEL.replace("@NAME@", name).replace("@ELEM@", elem)
-                   .replace("@THREADS@", str(TILE_THREADS)))
+                   .replace("@THREADS@", str(TILE_THREADS))
+                   .replace("@MINB@", os.environ.get("SPFEM_TILE_MINB", "1")))
     src.append("#else")
     src.append('extern "C" void %s_host(const SpfemArgs *P)\n{' % name)
     src.append("    for (long long k = 0; k < P->n; ++k) {")

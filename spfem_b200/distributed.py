@@ -1,0 +1,255 @@
+# -*- coding: utf-8 -*-
+"""Multi-GPU assembly: one process per GPU, element-partitioned mesh.
+
+The reference has no parallelism at all; this is the
+B200 design of BASELINE.json's north star.  Elements are put in Morton order
+and cut into ``world`` contiguous blocks.  Every global DOF row is *owned* by
+the lowest rank whose block contains an element touching it.  A rank assembles
+its block **plus the halo elements that touch rows it owns** (an O(surface)
+layer that the neighbouring rank computes as well), so every owned row is
+complete after the rank's own fused kernel:
+
+* no data-path collective, no partial sums crossing NVLink,
+* the summation order inside a CSR slot is fixed by the local contribution
+  lists => bitwise reproducible for a given partition,
+* the global ``indptr/indices`` are exactly the single-GPU pattern: ownership
+  only partitions rows, DOF numbering is never changed.
+
+The result stays row-distributed on the devices (:class:`DistResult`); it is
+gathered into one host SciPy object only on request (``gather``), through
+``torch.distributed`` (NCCL on GPUs, gloo in the CPU tests).
+
+``partition_global`` splits a replicated host mesh; ``strip_part`` builds the
+rank's piece of the weak-scaling benchmark mesh (a strip of ``world`` unit
+squares, each ``MeshTri().refine(R)``) without ever materialising the global
+mesh.
+"""
+import numpy as np
+from scipy.sparse import coo_matrix
+
+from . import mesh as _mesh
+from .assembly import AssemblerElement, Dofnum
+
+
+def morton_order_host(mesh, bits=20):
+    """Permutation of the elements along a Morton curve through the centroids
+    (host restatement of ``spfem_morton_order``; partitioning is set-up work)."""
+    dim = mesh.p.shape[0]
+    c = mesh.p[:, mesh.t].mean(axis=1)
+    lo = mesh.p.min(axis=1, keepdims=True)
+    ext = mesh.p.max(axis=1, keepdims=True) - lo
+    ext[ext == 0] = 1.0
+    q = np.minimum(((c - lo) / ext * (2 ** bits - 1)).astype(np.uint64),
+                   np.uint64(2 ** bits - 1))
+    key = np.zeros(c.shape[1], dtype=np.uint64)
+    for b in range(bits):
+        for d in range(dim):
+            key |= ((q[d] >> np.uint64(b)) & np.uint64(1)) << np.uint64(b * dim + d)
+    return np.argsort(key, kind="stable")
+
+
+class LocalPart(object):
+    """A rank's share of the mesh: the local mesh (own block + halo), the maps
+    from local to global DOFs and the mask of owned test DOFs (rows)."""
+
+    def __init__(self, mesh, l2g_u, l2g_v, owned_v, N_u, N_v, n_own_elements):
+        self.mesh, self.l2g_u, self.l2g_v = mesh, l2g_u, l2g_v
+        self.owned_v, self.N_u, self.N_v = owned_v, N_u, N_v
+        self.n_own_elements = n_own_elements
+
+
+def partition_global(mesh, elem_u, elem_v, world, rank):
+    """Split the replicated global ``mesh`` for ``rank`` of ``world``."""
+    nt = mesh.t.shape[1]
+    perm = morton_order_host(mesh)
+    rank_of_elem = np.empty(nt, dtype=np.int64)
+    bounds = [(nt * r) // world for r in range(world + 1)]
+    for r in range(world):
+        rank_of_elem[perm[bounds[r]:bounds[r + 1]]] = r
+    dn_u = Dofnum(mesh, elem_u)
+    dn_v = dn_u if elem_v is None or elem_v is elem_u else Dofnum(mesh, elem_v)
+    owner_v = np.full(dn_v.N, world, dtype=np.int64)
+    np.minimum.at(owner_v, dn_v.t_dof, rank_of_elem[None, :])
+    mine = (owner_v[dn_v.t_dof] == rank).any(axis=0)
+    elems = np.nonzero(mine)[0]
+    verts = np.unique(mesh.t[:, elems])
+    t_loc = np.searchsorted(verts, mesh.t[:, elems])
+    local = type(mesh)(np.ascontiguousarray(mesh.p[:, verts]), t_loc, validate=False)
+    ldn_u = Dofnum(local, elem_u)
+    ldn_v = ldn_u if dn_v is dn_u else Dofnum(local, elem_v)
+    l2g_u = np.empty(ldn_u.N, dtype=np.int64)
+    l2g_u[ldn_u.t_dof] = dn_u.t_dof[:, elems]
+    l2g_v = l2g_u
+    if ldn_v is not ldn_u:
+        l2g_v = np.empty(ldn_v.N, dtype=np.int64)
+        l2g_v[ldn_v.t_dof] = dn_v.t_dof[:, elems]
+    owned = owner_v[l2g_v] == rank
+    return LocalPart(local, l2g_u, l2g_v, owned, dn_u.N, dn_v.N,
+                     int(np.sum(rank_of_elem[elems] == rank)))
+
+
+def strip_part(rank, world, refine, unit=None):
+    """Rank ``rank``'s part of the weak-scaling mesh: ``world`` copies of the
+    unit-square mesh ``MeshTri().refine(refine)`` glued side by side along x
+    (copy r = unit mesh translated by (r, 0); the vertices on x = r+1 are
+    shared by copies r and r+1).  ElementTriP1 DOFs (vertices).
+
+    Global vertex numbering: copy r contributes its vertices except (r > 0)
+    those on its left edge, in unit-mesh order; vertex v of copy r gets id
+    ``r*(nv - nb) + c(v) + (nb if r > 0 ... )`` -- see ``gid`` below.  Ownership
+    follows the general rule (lowest rank touching the row): rank r owns every
+    vertex of its copy except its left edge.  The halo is the layer of copy
+    r+1's elements touching x = r+1."""
+    if unit is None:
+        unit = _mesh.MeshTri()
+        unit.refine(refine)
+    p, t = unit.p, unit.t
+    nv = p.shape[1]
+    left = np.nonzero(p[0] == 0.0)[0]
+    right = np.nonzero(p[0] == 1.0)[0]
+    # match left-edge and right-edge vertices by their y coordinate
+    lo = left[np.argsort(p[1, left], kind="stable")]
+    ro = right[np.argsort(p[1, right], kind="stable")]
+    assert np.array_equal(p[1, lo], p[1, ro])
+    nb = len(left)
+    is_left = np.zeros(nv, dtype=bool)
+    is_left[left] = True
+    # compact index of the non-left vertices of one copy
+    cidx = np.cumsum(~is_left) - 1
+    partner = np.full(nv, -1, dtype=np.int64)      # left vertex -> right vertex
+    partner[lo] = ro
+
+    def gid(copy, v):
+        """Global id of unit vertex ``v`` (array) in copy ``copy``."""
+        v = np.asarray(v)
+        out = np.empty(v.shape, dtype=np.int64)
+        if copy == 0:
+            return v.astype(np.int64)
+        base = nv + (copy - 1) * (nv - nb)
+        lf = is_left[v]
+        out[~lf] = base + cidx[v[~lf]]
+        out[lf] = gid(copy - 1, partner[v[lf]])
+        return out
+
+    N = nv + (world - 1) * (nv - nb)
+    # own elements + halo (copy rank+1's elements touching its left edge)
+    halo = np.nonzero(is_left[t].any(axis=0))[0] if rank < world - 1 else np.zeros(0, np.int64)
+    hv = np.unique(t[:, halo])
+    hv_new = hv[~is_left[hv]]                     # halo vertices not on the shared edge
+    # local numbering: unit vertices 0..nv-1, then the new halo vertices
+    hmap = np.full(nv, -1, dtype=np.int64)
+    hmap[hv_new] = nv + np.arange(len(hv_new))
+    hmap[lo] = ro                                  # shared edge: my right-edge vertices
+    p_loc = np.hstack((p + np.array([[float(rank)], [0.0]]),
+                       p[:, hv_new] + np.array([[float(rank + 1)], [0.0]])))
+    t_loc = np.hstack((t, hmap[t[:, halo]]))
+    local = _mesh.MeshTri(np.ascontiguousarray(p_loc), np.ascontiguousarray(t_loc),
+                          validate=False)
+    l2g = np.concatenate((gid(rank, np.arange(nv)), gid(rank + 1, hv_new)
+                          if len(hv_new) else np.zeros(0, np.int64)))
+    owned = np.zeros(p_loc.shape[1], dtype=bool)
+    owned[:nv] = True
+    if rank > 0:
+        owned[left] = False
+    return LocalPart(local, l2g, l2g, owned, N, N, t.shape[1])
+
+
+def strip_global(world, refine):
+    """The whole strip mesh with the global numbering of :func:`strip_part`
+    (tests only; small sizes)."""
+    parts = [strip_part(r, world, refine) for r in range(world)]
+    N = parts[0].N_v
+    P = np.zeros((2, N))
+    T = []
+    for part in parts:
+        P[:, part.l2g_v] = part.mesh.p
+        n_own = part.n_own_elements
+        # own elements come first in the local mesh (halo appended)
+        T.append(part.l2g_v[part.mesh.t[:, :n_own]])
+    return _mesh.MeshTri(P, np.hstack(T), validate=False)
+
+
+class DistResult(object):
+    """Row-distributed assembly result.  ``local`` is the rank's local result
+    (``engine.DeviceCSR`` / device tensor, or host objects in the CPU tests);
+    only the rows flagged in ``part.owned_v`` are meaningful."""
+
+    def __init__(self, local, part, bilinear, group):
+        self.local, self.part, self.bilinear, self.group = local, part, bilinear, group
+
+    def owned_triplets(self):
+        """Host COO triplets (global ids) of the owned rows."""
+        part = self.part
+        A = self.local.to_scipy() if hasattr(self.local, "to_scipy") else self.local
+        if self.bilinear:
+            A = A.tocsr()
+            rows = np.repeat(np.arange(A.shape[0]), np.diff(A.indptr))
+            keep = part.owned_v[rows]
+            return (part.l2g_v[rows[keep]], part.l2g_u[A.indices[keep]], A.data[keep])
+        v = A.cpu().numpy() if hasattr(A, "cpu") else np.asarray(A)
+        idx = np.nonzero(part.owned_v)[0]
+        return (part.l2g_v[idx], np.zeros(len(idx), dtype=np.int64), v[idx])
+
+    def gather(self, dst=0):
+        """Collect the global matrix / vector on rank ``dst`` (``None`` on the
+        other ranks).  Every row is owned by exactly one rank, so no value is
+        ever added across ranks."""
+        import torch.distributed as dist
+        trip = self.owned_triplets()
+        world = dist.get_world_size(self.group) if dist.is_initialized() else 1
+        if world == 1:
+            parts = [trip]
+        else:
+            rank = dist.get_rank(self.group)
+            parts = [None] * world if rank == dst else None
+            dist.gather_object(trip, parts, dst=dst, group=self.group)
+            if rank != dst:
+                return None
+        r = np.concatenate([x[0] for x in parts])
+        c = np.concatenate([x[1] for x in parts])
+        v = np.concatenate([x[2] for x in parts])
+        part = self.part
+        if self.bilinear:
+            return coo_matrix((v, (r, c)), shape=(part.N_v, part.N_u)).tocsr()
+        out = np.zeros(part.N_v)
+        out[r] = v
+        return out
+
+
+class DistributedAssembler(object):
+    """``AssemblerElement`` over an element-partitioned mesh, one rank per GPU.
+
+    ``DistributedAssembler(mesh, elem_u, elem_v=None)`` partitions the
+    replicated host ``mesh`` (every rank passes the same object) for this
+    process' rank; ``part=`` supplies a ready :class:`LocalPart` instead
+    (e.g. :func:`strip_part`).  ``iasm`` / ``fasm`` have the reference's
+    signatures and return a :class:`DistResult`."""
+
+    def __init__(self, mesh, elem_u, elem_v=None, group=None, part=None,
+                 rank=None, world=None, assemble=None):
+        import torch.distributed as dist
+        if world is None:
+            world = dist.get_world_size(group) if dist.is_initialized() else 1
+        if rank is None:
+            rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.rank, self.world, self.group = rank, world, group
+        self.part = part if part is not None else partition_global(
+            mesh, elem_u, elem_v, world, rank)
+        self.local = AssemblerElement(self.part.mesh, elem_u, elem_v)
+        self._assemble = assemble
+
+    def iasm(self, form, intorder=None, interp=None, to_host=False):
+        if interp is not None:
+            interp = {k: np.asarray(v)[self.part.l2g_u] for k, v in interp.items()}
+        bilinear = self.local.plan_iasm(form, intorder=intorder, interp=interp).bilinear
+        if self._assemble is not None:          # CPU tests inject the local assembly
+            loc = self._assemble(self.local, form, intorder=intorder, interp=interp)
+        elif to_host:
+            loc = self.local.iasm(form, intorder=intorder, interp=interp)
+        else:
+            loc = self.local.iasm_device(form, intorder=intorder, interp=interp)
+        return DistResult(loc, self.part, bilinear, self.group)
+
+    def prepare_iasm(self, form, intorder=None):
+        """Staged local assembly (see ``AssemblerElement.prepare_iasm``)."""
+        return self.local.prepare_iasm(form, intorder=intorder)

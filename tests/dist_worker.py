@@ -1,0 +1,68 @@
+# -*- coding: utf-8 -*-
+"""Worker of tests/test_distributed.py: world_size-N run of the partitioned
+assembly with the gloo backend on the CPU.  The rank-local assembly is the host
+emulation of the generated kernels (tests/hostemu.py); everything else --
+partitioning, ownership, halo, gather -- is the product code."""
+import os
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+for p in (ROOT, HERE, os.path.join(ROOT, "oracle")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np
+import torch.distributed as dist
+
+import spfem_b200 as sp
+from spfem_b200.distributed import (DistributedAssembler, strip_part, strip_global)
+import cases
+import hostemu
+import util
+
+
+def host_assemble(asm, form, intorder=None, interp=None):
+    return hostemu.iasm(asm, form, intorder=intorder, interp=interp)
+
+
+def main():
+    dist.init_process_group("gloo")
+    rank, world = dist.get_rank(), dist.get_world_size()
+    ok = True
+    # 1. replicated global meshes, general partitioner
+    for name in ("trip1_lap", "trip2_mass", "vecp2_elasticity", "stokes_b",
+                 "tetp2_lap", "trip1_load_sin_h", "q2_lap"):
+        case = cases.BY_NAME[name]
+        m = util.mesh_for(case)
+        eu = util.element(case.eu, case.ncu)
+        ev = None
+        if not (case.ev is None and case.ncv == case.ncu):
+            ev = util.element(case.ev or case.eu, case.ncv)
+        da = DistributedAssembler(m, eu, ev, assemble=host_assemble)
+        res = da.iasm(case.form).gather(0)
+        owned = np.array([int(da.part.owned_v.sum())])
+        if rank == 0:
+            util.check(res, util.golden(case))
+            print("dist ok", name, "world", world)
+    # 2. weak-scaling strip mesh built per rank, against the oracle on the
+    #    explicitly assembled global strip
+    part = strip_part(rank, world, 3)
+    da = DistributedAssembler(None, sp.ElementTriP1(), part=part, assemble=host_assemble)
+    for form in (cases.lap2, cases.mass, cases.load1):
+        res = da.iasm(form).gather(0)
+        if rank == 0:
+            import asm_oracle
+            g = strip_global(world, 3)
+            ref = asm_oracle.iasm(g, "TriP1", form)
+            if hasattr(ref, "indptr"):
+                cases.compare_csr(res, ref)
+            else:
+                cases.compare_vec(res, ref)
+            print("strip ok", form.__name__)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
