@@ -124,18 +124,65 @@ class DeviceCSR(object):
         return self.pattern.nnz
 
     def to_scipy(self):
-        """Host ``scipy.sparse.csr_matrix`` with fresh arrays (the pattern
-        arrays are copies of the cached host pattern; the values come through
-        a pinned buffer so the device-to-host copy runs at PCIe speed)."""
+        """Host ``scipy.sparse.csr_matrix`` with fresh arrays: the values come
+        through a pinned buffer (asynchronous device-to-host copy at PCIe
+        speed) while the cached host pattern is copied by worker threads."""
+        import torch
         indptr, indices = self.pattern.host()
-        data = _to_host(self.values)
+        host = None
+        if self.values.numel():
+            host = torch.empty(self.values.shape, dtype=self.values.dtype, pin_memory=True)
+            host.copy_(self.values, non_blocking=True)
+        ind_c = _host_copy(indices)
+        ptr_c = _host_copy(indptr)
+        if host is not None:
+            torch.cuda.current_stream(self.values.device).synchronize()
+            data = host.numpy()
+        else:
+            data = np.zeros(0, dtype=np.float64)
         A = csr_matrix(self.shape, dtype=np.float64)
         A.data = data
-        A.indices = indices.copy()
-        A.indptr = indptr.copy()
+        A.indices = ind_c
+        A.indptr = ptr_c
         A.has_sorted_indices = True
         A.has_canonical_format = True
         return A
+
+
+_POOL = None
+
+
+def _chunks(n, parts):
+    step = (n + parts - 1) // parts
+    return [(i, min(n, i + step)) for i in range(0, n, step)]
+
+
+def _parallel(fn, n, min_chunk=1 << 21):
+    """Run ``fn(lo, hi)`` over [0, n) on a few worker threads (NumPy releases
+    the GIL inside copies / casts)."""
+    global _POOL
+    parts = min(8, max(1, n // min_chunk))
+    if parts <= 1:
+        fn(0, n)
+        return
+    if _POOL is None:
+        from concurrent.futures import ThreadPoolExecutor
+        _POOL = ThreadPoolExecutor(max_workers=8)
+    list(_POOL.map(lambda ab: fn(*ab), _chunks(n, parts)))
+
+
+def _host_copy(arr):
+    """Fresh copy of a cached host array in recycled pinned memory."""
+    import torch
+    if arr.size == 0:
+        return arr.copy()
+    out = torch.empty(arr.shape, dtype=torch.from_numpy(arr[:0]).dtype,
+                      pin_memory=True).numpy()
+
+    def work(lo, hi):
+        out[lo:hi] = arr[lo:hi]
+    _parallel(work, arr.shape[0])
+    return out
 
 
 def _to_host(t):
@@ -274,8 +321,16 @@ class Engine(object):
             # them and sent with asynchronous copies at PCIe speed
             self._pin_p = torch.empty(mesh.p.shape, dtype=torch.float64, pin_memory=True)
             self._pin_t = torch.empty(mesh.t.shape, dtype=torch.int32, pin_memory=True)
-        np.copyto(self._pin_p.numpy(), mesh.p)
-        np.copyto(self._pin_t.numpy(), mesh.t, casting="unsafe")
+        pp, pt = self._pin_p.numpy(), self._pin_t.numpy()
+        hp, ht = mesh.p, mesh.t
+
+        def cp_p(lo, hi):
+            pp[:, lo:hi] = hp[:, lo:hi]
+
+        def cp_t(lo, hi):
+            pt[:, lo:hi] = ht[:, lo:hi]      # int64 -> int32 on the fly
+        _parallel(cp_p, hp.shape[1], 1 << 19)
+        _parallel(cp_t, ht.shape[1], 1 << 19)
         self.p = self._pin_p.to(self.device, non_blocking=True)
         t32 = self._pin_t.to(self.device, non_blocking=True)
         self.h2d_bytes = self.p.numel() * 8 + t32.numel() * 4
