@@ -121,7 +121,7 @@ extern "C" __global__ void __launch_bounds__(@THREADS@, @MINB@) @NAME@_tile(cons
     extern __shared__ __align__(128) unsigned char spfem_smem_raw[];
     const int ldl = T.ldl;
     double *sL = (double *)spfem_smem_raw;
-    unsigned char *sA = spfem_smem_raw + (((size_t)8 * SPFEM_NENTRIES * ldl + 15) & ~(size_t)15);
+    unsigned char *sA = spfem_smem_raw + (((size_t)8 * SPFEM_NUNIQUE * ldl + 15) & ~(size_t)15);
     unsigned char *sB = sA + T.max_a;
     double *sV = (double *)(sB + T.max_b);
     unsigned long long *bars = (unsigned long long *)(sV + T.max_ns);
@@ -144,8 +144,8 @@ extern "C" __global__ void __launch_bounds__(@THREADS@, @MINB@) @NAME@_tile(cons
     const double *pc = (const double *)(sA + d[12]);          /* tile-local coordinates */
     const long long ldpc = d[11];
     for (int el = threadIdx.x; el < ne; el += blockDim.x)
-        @NAME@_body(T.base, @ELEM@, vt, (long long)ne_pad, (long long)el, pc, ldpc,
-                    sL, (long long)ldl, (long long)el);
+        @NAME@_body<true>(T.base, @ELEM@, vt, (long long)ne_pad, (long long)el, pc, ldpc,
+                          sL, (long long)ldl, (long long)el);
     /* phase B1: one thread per owned row walks the row's contribution list
        (bit 15 of an entry = last contribution of a CSR slot) and adds in list
        order -- fixed order => bitwise reproducible.  The finished slot value
@@ -558,6 +558,11 @@ def generate_interior(spec, name="spfem_elem"):
         names[(node.uid, scope)] = em.name(node, scope, symname)
     body += [ln.strip() for ln in em.lines]
 
+    # Entries with identical term lists (symmetric forms: A_loc[j,i] == A_loc[i,j];
+    # P1 mass: all off-diagonal entries) are *aliases*: the fused tile kernel
+    # computes and stores each distinct value once (``alias[idx]`` = its slot in
+    # shared memory); the two-kernel route stores every entry.
+    groups, order_u, alias = {}, [], [0] * len(entries)
     for idx, terms in enumerate(entries):
         # merge terms that multiply the same coefficient (e.g. G^{12} == G^{21})
         merged, order = {}, []
@@ -569,19 +574,34 @@ def generate_interior(spec, name="spfem_elem"):
                 merged[key] = (K, node, scope)
                 order.append(key)
         terms = [merged[k] for k in order if merged[k][0] != 0.0]
-        if not terms:
-            body.append("SPFEM_STORE(%d, 0.0);" % idx)
-            continue
-        expr = " + ".join("%s * %s" % (lit(K), names[(node.uid, scope)])
-                          for K, node, scope in terms)
-        body.append("SPFEM_STORE(%d, %s);" % (idx, expr))
+        gkey = tuple(sorted((node.uid, scope, float(K).hex()) for K, node, scope in terms))
+        if gkey not in groups:
+            if terms:
+                expr = " + ".join("%s * %s" % (lit(K), names[(node.uid, scope)])
+                                  for K, node, scope in terms)
+            else:
+                expr = "0.0"
+            groups[gkey] = (len(order_u), expr, [])
+            order_u.append(gkey)
+        groups[gkey][2].append(idx)
+        alias[idx] = groups[gkey][0]
+    for gkey in order_u:
+        u, expr, idxs = groups[gkey]
+        body.append("{ const double val = %s;" % expr)
+        body.append("  if (TILED) { out[(long long)%d * ldo + k] = val; } else {" % u)
+        for idx in idxs:
+            body.append("    out[(long long)%d * ldo + k] = val;" % idx)
+        body.append("  } }")
+    spec.alias = alias
+    spec.n_unique = len(order_u)
 
     src = [PRELUDE]
     src.append("#define SPFEM_NENTRIES %d" % spec.n_entries)
-    src.append("#define SPFEM_STORE(idx, val) out[(long long)(idx) * ldo + k] = (val)")
-    # body(P, e, vt, ldv, ev, out, ldo, k): local matrix of element e whose
-    # vertex ids are vt[r*ldv + ev]  ->  out[idx*ldo + k]
-    src.append("template <typename VT, typename OUT>")
+    src.append("#define SPFEM_NUNIQUE %d" % spec.n_unique)
+    # body<TILED>(P, e, vt, ldv, ev, pc, ldpc, out, ldo, k): local matrix of
+    # element e whose vertex ids are vt[r*ldv + ev]  ->  out[idx*ldo + k]
+    # (TILED: only the distinct values, out[alias*ldo + k])
+    src.append("template <bool TILED, typename VT, typename OUT>")
     src.append("SPFEM_DEVICE void %s_body(const SpfemArgs &P, const long long e, "
                "const VT *__restrict__ vt, const long long ldv, const long long ev, "
                "const double *__restrict__ pc, const long long ldpc, "
@@ -593,7 +613,7 @@ def generate_interior(spec, name="spfem_elem"):
     src.append("    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;")
     src.append("    if (k >= P.n) return;")
     src.append("    const long long e = P.sel ? (long long)P.sel[k] : k;")
-    src.append("    %s_body(P, e, P.t, P.ldt, e, P.p, P.ldp, P.out, P.ldo, k);" % name)
+    src.append("    %s_body<false>(P, e, P.t, P.ldt, e, P.p, P.ldp, P.out, P.ldo, k);" % name)
     src.append("}")
     if spec.bilinear:
         nve = 4 if quad else dim + 1
@@ -606,7 +626,7 @@ def generate_interior(spec, name="spfem_elem"):
     src.append('extern "C" void %s_host(const SpfemArgs *P)\n{' % name)
     src.append("    for (long long k = 0; k < P->n; ++k) {")
     src.append("        const long long e = P->sel ? (long long)P->sel[k] : k;")
-    src.append("        %s_body(*P, e, P->t, P->ldt, e, P->p, P->ldp, P->out, P->ldo, k);" % name)
+    src.append("        %s_body<false>(*P, e, P->t, P->ldt, e, P->p, P->ldp, P->out, P->ldo, k);" % name)
     src.append("    }")
     src.append("}")
     src.append("#endif")

@@ -257,8 +257,10 @@ class TiledPrepared(Prepared):
         ta.max_ns = tp["max_ns"]
         ta.max_nr = tp["max_nr"]
         self.targs = ta
-        self.smem = tile_smem_bytes(plan.spec.n_entries, tp)
-        self.threads = codegen_tile_threads()
+        self.smem = tile_smem_bytes(plan.spec.n_unique, tp)
+        # threads per CTA: enough for one element / one owned row per thread
+        need = max(tp["max_ne"], tp["max_nr"])
+        self.threads = int(min(codegen_tile_threads(), max(64, (need + 31) // 32 * 32)))
         self.n_launches = 1
 
     def launch(self):
@@ -478,7 +480,7 @@ class Engine(object):
             a.interp[s] = w.data_ptr()
         tp = None
         if tind is None and plan.bilinear and self.fused:
-            tp = self.tile_plan(pat, n, spec.n_entries, spec.nw > 0)
+            tp = self.tile_plan(pat, n, spec.n_entries, spec.nw > 0, tuple(spec.alias))
         if tp is not None:
             tk = get_kernel(plan.source, plan.name + "_tile")
             return TiledPrepared(self, plan, kernel, tk, a, None, pat, tp, keep=(wt,))
@@ -486,13 +488,14 @@ class Engine(object):
         a.out = local.data_ptr()
         return Prepared(self, plan, kernel, a, 128, local, pat, keep=(sel, wt))
 
-    def tile_plan(self, pat, n, nent, with_el=False):
+    def tile_plan(self, pat, n, nent, with_el=False, alias=None):
         """Tile plan of the fused kernel for ``pat`` (cached on the pattern);
         ``None`` if a tile does not fit in shared memory / 16-bit indices."""
         cache = getattr(pat, "_tile_plans", None)
         if cache is None:
             cache = pat._tile_plans = {}
-        ckey = (nent, with_el)
+        ckey = (nent, with_el, alias)
+        nuniq = (max(alias) + 1) if alias else nent
         if ckey in cache:
             return cache[ckey]
         from .tileplan import build_tile_plan
@@ -501,7 +504,7 @@ class Engine(object):
         if E <= 0:
             # about one element per thread, and the local matrices of a tile
             # within ~64 KB of shared memory
-            E = min(int(threads / 1.15), (64 * 1024) // (8 * nent)) // 32 * 32
+            E = min(int(threads / 1.15), (64 * 1024) // (8 * nuniq)) // 32 * 32
             E = max(E, 32)
         tp = None
         t0 = time.perf_counter()
@@ -509,13 +512,19 @@ class Engine(object):
             try:
                 tp = build_tile_plan(self.torch, pat.indptr, pat.cptr, pat.contrib,
                                      n, nent, E, self.t, with_el=with_el,
-                                     dim=self.p.shape[0])
+                                     dim=self.p.shape[0], alias=alias)
             except ValueError:
                 tp = None
-            if tp is not None and tile_smem_bytes(nent, tp) <= 220 * 1024:
+            if tp is not None and tile_smem_bytes(nuniq, tp) <= 220 * 1024:
                 break
             tp = None
             E //= 2
+        # the fused kernel pays off while the halo stays thin and the local
+        # matrix is small (measured: profiles/r01_configs.json); otherwise the
+        # two-kernel route is faster
+        if tp is not None and os.environ.get("SPFEM_FUSED", "1") != "force":
+            if tp["halo_factor"] > 1.35 or nuniq > 40:
+                tp = None
         if tp is not None:
             from .tileplan import fill_coordinates
             fill_coordinates(tp, self.p)

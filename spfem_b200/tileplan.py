@@ -43,7 +43,8 @@ def _pad(x, m):
     return (x + m - 1) // m * m
 
 
-def build_tile_plan(torch, indptr, cptr, contrib, n, nent, E, vt, with_el=True, dim=2):
+def build_tile_plan(torch, indptr, cptr, contrib, n, nent, E, vt, with_el=True, dim=2,
+                    alias=None):
     """All tensor arguments live on one device.  ``vt``: int32 ``(nve, n)``
     vertex table in device element order.  Returns a dict of tensors/ints."""
     dev = indptr.device
@@ -90,6 +91,10 @@ def build_tile_plan(torch, indptr, cptr, contrib, n, nent, E, vt, with_el=True, 
     ldl = _pad(ne_max, 32) + 1           # odd: consecutive idx rows shift banks
     if nent * ldl > 65535:
         raise ValueError("tile too large for 16-bit shared-memory indices")
+    if alias is not None:
+        # aliased local entries share one shared-memory value (codegen)
+        ij_s = torch.as_tensor(alias, dtype=i64, device=dev)[ij_s]
+        nent = int(max(alias)) + 1
     contrib16 = ij_s * ldl + eloc
     # per-slot contribution list starts (relative to the tile's base)
     counts_s = counts[slot_order]
@@ -187,12 +192,13 @@ def build_tile_plan(torch, indptr, cptr, contrib, n, nent, E, vt, with_el=True, 
     if int(desc.max().item()) > 2 ** 31 - 1:
         raise ValueError("tile plan offsets exceed 32 bits")
     return {
-        "ntiles": ntiles, "ldl": ldl, "E": E, "nve": nve,
+        "ntiles": ntiles, "ldl": ldl, "E": E, "nve": nve, "nuniq": nent,
         "desc": desc.to(torch.int32).contiguous(),
         "blob": blob,
         "max_bytes_a": int(bytes_a.max().item()),
         "max_bytes_b": int(bytes_b.max().item()),
         "max_ns": int(ns.max().item()), "max_nr": int(nr.max().item()),
+        "max_ne": ne_max,
         "tile_elems": (elems, e0, ne),
         "vid": vid, "pc_index": pc_index, "pc_stride": pc_stride, "dim": dim,
         "tile_vertices": float(nvt.sum().item()),

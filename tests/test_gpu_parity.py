@@ -125,6 +125,7 @@ def test_both_assembly_paths(name, mode, monkeypatch):
         monkeypatch.setenv("SPFEM_FUSED", "0")
     else:
         monkeypatch.setenv("SPFEM_TILE_E", "32")
+        monkeypatch.setenv("SPFEM_FUSED", "force")   # bypass the "is it worth it" heuristic
     case = cases.BY_NAME[name]
     asm = util.assembler_for(case)
     kw = cases.case_inputs(case, asm.mesh, asm.dofnum_u.N)

@@ -118,8 +118,14 @@ def test_no_cpu_fallback_without_gpu():
 
 def test_tensor_mode_precontracts_quadrature():
     """Element-constant coefficients fold the quadrature sum into constants:
-    the P1 Laplace kernel has no per-point code at all."""
+    the P1 Laplace kernel has no per-point code at all, and symmetric /
+    repeated local entries are computed once (6 distinct values for the P1
+    stiffness matrix; the P1 mass matrix tables differ in the last bit, so only
+    exactly equal entries are shared)."""
     m = sp.MeshTri()
     a = AssemblerElement(m, sp.ElementTriP1())
-    src = a.plan_iasm(cases.lap2).source
-    assert "x0_" not in src and src.count("SPFEM_STORE(") == 9 + 1
+    plan = a.plan_iasm(cases.lap2)
+    assert "x0_" not in plan.source
+    assert plan.spec.n_entries == 9 and plan.spec.n_unique == 6
+    assert plan.spec.alias[1] == plan.spec.alias[3]          # A[0,1] == A[1,0]
+    assert a.plan_iasm(cases.mass).spec.n_unique <= 6

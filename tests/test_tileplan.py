@@ -60,10 +60,15 @@ def test_tile_plan_reproduces_assembly(name, E):
     vt = np.ascontiguousarray(asm.mesh.t[:, perm], dtype=np.int32)
     tp = build_tile_plan(torch, torch.from_numpy(indptr), torch.from_numpy(cptr),
                          torch.from_numpy(contrib), n, plan.spec.n_entries, E,
-                         torch.from_numpy(vt), dim=asm.mesh.p.shape[0])
+                         torch.from_numpy(vt), dim=asm.mesh.p.shape[0],
+                         alias=plan.spec.alias)
     fill_coordinates(tp, torch.from_numpy(np.ascontiguousarray(asm.mesh.p)))
     assert check_vertex_table(tp, vt, asm.mesh.p)
-    values, written = emulate(tp, local, nnz)
+    # shared-memory image of the tile kernel: one row per distinct local value
+    uniq = np.zeros((plan.spec.n_unique, local.shape[1]))
+    uniq[plan.spec.alias, :] = local
+    assert np.array_equal(uniq[plan.spec.alias, :], local)   # aliases really are equal
+    values, written = emulate(tp, uniq, nnz)
     assert np.all(written == 1)
     ref = util.golden(case)
     assert nnz == ref.nnz
