@@ -47,6 +47,7 @@ PRELUDE = r"""
 #define __dsub_rn(a, b) ((a) - (b))
 #define __ddiv_rn(a, b) ((a) / (b))
 #define __restrict__
+struct double2 { double x, y; };
 #else
 #define SPFEM_DEVICE static __device__ __forceinline__
 #endif
@@ -121,7 +122,7 @@ extern "C" __global__ void __launch_bounds__(@THREADS@, @MINB@) @NAME@_tile(cons
     extern __shared__ __align__(128) unsigned char spfem_smem_raw[];
     const int ldl = T.ldl;
     double *sL = (double *)spfem_smem_raw;
-    unsigned char *sA = spfem_smem_raw + (((size_t)8 * SPFEM_NUNIQUE * ldl + 15) & ~(size_t)15);
+    unsigned char *sA = spfem_smem_raw + (((size_t)8 * (SPFEM_NUNIQUE * ldl + 1) + 15) & ~(size_t)15);
     unsigned char *sB = sA + T.max_a;
     double *sV = (double *)(sB + T.max_b);
     unsigned long long *bars = (unsigned long long *)(sV + T.max_ns);
@@ -130,6 +131,7 @@ extern "C" __global__ void __launch_bounds__(@THREADS@, @MINB@) @NAME@_tile(cons
     const int bytes_a = d[1], bytes_b = d[2], ne = d[3], ne_pad = d[4], ns = d[5], nr = d[9];
     if (ne == 0 || ns == 0) return;
     if (threadIdx.x == 0) {
+        sL[SPFEM_NUNIQUE * ldl] = 0.0;            /* target of list padding entries */
         spfem_mbar_init(&bars[0], 1);
         spfem_mbar_init(&bars[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -152,18 +154,26 @@ extern "C" __global__ void __launch_bounds__(@THREADS@, @MINB@) @NAME@_tile(cons
        and its CSR position are staged in shared memory.                       */
     spfem_mbar_wait(&bars[1], 0);
     const int2 *rinfo = (const int2 *)sB;      /* {gdelta, s_start | k_start<<16} */
-    const unsigned short *cb = (const unsigned short *)(sB + d[8]);
+    const unsigned *cb = (const unsigned *)(sB + d[8]);   /* pairs of 16-bit entries */
     __syncthreads();
     for (int row = threadIdx.x; row < nr; row += blockDim.x) {
         const int2 ri = rinfo[row];
-        const unsigned kend = ((unsigned)rinfo[row + 1].y) >> 16;
+        const unsigned kend = ((unsigned)rinfo[row + 1].y) >> 17;
         unsigned s = (unsigned)ri.y & 0xffffu;
         int g = ri.x + (int)s;
         double acc = 0.0;
-        for (unsigned k = ((unsigned)ri.y) >> 16; k < kend; ++k) {
-            const unsigned c = cb[k];
-            acc += sL[c & 0x7fffu];
-            if (c & 0x8000u) {
+        for (unsigned k = ((unsigned)ri.y) >> 17; k < kend; ++k) {
+            const unsigned cc = cb[k];
+            acc += sL[cc & 0x7fffu];
+            if (cc & 0x8000u) {
+                sV[s] = acc;
+                sG[s] = g;
+                acc = 0.0;
+                ++s;
+                ++g;
+            }
+            acc += sL[(cc >> 16) & 0x7fffu];
+            if (cc & 0x80000000u) {
                 sV[s] = acc;
                 sG[s] = g;
                 acc = 0.0;
@@ -302,7 +312,7 @@ def _neg(a):
 
 
 def affine_geometry(dim, sfx="", elem="e", vt="P.t", ldv="P.ldt",
-                    fast_inverse=False, pc="P.p", ldpc="P.ldp"):
+                    fast_inverse=False, pc="P.p", ldpc="P.ldp", tiled_pairs=False):
     """C statements computing ``A, b, detA, invA`` of element ``elem`` with
     the operation order of spfem/mapping.py:207-229 (tri) / 244-279 (tet).
     Variables carry the suffix ``sfx`` (facet kernels have two elements)."""
@@ -310,12 +320,23 @@ def affine_geometry(dim, sfx="", elem="e", vt="P.t", ldv="P.ldt",
     nve = dim + 1
     for k in range(nve):
         L.append("const int vtx%s_%d = %s[%d * %s + %s];" % (sfx, k, vt, k, ldv, elem))
+    # vertex coordinates X{sfx}_{i}_{k}: coordinate i of local vertex k
+    for k in range(nve):
+        if tiled_pairs and dim == 2:
+            L.append("double X%s_0_%d, X%s_1_%d;" % (sfx, k, sfx, k))
+            L.append("if (TILED) { const double2 cxy = reinterpret_cast<const double2 *>(%s)[vtx%s_%d]; "
+                     "X%s_0_%d = cxy.x; X%s_1_%d = cxy.y; } else { X%s_0_%d = %s[vtx%s_%d]; "
+                     "X%s_1_%d = %s[%s + vtx%s_%d]; }"
+                     % (pc, sfx, k, sfx, k, sfx, k, sfx, k, pc, sfx, k, sfx, k, pc, ldpc, sfx, k))
+        else:
+            for i in range(dim):
+                L.append("const double X%s_%d_%d = %s[%d * %s + vtx%s_%d];"
+                         % (sfx, i, k, pc, i, ldpc, sfx, k))
     for i in range(dim):
-        L.append("const double b%s_%d = %s[%d * %s + vtx%s_0];" % (sfx, i, pc, i, ldpc, sfx))
+        L.append("const double b%s_%d = X%s_%d_0;" % (sfx, i, sfx, i))
         for j in range(dim):
             L.append("const double A%s_%d%d = %s;" % (
-                sfx, i, j, _sub("%s[%d * %s + vtx%s_%d]" % (pc, i, ldpc, sfx, j + 1),
-                                "b%s_%d" % (sfx, i))))
+                sfx, i, j, _sub("X%s_%d_%d" % (sfx, i, j + 1), "b%s_%d" % (sfx, i))))
     A = lambda i, j: "A%s_%d%d" % (sfx, i, j)
     if dim == 2:
         L.append("const double detA%s = %s;" % (
@@ -498,10 +519,11 @@ def generate_interior(spec, name="spfem_elem"):
     if quad:
         for k in range(4):
             body.append("const int vtx_%d = vt[%d * ldv + ev];" % (k, k))
-        for i in range(2):
-            for k in range(4):
-                body.append("const double Q%d_%d = pc[%d * ldpc + vtx_%d];"
-                            % (i, k, i, k))
+        for k in range(4):
+            body.append("double Q0_%d, Q1_%d;" % (k, k))
+            body.append("if (TILED) { const double2 cxy = reinterpret_cast<const double2 *>(pc)[vtx_%d]; "
+                        "Q0_%d = cxy.x; Q1_%d = cxy.y; } else { Q0_%d = pc[vtx_%d]; "
+                        "Q1_%d = pc[ldpc + vtx_%d]; }" % (k, k, k, k, k, k, k))
         for q in range(nq):
             body += q1_geometry_q("%d" % q, spec.X[0, q], spec.X[1, q])
             if "hq" in syms:
@@ -509,7 +531,7 @@ def generate_interior(spec, name="spfem_elem"):
                             % (q, q, lit(1.0 / dim)))
     else:
         body += affine_geometry(dim, vt="vt", ldv="ldv", elem="ev", fast_inverse=True,
-                                pc="pc", ldpc="ldpc")
+                                pc="pc", ldpc="ldpc", tiled_pairs=True)
         if "h" in syms:
             body.append("const double h = pow(absdet, %s);" % lit(1.0 / dim))
     # global coordinates of the quadrature points (only if the form uses x)

@@ -29,7 +29,7 @@ from .codegen import source_key
 
 def tile_smem_bytes(nent, tp):
     """Dynamic shared memory of the tile kernel (layout in codegen.TILE_KERNEL)."""
-    sl = (8 * nent * tp["ldl"] + 15) // 16 * 16
+    sl = (8 * (nent * tp["ldl"] + 1) + 15) // 16 * 16
     return (sl + tp["max_bytes_a"] + tp["max_bytes_b"] + 8 * tp["max_ns"] + 16
             + 4 * tp["max_ns"] + 16)
 
@@ -124,26 +124,16 @@ class DeviceCSR(object):
         return self.pattern.nnz
 
     def to_scipy(self):
-        """Host ``scipy.sparse.csr_matrix`` with fresh arrays: the values come
-        through a pinned buffer (asynchronous device-to-host copy at PCIe
-        speed) while the cached host pattern is copied by worker threads."""
-        import torch
+        """Host ``scipy.sparse.csr_matrix`` with fresh arrays: the values are
+        streamed through a persistent pinned staging buffer in chunks
+        (asynchronous device-to-host copies at PCIe speed) while worker threads
+        copy finished chunks and the cached host pattern into the new arrays."""
         indptr, indices = self.pattern.host()
-        host = None
-        if self.values.numel():
-            host = torch.empty(self.values.shape, dtype=self.values.dtype, pin_memory=True)
-            host.copy_(self.values, non_blocking=True)
-        ind_c = _host_copy(indices)
-        ptr_c = _host_copy(indptr)
-        if host is not None:
-            torch.cuda.current_stream(self.values.device).synchronize()
-            data = host.numpy()
-        else:
-            data = np.zeros(0, dtype=np.float64)
         A = csr_matrix(self.shape, dtype=np.float64)
-        A.data = data
-        A.indices = ind_c
-        A.indptr = ptr_c
+        pending = _to_host_begin(self.values)       # DMA runs while we copy the pattern
+        A.indices = _host_copy(indices)
+        A.indptr = _host_copy(indptr)
+        A.data = _to_host_finish(pending)
         A.has_sorted_indices = True
         A.has_canonical_format = True
         return A
@@ -172,12 +162,11 @@ def _parallel(fn, n, min_chunk=1 << 21):
 
 
 def _host_copy(arr):
-    """Fresh copy of a cached host array in recycled pinned memory."""
-    import torch
+    """Fresh copy of a cached host array (threaded: first-touch page faults and
+    the copy itself are spread over the workers)."""
+    out = np.empty_like(arr)
     if arr.size == 0:
-        return arr.copy()
-    out = torch.empty(arr.shape, dtype=torch.from_numpy(arr[:0]).dtype,
-                      pin_memory=True).numpy()
+        return out
 
     def work(lo, hi):
         out[lo:hi] = arr[lo:hi]
@@ -185,16 +174,63 @@ def _host_copy(arr):
     return out
 
 
-def _to_host(t):
-    """Device tensor -> NumPy array backed by pinned host memory (PyTorch's
-    caching host allocator recycles the block once the array is released)."""
+_STAGING = {}
+
+
+def _staging(dtype, n):
+    """Persistent pinned staging buffer (grown on demand, never handed out)."""
     import torch
-    if t.numel() == 0:
-        return np.zeros(0, dtype=np.float64)
-    host = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
-    host.copy_(t, non_blocking=True)
-    torch.cuda.current_stream(t.device).synchronize()
-    return host.numpy()
+    buf = _STAGING.get(dtype)
+    if buf is None or buf.numel() < n:
+        buf = torch.empty(int(n * 1.25) + 1024, dtype=dtype, pin_memory=True)
+        _STAGING[dtype] = buf
+    return buf
+
+
+def _to_host_begin(t, nchunks=8):
+    """Start the chunked asynchronous device-to-host copy of a 1-D tensor into
+    the pinned staging buffer; returns a handle for :func:`_to_host_finish`."""
+    import torch
+    n = t.numel()
+    out = np.empty(n, dtype=torch.empty(0, dtype=t.dtype).numpy().dtype)
+    if n == 0:
+        return out, None, None, None
+    stage = _staging(t.dtype, n)
+    parts = _chunks(n, max(1, min(nchunks, n // (1 << 20) + 1)))
+    events = []
+    for lo, hi in parts:
+        stage[lo:hi].copy_(t[lo:hi], non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        events.append(ev)
+    return out, stage.numpy(), parts, events
+
+
+def _to_host_finish(handle):
+    """Worker threads wait for each chunk's event and move it from the staging
+    buffer into the fresh (pageable) result array."""
+    out, stage_np, parts, events = handle
+    if parts is None:
+        return out
+
+    def work(i):
+        lo, hi = parts[i]
+        events[i].synchronize()
+        out[lo:hi] = stage_np[lo:hi]
+    global _POOL
+    if len(parts) == 1:
+        work(0)
+    else:
+        if _POOL is None:
+            from concurrent.futures import ThreadPoolExecutor
+            _POOL = ThreadPoolExecutor(max_workers=8)
+        list(_POOL.map(work, range(len(parts))))
+    return out
+
+
+def _to_host(t):
+    """1-D device tensor -> fresh NumPy array (see :func:`_to_host_begin`)."""
+    return _to_host_finish(_to_host_begin(t))
 
 
 class Prepared(object):

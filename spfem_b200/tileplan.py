@@ -76,7 +76,7 @@ def build_tile_plan(torch, indptr, cptr, contrib, n, nent, E, vt, with_el=True, 
     newpos[slot_order] = ar_nnz
     # contributions in (tile, slot, original) order
     cpos = newpos[slot_of_c]
-    _, c_order = torch.sort(cpos, stable=True)
+    cpos_sorted, c_order = torch.sort(cpos, stable=True)
     k_s, ij_s = k[c_order], ij[c_order]
     tile_c = tile_of_slot[slot_of_c][c_order]
     del cpos, slot_of_c, row_of_c
@@ -96,15 +96,7 @@ def build_tile_plan(torch, indptr, cptr, contrib, n, nent, E, vt, with_el=True, 
         ij_s = torch.as_tensor(alias, dtype=i64, device=dev)[ij_s]
         nent = int(max(alias)) + 1
     contrib16 = ij_s * ldl + eloc
-    # per-slot contribution list starts (relative to the tile's base)
     counts_s = counts[slot_order]
-    cstart = torch.cumsum(counts_s, 0) - counts_s
-    nc = torch.zeros(ntiles, dtype=i64, device=dev)
-    nc.scatter_add_(0, tile_sorted, counts_s)
-    c0 = torch.cumsum(nc, 0) - nc
-    lstart = cstart - c0[tile_sorted]
-    if int(nc.max().item()) > 32767:
-        raise ValueError("more than 32767 contributions in one tile")
     rows_s = row_of_slot[slot_order]
     head = torch.ones(nnz, dtype=i64, device=dev)
     if nnz > 1:
@@ -115,6 +107,22 @@ def build_tile_plan(torch, indptr, cptr, contrib, n, nent, E, vt, with_el=True, 
     r0 = torch.cumsum(nr, 0) - nr
     hidx = torch.nonzero(head).squeeze(1)
     gdelta = slot_order[hidx] - (hidx - s0[tile_sorted[hidx]])
+    # contribution lists: one list per owned row, padded to an even length so
+    # that the kernel can read two 16-bit entries with one 32-bit load
+    row_c = heads_cum[cpos_sorted] - 1               # owned-row index of every contribution
+    n_rows_tot = int(heads_cum[-1].item()) if nnz > 0 else 0
+    rc = torch.bincount(row_c, minlength=n_rows_tot)
+    rcp = rc + (rc & 1)
+    row_k0 = torch.cumsum(rcp, 0) - rcp              # padded start of every row's list
+    first_c = torch.cumsum(rc, 0) - rc
+    tile_of_row = tile_sorted[hidx]
+    nc = torch.zeros(ntiles, dtype=i64, device=dev)
+    nc.scatter_add_(0, tile_of_row, rcp)
+    c0 = torch.cumsum(nc, 0) - nc
+    if int(nc.max().item()) > 65535:
+        raise ValueError("more than 65535 contributions in one tile")
+    cdest = row_k0[row_c] + (torch.arange(row_c.numel(), device=dev) - first_c[row_c])
+    kstart_local = row_k0 - c0[tile_of_row]          # per row, relative to the tile
     nchunk = (ns + 31) // 32
     rb0 = torch.cumsum(nchunk, 0) - nchunk
     tot_chunks = int(nchunk.sum().item())
@@ -164,27 +172,36 @@ def build_tile_plan(torch, indptr, cptr, contrib, n, nent, E, vt, with_el=True, 
     # destination (in float64 units) of coordinate d of every tile vertex:
     # pc_index + d * pc_stride
     v_local = torch.arange(vid.numel(), device=dev) - v0[tile_of_v]
-    pc_index = ((blob_off + off_pc) // 8)[tile_of_v] + v_local
-    pc_stride = nvt_pad[tile_of_v]
+    if dim == 2:
+        # interleaved (x, y) pairs: one 128-bit shared-memory load per vertex
+        pc_index = ((blob_off + off_pc) // 8)[tile_of_v] + 2 * v_local
+        pc_stride = torch.ones_like(v_local)
+    else:
+        pc_index = ((blob_off + off_pc) // 8)[tile_of_v] + v_local
+        pc_stride = nvt_pad[tile_of_v]
     # section B
-    if nent * ldl > 32767:
+    if nent * ldl + 1 > 32767:
         raise ValueError("tile too large for 15-bit shared-memory indices")
     bbase = blob_off + bytes_a
     hrow_local = heads_cum[hidx] - 1 - r0[tile_sorted[hidx]]
     slot_local = ar_nnz - s0[tile_sorted]
     ri_base = (bbase // 4)[tile_sorted[hidx]] + 2 * hrow_local
     b32[ri_base] = gdelta.to(torch.int32)
-    packed = slot_local[hidx] + (lstart[hidx] << 16)
+    packed = slot_local[hidx] + (kstart_local << 16)
     b32[ri_base + 1] = torch.where(packed >= 2 ** 31, packed - 2 ** 32, packed).to(torch.int32)
     # terminating entry of every tile: {0, ns | nc << 16}
     endp = ns + (nc << 16)
     b32[(bbase // 4) + 2 * nr + 1] = torch.where(endp >= 2 ** 31, endp - 2 ** 32, endp).to(torch.int32)
-    c_local = torch.arange(contrib16.numel(), device=dev) - c0[tile_c]
     # last contribution of every slot: the next contribution starts a new slot
-    cend = torch.cumsum(counts_s, 0) - 1          # global position of each slot's last entry
+    cend = torch.cumsum(counts_s, 0) - 1          # position of each slot's last entry
     last = torch.zeros(contrib16.numel(), dtype=i64, device=dev)
     last[cend[counts_s > 0]] = 1
-    b16[((bbase + off_contrib) // 2)[tile_c] + c_local] = (contrib16 + (last << 15)).to(torch.int16)
+    cb_base = ((bbase + off_contrib) // 2)
+    b16[cb_base[tile_c] + (cdest - c0[tile_c])] = (contrib16 + (last << 15)).to(torch.int16)
+    # padding entries point at the always-zero cell behind the local matrices
+    odd = torch.nonzero(rc & 1).squeeze(1)
+    if odd.numel():
+        b16[cb_base[tile_of_row[odd]] + (row_k0[odd] + rc[odd] - c0[tile_of_row[odd]])] = nent * ldl
     z = torch.zeros_like(ne)
     desc = torch.stack([blob_off // 16, bytes_a, bytes_b, ne, ne_pad, ns, off_cptr,
                         off_rowbase, off_contrib, nr, nc, nvt_pad, off_pc,
@@ -224,9 +241,10 @@ def emulate(plan, local, nnz):
         elems = all_elems[e0s[ti]: e0s[ti] + ne]
         rinfo = B[:(nr + 1) * 8].view(np.int32).astype(np.int64).reshape(nr + 1, 2)
         contrib = B[o_cb:o_cb + 2 * nc].view(np.uint16).astype(np.int64)
-        sL = np.zeros(nent * ldl)
+        sLz = np.zeros(nent * ldl + 1)
         for idx in range(nent):
-            sL[idx * ldl: idx * ldl + ne] = local[idx, elems]
+            sLz[idx * ldl: idx * ldl + ne] = local[idx, elems]
+        assert sLz[nent * ldl] == 0.0
         for row in range(nr):
             packed = rinfo[row, 1] & 0xffffffff
             kend = (rinfo[row + 1, 1] & 0xffffffff) >> 16
@@ -235,7 +253,7 @@ def emulate(plan, local, nnz):
             acc = 0.0
             for kk in range(packed >> 16, kend):
                 c = contrib[kk]
-                acc += sL[c & 0x7fff]
+                acc += sLz[c & 0x7fff]
                 if c & 0x8000:
                     values[g] = acc
                     written[g] += 1
@@ -266,7 +284,8 @@ def check_vertex_table(plan, vt, p):
         off16, ba, ne, ne_pad, nvt_pad, off_pc = d[0], d[1], d[3], d[4], d[11], d[12]
         A = blob[off16 * 16: off16 * 16 + ba]
         loc = A[:nve * ne_pad * 2].view(np.uint16).reshape(nve, ne_pad)[:, :ne]
-        pc = A[off_pc: off_pc + dim * nvt_pad * 8].view(np.float64).reshape(dim, nvt_pad)
+        pc = A[off_pc: off_pc + dim * nvt_pad * 8].view(np.float64)
+        pc = pc.reshape(nvt_pad, 2).T if dim == 2 else pc.reshape(dim, nvt_pad)
         elems = all_elems[e0s[ti]: e0s[ti] + ne]
         for r in range(nve):
             for k in range(dim):
