@@ -140,9 +140,23 @@ def build_tile_plan(torch, indptr, cptr, contrib, n, nent, E, vt, with_el=True, 
     vid = uv % nv_glob                               # global id of every tile vertex
     nvt = torch.bincount(tile_of_v, minlength=ntiles)[:ntiles]
     v0 = torch.cumsum(nvt, 0) - nvt
-    vloc = vinv.reshape(nve, -1) - v0[tile_of_u].unsqueeze(0)
     if int(nvt.max().item()) > 65535:
         raise ValueError("more than 65535 vertices in one tile")
+    # number the tile's vertices in order of first use by its elements, so the
+    # threads of a warp (consecutive elements) read mostly consecutive
+    # coordinates from shared memory (few bank conflicts)
+    nte = elems.numel()
+    use_pos = (torch.arange(nte, device=dev).unsqueeze(0) * nve
+               + torch.arange(nve, device=dev).unsqueeze(1)).reshape(-1)
+    first_use = torch.full((uv.numel(),), nte * nve, dtype=i64, device=dev)
+    first_use.scatter_reduce_(0, vinv.reshape(-1), use_pos, reduce="amin")
+    # first_use increases with the tile index, so one argsort orders every tile
+    vorder = torch.argsort(first_use)
+    vrank = torch.empty_like(vorder)
+    vrank[vorder] = torch.arange(uv.numel(), device=dev)
+    tile_of_v = tile_of_v[vorder]
+    vid = vid[vorder]
+    vloc = vrank[vinv].reshape(nve, -1) - v0[tile_of_u].unsqueeze(0)
     # ---- pack the per-tile blobs ------------------------------------------
     ne_pad = (ne + 7) // 8 * 8
     nvt_pad = (nvt + 1) // 2 * 2
