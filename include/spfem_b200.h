@@ -112,6 +112,27 @@ int spfem_reduce(const double *d_local, const int *d_cptr,
                  const int *d_contrib, long long nslots, double *d_values,
                  void *stream);
 
+/* ---- bank-conflict-free schedule of the fused kernel's row reductions ------
+ * Set-up step of the tile plan (spfem_b200/tileplan.py).  For every group of
+ * <= 16 consecutive owned rows of a tile, re-orders each row's contribution list
+ * (idx = shared-memory word index, endf = last contribution of a CSR slot) so
+ * that the entries read at the same step by the 16 lanes of a half-warp fall
+ * into distinct shared-memory banks; idle steps read one of 16 zero cells at
+ * `zero_base`.  out_idx: stride entries per row (bit 15 = slot finished),
+ * out_len: scheduled length per row (0 = row group could not be scheduled, keep
+ * the original list), out_perm: CSR position (within the row) of the j-th
+ * finished slot.  mode 0 = full schedule (slots and contributions in any order,
+ * idle steps allowed: conflict free but ~1.4-1.8 x longer lists -- measured
+ * slower, kept for reference); mode 1 = keep slot order and list length, only
+ * choose the order of the contributions inside each slot (used by default).
+ * on_device = 0 runs on the host with host pointers (tests).                   */
+int spfem_schedule_rows(const int *idx, const unsigned char *endf,
+                        const long long *row_first, const int *row_count,
+                        const long long *grp_row0, const int *grp_nrows,
+                        long long ngroups, int stride, int max_slots, int zero_base,
+                        unsigned short *out_idx, int *out_len, unsigned char *out_perm,
+                        int mode, int on_device, void *stream);
+
 /* ---- element ordering -------------------------------------------------------
  * Morton (Z-order) permutation of the elements by centroid: d_perm[k] = index
  * of the k-th element along the curve.  ws: spfem_morton_ws_bytes(nt).        */

@@ -74,6 +74,10 @@ SYMBOLS = {
                                      C.c_void_p, C.c_void_p, C.c_void_p]),
     "spfem_reduce": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p,
                                C.c_longlong, C.c_void_p, C.c_void_p]),
+    "spfem_schedule_rows": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                      C.c_void_p, C.c_void_p, C.c_longlong, C.c_int,
+                                      C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                      C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "spfem_morton_ws_bytes": (C.c_size_t, [C.c_longlong]),
     "spfem_morton_order": (C.c_int, [C.c_void_p, C.c_longlong, C.c_int,
                                      C.c_void_p, C.c_longlong, C.c_int,

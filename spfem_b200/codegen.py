@@ -122,7 +122,7 @@ extern "C" __global__ void __launch_bounds__(@THREADS@, @MINB@) @NAME@_tile(cons
     extern __shared__ __align__(128) unsigned char spfem_smem_raw[];
     const int ldl = T.ldl;
     double *sL = (double *)spfem_smem_raw;
-    unsigned char *sA = spfem_smem_raw + (((size_t)8 * (SPFEM_NUNIQUE * ldl + 1) + 15) & ~(size_t)15);
+    unsigned char *sA = spfem_smem_raw + (((size_t)8 * (SPFEM_NUNIQUE * ldl + 16) + 15) & ~(size_t)15);
     unsigned char *sB = sA + T.max_a;
     double *sV = (double *)(sB + T.max_b);
     unsigned long long *bars = (unsigned long long *)(sV + T.max_ns);
@@ -130,8 +130,8 @@ extern "C" __global__ void __launch_bounds__(@THREADS@, @MINB@) @NAME@_tile(cons
     const int *d = T.desc + 16 * (size_t)blockIdx.x;
     const int bytes_a = d[1], bytes_b = d[2], ne = d[3], ne_pad = d[4], ns = d[5], nr = d[9];
     if (ne == 0 || ns == 0) return;
+    if (threadIdx.x < 16) sL[SPFEM_NUNIQUE * ldl + threadIdx.x] = 0.0;   /* idle-step targets */
     if (threadIdx.x == 0) {
-        sL[SPFEM_NUNIQUE * ldl] = 0.0;            /* target of list padding entries */
         spfem_mbar_init(&bars[0], 1);
         spfem_mbar_init(&bars[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -150,42 +150,36 @@ extern "C" __global__ void __launch_bounds__(@THREADS@, @MINB@) @NAME@_tile(cons
                           sL, (long long)ldl, (long long)el);
     /* phase B1: one thread per owned row walks the row's contribution list
        (bit 15 of an entry = last contribution of a CSR slot) and adds in list
-       order -- fixed order => bitwise reproducible.  The finished slot value
-       and its CSR position are staged in shared memory.                       */
+       order -- fixed order => bitwise reproducible.  The lists are scheduled
+       (spfem_schedule_rows) so that the 16 rows of a half-warp read distinct
+       shared-memory banks in every step.  Finished slot values and the CSR
+       position of their row are staged in shared memory.                      */
     spfem_mbar_wait(&bars[1], 0);
     const int2 *rinfo = (const int2 *)sB;      /* {gdelta, s_start | k_start<<16} */
-    const unsigned *cb = (const unsigned *)(sB + d[8]);   /* pairs of 16-bit entries */
+    const unsigned short *cb = (const unsigned short *)(sB + d[8]);
     __syncthreads();
     for (int row = threadIdx.x; row < nr; row += blockDim.x) {
         const int2 ri = rinfo[row];
-        const unsigned kend = ((unsigned)rinfo[row + 1].y) >> 17;
         unsigned s = (unsigned)ri.y & 0xffffu;
-        int g = ri.x + (int)s;
-        double acc = 0.0;
-        for (unsigned k = ((unsigned)ri.y) >> 17; k < kend; ++k) {
-            const unsigned cc = cb[k];
-            acc += sL[cc & 0x7fffu];
-            if (cc & 0x8000u) {
-                sV[s] = acc;
-                sG[s] = g;
-                acc = 0.0;
-                ++s;
-                ++g;
-            }
-            acc += sL[(cc >> 16) & 0x7fffu];
-            if (cc & 0x80000000u) {
-                sV[s] = acc;
-                sG[s] = g;
-                acc = 0.0;
-                ++s;
-                ++g;
-            }
+        const unsigned s_end = (unsigned)rinfo[row + 1].y & 0xffffu;
+        const int g0 = ri.x + (int)s;               /* CSR position of the row's first slot */
+        unsigned k = ((unsigned)ri.y) >> 16;
+        for (; s < s_end; ++s) {                    /* slots, largest first */
+            double acc = 0.0;
+            unsigned c;
+            do {
+                c = cb[k++];
+                acc += sL[c & 0x7fffu];
+            } while (!(c & 0x8000u));
+            sV[s] = acc;
+            sG[s] = g0;
         }
     }
     __syncthreads();
     /* phase B2: coalesced store of the tile's CSR values */
+    const unsigned char *pm = (const unsigned char *)(sB + d[6]);   /* slot order -> CSR order */
     for (int s = threadIdx.x; s < ns; s += blockDim.x)
-        T.values[sG[s]] = sV[s];
+        T.values[sG[s] + (int)pm[s]] = sV[s];
 }
 """
 

@@ -29,7 +29,7 @@ from .codegen import source_key
 
 def tile_smem_bytes(nent, tp):
     """Dynamic shared memory of the tile kernel (layout in codegen.TILE_KERNEL)."""
-    sl = (8 * (nent * tp["ldl"] + 1) + 15) // 16 * 16
+    sl = (8 * (nent * tp["ldl"] + 16) + 15) // 16 * 16
     return (sl + tp["max_bytes_a"] + tp["max_bytes_b"] + 8 * tp["max_ns"] + 16
             + 4 * tp["max_ns"] + 16)
 
@@ -548,7 +548,9 @@ class Engine(object):
             try:
                 tp = build_tile_plan(self.torch, pat.indptr, pat.cptr, pat.contrib,
                                      n, nent, E, self.t, with_el=with_el,
-                                     dim=self.p.shape[0], alias=alias)
+                                     dim=self.p.shape[0], alias=alias,
+                                     schedule={"0": False, "full": "full"}.get(
+                                         os.environ.get("SPFEM_SCHEDULE", "inslot"), "inslot"))
             except ValueError:
                 tp = None
             if tp is not None and tile_smem_bytes(nuniq, tp) <= 220 * 1024:

@@ -29,11 +29,16 @@ shared memory with two TMA bulk copies (``cp.async.bulk``):
                          minus its tile slot index, tile slot index of the first
                          slot | start of the row's contribution list << 16}
     contrib uint16 [nc]  shared-memory index ``idx*ldl + el`` of a contribution;
-                         bit 15 marks the last contribution of a CSR slot
+                         bit 15 marks the last contribution of a CSR slot.  Every
+                         row's list is re-ordered by ``spfem_schedule_rows`` so
+                         that the 16 rows of a half-warp never hit the same
+                         shared-memory bank in the same step (idle steps read a
+                         zero cell); slots of a row may finish in any order
+    perm   uint8  [ns]   CSR position (inside its row) of the j-th finished slot
 
 Descriptor (int32 x 16 per tile):
   0 blob offset / 16   1 bytes A   2 bytes B   3 ne   4 ne_pad   5 ns
-  6 unused   7 unused   8 byte offset of contrib in B   9 nr  10 nc
+  6 byte offset of perm in B   7 unused   8 byte offset of contrib in B   9 nr  10 nc
   11 nvt_pad  12 byte offset of pc in A  13 byte offset of el in A  14 nvt  15 0
 """
 import numpy as np
@@ -44,7 +49,7 @@ def _pad(x, m):
 
 
 def build_tile_plan(torch, indptr, cptr, contrib, n, nent, E, vt, with_el=True, dim=2,
-                    alias=None):
+                    alias=None, schedule="inslot"):
     """All tensor arguments live on one device.  ``vt``: int32 ``(nve, n)``
     vertex table in device element order.  Returns a dict of tensors/ints."""
     dev = indptr.device
@@ -68,8 +73,16 @@ def build_tile_plan(torch, indptr, cptr, contrib, n, nent, E, vt, with_el=True, 
     owner = torch.full((N,), ntiles, dtype=i64, device=dev)
     owner.scatter_reduce_(0, row_of_c, k // E, reduce="amin")
     tile_of_slot = owner[row_of_slot]
-    # slots in (tile, CSR position) order
-    tile_sorted, slot_order = torch.sort(tile_of_slot, stable=True)
+    # slots in (tile, row, descending contribution count, CSR position) order:
+    # rows of a regular mesh then finish their slots at the same steps, so the
+    # lanes of a warp leave the inner accumulation loop together
+    csr_pos = ar_nnz - indptr[row_of_slot]           # position of the slot inside its row
+    if int(csr_pos.max().item()) > 255 or int(counts.max().item()) > 65535:
+        within = ar_nnz                               # very long rows: keep CSR order
+    else:
+        within = torch.argsort((row_of_slot << 32) | ((65535 - counts) << 16) | csr_pos)
+    tile_sorted, o2 = torch.sort(tile_of_slot[within], stable=True)
+    slot_order = within[o2]
     ns = torch.bincount(tile_of_slot, minlength=ntiles)[:ntiles]
     s0 = torch.cumsum(ns, 0) - ns
     newpos = torch.empty(nnz, dtype=i64, device=dev)
@@ -106,23 +119,90 @@ def build_tile_plan(torch, indptr, cptr, contrib, n, nent, E, vt, with_el=True, 
     nr.scatter_add_(0, tile_sorted, head)
     r0 = torch.cumsum(nr, 0) - nr
     hidx = torch.nonzero(head).squeeze(1)
-    gdelta = slot_order[hidx] - (hidx - s0[tile_sorted[hidx]])
+    gdelta = indptr[rows_s[hidx]] - (hidx - s0[tile_sorted[hidx]])
     # contribution lists: one list per owned row, padded to an even length so
     # that the kernel can read two 16-bit entries with one 32-bit load
     row_c = heads_cum[cpos_sorted] - 1               # owned-row index of every contribution
     n_rows_tot = int(heads_cum[-1].item()) if nnz > 0 else 0
     rc = torch.bincount(row_c, minlength=n_rows_tot)
-    rcp = rc + (rc & 1)
-    row_k0 = torch.cumsum(rcp, 0) - rcp              # padded start of every row's list
     first_c = torch.cumsum(rc, 0) - rc
     tile_of_row = tile_sorted[hidx]
+    ar_rows = torch.arange(n_rows_tot, device=dev)
+    zero_base = nent * ldl                           # 16 zero cells behind the local matrices
+    if zero_base + 15 > 32767:
+        raise ValueError("tile too large for 15-bit shared-memory indices")
+    # last contribution of every slot: the next contribution starts a new slot
+    cend = torch.cumsum(counts_s, 0) - 1
+    last = torch.zeros(contrib16.numel(), dtype=i64, device=dev)
+    last[cend[counts_s > 0]] = 1
+    nslots_row = torch.bincount(heads_cum - 1, minlength=n_rows_tot)   # slots per row
+    max_slots = int(nslots_row.max().item()) if n_rows_tot else 1
+    sched_len = torch.zeros(n_rows_tot, dtype=torch.int32, device=dev)
+    out_idx = out_perm = None
+    stride = 0
+    if schedule and n_rows_tot and max_slots <= 255:
+        from . import _lib
+        import ctypes as C
+        lib = _lib.load()
+        stride = (2 * int(rc.max().item()) + 8 + 1) // 2 * 2
+        ngr = (nr + 15) // 16
+        g0 = torch.cumsum(ngr, 0) - ngr
+        grp_tile = torch.repeat_interleave(ar_t, ngr)
+        grp_i = torch.arange(int(ngr.sum().item()), device=dev) - g0[grp_tile]
+        grp_row0 = (r0[grp_tile] + 16 * grp_i).contiguous()
+        grp_nrows = torch.clamp(nr[grp_tile] - 16 * grp_i, max=16).to(torch.int32).contiguous()
+        idx32 = contrib16.to(torch.int32).contiguous()
+        endf = last.to(torch.uint8).contiguous()
+        rf = first_c.contiguous()
+        rcount = rc.to(torch.int32).contiguous()
+        out_idx = torch.zeros(n_rows_tot * stride, dtype=torch.int16, device=dev)
+        out_perm = torch.zeros(n_rows_tot * max_slots, dtype=torch.uint8, device=dev)
+        on_dev = 1 if dev.type == "cuda" else 0
+        stream = None
+        if on_dev:
+            stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        _lib.check(lib.spfem_schedule_rows(
+            C.c_void_p(idx32.data_ptr()), C.c_void_p(endf.data_ptr()),
+            C.c_void_p(rf.data_ptr()), C.c_void_p(rcount.data_ptr()),
+            C.c_void_p(grp_row0.data_ptr()), C.c_void_p(grp_nrows.data_ptr()),
+            int(grp_row0.numel()), stride, max_slots, zero_base,
+            C.c_void_p(out_idx.data_ptr()), C.c_void_p(sched_len.data_ptr()),
+            C.c_void_p(out_perm.data_ptr()), 1 if schedule == "inslot" else 0,
+            on_dev, stream))
+        if on_dev:
+            torch.cuda.synchronize(dev)
+    sched = sched_len > 0
+    rcp = torch.where(sched, sched_len.to(i64), rc + (rc & 1))
+    row_k0 = torch.cumsum(rcp, 0) - rcp              # start of every row's (final) list
     nc = torch.zeros(ntiles, dtype=i64, device=dev)
     nc.scatter_add_(0, tile_of_row, rcp)
     c0 = torch.cumsum(nc, 0) - nc
     if int(nc.max().item()) > 65535:
         raise ValueError("more than 65535 contributions in one tile")
-    cdest = row_k0[row_c] + (torch.arange(row_c.numel(), device=dev) - first_c[row_c])
     kstart_local = row_k0 - c0[tile_of_row]          # per row, relative to the tile
+    # final entry stream (all tiles, rows back to back)
+    ent_row = torch.repeat_interleave(ar_rows, rcp)
+    ent_t = torch.arange(ent_row.numel(), device=dev) - row_k0[ent_row]
+    orig = contrib16 + (last << 15)
+    in_orig = ent_t < rc[ent_row]
+    src = first_c[ent_row] + torch.where(in_orig, ent_t, torch.zeros_like(ent_t))
+    src = torch.clamp(src, max=max(orig.numel() - 1, 0))
+    ent_val = torch.where(in_orig, orig[src], torch.full_like(ent_t, zero_base))
+    if out_idx is not None:
+        sidx = ent_row * stride + torch.clamp(ent_t, max=stride - 1)
+        sval = out_idx[sidx].to(i64) & 0xffff
+        ent_val = torch.where(sched[ent_row], sval, ent_val)
+    ent_tile = tile_of_row[ent_row]
+    # slot permutation: CSR position (inside the row) of the j-th finished slot
+    slot_row = heads_cum - 1                          # owned-row index of every tile slot
+    slot_j = ar_nnz - hidx[slot_row]                  # list position of the slot inside its row
+    csr_of_list = csr_pos[slot_order]                 # CSR position of every tile slot
+    perm8 = csr_of_list.clone()
+    if out_perm is not None:
+        pidx = slot_row * max_slots + torch.clamp(slot_j, max=max_slots - 1)
+        fin = hidx[slot_row] + out_perm[pidx].to(i64)   # tile slot that finishes j-th
+        perm8 = torch.where(sched[slot_row], csr_of_list[torch.clamp(fin, max=nnz - 1)],
+                            csr_of_list)
     nchunk = (ns + 31) // 32
     rb0 = torch.cumsum(nchunk, 0) - nchunk
     tot_chunks = int(nchunk.sum().item())
@@ -163,9 +243,9 @@ def build_tile_plan(torch, indptr, cptr, contrib, n, nent, E, vt, with_el=True, 
     off_el = nve * ne_pad * 2
     off_pc = off_el + (ne_pad * 4 if with_el else 0)
     bytes_a = off_pc + dim * nvt_pad * 8
-    off_cptr = torch.zeros_like(nr)
     off_rowbase = torch.zeros_like(nr)
-    off_contrib = ((nr + 1) * 8 + 15) // 16 * 16
+    off_cptr = ((nr + 1) * 8 + 15) // 16 * 16          # = offset of the perm section
+    off_contrib = off_cptr + (ns + 15) // 16 * 16
     bytes_b = off_contrib + (nc * 2 + 15) // 16 * 16
     tile_bytes = bytes_a + bytes_b
     blob_off = torch.cumsum(tile_bytes, 0) - tile_bytes
@@ -194,8 +274,6 @@ def build_tile_plan(torch, indptr, cptr, contrib, n, nent, E, vt, with_el=True, 
         pc_index = ((blob_off + off_pc) // 8)[tile_of_v] + v_local
         pc_stride = nvt_pad[tile_of_v]
     # section B
-    if nent * ldl + 1 > 32767:
-        raise ValueError("tile too large for 15-bit shared-memory indices")
     bbase = blob_off + bytes_a
     hrow_local = heads_cum[hidx] - 1 - r0[tile_sorted[hidx]]
     slot_local = ar_nnz - s0[tile_sorted]
@@ -206,16 +284,9 @@ def build_tile_plan(torch, indptr, cptr, contrib, n, nent, E, vt, with_el=True, 
     # terminating entry of every tile: {0, ns | nc << 16}
     endp = ns + (nc << 16)
     b32[(bbase // 4) + 2 * nr + 1] = torch.where(endp >= 2 ** 31, endp - 2 ** 32, endp).to(torch.int32)
-    # last contribution of every slot: the next contribution starts a new slot
-    cend = torch.cumsum(counts_s, 0) - 1          # position of each slot's last entry
-    last = torch.zeros(contrib16.numel(), dtype=i64, device=dev)
-    last[cend[counts_s > 0]] = 1
     cb_base = ((bbase + off_contrib) // 2)
-    b16[cb_base[tile_c] + (cdest - c0[tile_c])] = (contrib16 + (last << 15)).to(torch.int16)
-    # padding entries point at the always-zero cell behind the local matrices
-    odd = torch.nonzero(rc & 1).squeeze(1)
-    if odd.numel():
-        b16[cb_base[tile_of_row[odd]] + (row_k0[odd] + rc[odd] - c0[tile_of_row[odd]])] = nent * ldl
+    b16[cb_base[ent_tile] + (row_k0[ent_row] + ent_t - c0[ent_tile])] = ent_val.to(torch.int16)
+    blob[(bbase + off_cptr)[tile_sorted] + slot_local] = perm8.to(torch.uint8)
     z = torch.zeros_like(ne)
     desc = torch.stack([blob_off // 16, bytes_a, bytes_b, ne, ne_pad, ns, off_cptr,
                         off_rowbase, off_contrib, nr, nc, nvt_pad, off_pc,
@@ -233,6 +304,8 @@ def build_tile_plan(torch, indptr, cptr, contrib, n, nent, E, vt, with_el=True, 
         "tile_elems": (elems, e0, ne),
         "vid": vid, "pc_index": pc_index, "pc_stride": pc_stride, "dim": dim,
         "tile_vertices": float(nvt.sum().item()),
+        "scheduled_rows": float(sched.sum().item()) / max(n_rows_tot, 1),
+        "list_growth": float(rcp.sum().item()) / max(float(rc.sum().item()), 1.0),
         "halo_factor": float(ne.sum().item()) / float(n),
         "blob_bytes": total,
     }
@@ -254,26 +327,26 @@ def emulate(plan, local, nnz):
         B = blob[off16 * 16 + ba: off16 * 16 + ba + bb]
         elems = all_elems[e0s[ti]: e0s[ti] + ne]
         rinfo = B[:(nr + 1) * 8].view(np.int32).astype(np.int64).reshape(nr + 1, 2)
+        perm = B[o_cp:o_cp + ns].astype(np.int64)
         contrib = B[o_cb:o_cb + 2 * nc].view(np.uint16).astype(np.int64)
-        sLz = np.zeros(nent * ldl + 1)
+        sLz = np.zeros(nent * ldl + 16)
         for idx in range(nent):
             sLz[idx * ldl: idx * ldl + ne] = local[idx, elems]
-        assert sLz[nent * ldl] == 0.0
         for row in range(nr):
             packed = rinfo[row, 1] & 0xffffffff
             kend = (rinfo[row + 1, 1] & 0xffffffff) >> 16
             s = packed & 0xffff
-            g = rinfo[row, 0] + s
+            g0 = rinfo[row, 0] + s
             acc = 0.0
             for kk in range(packed >> 16, kend):
                 c = contrib[kk]
                 acc += sLz[c & 0x7fff]
                 if c & 0x8000:
+                    g = g0 + perm[s]
                     values[g] = acc
                     written[g] += 1
                     acc = 0.0
                     s += 1
-                    g += 1
     return values, written
 
 
@@ -306,3 +379,27 @@ def check_vertex_table(plan, vt, p):
                 if not np.array_equal(pc[k, loc[r]], p[k, vt[r, elems]]):
                     return False
     return True
+
+
+def bank_conflicts(plan):
+    """Tests only: average number of shared-memory wavefronts per half-warp
+    step of phase B1 (1.0 = conflict free) and the schedule's length growth."""
+    desc = plan["desc"].cpu().numpy().astype(np.int64)
+    blob = plan["blob"].cpu().numpy()
+    waves = steps = 0
+    for d in desc:
+        off16, ba, bb, ns, o_cb, nr, nc = d[0], d[1], d[2], d[5], d[8], d[9], d[10]
+        B = blob[off16 * 16 + ba: off16 * 16 + ba + bb]
+        rinfo = B[:(nr + 1) * 8].view(np.int32).astype(np.int64).reshape(nr + 1, 2)
+        contrib = B[o_cb:o_cb + 2 * nc].view(np.uint16).astype(np.int64)
+        k0 = (rinfo[:, 1] & 0xffffffff) >> 16
+        for r0 in range(0, nr, 16):
+            rows = range(r0, min(nr, r0 + 16))
+            L = max(k0[r + 1] - k0[r] for r in rows)
+            for t in range(L):
+                addr = set(int(contrib[k0[r] + t] & 0x7fff) for r in rows
+                           if t < k0[r + 1] - k0[r])
+                banks = np.bincount([a & 15 for a in addr], minlength=16)
+                waves += banks.max()
+                steps += 1
+    return waves / max(steps, 1)

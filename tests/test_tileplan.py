@@ -10,7 +10,7 @@ import cases
 import util
 import hostemu
 from spfem_b200.tileplan import (build_tile_plan, emulate, check_vertex_table,
-                                 fill_coordinates)
+                                 fill_coordinates, bank_conflicts)
 
 
 def _morton(mesh):
@@ -61,7 +61,7 @@ def test_tile_plan_reproduces_assembly(name, E):
     tp = build_tile_plan(torch, torch.from_numpy(indptr), torch.from_numpy(cptr),
                          torch.from_numpy(contrib), n, plan.spec.n_entries, E,
                          torch.from_numpy(vt), dim=asm.mesh.p.shape[0],
-                         alias=plan.spec.alias)
+                         alias=plan.spec.alias, schedule="full")
     fill_coordinates(tp, torch.from_numpy(np.ascontiguousarray(asm.mesh.p)))
     assert check_vertex_table(tp, vt, asm.mesh.p)
     # shared-memory image of the tile kernel: one row per distinct local value
@@ -75,3 +75,23 @@ def test_tile_plan_reproduces_assembly(name, E):
     scale = np.abs(ref.data).max()
     assert np.max(np.abs(values - ref.data)) <= 1e-12 * scale
     assert 1.0 <= tp["halo_factor"] < 3.0
+    # the scheduled contribution lists are bank-conflict free
+    assert tp["scheduled_rows"] > 0.9    # very long rows fall back to their CSR order
+    if tp["scheduled_rows"] > 0.99:
+        assert bank_conflicts(tp) < 1.05
+    assert tp["list_growth"] < 2.5
+    tp0 = build_tile_plan(torch, torch.from_numpy(indptr), torch.from_numpy(cptr),
+                          torch.from_numpy(contrib), n, plan.spec.n_entries, E,
+                          torch.from_numpy(vt), dim=asm.mesh.p.shape[0],
+                          alias=plan.spec.alias, schedule=False)
+    v0, w0 = emulate(tp0, uniq, nnz)
+    assert np.all(w0 == 1) and np.max(np.abs(v0 - ref.data)) <= 1e-12 * scale
+    assert bank_conflicts(tp0) > 1.5
+    # default: contributions re-ordered inside their slots only (no list growth)
+    tp1 = build_tile_plan(torch, torch.from_numpy(indptr), torch.from_numpy(cptr),
+                          torch.from_numpy(contrib), n, plan.spec.n_entries, E,
+                          torch.from_numpy(vt), dim=asm.mesh.p.shape[0],
+                          alias=plan.spec.alias, schedule="inslot")
+    v1, w1 = emulate(tp1, uniq, nnz)
+    assert np.all(w1 == 1) and np.max(np.abs(v1 - ref.data)) <= 1e-12 * scale
+    assert tp1["list_growth"] < 1.06
