@@ -359,76 +359,111 @@ __host__ __device__ inline void order_group_inslot(const SchedArgs &a, long long
 {
     const int nrows = a.grp_nrows[g];
     const long long r0 = a.grp_row0[g];
-    int cnt[16], pos[16];
-    int maxc = 0;
+    // per row: slot table (start, size) in list order (sizes are non-increasing)
+    short sstart[16][SPFEM_SCHED_MAXS], ssize[16][SPFEM_SCHED_MAXS];
+    unsigned char sdone[16][SPFEM_SCHED_MAXS];
+    int nsl[16], cnt[16], outpos[16], nfin[16], cur[16];
+    bool ok = true;
     for (int i = 0; i < nrows; ++i) {
         cnt[i] = a.row_count[r0 + i];
-        pos[i] = 0;
-        if (cnt[i] > maxc) maxc = cnt[i];
-        if (cnt[i] > a.stride) {
-            for (int q = 0; q < nrows; ++q) a.out_len[r0 + q] = 0;
-            return;
-        }
+        if (cnt[i] > a.stride || cnt[i] > 32767) ok = false;
     }
-    // slot boundaries per row are found on the fly from the end flags
-    bool any = true;
-    int slot_end[16];
+    for (int i = 0; i < nrows && ok; ++i) {
+        const long long f = a.row_first[r0 + i];
+        int n = 0, st = 0;
+        for (int c = 0; c < cnt[i]; ++c)
+            if (a.endf[f + c]) {
+                if (n >= SPFEM_SCHED_MAXS || n >= a.max_slots) { ok = false; break; }
+                sstart[i][n] = (short)st;
+                ssize[i][n] = (short)(c + 1 - st);
+                sdone[i][n] = 0;
+                st = c + 1;
+                ++n;
+            }
+        nsl[i] = n; outpos[i] = 0; nfin[i] = 0;
+    }
+    if (!ok) {
+        for (int i = 0; i < nrows; ++i) a.out_len[r0 + i] = 0;
+        return;
+    }
     unsigned char taken[16][64];
-    while (any) {
-        any = false;
-        int maxsz = 0;
-        for (int i = 0; i < nrows; ++i) {      // next slot of every row
-            if (pos[i] >= cnt[i]) { slot_end[i] = pos[i]; continue; }
-            const long long f = a.row_first[r0 + i];
-            int e = pos[i];
-            while (!a.endf[f + e]) ++e;
-            slot_end[i] = e + 1;
-            const int sz = slot_end[i] - pos[i];
-            if (sz > maxsz) maxsz = sz;
-            for (int c = 0; c < sz && c < 64; ++c) taken[i][c] = 0;
-            any = true;
+    for (;;) {
+        // round: every row with slots left processes one slot; the slot is chosen
+        // among the row's remaining slots of the largest remaining size
+        int maxsz = 0, active = 0;
+        for (int i = 0; i < nrows; ++i) {
+            cur[i] = -1;
+            if (nfin[i] >= nsl[i]) continue;
+            ++active;
+            for (int q = 0; q < nsl[i]; ++q)
+                if (!sdone[i][q]) { if (ssize[i][q] > maxsz) maxsz = ssize[i][q]; break; }
         }
-        if (!any) break;
+        if (!active) break;
         for (int it = 0; it < maxsz; ++it) {
             unsigned char load[16];
             for (int b = 0; b < 16; ++b) load[b] = 0;
             for (int j = 0; j < nrows; ++j) {
                 const int i = (j + it) % nrows;
-                const int sz = slot_end[i] - pos[i];
-                if (it >= sz) continue;
+                if (nfin[i] >= nsl[i] && cur[i] < 0) continue;
                 const long long f = a.row_first[r0 + i];
                 unsigned short *o = a.out_idx + (r0 + i) * (long long)a.stride;
-                int pick = -1, best = 1000;
-                if (sz > 64) {
-                    pick = it;                  // very long slot: keep the order
-                } else {
-                    for (int c = 0; c < sz; ++c) {
-                        if (taken[i][c]) continue;
-                        const int l = load[a.idx[f + pos[i] + c] & 15];
-                        if (l < best) { best = l; pick = c; }
+                if (it == 0) {
+                    // choose the slot: first undone slot's size class, least loaded bank
+                    int first = 0;
+                    while (sdone[i][first]) ++first;
+                    const int sz0 = ssize[i][first];
+                    int bslot = first, bc = 0, best = 1000;
+                    for (int q = first; q < nsl[i] && ssize[i][q] == sz0; ++q) {
+                        if (sdone[i][q]) continue;
+                        const int lim = sz0 < 64 ? sz0 : 1;
+                        for (int c = 0; c < lim; ++c) {
+                            const int l = load[a.idx[f + sstart[i][q] + c] & 15];
+                            if (l < best) { best = l; bslot = q; bc = c; }
+                        }
                     }
-                    taken[i][pick] = 1;
+                    cur[i] = bslot;
+                    sdone[i][bslot] = 1;
+                    const int sz = ssize[i][bslot];
+                    for (int c = 0; c < sz && c < 64; ++c) taken[i][c] = 0;
+                    int pick = sz > 64 ? 0 : bc;
+                    if (sz <= 64) taken[i][pick] = 1;
+                    const int v = a.idx[f + sstart[i][bslot] + pick];
+                    ++load[v & 15];
+                    unsigned short e = (unsigned short)v;
+                    if (sz == 1) e |= 0x8000u;
+                    o[outpos[i]] = e;
+                } else {
+                    if (cur[i] < 0) continue;
+                    const int q = cur[i];
+                    const int sz = ssize[i][q];
+                    if (it >= sz) continue;
+                    int pick = -1, best = 1000;
+                    if (sz > 64) {
+                        pick = it;
+                    } else {
+                        for (int c = 0; c < sz; ++c) {
+                            if (taken[i][c]) continue;
+                            const int l = load[a.idx[f + sstart[i][q] + c] & 15];
+                            if (l < best) { best = l; pick = c; }
+                        }
+                        taken[i][pick] = 1;
+                    }
+                    const int v = a.idx[f + sstart[i][q] + pick];
+                    ++load[v & 15];
+                    unsigned short e = (unsigned short)v;
+                    if (it == sz - 1) e |= 0x8000u;
+                    o[outpos[i] + it] = e;
                 }
-                const int v = a.idx[f + pos[i] + pick];
-                ++load[v & 15];
-                unsigned short e = (unsigned short)v;
-                if (it == sz - 1) e |= 0x8000u;
-                o[pos[i] + it] = e;
             }
         }
-        for (int i = 0; i < nrows; ++i) pos[i] = slot_end[i];
+        for (int i = 0; i < nrows; ++i) {
+            if (cur[i] < 0) continue;
+            a.out_perm[(r0 + i) * (long long)a.max_slots + nfin[i]] = (unsigned char)cur[i];
+            outpos[i] += ssize[i][cur[i]];
+            ++nfin[i];
+        }
     }
-    for (int i = 0; i < nrows; ++i) {
-        a.out_len[r0 + i] = cnt[i];
-        // slot order is unchanged: identity permutation
-        const long long f = a.row_first[r0 + i];
-        int sl = 0;
-        for (int c = 0; c < cnt[i]; ++c)
-            if (a.endf[f + c]) {
-                if (sl < a.max_slots) a.out_perm[(r0 + i) * (long long)a.max_slots + sl] = (unsigned char)sl;
-                ++sl;
-            }
-    }
+    for (int i = 0; i < nrows; ++i) a.out_len[r0 + i] = cnt[i];
 }
 
 __global__ void k_schedule(SchedArgs a)
