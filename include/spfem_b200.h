@@ -45,7 +45,9 @@ typedef struct SpfemArgs {
     const int *e1;           /* facet kernels: first / second adjacent element    */
     const int *e2;
     const int *lf1;          /* facet kernels: local facet index inside e1        */
-    double *out;             /* local entries out[entry*ldo + k]                  */
+    double *out;             /* local entries out[entry*ldo + k*ldk]              */
+    long long ldk;           /* 1: entry-major planes; Nu*Nv (with ldo = 1):       */
+                             /* element-major local matrices                        */
 } SpfemArgs;
 
 int         spfem_abi_version(void);

@@ -30,6 +30,7 @@ class SpfemArgs(C.Structure):
         ("fv", C.c_void_p), ("e1", C.c_void_p), ("e2", C.c_void_p),
         ("lf1", C.c_void_p),
         ("out", C.c_void_p),
+        ("ldk", C.c_longlong),
     ]
 
 
@@ -40,6 +41,15 @@ class SpfemTileArgs(C.Structure):
         ("desc", C.c_void_p), ("blob", C.c_void_p), ("values", C.c_void_p),
         ("ldl", C.c_int), ("max_a", C.c_int), ("max_b", C.c_int),
         ("max_ns", C.c_int), ("max_nr", C.c_int),
+    ]
+
+
+class SpfemFanArgs(C.Structure):
+    """Mirror of ``struct SpfemFanArgs`` (generated source, codegen.FAN_KERNEL)."""
+    _fields_ = [
+        ("base", SpfemArgs),
+        ("desc", C.c_void_p), ("blob", C.c_void_p), ("values", C.c_void_p),
+        ("max_a", C.c_int), ("max_b", C.c_int), ("max_ns", C.c_int),
     ]
 
 

@@ -66,7 +66,8 @@ struct SpfemArgs {
     const int *e1;            /* facet kernels: first / second element          */
     const int *e2;
     const int *lf1;           /* facet kernels: local facet index inside e1     */
-    double *out;              /* out[entry*ldo + k]                             */
+    double *out;              /* out[entry*ldo + k*ldk]                         */
+    long long ldk;
 };
 """
 
@@ -79,16 +80,8 @@ struct SpfemArgs {
 # its contributions from shared memory in a fixed order and writes the CSR value
 # exactly once -- no atomics, no partial sums in HBM.
 TILE_THREADS = int(os.environ.get("SPFEM_TILE_T", "512"))
-TILE_KERNEL = r"""
-struct SpfemTileArgs {
-    SpfemArgs base;
-    const int *desc;              /* 16 ints per tile (tileplan.py)              */
-    const unsigned char *blob;    /* packed per-tile data, 16-byte aligned       */
-    double *values;               /* CSR values                                   */
-    int ldl;                      /* leading dimension of the smem tile           */
-    int max_a, max_b;             /* smem bytes reserved for blob sections A / B  */
-    int max_ns, max_nr;           /* largest slot / row count of a tile           */
-};
+DEVICE_HELPERS = r"""
+#ifndef SPFEM_HOST
 static __device__ __forceinline__ unsigned spfem_smem(const void *p)
 {
     return (unsigned)__cvta_generic_to_shared(p);
@@ -117,6 +110,18 @@ static __device__ __forceinline__ void spfem_mbar_wait(void *bar, unsigned parit
         "SPFEM_DONE:\n"
         "}\n" ::"r"(spfem_smem(bar)), "r"(parity) : "memory");
 }
+#endif
+"""
+TILE_KERNEL = r"""
+struct SpfemTileArgs {
+    SpfemArgs base;
+    const int *desc;              /* 16 ints per tile (tileplan.py)              */
+    const unsigned char *blob;    /* packed per-tile data, 16-byte aligned       */
+    double *values;               /* CSR values                                   */
+    int ldl;                      /* leading dimension of the smem tile           */
+    int max_a, max_b;             /* smem bytes reserved for blob sections A / B  */
+    int max_ns, max_nr;           /* largest slot / row count of a tile           */
+};
 extern "C" __global__ void __launch_bounds__(@THREADS@, @MINB@) @NAME@_tile(const SpfemTileArgs T)
 {
     extern __shared__ __align__(128) unsigned char spfem_smem_raw[];
@@ -181,6 +186,118 @@ extern "C" __global__ void __launch_bounds__(@THREADS@, @MINB@) @NAME@_tile(cons
     for (int s = threadIdx.x; s < ns; s += blockDim.x)
         T.values[sG[s] + (int)pm[s]] = sV[s];
 }
+"""
+
+# Vertex-fan kernel (scalar P1 on triangles, element-constant coefficients).
+# One thread per CSR row = mesh vertex r.  The thread walks the triangles around
+# r in counter-clockwise ring order, recomputes the local row of r for each of
+# them from the vertex coordinates (registers; each triangle is computed by its
+# three vertices -- redundant flops instead of shared-memory traffic) and keeps
+# one accumulator per ring neighbour: slot (r, n_q) receives exactly the two
+# triangles that share the edge, in a fixed order.  No local matrices in shared
+# memory, no contribution lists, no atomics.  Per-row record (48 B, fanplan.py):
+#   g0 CSR position of the row | s0 tile slot offset | nfan | closed |
+#   ring neighbours (tile-local vertex ids) | CSR position of each neighbour
+FAN_THREADS = int(os.environ.get("SPFEM_FAN_T", "128"))
+FAN_KERNEL = r"""
+struct SpfemFanRow {
+    int g0; unsigned short s0; unsigned char nfan, closed;
+    unsigned short nbr[12];
+    unsigned char pos[12];
+    unsigned char posdiag, pad[3];
+};
+struct SpfemFanArgs {
+    SpfemArgs base;
+    const int *desc;              /* 8 ints per tile: off16, bytes A, bytes B, nr, ns, nvt */
+    const unsigned char *blob;
+    double *values;
+    int max_a, max_b, max_ns;
+};
+SPFEM_DEVICE void @NAME@_fan_row(const SpfemArgs &P, const double2 *__restrict__ pc2,
+                                 const SpfemFanRow *__restrict__ rows, const int row,
+                                 double *__restrict__ sV, int *__restrict__ sG)
+{
+    const SpfemFanRow R = rows[row];
+    const double2 cr = pc2[row];                 /* rows are the first vertices of a tile */
+    const int nfan = R.nfan;
+    const int nn = nfan + (R.closed ? 0 : 1);    /* ring neighbours */
+    double acc[13];
+#pragma unroll
+    for (int q = 0; q < 13; ++q) acc[q] = 0.0;
+    double diag = 0.0;
+    const double2 c0 = pc2[R.nbr[0]];
+    double2 ca = c0;
+#pragma unroll
+    for (int f = 0; f < 12; ++f) {
+        if (f < nfan) {
+            double2 cb = c0;                     /* closed ring wraps to neighbour 0 */
+            if (f + 1 < nn) cb = pc2[R.nbr[(f + 1) < 12 ? (f + 1) : 11]];
+            double L[SPFEM_NUNIQUE];
+            @NAME@_core(P, cr.x, cr.y, ca.x, ca.y, cb.x, cb.y, L);
+            diag += L[@A00@];                    /* (test r, trial r)       */
+            acc[f] += L[@A10@];                  /* (test r, trial n_f)     */
+            acc[f + 1] += L[@A20@];              /* (test r, trial n_{f+1}) */
+            ca = cb;
+        }
+    }
+    if (R.closed) {                              /* the last triangle's n_{f+1} is n_0 */
+        double wrap = 0.0;
+#pragma unroll
+        for (int q = 1; q < 13; ++q) if (q == nfan) wrap = acc[q];
+        acc[0] += wrap;
+    }
+    const int s0 = R.s0;
+    sV[s0 + R.posdiag] = diag;
+    sG[s0 + R.posdiag] = R.g0 + R.posdiag;
+#pragma unroll
+    for (int q = 0; q < 12; ++q)
+        if (q < nn) {
+            sV[s0 + R.pos[q]] = acc[q];
+            sG[s0 + R.pos[q]] = R.g0 + R.pos[q];
+        }
+}
+#ifndef SPFEM_HOST
+extern "C" __global__ void __launch_bounds__(@FANTHREADS@, @FANMINB@) @NAME@_fan(const SpfemFanArgs T)
+{
+    extern __shared__ __align__(128) unsigned char spfem_smem_raw[];
+    unsigned char *sA = spfem_smem_raw;
+    unsigned char *sB = sA + T.max_a;
+    double *sV = (double *)(sB + T.max_b);
+    unsigned long long *bars = (unsigned long long *)(sV + T.max_ns);
+    int *sG = (int *)(bars + 2);
+    const int *d = T.desc + 8 * (size_t)blockIdx.x;
+    const int bytes_a = d[1], bytes_b = d[2], nr = d[3], ns = d[4];
+    if (nr == 0) return;
+    if (threadIdx.x == 0) {
+        spfem_mbar_init(&bars[0], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        const unsigned char *src = T.blob + (size_t)(unsigned)d[0] * 16;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
+                     ::"r"(spfem_smem(&bars[0])), "r"((unsigned)(bytes_a + bytes_b)) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(spfem_smem(sA)), "l"(src), "r"((unsigned)bytes_a), "r"(spfem_smem(&bars[0])) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(spfem_smem(sB)), "l"(src + bytes_a), "r"((unsigned)bytes_b), "r"(spfem_smem(&bars[0])) : "memory");
+    }
+    __syncthreads();
+    spfem_mbar_wait(&bars[0], 0);
+    for (int row = threadIdx.x; row < nr; row += blockDim.x)
+        @NAME@_fan_row(T.base, (const double2 *)sA, (const SpfemFanRow *)sB, row, sV, sG);
+    __syncthreads();
+    for (int s = threadIdx.x; s < ns; s += blockDim.x) T.values[sG[s]] = sV[s];
+}
+#else
+extern "C" void @NAME@_fan_host(const SpfemFanArgs *T, int ntiles, double *sV, int *sG)
+{
+    for (int t = 0; t < ntiles; ++t) {
+        const int *d = T->desc + 8 * (size_t)t;
+        const unsigned char *src = T->blob + (size_t)(unsigned)d[0] * 16;
+        for (int row = 0; row < d[3]; ++row)
+            @NAME@_fan_row(T->base, (const double2 *)src, (const SpfemFanRow *)(src + d[1]), row, sV, sG);
+        for (int s = 0; s < d[4]; ++s) T->values[sG[s]] = sV[s];
+    }
+}
+#endif
 """
 
 
@@ -306,16 +423,21 @@ def _neg(a):
 
 
 def affine_geometry(dim, sfx="", elem="e", vt="P.t", ldv="P.ldt",
-                    fast_inverse=False, pc="P.p", ldpc="P.ldp", tiled_pairs=False):
+                    fast_inverse=False, pc="P.p", ldpc="P.ldp", tiled_pairs=False,
+                    coords_given=False):
     """C statements computing ``A, b, detA, invA`` of element ``elem`` with
     the operation order of spfem/mapping.py:207-229 (tri) / 244-279 (tet).
     Variables carry the suffix ``sfx`` (facet kernels have two elements)."""
     L = []
     nve = dim + 1
     for k in range(nve):
+        if coords_given:
+            break
         L.append("const int vtx%s_%d = %s[%d * %s + %s];" % (sfx, k, vt, k, ldv, elem))
     # vertex coordinates X{sfx}_{i}_{k}: coordinate i of local vertex k
     for k in range(nve):
+        if coords_given:
+            break
         if tiled_pairs and dim == 2:
             L.append("double X%s_0_%d, X%s_1_%d;" % (sfx, k, sfx, k))
             L.append("if (TILED) { const double2 cxy = reinterpret_cast<const double2 *>(%s)[vtx%s_%d]; "
@@ -526,6 +648,7 @@ def generate_interior(spec, name="spfem_elem"):
     else:
         body += affine_geometry(dim, vt="vt", ldv="ldv", elem="ev", fast_inverse=True,
                                 pc="pc", ldpc="ldpc", tiled_pairs=True)
+        n_geom_lines = len(body)
         if "h" in syms:
             body.append("const double h = pow(absdet, %s);" % lit(1.0 / dim))
     # global coordinates of the quadrature points (only if the form uses x)
@@ -610,8 +733,17 @@ def generate_interior(spec, name="spfem_elem"):
         body.append("  } }")
     spec.alias = alias
     spec.n_unique = len(order_u)
+    # Vertex-fan variant (TriP1-like: one DOF per vertex, element-constant
+    # coefficients): the same computation with the vertex coordinates passed in
+    spec.fan_ok = (spec.refdom == "tri" and spec.bilinear and spec.ncu == 1 and spec.ncv == 1
+                   and spec.nbu == 3 and spec.nbv == 3
+                   and not any(nm[0] in "xw" for nm in syms))
+    core = []
+    if spec.fan_ok:
+        core = (affine_geometry(dim, fast_inverse=True, coords_given=True)
+                + body[n_geom_lines:])
 
-    src = [PRELUDE]
+    src = [PRELUDE, DEVICE_HELPERS]
     src.append("#define SPFEM_NENTRIES %d" % spec.n_entries)
     src.append("#define SPFEM_NUNIQUE %d" % spec.n_unique)
     # body<TILED>(P, e, vt, ldv, ev, pc, ldpc, out, ldo, k): local matrix of
@@ -624,12 +756,24 @@ def generate_interior(spec, name="spfem_elem"):
                "OUT *__restrict__ out, const long long ldo, const long long k)\n{" % name)
     src += ["    " + ln for ln in body]
     src.append("}")
+    if spec.fan_ok:
+        # core(P, x0,y0, x1,y1, x2,y2, out): distinct local values out[alias]
+        src.append("SPFEM_DEVICE void %s_core(const SpfemArgs &P, const double X_0_0, "
+                   "const double X_1_0, const double X_0_1, const double X_1_1, "
+                   "const double X_0_2, const double X_1_2, double *__restrict__ out)\n{" % name)
+        src.append("    const bool TILED = true; const long long ldo = 1, k = 0;")
+        src += ["    " + ln for ln in core]
+        src.append("}")
+        src.append(FAN_KERNEL.replace("@NAME@", name).replace("@FANTHREADS@", str(FAN_THREADS))
+                   .replace("@FANMINB@", os.environ.get("SPFEM_FAN_MINB", "6"))
+                   .replace("@A00@", str(alias[0])).replace("@A10@", str(alias[3]))
+                   .replace("@A20@", str(alias[6])))
     src.append("#ifndef SPFEM_HOST")
     src.append('extern "C" __global__ void __launch_bounds__(128) %s(const SpfemArgs P)\n{' % name)
     src.append("    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;")
     src.append("    if (k >= P.n) return;")
     src.append("    const long long e = P.sel ? (long long)P.sel[k] : k;")
-    src.append("    %s_body<false>(P, e, P.t, P.ldt, e, P.p, P.ldp, P.out, P.ldo, k);" % name)
+    src.append("    %s_body<false>(P, e, P.t, P.ldt, e, P.p, P.ldp, P.out, P.ldo, k * P.ldk);" % name)
     src.append("}")
     if spec.bilinear:
         nve = 4 if quad else dim + 1
@@ -642,7 +786,7 @@ def generate_interior(spec, name="spfem_elem"):
     src.append('extern "C" void %s_host(const SpfemArgs *P)\n{' % name)
     src.append("    for (long long k = 0; k < P->n; ++k) {")
     src.append("        const long long e = P->sel ? (long long)P->sel[k] : k;")
-    src.append("        %s_body<false>(*P, e, P->t, P->ldt, e, P->p, P->ldp, P->out, P->ldo, k);" % name)
+    src.append("        %s_body<false>(*P, e, P->t, P->ldt, e, P->p, P->ldp, P->out, P->ldo, k * P->ldk);" % name)
     src.append("    }")
     src.append("}")
     src.append("#endif")

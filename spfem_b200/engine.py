@@ -260,8 +260,11 @@ class Prepared(object):
             cptr, nslots = pat.cptr, pat.nnz
         else:
             cptr, nslots = pat.rowstart, pat.nrows
+        contrib = getattr(self, "contrib_override", None)
+        if contrib is None:
+            contrib = pat.contrib
         _lib.check(e.lib.spfem_reduce(e._ptr(self.local), e._ptr(cptr),
-                                      e._ptr(pat.contrib), nslots,
+                                      e._ptr(contrib), nslots,
                                       e._ptr(self.values), e._stream()))
 
     def launch(self):
@@ -307,6 +310,36 @@ class TiledPrepared(Prepared):
         self.targs.base = a
         _lib.check(e.lib.spfem_launch_tiled(self.tile_kernel, C.byref(self.targs),
                                             self.tp["ntiles"], self.threads,
+                                            self.smem, e._stream()))
+        return self.values
+
+
+class FanPrepared(Prepared):
+    """Vertex-fan variant (scalar P1 on triangles, element-constant
+    coefficients): one launch of ``<name>_fan`` (codegen.FAN_KERNEL), one thread
+    per CSR row, local rows recomputed from coordinates in registers."""
+
+    def __init__(self, engine, plan, kernel, fan_kernel, args, pattern, fp):
+        Prepared.__init__(self, engine, plan, kernel, args, 128, None, pattern, ())
+        self.fan_kernel, self.fp = fan_kernel, fp
+        fa = _lib.SpfemFanArgs()
+        fa.desc = fp["desc"].data_ptr()
+        fa.blob = fp["blob"].data_ptr()
+        fa.values = self.values.data_ptr()
+        fa.max_a, fa.max_b, fa.max_ns = fp["max_a"], fp["max_b"], fp["max_ns"]
+        self.fargs = fa
+        self.smem = fp["max_a"] + fp["max_b"] + 12 * fp["max_ns"] + 64
+        from . import codegen
+        self.threads = codegen.FAN_THREADS
+        self.n_launches = 1
+        self.tp = {"E": fp["rows_per_tile"], "ldl": 0, "ntiles": fp["ntiles"],
+                   "halo_factor": fp["halo_factor"], "kind": "vertex-fan"}
+
+    def launch(self):
+        e = self.engine
+        self.fargs.base = self.args
+        _lib.check(e.lib.spfem_launch_tiled(self.fan_kernel, C.byref(self.fargs),
+                                            self.fp["ntiles"], self.threads,
                                             self.smem, e._stream()))
         return self.values
 
@@ -509,11 +542,17 @@ class Engine(object):
                                      asm.dofnum_u.N if plan.bilinear else 1)
         wt = self._interp_tensors(plan, interp)
         a = _lib.SpfemArgs()
-        a.n, a.ldo = n, n
+        a.n, a.ldo, a.ldk = n, n, 1
         a.sel = sel.data_ptr() if sel is not None else None
         a.tdof_u, a.ldd = self.tdof_u.data_ptr(), self.tdof_u.shape[1]
         for s, w in enumerate(wt):
             a.interp[s] = w.data_ptr()
+        if (tind is None and plan.bilinear and self.fused and getattr(spec, "fan_ok", False)
+                and os.environ.get("SPFEM_FAN", "1") != "0"):
+            fp = self.fan_plan(pat)
+            if fp is not None:
+                fk = get_kernel(plan.source, plan.name + "_fan")
+                return FanPrepared(self, plan, kernel, fk, a, pat, fp)
         tp = None
         if tind is None and plan.bilinear and self.fused:
             tp = self.tile_plan(pat, n, spec.n_entries, spec.nw > 0, tuple(spec.alias))
@@ -522,7 +561,52 @@ class Engine(object):
             return TiledPrepared(self, plan, kernel, tk, a, None, pat, tp, keep=(wt,))
         local = self._empty(max(spec.n_entries * n, 1), torch.float64)
         a.out = local.data_ptr()
-        return Prepared(self, plan, kernel, a, 128, local, pat, keep=(sel, wt))
+        prep = Prepared(self, plan, kernel, a, 128, local, pat, keep=(sel, wt))
+        if os.environ.get("SPFEM_LOCAL_LAYOUT", "entry") == "elem" and spec.n_entries > 1:
+            # element-major local matrices: the gathers of neighbouring CSR slots
+            # hit the same few 32-byte sectors
+            a.ldo, a.ldk = 1, spec.n_entries
+            ce = getattr(pat, "_contrib_elem", None)
+            if ce is None:
+                c = pat.contrib.long()
+                ce = pat._contrib_elem = ((c % n) * spec.n_entries + c // n).to(torch.int32)
+            prep.contrib_override = ce
+        return prep
+
+    def fan_plan(self, pat):
+        """Plan of the vertex-fan kernel for ``pat`` (cached on the pattern), or
+        ``None`` when the assembler is not scalar-P1-on-triangles shaped."""
+        if hasattr(pat, "_fan_plan"):
+            return pat._fan_plan
+        asm, torch = self.asm, self.torch
+        pat._fan_plan = None
+        mesh = asm.mesh
+        if (asm.dofnum_u is not asm.dofnum_v or mesh.refdom != "tri"
+                or asm.dofnum_u.t_dof.shape != mesh.t.shape
+                or not np.array_equal(asm.dofnum_u.t_dof, mesh.t)):
+            return None
+        from .fanplan import build_fan_plan, FanPlanError
+        from .tileplan import fill_coordinates
+        t0 = time.perf_counter()
+        indptr, indices = pat.host()
+        try:
+            hp = build_fan_plan(mesh, indptr, indices,
+                                int(os.environ.get("SPFEM_FAN_ROWS", "128")))
+        except FanPlanError:
+            return None
+        fp = dict(hp)
+        fp["desc"] = torch.from_numpy(hp["desc"]).to(self.device).contiguous()
+        fp["blob"] = torch.from_numpy(hp["blob"]).to(self.device)
+        fp["vid"] = torch.from_numpy(hp["vid"]).to(self.device)
+        fp["pc_index"] = torch.from_numpy(hp["pc_index"]).to(self.device)
+        fp["pc_stride"] = 1
+        fp["dim"] = 2
+        fill_coordinates(fp, self.p)
+        self._tile_plans.append(fp)
+        self.torch.cuda.synchronize(self.device)
+        self.stats["fan_plan_s"] = time.perf_counter() - t0
+        pat._fan_plan = fp
+        return fp
 
     def tile_plan(self, pat, n, nent, with_el=False, alias=None):
         """Tile plan of the fused kernel for ``pat`` (cached on the pattern);
@@ -600,7 +684,7 @@ class Engine(object):
         local = self._empty(max(spec.n_entries * nblk * n, 1), torch.float64)
         wt = self._interp_tensors(plan, interp)
         a = _lib.SpfemArgs()
-        a.n, a.ldo = n, nblk * n
+        a.n, a.ldo, a.ldk = n, nblk * n, 1
         a.tdof_u, a.ldd = self.tdof_u.data_ptr(), self.tdof_u.shape[1]
         for s, w in enumerate(wt):
             a.interp[s] = w.data_ptr()

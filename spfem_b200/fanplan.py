@@ -1,0 +1,222 @@
+# -*- coding: utf-8 -*-
+"""Plan of the vertex-fan kernel (``codegen.FAN_KERNEL``).
+
+For scalar P1 on triangles (one DOF per vertex) with element-constant
+coefficients every CSR row is a mesh vertex ``r`` and its columns are ``r`` and
+its ring neighbours.  The kernel gives each row to one thread that walks the
+triangles around ``r`` in counter-clockwise order and recomputes the local row
+of ``r`` from vertex coordinates -- no local matrices in shared memory.  This
+module builds, once per mesh (host NumPy; set-up, not the hot path):
+
+* the ring order of the triangles / neighbours around every vertex, from the
+  mesh's own topology (``t2f`` / ``f2t``),
+* tiles of ``R`` Morton-consecutive rows with their tile-local vertex numbering
+  (the rows themselves first, then the halo vertices),
+* one 16-byte aligned blob per tile: section A = interleaved ``(x, y)``
+  coordinates of the tile's vertices, section B = one 48-byte record per row
+  (``SpfemFanRow``: CSR position, tile slot offset, fan size, open/closed ring,
+  ring neighbours as tile-local ids, CSR position of every neighbour).
+
+Descriptor per tile (int32 x 8): blob offset / 16, bytes A, bytes B, rows,
+slots, vertices, 0, 0.
+"""
+import numpy as np
+
+ROW_DTYPE = np.dtype([("g0", "<i4"), ("s0", "<u2"), ("nfan", "u1"), ("closed", "u1"),
+                      ("nbr", "<u2", (12,)), ("pos", "u1", (12,)),
+                      ("posdiag", "u1"), ("pad", "u1", (3,))])
+assert ROW_DTYPE.itemsize == 48
+MAXN = 12
+
+
+class FanPlanError(Exception):
+    """The mesh / pattern does not fit the vertex-fan kernel (caller falls back)."""
+
+
+def _morton_vertices(p, bits=20):
+    lo = p.min(axis=1, keepdims=True)
+    ext = p.max(axis=1, keepdims=True) - lo
+    ext[ext == 0] = 1.0
+    q = np.minimum(((p - lo) / ext * (2 ** bits - 1)).astype(np.uint64),
+                   np.uint64(2 ** bits - 1))
+    key = np.zeros(p.shape[1], dtype=np.uint64)
+    for b in range(bits):
+        for d in range(p.shape[0]):
+            key |= ((q[d] >> np.uint64(b)) & np.uint64(1)) << np.uint64(b * p.shape[0] + d)
+    return np.argsort(key, kind="stable")
+
+
+def vertex_rings(mesh):
+    """Counter-clockwise ring of neighbours around every vertex.
+
+    Returns ``(nb, nfan, closed)``: ``nb[k, v]`` = k-th ring neighbour of vertex
+    ``v`` (-1 beyond the ring), ``nfan[v]`` = number of triangles around ``v``,
+    ``closed[v]`` = interior vertex (the ring closes).  Triangle ``k`` of the fan
+    is ``(v, nb[k], nb[k+1])`` (indices modulo ``nfan`` for a closed ring)."""
+    p, t = mesh.p, np.asarray(mesh.t)
+    nt, nv = t.shape[1], p.shape[1]
+    ar = np.arange(nt)
+    x, y = p[0][t], p[1][t]
+    det = (x[1] - x[0]) * (y[2] - y[0]) - (x[2] - x[0]) * (y[1] - y[0])
+    if np.any(det == 0):
+        raise FanPlanError("degenerate triangle")
+    ccw = det > 0
+    li = np.arange(3)[:, None]
+    nxt = np.where(ccw[None, :], (li + 1) % 3, (li + 2) % 3)     # CCW successor of local i
+    prv = np.where(ccw[None, :], (li + 2) % 3, (li + 1) % 3)
+    LF = np.array([[-1, 0, 2], [0, -1, 1], [2, 1, -1]])          # local facet of a vertex pair
+
+    def across(i, j):
+        fid = mesh.t2f[LF[i, j], ar]
+        f0, f1 = mesh.f2t[0, fid], mesh.f2t[1, fid]
+        return np.where(f0 == ar, f1, f0)
+
+    next_corner = np.full(3 * nt, -1, dtype=np.int64)
+    has_prev = np.zeros(3 * nt, dtype=bool)
+    for i in range(3):
+        ii = np.full(nt, i)
+        r = t[i]
+        tn = across(ii, prv[i])                  # next triangle CCW around r: across edge (r, b)
+        ok = tn >= 0
+        tnc = np.where(ok, tn, 0)
+        iloc = np.argmax(t[:, tnc] == r[None, :], axis=0)
+        next_corner[i * nt + ar] = np.where(ok, iloc * nt + tnc, -1)
+        has_prev[i * nt + ar] = across(ii, nxt[i]) >= 0
+    corner_vertex = t.reshape(-1)                # corner c = i*nt + T  ->  vertex
+    valence = np.bincount(corner_vertex, minlength=nv)
+    if valence.min() == 0:
+        raise FanPlanError("vertex without elements")
+    K = int(valence.max())
+    if K > MAXN:
+        raise FanPlanError("vertex valence %d > %d" % (K, MAXN))
+    # start corner: the one without a predecessor (boundary), else the smallest
+    order = np.argsort(corner_vertex, kind="stable")
+    first = np.searchsorted(corner_vertex[order], np.arange(nv))
+    start = order[first]
+    nopred = np.nonzero(~has_prev)[0]
+    start[corner_vertex[nopred]] = nopred
+    cnxt = np.take(nxt.reshape(-1), np.arange(3 * nt))          # local index arrays per corner
+    cprv = np.take(prv.reshape(-1), np.arange(3 * nt))
+    corner_T = np.tile(ar, 3)
+    a_of = t[cnxt, corner_T]                      # vertex following r (CCW) in the corner's triangle
+    b_of = t[cprv, corner_T]
+    nb = np.full((K + 1, nv), -1, dtype=np.int64)
+    nfan = np.zeros(nv, dtype=np.int64)
+    closed = np.zeros(nv, dtype=bool)
+    cur = start.copy()
+    alive = np.ones(nv, dtype=bool)
+    last_b = np.full(nv, -1, dtype=np.int64)
+    for k in range(K):
+        idx = np.nonzero(alive)[0]
+        c = cur[idx]
+        nb[k, idx] = a_of[c]
+        last_b[idx] = b_of[c]
+        nfan[idx] += 1
+        nc = next_corner[c]
+        back = nc == start[idx]
+        closed[idx[back]] = True
+        stop = back | (nc < 0)
+        alive[idx[stop]] = False
+        cur[idx] = nc
+    if alive.any() or not np.array_equal(nfan, valence):
+        raise FanPlanError("non-manifold vertex fan")
+    opn = np.nonzero(~closed)[0]
+    nb[nfan[opn], opn] = last_b[opn]              # open fans have one more neighbour
+    return nb, nfan, closed
+
+
+def build_fan_plan(mesh, indptr, indices, rows_per_tile=256):
+    """Host arrays of the vertex-fan plan for the CSR pattern ``indptr/indices``
+    (rows = columns = vertices).  Raises :class:`FanPlanError` if it does not
+    apply."""
+    p = mesh.p
+    nv = p.shape[1]
+    if p.shape[0] != 2 or len(indptr) != nv + 1:
+        raise FanPlanError("not a scalar vertex-based pattern on a 2-D mesh")
+    nb, nfan, closed = vertex_rings(mesh)
+    nn = nfan + (~closed)
+    if int(nn.max()) > MAXN:
+        raise FanPlanError("more than %d ring neighbours" % MAXN)
+    indptr = np.asarray(indptr, dtype=np.int64)
+    indices = np.asarray(indices, dtype=np.int64)
+    rowlen = np.diff(indptr)
+    if not np.array_equal(rowlen, nn + 1):
+        raise FanPlanError("pattern rows are not vertex stars")
+    if indptr[-1] > 2 ** 31 - 1:
+        raise FanPlanError("nnz exceeds 32-bit positions")
+    # CSR position (inside its row) of every ring neighbour and of the diagonal
+    rowkey = np.repeat(np.arange(nv), rowlen) * nv + indices
+    K1 = nb.shape[0]
+    vv = np.broadcast_to(np.arange(nv), (K1, nv))
+    valid = nb >= 0
+    gpos = np.searchsorted(rowkey, vv[valid] * nv + nb[valid])
+    if not np.array_equal(indices[np.minimum(gpos, len(indices) - 1)], nb[valid]):
+        raise FanPlanError("ring neighbour missing from the pattern")
+    pos = np.zeros((K1, nv), dtype=np.int64)
+    pos[valid] = gpos - indptr[vv[valid]]
+    dpos = np.searchsorted(rowkey, np.arange(nv) * nv + np.arange(nv)) - indptr[:-1]
+    nb12 = np.full((MAXN, nv), -1, dtype=np.int64)
+    pos12 = np.zeros((MAXN, nv), dtype=np.int64)
+    kk = min(K1, MAXN)
+    nb12[:kk], pos12[:kk] = nb[:kk], pos[:kk]
+    # tiles of Morton-consecutive rows
+    vperm = _morton_vertices(p)
+    R = int(rows_per_tile)
+    ntiles = (nv + R - 1) // R
+    loc = np.full(nv, -1, dtype=np.int64)
+    desc = np.zeros((ntiles, 8), dtype=np.int64)
+    recs, vids, pcidx = [], [], []
+    off = 0
+    max_a = max_b = max_ns = 0
+    for ti in range(ntiles):
+        rows = vperm[ti * R:(ti + 1) * R]
+        nr = len(rows)
+        nbr = nb12[:, rows]                              # (12, nr)
+        ok = nbr >= 0
+        loc[rows] = np.arange(nr)
+        cand = np.unique(nbr[ok])
+        extra = cand[loc[cand] < 0]
+        loc[extra] = nr + np.arange(len(extra))
+        nvt = nr + len(extra)
+        if nvt > 65535:
+            raise FanPlanError("tile with more than 65535 vertices")
+        rec = np.zeros(nr, dtype=ROW_DTYPE)
+        rec["g0"] = indptr[rows]
+        lens = rowlen[rows]
+        s0 = np.cumsum(lens) - lens
+        ns = int(lens.sum())
+        rec["s0"] = s0
+        rec["nfan"] = nfan[rows]
+        rec["closed"] = closed[rows]
+        rec["nbr"] = np.where(ok, loc[np.where(ok, nbr, 0)], 0).T
+        rec["pos"] = np.where(ok, pos12[:, rows], 0).T
+        rec["posdiag"] = dpos[rows]
+        loc[rows] = -1
+        loc[extra] = -1
+        bytes_a = (nvt * 16 + 15) // 16 * 16
+        bytes_b = nr * 48
+        desc[ti, :6] = (off // 16, bytes_a, bytes_b, nr, ns, nvt)
+        vids.append(np.concatenate((rows, extra)))
+        pcidx.append(off // 8 + 2 * np.arange(nvt))
+        recs.append((off + bytes_a, rec))
+        off += bytes_a + bytes_b
+        max_a, max_b, max_ns = max(max_a, bytes_a), max(max_b, bytes_b), max(max_ns, ns)
+    blob = np.zeros(off, dtype=np.uint8)
+    for o, rec in recs:
+        blob[o:o + rec.nbytes] = rec.view(np.uint8)
+    if desc.max() > 2 ** 31 - 1:
+        raise FanPlanError("fan plan offsets exceed 32 bits")
+    return {
+        "ntiles": ntiles, "rows_per_tile": R,
+        "desc": desc.astype(np.int32), "blob": blob,
+        "vid": np.concatenate(vids), "pc_index": np.concatenate(pcidx),
+        "max_a": int(max_a), "max_b": int(max_b), "max_ns": int(max_ns),
+        "halo_factor": float(sum(len(v) for v in vids)) / nv,
+    }
+
+
+def fill_coordinates_host(plan, p):
+    """Host version of the coordinate refresh (tests)."""
+    b64 = plan["blob"].view(np.float64)
+    b64[plan["pc_index"]] = p[0][plan["vid"]]
+    b64[plan["pc_index"] + 1] = p[1][plan["vid"]]

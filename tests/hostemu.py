@@ -56,7 +56,7 @@ def run_interior(asm, plan, tind=None, interp=None):
     n = t.shape[1] if sel is None else sel.shape[0]
     out = np.zeros((plan.spec.n_entries, n))
     a = SpfemArgs()
-    a.n, a.ldo = n, n
+    a.n, a.ldo, a.ldk = n, n, 1
     a.sel = _ptr(sel) if sel is not None else None
     a.t, a.ldt = _ptr(t), t.shape[1]
     a.p, a.ldp = _ptr(p), p.shape[1]
@@ -109,7 +109,7 @@ def fasm(asm, form, find=None, interior=False, intorder=None, normals=True,
     lf1 = np.ascontiguousarray(lf1, dtype=np.int32)
     out = np.zeros((plan.spec.n_entries, nblk * n))
     a = SpfemArgs()
-    a.n, a.ldo = n, nblk * n
+    a.n, a.ldo, a.ldk = n, nblk * n, 1
     a.t, a.ldt = _ptr(t), t.shape[1]
     a.p, a.ldp = _ptr(p), p.shape[1]
     a.tdof_u, a.ldd = _ptr(tdu), tdu.shape[1]
@@ -130,3 +130,31 @@ def fasm(asm, form, find=None, interior=False, intorder=None, normals=True,
                           shape=(asm.dofnum_v.N, asm.dofnum_u.N)).tocsr()
     return coo_matrix((out.reshape(-1), (rows.reshape(-1), np.zeros(rows.size, dtype=np.int64))),
                       shape=(asm.dofnum_v.N, 1)).toarray().T[0]
+
+
+def fan_iasm(asm, form, rows_per_tile=64):
+    """Host emulation of the vertex-fan kernel: plan (spfem_b200/fanplan.py) +
+    the generated ``<name>_fan_host`` loop; pattern from the plain emulation."""
+    from spfem_b200._lib import SpfemFanArgs
+    from spfem_b200.fanplan import build_fan_plan, fill_coordinates_host
+    ref = iasm(asm, form)
+    plan = asm.plan_iasm(form)
+    assert plan.spec.fan_ok
+    fp = build_fan_plan(asm.mesh, ref.indptr, ref.indices, rows_per_tile)
+    fill_coordinates_host(fp, asm.mesh.p)
+    key = hashlib.sha256(plan.source.encode()).hexdigest()[:20]
+    compile_host(plan)
+    lib = C.CDLL(os.path.join(_TMP, key + ".so"))
+    fn = getattr(lib, plan.name + "_fan_host")
+    fn.argtypes = [C.POINTER(SpfemFanArgs), C.c_int, C.c_void_p, C.c_void_p]
+    fn.restype = None
+    values = np.full(ref.nnz, np.nan)
+    sV = np.zeros(fp["max_ns"] + 16)
+    sG = np.zeros(fp["max_ns"] + 16, dtype=np.int32)
+    a = SpfemFanArgs()
+    a.desc, a.blob, a.values = _ptr(fp["desc"]), _ptr(fp["blob"]), _ptr(values)
+    a.max_a, a.max_b, a.max_ns = fp["max_a"], fp["max_b"], fp["max_ns"]
+    fn(C.byref(a), fp["ntiles"], _ptr(sV), _ptr(sG))
+    out = ref.copy()
+    out.data = values
+    return out, fp

@@ -1,0 +1,70 @@
+# -*- coding: utf-8 -*-
+"""Vertex-fan kernel on the CPU: ring construction, plan and the generated
+``_fan_host`` loop against the reference's golden matrices."""
+import numpy as np
+import pytest
+
+import spfem_b200 as sp
+from spfem_b200.assembly import AssemblerElement
+from spfem_b200.fanplan import vertex_rings, build_fan_plan, FanPlanError
+import cases
+import util
+import hostemu
+
+
+def test_rings_are_vertex_stars():
+    m = sp.MeshTri()
+    m.refine(3)
+    nb, nfan, closed = vertex_rings(m)
+    nv = m.p.shape[1]
+    assert np.array_equal(nfan, np.bincount(m.t.reshape(-1), minlength=nv))
+    bnd = np.zeros(nv, dtype=bool)
+    bnd[m.boundary_nodes()] = True
+    assert np.array_equal(closed, ~bnd)
+    # neighbours of v = vertices sharing an edge with v
+    for v in (0, 5, 17, nv - 1):
+        ring = set(nb[:, v][nb[:, v] >= 0].tolist())
+        edges = m.facets[:, (m.facets == v).any(axis=0)]
+        assert ring == set(edges.reshape(-1).tolist()) - {v}
+    # counter-clockwise order: consecutive neighbours span positively oriented triangles
+    v = int(np.nonzero(closed)[0][0])
+    r = nb[:nfan[v], v]
+    for k in range(nfan[v]):
+        a, b = m.p[:, r[k]] - m.p[:, v], m.p[:, r[(k + 1) % nfan[v]]] - m.p[:, v]
+        assert a[0] * b[1] - a[1] * b[0] > 0
+
+
+@pytest.mark.parametrize("name", ["trip1_lap", "trip1_mass", "trip1_lap_r6"])
+def test_fan_kernel_matches_reference(name):
+    case = cases.BY_NAME[name]
+    asm = util.assembler_for(case)
+    out, fp = hostemu.fan_iasm(asm, case.form, rows_per_tile=64)
+    assert not np.isnan(out.data).any()            # every CSR value written
+    util.check(out, util.golden(case))
+    assert fp["halo_factor"] < 2.0
+
+
+def test_fan_kernel_on_jiggled_symmetric_mesh():
+    """Irregular valences (4..8) and a form using h."""
+    m = sp.MeshTri(initmesh="symmetric")
+    m.refine(3)
+    rng = np.random.default_rng(1)
+    I = m.interior_nodes()
+    m.p[:, I] += 0.01 * rng.standard_normal((2, len(I)))
+    asm = AssemblerElement(m, sp.ElementTriP1())
+    form = lambda u, v, du, dv, h: h * (du[0] * dv[0] + 2.0 * du[1] * dv[1]) + u * v + du[0] * v
+    out, _ = hostemu.fan_iasm(asm, form, rows_per_tile=32)
+    ref = hostemu.iasm(asm, form)
+    cases.compare_csr(out, ref)
+
+
+def test_fan_plan_rejects_other_patterns():
+    m = sp.MeshTri()
+    m.refine(2)
+    asm = AssemblerElement(m, sp.ElementTriP2())
+    A = hostemu.iasm(asm, cases.mass)
+    with pytest.raises(FanPlanError):
+        build_fan_plan(m, A.indptr, A.indices)
+    assert not asm.plan_iasm(cases.mass).spec.fan_ok
+    a1 = AssemblerElement(m, sp.ElementTriP1())
+    assert not a1.plan_iasm(cases.mass_x2).spec.fan_ok      # x-dependent coefficient

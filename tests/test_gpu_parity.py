@@ -126,6 +126,7 @@ def test_both_assembly_paths(name, mode, monkeypatch):
     else:
         monkeypatch.setenv("SPFEM_TILE_E", "32")
         monkeypatch.setenv("SPFEM_FUSED", "force")   # bypass the "is it worth it" heuristic
+        monkeypatch.setenv("SPFEM_FAN", "0")         # (the tile kernel, not the vertex-fan kernel)
     case = cases.BY_NAME[name]
     asm = util.assembler_for(case)
     kw = cases.case_inputs(case, asm.mesh, asm.dofnum_u.N)
@@ -133,3 +134,56 @@ def test_both_assembly_paths(name, mode, monkeypatch):
     assert prep.n_launches == (2 if mode == "unfused" else 1)
     prep.launch()
     util.check(prep.result(), util.golden(case))
+
+
+@pytest.mark.parametrize("name", ["trip1_lap_r6", "vecp2_elasticity", "tetp2_lap", "stokes_b"])
+def test_element_major_local_layout(name, monkeypatch):
+    """Two-kernel route with element-major local matrices (ldk = Nu*Nv)."""
+    monkeypatch.setenv("SPFEM_FUSED", "0")
+    monkeypatch.setenv("SPFEM_LOCAL_LAYOUT", "elem")
+    case = cases.BY_NAME[name]
+    asm = util.assembler_for(case)
+    prep = asm.prepare_iasm(case.form)
+    assert prep.n_launches == 2 and prep.args.ldk == prep.plan.spec.n_entries
+    prep.launch()
+    util.check(prep.result(), util.golden(case))
+
+
+@pytest.mark.parametrize("name", ["trip1_lap", "trip1_mass", "trip1_lap_r6"])
+@pytest.mark.parametrize("rows", ["256", "32"])
+def test_vertex_fan_kernel(name, rows, monkeypatch):
+    """Scalar P1 on triangles with element-constant coefficients runs the
+    vertex-fan kernel (one thread per CSR row, no local matrices in shared
+    memory)."""
+    monkeypatch.setenv("SPFEM_FAN_ROWS", rows)
+    case = cases.BY_NAME[name]
+    asm = util.assembler_for(case)
+    prep = asm.prepare_iasm(case.form)
+    assert type(prep).__name__ == "FanPrepared" and prep.n_launches == 1
+    prep.launch()
+    A = prep.result()
+    util.check(A, util.golden(case))
+    prep.launch()
+    assert np.array_equal(A.data.view(np.int64), prep.result().data.view(np.int64))
+
+
+def test_vertex_fan_irregular_mesh_and_refresh():
+    """Irregular valences; coordinates changed in place + upload_mesh()."""
+    import spfem_b200 as sp
+    from spfem_b200.assembly import AssemblerElement
+    import asm_oracle
+    m = sp.MeshTri(initmesh="symmetric")
+    m.refine(4)
+    rng = np.random.default_rng(1)
+    I = m.interior_nodes()
+    m.p[:, I] += 0.005 * rng.standard_normal((2, len(I)))
+    a = AssemblerElement(m, sp.ElementTriP1())
+    form = lambda u, v, du, dv, h: h * (du[0] * dv[0] + 2.0 * du[1] * dv[1]) + u * v + du[0] * v
+    prep = a.prepare_iasm(form)
+    assert type(prep).__name__ == "FanPrepared"
+    prep.launch()
+    cases.compare_csr(prep.result(), asm_oracle.iasm(m, "TriP1", form))
+    m.p[:, I] += 0.002 * rng.standard_normal((2, len(I)))
+    a._get_engine().upload_mesh()
+    prep.launch()
+    cases.compare_csr(prep.result(), asm_oracle.iasm(m, "TriP1", form))
