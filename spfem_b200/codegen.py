@@ -48,6 +48,7 @@ PRELUDE = r"""
 #define __ddiv_rn(a, b) ((a) / (b))
 #define __restrict__
 struct double2 { double x, y; };
+struct uint4 { unsigned x, y, z, w; };
 #else
 #define SPFEM_DEVICE static __device__ __forceinline__
 #endif
@@ -213,51 +214,68 @@ struct SpfemFanArgs {
     double *values;
     int max_a, max_b, max_ns;
 };
+template <int MAXN>
 SPFEM_DEVICE void @NAME@_fan_row(const SpfemArgs &P, const double2 *__restrict__ pc2,
                                  const SpfemFanRow *__restrict__ rows, const int row,
                                  double *__restrict__ sV, int *__restrict__ sG)
 {
-    const SpfemFanRow R = rows[row];
+    /* the 48-byte record as 12 words in registers; fields extracted with shifts */
+    unsigned w[12];
+    {
+        const uint4 *rp = reinterpret_cast<const uint4 *>(rows + row);
+        const uint4 r0 = rp[0], r1 = rp[1], r2 = rp[2];
+        w[0] = r0.x; w[1] = r0.y; w[2] = r0.z; w[3] = r0.w;
+        w[4] = r1.x; w[5] = r1.y; w[6] = r1.z; w[7] = r1.w;
+        w[8] = r2.x; w[9] = r2.y; w[10] = r2.z; w[11] = r2.w;
+    }
+#define SPFEM_NBR(q) ((w[2 + ((q) >> 1)] >> (16 * ((q) & 1))) & 0xffffu)
+#define SPFEM_POS(q) ((w[8 + ((q) >> 2)] >> (8 * ((q) & 3))) & 0xffu)
+    const int g0 = (int)w[0];
+    const int s0 = (int)(w[1] & 0xffffu);
+    const int nfan = (int)((w[1] >> 16) & 0xffu);
+    const bool closed = ((w[1] >> 24) & 0xffu) != 0u;
+    const int posdiag = (int)(w[11] & 0xffu);
     const double2 cr = pc2[row];                 /* rows are the first vertices of a tile */
-    const int nfan = R.nfan;
-    const int nn = nfan + (R.closed ? 0 : 1);    /* ring neighbours */
-    double acc[13];
+    const int nn = nfan + (closed ? 0 : 1);      /* ring neighbours */
+    double acc[MAXN + 1];
 #pragma unroll
-    for (int q = 0; q < 13; ++q) acc[q] = 0.0;
+    for (int q = 0; q < MAXN + 1; ++q) acc[q] = 0.0;
     double diag = 0.0;
-    const double2 c0 = pc2[R.nbr[0]];
+    const double2 c0 = pc2[SPFEM_NBR(0)];
     double2 ca = c0;
 #pragma unroll
-    for (int f = 0; f < 12; ++f) {
-        if (f < nfan) {
-            double2 cb = c0;                     /* closed ring wraps to neighbour 0 */
-            if (f + 1 < nn) cb = pc2[R.nbr[(f + 1) < 12 ? (f + 1) : 11]];
-            double L[SPFEM_NUNIQUE];
-            @NAME@_core(P, cr.x, cr.y, ca.x, ca.y, cb.x, cb.y, L);
-            diag += L[@A00@];                    /* (test r, trial r)       */
-            acc[f] += L[@A10@];                  /* (test r, trial n_f)     */
-            acc[f + 1] += L[@A20@];              /* (test r, trial n_{f+1}) */
-            ca = cb;
-        }
+    for (int f = 0; f < MAXN; ++f) {
+        if (f >= nfan) break;
+        double2 cb = c0;                         /* closed ring wraps to neighbour 0 */
+        if (f + 1 < nn) cb = pc2[SPFEM_NBR((f + 1) < MAXN ? (f + 1) : MAXN - 1)];
+        double L[SPFEM_NUNIQUE];
+        @NAME@_core(P, cr.x, cr.y, ca.x, ca.y, cb.x, cb.y, L);
+        diag += L[@A00@];                        /* (test r, trial r)       */
+        acc[f] += L[@A10@];                      /* (test r, trial n_f)     */
+        acc[f + 1] += L[@A20@];                  /* (test r, trial n_{f+1}) */
+        ca = cb;
     }
-    if (R.closed) {                              /* the last triangle's n_{f+1} is n_0 */
+    if (closed) {                                /* the last triangle's n_{f+1} is n_0 */
         double wrap = 0.0;
 #pragma unroll
-        for (int q = 1; q < 13; ++q) if (q == nfan) wrap = acc[q];
+        for (int q = 1; q < MAXN + 1; ++q) if (q == nfan) wrap = acc[q];
         acc[0] += wrap;
     }
-    const int s0 = R.s0;
-    sV[s0 + R.posdiag] = diag;
-    sG[s0 + R.posdiag] = R.g0 + R.posdiag;
+    sV[s0 + posdiag] = diag;
+    sG[s0 + posdiag] = g0 + posdiag;
 #pragma unroll
-    for (int q = 0; q < 12; ++q)
-        if (q < nn) {
-            sV[s0 + R.pos[q]] = acc[q];
-            sG[s0 + R.pos[q]] = R.g0 + R.pos[q];
-        }
+    for (int q = 0; q < MAXN; ++q) {
+        if (q >= nn) break;
+        const int ps = (int)SPFEM_POS(q);
+        sV[s0 + ps] = acc[q];
+        sG[s0 + ps] = g0 + ps;
+    }
+#undef SPFEM_NBR
+#undef SPFEM_POS
 }
 #ifndef SPFEM_HOST
-extern "C" __global__ void __launch_bounds__(@FANTHREADS@, @FANMINB@) @NAME@_fan(const SpfemFanArgs T)
+template <int MAXN>
+static __device__ __forceinline__ void @NAME@_fan_tile(const SpfemFanArgs &T)
 {
     extern __shared__ __align__(128) unsigned char spfem_smem_raw[];
     unsigned char *sA = spfem_smem_raw;
@@ -282,9 +300,19 @@ extern "C" __global__ void __launch_bounds__(@FANTHREADS@, @FANMINB@) @NAME@_fan
     __syncthreads();
     spfem_mbar_wait(&bars[0], 0);
     for (int row = threadIdx.x; row < nr; row += blockDim.x)
-        @NAME@_fan_row(T.base, (const double2 *)sA, (const SpfemFanRow *)sB, row, sV, sG);
+        @NAME@_fan_row<MAXN>(T.base, (const double2 *)sA, (const SpfemFanRow *)sB, row, sV, sG);
     __syncthreads();
     for (int s = threadIdx.x; s < ns; s += blockDim.x) T.values[sG[s]] = sV[s];
+}
+/* two instantiations: meshes whose vertices have at most 8 ring neighbours
+   (fewer registers, higher occupancy) and the general case (<= 12)         */
+extern "C" __global__ void __launch_bounds__(@FANTHREADS@, @FANMINB8@) @NAME@_fan8(const SpfemFanArgs T)
+{
+    @NAME@_fan_tile<8>(T);
+}
+extern "C" __global__ void __launch_bounds__(@FANTHREADS@, @FANMINB@) @NAME@_fan(const SpfemFanArgs T)
+{
+    @NAME@_fan_tile<12>(T);
 }
 #else
 extern "C" void @NAME@_fan_host(const SpfemFanArgs *T, int ntiles, double *sV, int *sG)
@@ -293,7 +321,7 @@ extern "C" void @NAME@_fan_host(const SpfemFanArgs *T, int ntiles, double *sV, i
         const int *d = T->desc + 8 * (size_t)t;
         const unsigned char *src = T->blob + (size_t)(unsigned)d[0] * 16;
         for (int row = 0; row < d[3]; ++row)
-            @NAME@_fan_row(T->base, (const double2 *)src, (const SpfemFanRow *)(src + d[1]), row, sV, sG);
+            @NAME@_fan_row<12>(T->base, (const double2 *)src, (const SpfemFanRow *)(src + d[1]), row, sV, sG);
         for (int s = 0; s < d[4]; ++s) T->values[sG[s]] = sV[s];
     }
 }
@@ -765,6 +793,7 @@ def generate_interior(spec, name="spfem_elem"):
         src += ["    " + ln for ln in core]
         src.append("}")
         src.append(FAN_KERNEL.replace("@NAME@", name).replace("@FANTHREADS@", str(FAN_THREADS))
+                   .replace("@FANMINB8@", os.environ.get("SPFEM_FAN_MINB8", "8"))
                    .replace("@FANMINB@", os.environ.get("SPFEM_FAN_MINB", "6"))
                    .replace("@A00@", str(alias[0])).replace("@A10@", str(alias[3]))
                    .replace("@A20@", str(alias[6])))

@@ -551,7 +551,8 @@ class Engine(object):
                 and os.environ.get("SPFEM_FAN", "1") != "0"):
             fp = self.fan_plan(pat)
             if fp is not None:
-                fk = get_kernel(plan.source, plan.name + "_fan")
+                fk = get_kernel(plan.source, plan.name + (
+                    "_fan8" if fp["max_neighbours"] <= 8 else "_fan"))
                 return FanPrepared(self, plan, kernel, fk, a, pat, fp)
         tp = None
         if tind is None and plan.bilinear and self.fused:

@@ -212,6 +212,7 @@ def build_fan_plan(mesh, indptr, indices, rows_per_tile=256):
         "vid": np.concatenate(vids), "pc_index": np.concatenate(pcidx),
         "max_a": int(max_a), "max_b": int(max_b), "max_ns": int(max_ns),
         "halo_factor": float(sum(len(v) for v in vids)) / nv,
+        "max_neighbours": int(nn.max()),
     }
 
 
