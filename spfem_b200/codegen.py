@@ -219,22 +219,37 @@ SPFEM_DEVICE void @NAME@_fan_row(const SpfemArgs &P, const double2 *__restrict__
                                  const SpfemFanRow *__restrict__ rows, const int row,
                                  double *__restrict__ sV, int *__restrict__ sG)
 {
-    /* the 48-byte record as 12 words in registers; fields extracted with shifts */
+    /* the row record in registers (48 bytes; 32 bytes for the <= 8 neighbour
+       layout); fields are extracted with shifts                                */
     unsigned w[12];
-    {
+    int g0, s0, nfan, posdiag;
+    bool closed;
+    if (MAXN <= 8) {
+        const uint4 *rp = reinterpret_cast<const uint4 *>(
+            reinterpret_cast<const unsigned char *>(rows) + (size_t)32 * row);
+        const uint4 r0 = rp[0], r1 = rp[1];
+        /* words 2..5 neighbours, 8..9 positions (same slots as the wide layout) */
+        w[0] = r0.x; w[1] = r0.y; w[2] = r0.z; w[3] = r0.w;
+        w[4] = r1.x; w[5] = r1.y; w[8] = r1.z; w[9] = r1.w;
+        g0 = (int)w[0];
+        s0 = (int)(w[1] & 0xffffu);
+        nfan = (int)((w[1] >> 16) & 0xfu);
+        closed = ((w[1] >> 20) & 0xfu) != 0u;
+        posdiag = (int)((w[1] >> 24) & 0xffu);
+    } else {
         const uint4 *rp = reinterpret_cast<const uint4 *>(rows + row);
         const uint4 r0 = rp[0], r1 = rp[1], r2 = rp[2];
         w[0] = r0.x; w[1] = r0.y; w[2] = r0.z; w[3] = r0.w;
         w[4] = r1.x; w[5] = r1.y; w[6] = r1.z; w[7] = r1.w;
         w[8] = r2.x; w[9] = r2.y; w[10] = r2.z; w[11] = r2.w;
+        g0 = (int)w[0];
+        s0 = (int)(w[1] & 0xffffu);
+        nfan = (int)((w[1] >> 16) & 0xffu);
+        closed = ((w[1] >> 24) & 0xffu) != 0u;
+        posdiag = (int)(w[11] & 0xffu);
     }
 #define SPFEM_NBR(q) ((w[2 + ((q) >> 1)] >> (16 * ((q) & 1))) & 0xffffu)
 #define SPFEM_POS(q) ((w[8 + ((q) >> 2)] >> (8 * ((q) & 3))) & 0xffu)
-    const int g0 = (int)w[0];
-    const int s0 = (int)(w[1] & 0xffffu);
-    const int nfan = (int)((w[1] >> 16) & 0xffu);
-    const bool closed = ((w[1] >> 24) & 0xffu) != 0u;
-    const int posdiag = (int)(w[11] & 0xffu);
     const double2 cr = pc2[row];                 /* rows are the first vertices of a tile */
     const int nn = nfan + (closed ? 0 : 1);      /* ring neighbours */
     double acc[MAXN + 1];
@@ -315,13 +330,16 @@ extern "C" __global__ void __launch_bounds__(@FANTHREADS@, @FANMINB@) @NAME@_fan
     @NAME@_fan_tile<12>(T);
 }
 #else
-extern "C" void @NAME@_fan_host(const SpfemFanArgs *T, int ntiles, double *sV, int *sG)
+extern "C" void @NAME@_fan_host(const SpfemFanArgs *T, int ntiles, double *sV, int *sG, int maxn)
 {
     for (int t = 0; t < ntiles; ++t) {
         const int *d = T->desc + 8 * (size_t)t;
         const unsigned char *src = T->blob + (size_t)(unsigned)d[0] * 16;
         for (int row = 0; row < d[3]; ++row)
-            @NAME@_fan_row<12>(T->base, (const double2 *)src, (const SpfemFanRow *)(src + d[1]), row, sV, sG);
+            if (maxn <= 8)
+                @NAME@_fan_row<8>(T->base, (const double2 *)src, (const SpfemFanRow *)(src + d[1]), row, sV, sG);
+            else
+                @NAME@_fan_row<12>(T->base, (const double2 *)src, (const SpfemFanRow *)(src + d[1]), row, sV, sG);
         for (int s = 0; s < d[4]; ++s) T->values[sG[s]] = sV[s];
     }
 }

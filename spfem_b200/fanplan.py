@@ -26,6 +26,10 @@ ROW_DTYPE = np.dtype([("g0", "<i4"), ("s0", "<u2"), ("nfan", "u1"), ("closed", "
                       ("nbr", "<u2", (12,)), ("pos", "u1", (12,)),
                       ("posdiag", "u1"), ("pad", "u1", (3,))])
 assert ROW_DTYPE.itemsize == 48
+#: compact record for meshes with at most 8 ring neighbours per vertex
+ROW8_DTYPE = np.dtype([("g0", "<i4"), ("s0", "<u2"), ("nfc", "u1"), ("posdiag", "u1"),
+                       ("nbr", "<u2", (8,)), ("pos", "u1", (8,))])
+assert ROW8_DTYPE.itemsize == 32
 MAXN = 12
 
 
@@ -90,16 +94,19 @@ def vertex_rings(mesh):
     if K > MAXN:
         raise FanPlanError("vertex valence %d > %d" % (K, MAXN))
     # start corner: the one without a predecessor (boundary), else the smallest
-    order = np.argsort(corner_vertex, kind="stable")
-    first = np.searchsorted(corner_vertex[order], np.arange(nv))
-    start = order[first]
-    nopred = np.nonzero(~has_prev)[0]
-    start[corner_vertex[nopred]] = nopred
     cnxt = np.take(nxt.reshape(-1), np.arange(3 * nt))          # local index arrays per corner
     cprv = np.take(prv.reshape(-1), np.arange(3 * nt))
     corner_T = np.tile(ar, 3)
     a_of = t[cnxt, corner_T]                      # vertex following r (CCW) in the corner's triangle
     b_of = t[cprv, corner_T]
+    # closed fans start at the neighbour with the smallest polar angle, so that
+    # on a regular mesh the q-th neighbour of every vertex lies in the same
+    # direction (neighbouring threads then read neighbouring coordinates)
+    ang = np.arctan2(p[1][a_of] - p[1][corner_vertex], p[0][a_of] - p[0][corner_vertex])
+    ordk = np.lexsort((ang, corner_vertex))
+    start = ordk[np.searchsorted(corner_vertex[ordk], np.arange(nv))]
+    nopred = np.nonzero(~has_prev)[0]
+    start[corner_vertex[nopred]] = nopred
     nb = np.full((K + 1, nv), -1, dtype=np.int64)
     nfan = np.zeros(nv, dtype=np.int64)
     closed = np.zeros(nv, dtype=bool)
@@ -161,6 +168,8 @@ def build_fan_plan(mesh, indptr, indices, rows_per_tile=256):
     nb12[:kk], pos12[:kk] = nb[:kk], pos[:kk]
     # tiles of Morton-consecutive rows
     vperm = _morton_vertices(p)
+    compact = int(nn.max()) <= 8
+    rdt = ROW8_DTYPE if compact else ROW_DTYPE
     R = int(rows_per_tile)
     ntiles = (nv + R - 1) // R
     loc = np.full(nv, -1, dtype=np.int64)
@@ -170,6 +179,8 @@ def build_fan_plan(mesh, indptr, indices, rows_per_tile=256):
     max_a = max_b = max_ns = 0
     for ti in range(ntiles):
         rows = vperm[ti * R:(ti + 1) * R]
+        # inside the tile: rows along mesh lines (y, then x)
+        rows = rows[np.lexsort((p[0][rows], p[1][rows]))]
         nr = len(rows)
         nbr = nb12[:, rows]                              # (12, nr)
         ok = nbr >= 0
@@ -180,21 +191,28 @@ def build_fan_plan(mesh, indptr, indices, rows_per_tile=256):
         nvt = nr + len(extra)
         if nvt > 65535:
             raise FanPlanError("tile with more than 65535 vertices")
-        rec = np.zeros(nr, dtype=ROW_DTYPE)
+        rec = np.zeros(nr, dtype=rdt)
         rec["g0"] = indptr[rows]
         lens = rowlen[rows]
         s0 = np.cumsum(lens) - lens
         ns = int(lens.sum())
         rec["s0"] = s0
-        rec["nfan"] = nfan[rows]
-        rec["closed"] = closed[rows]
-        rec["nbr"] = np.where(ok, loc[np.where(ok, nbr, 0)], 0).T
-        rec["pos"] = np.where(ok, pos12[:, rows], 0).T
+        nbl = np.where(ok, loc[np.where(ok, nbr, 0)], 0).T
+        psl = np.where(ok, pos12[:, rows], 0).T
+        if compact:
+            rec["nfc"] = nfan[rows] | (closed[rows].astype(np.int64) << 4)
+            rec["nbr"] = nbl[:, :8]
+            rec["pos"] = psl[:, :8]
+        else:
+            rec["nfan"] = nfan[rows]
+            rec["closed"] = closed[rows]
+            rec["nbr"] = nbl
+            rec["pos"] = psl
         rec["posdiag"] = dpos[rows]
         loc[rows] = -1
         loc[extra] = -1
         bytes_a = (nvt * 16 + 15) // 16 * 16
-        bytes_b = nr * 48
+        bytes_b = nr * rdt.itemsize
         desc[ti, :6] = (off // 16, bytes_a, bytes_b, nr, ns, nvt)
         vids.append(np.concatenate((rows, extra)))
         pcidx.append(off // 8 + 2 * np.arange(nvt))

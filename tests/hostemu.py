@@ -146,7 +146,7 @@ def fan_iasm(asm, form, rows_per_tile=64):
     compile_host(plan)
     lib = C.CDLL(os.path.join(_TMP, key + ".so"))
     fn = getattr(lib, plan.name + "_fan_host")
-    fn.argtypes = [C.POINTER(SpfemFanArgs), C.c_int, C.c_void_p, C.c_void_p]
+    fn.argtypes = [C.POINTER(SpfemFanArgs), C.c_int, C.c_void_p, C.c_void_p, C.c_int]
     fn.restype = None
     values = np.full(ref.nnz, np.nan)
     sV = np.zeros(fp["max_ns"] + 16)
@@ -154,7 +154,7 @@ def fan_iasm(asm, form, rows_per_tile=64):
     a = SpfemFanArgs()
     a.desc, a.blob, a.values = _ptr(fp["desc"]), _ptr(fp["blob"]), _ptr(values)
     a.max_a, a.max_b, a.max_ns = fp["max_a"], fp["max_b"], fp["max_ns"]
-    fn(C.byref(a), fp["ntiles"], _ptr(sV), _ptr(sG))
+    fn(C.byref(a), fp["ntiles"], _ptr(sV), _ptr(sG), fp["max_neighbours"])
     out = ref.copy()
     out.data = values
     return out, fp

@@ -68,3 +68,22 @@ def test_fan_plan_rejects_other_patterns():
     assert not asm.plan_iasm(cases.mass).spec.fan_ok
     a1 = AssemblerElement(m, sp.ElementTriP1())
     assert not a1.plan_iasm(cases.mass_x2).spec.fan_ok      # x-dependent coefficient
+
+
+def _wheel_mesh(k=10, refine=2):
+    """A vertex with ``k`` triangles around it (the wide, 12-neighbour record
+    layout and kernel instantiation)."""
+    ang = 2 * np.pi * np.arange(k) / k
+    p = np.hstack((np.zeros((2, 1)), np.vstack((np.cos(ang), np.sin(ang)))))
+    t = np.array([[0, 1 + i, 1 + (i + 1) % k] for i in range(k)]).T
+    m = sp.MeshTri(p, t)
+    m.refine(refine)
+    return m
+
+
+def test_fan_kernel_wide_records():
+    m = _wheel_mesh()
+    asm = AssemblerElement(m, sp.ElementTriP1())
+    out, fp = hostemu.fan_iasm(asm, cases.lap2, rows_per_tile=16)
+    assert fp["max_neighbours"] == 10
+    cases.compare_csr(out, hostemu.iasm(asm, cases.lap2))

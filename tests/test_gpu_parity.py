@@ -187,3 +187,17 @@ def test_vertex_fan_irregular_mesh_and_refresh():
     a._get_engine().upload_mesh()
     prep.launch()
     cases.compare_csr(prep.result(), asm_oracle.iasm(m, "TriP1", form))
+
+
+def test_vertex_fan_wide_records():
+    """Valence-10 vertex: the 12-neighbour instantiation / 48-byte records."""
+    import asm_oracle
+    from test_fanplan import _wheel_mesh
+    from spfem_b200.assembly import AssemblerElement
+    import spfem_b200 as sp
+    m = _wheel_mesh(10, 3)
+    a = AssemblerElement(m, sp.ElementTriP1())
+    prep = a.prepare_iasm(cases.lap2)
+    assert type(prep).__name__ == "FanPrepared" and prep.fp["max_neighbours"] == 10
+    prep.launch()
+    cases.compare_csr(prep.result(), asm_oracle.iasm(m, "TriP1", cases.lap2))
