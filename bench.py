@@ -51,7 +51,7 @@ def algorithmic_bytes(nt, nv, nnz, nve=3, dim=2):
 # clocks
 # ---------------------------------------------------------------------------
 class ClockSampler(threading.Thread):
-    def __init__(self, index=0, period=0.01):
+    def __init__(self, index=0, period=0.002):
         threading.Thread.__init__(self, daemon=True)
         self.index, self.period = index, period
         self.samples, self.reasons = [], set()
@@ -268,7 +268,11 @@ def run_gpu_arm(args):
     t_red = np.mean([ev[s][1 + 2 * i].elapsed_time(ev[s][2 + 2 * i])
                      for s in range(args.steps) for i in range(len(preps))])
     if fused:
-        kernels = {"spfem_elem_tile_ms": float(t_red)}
+        kname = {"FanPrepared": "spfem_elem_fan", "TiledPrepared": "spfem_elem_tile"}.get(
+            type(preps[0]).__name__, "fused")
+        if kname == "spfem_elem_fan" and preps[0].fp["max_neighbours"] <= 8:
+            kname = "spfem_elem_fan8"
+        kernels = {kname + "_ms": float(t_red)}
         t_elem = 0.0
     else:
         kernels = {"spfem_elem_ms": float(t_elem), "k_reduce_ms": float(t_red)}
@@ -359,10 +363,12 @@ def run_gpu_arm(args):
                      "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                      "peak_source": peak_src,
                      "kernels": kernels, "fused": bool(fused),
-                     "tile": ({"E": preps[0].tp["E"], "ldl": preps[0].tp["ldl"],
+                     "tile": ({"kind": preps[0].tp.get("kind", "element-tile"),
+                               "E": preps[0].tp["E"], "ldl": preps[0].tp["ldl"],
                                "ntiles": preps[0].tp["ntiles"],
                                "halo_factor": preps[0].tp["halo_factor"],
-                               "smem_bytes": preps[0].smem} if fused else None),
+                               "smem_bytes": preps[0].smem,
+                               "threads": preps[0].threads} if fused else None),
                      "algorithmic_bytes_per_assembly": balg},
         "cpu_baseline": cpu,
         "e2e": {"value": e2e_value, "unit": UNIT, "steps": e2e_steps,

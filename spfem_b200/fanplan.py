@@ -166,70 +166,85 @@ def build_fan_plan(mesh, indptr, indices, rows_per_tile=256):
     pos12 = np.zeros((MAXN, nv), dtype=np.int64)
     kk = min(K1, MAXN)
     nb12[:kk], pos12[:kk] = nb[:kk], pos[:kk]
-    # tiles of Morton-consecutive rows
-    vperm = _morton_vertices(p)
+    # tiles of Morton-consecutive rows; inside a tile the rows follow mesh lines
     compact = int(nn.max()) <= 8
     rdt = ROW8_DTYPE if compact else ROW_DTYPE
+    W = 8 if compact else MAXN
     R = int(rows_per_tile)
     ntiles = (nv + R - 1) // R
-    loc = np.full(nv, -1, dtype=np.int64)
+    vperm = _morton_vertices(p)
+    tile_of_pos = np.arange(nv) // R
+    order = np.lexsort((p[0][vperm], p[1][vperm], tile_of_pos))
+    rows = vperm[order]                                   # all rows, tile after tile
+    tile_of_row = tile_of_pos                             # (positions are tile-major)
+    nr = np.bincount(tile_of_row, minlength=ntiles)
+    r0 = np.cumsum(nr) - nr
+    row_local = np.arange(nv) - r0[tile_of_row]
+    tile_of_vertex = np.empty(nv, dtype=np.int64)
+    tile_of_vertex[rows] = tile_of_row
+    local_of_vertex = np.empty(nv, dtype=np.int64)
+    local_of_vertex[rows] = row_local
+    # ring neighbours of every row, (W, nv) in row order
+    nbr = nb12[:W, rows]
+    ok = nbr >= 0
+    nbr0 = np.where(ok, nbr, 0)
+    tl = np.broadcast_to(tile_of_row, nbr.shape)
+    inside = ok & (tile_of_vertex[nbr0] == tl)
+    # halo vertices: unique (tile, vertex) pairs that are not rows of the tile
+    hk = (tl[ok & ~inside] * nv + nbr[ok & ~inside])
+    uh = np.unique(hk)
+    h_tile = uh // nv
+    nh = np.bincount(h_tile, minlength=ntiles)
+    h0 = np.cumsum(nh) - nh
+    nvt = nr + nh
+    if int(nvt.max()) > 65535:
+        raise FanPlanError("tile with more than 65535 vertices")
+    loc = np.zeros(nbr.shape, dtype=np.int64)
+    loc[inside] = local_of_vertex[nbr[inside]]
+    out = ok & ~inside
+    hidx = np.searchsorted(uh, tl[out] * nv + nbr[out])
+    loc[out] = nr[tl[out]] + (hidx - h0[tl[out]])
+    # row records
+    rec = np.zeros(nv, dtype=rdt)
+    lens = rowlen[rows]
+    ns = np.bincount(tile_of_row, weights=lens, minlength=ntiles).astype(np.int64)
+    cl = np.cumsum(lens) - lens
+    rec["g0"] = indptr[rows]
+    rec["s0"] = cl - cl[r0[tile_of_row]]
+    psl = np.where(ok, pos12[:W, rows], 0).T
+    if compact:
+        rec["nfc"] = nfan[rows] | (closed[rows].astype(np.int64) << 4)
+    else:
+        rec["nfan"] = nfan[rows]
+        rec["closed"] = closed[rows]
+    rec["nbr"] = loc.T
+    rec["pos"] = psl
+    rec["posdiag"] = dpos[rows]
+    # blob layout
+    bytes_a = (nvt * 16 + 15) // 16 * 16
+    bytes_b = nr * rdt.itemsize
+    tb = bytes_a + bytes_b
+    off = np.cumsum(tb) - tb
+    total = int(tb.sum())
+    blob = np.zeros(total, dtype=np.uint8)
+    dest = (off + bytes_a)[tile_of_row] + rdt.itemsize * row_local
+    blob[dest[:, None] + np.arange(rdt.itemsize)[None, :]] = rec.view(np.uint8).reshape(nv, rdt.itemsize)
     desc = np.zeros((ntiles, 8), dtype=np.int64)
-    recs, vids, pcidx = [], [], []
-    off = 0
-    max_a = max_b = max_ns = 0
-    for ti in range(ntiles):
-        rows = vperm[ti * R:(ti + 1) * R]
-        # inside the tile: rows along mesh lines (y, then x)
-        rows = rows[np.lexsort((p[0][rows], p[1][rows]))]
-        nr = len(rows)
-        nbr = nb12[:, rows]                              # (12, nr)
-        ok = nbr >= 0
-        loc[rows] = np.arange(nr)
-        cand = np.unique(nbr[ok])
-        extra = cand[loc[cand] < 0]
-        loc[extra] = nr + np.arange(len(extra))
-        nvt = nr + len(extra)
-        if nvt > 65535:
-            raise FanPlanError("tile with more than 65535 vertices")
-        rec = np.zeros(nr, dtype=rdt)
-        rec["g0"] = indptr[rows]
-        lens = rowlen[rows]
-        s0 = np.cumsum(lens) - lens
-        ns = int(lens.sum())
-        rec["s0"] = s0
-        nbl = np.where(ok, loc[np.where(ok, nbr, 0)], 0).T
-        psl = np.where(ok, pos12[:, rows], 0).T
-        if compact:
-            rec["nfc"] = nfan[rows] | (closed[rows].astype(np.int64) << 4)
-            rec["nbr"] = nbl[:, :8]
-            rec["pos"] = psl[:, :8]
-        else:
-            rec["nfan"] = nfan[rows]
-            rec["closed"] = closed[rows]
-            rec["nbr"] = nbl
-            rec["pos"] = psl
-        rec["posdiag"] = dpos[rows]
-        loc[rows] = -1
-        loc[extra] = -1
-        bytes_a = (nvt * 16 + 15) // 16 * 16
-        bytes_b = nr * rdt.itemsize
-        desc[ti, :6] = (off // 16, bytes_a, bytes_b, nr, ns, nvt)
-        vids.append(np.concatenate((rows, extra)))
-        pcidx.append(off // 8 + 2 * np.arange(nvt))
-        recs.append((off + bytes_a, rec))
-        off += bytes_a + bytes_b
-        max_a, max_b, max_ns = max(max_a, bytes_a), max(max_b, bytes_b), max(max_ns, ns)
-    blob = np.zeros(off, dtype=np.uint8)
-    for o, rec in recs:
-        blob[o:o + rec.nbytes] = rec.view(np.uint8)
+    desc[:, 0], desc[:, 1], desc[:, 2] = off // 16, bytes_a, bytes_b
+    desc[:, 3], desc[:, 4], desc[:, 5] = nr, ns, nvt
     if desc.max() > 2 ** 31 - 1:
         raise FanPlanError("fan plan offsets exceed 32 bits")
+    # tile vertex lists: the rows first, then the halo vertices
+    vid = np.concatenate((rows, uh % nv))
+    vtile = np.concatenate((tile_of_row, h_tile))
+    vloc = np.concatenate((row_local, nr[h_tile] + np.arange(len(uh)) - h0[h_tile]))
+    pc_index = off[vtile] // 8 + 2 * vloc
     return {
         "ntiles": ntiles, "rows_per_tile": R,
         "desc": desc.astype(np.int32), "blob": blob,
-        "vid": np.concatenate(vids), "pc_index": np.concatenate(pcidx),
-        "max_a": int(max_a), "max_b": int(max_b), "max_ns": int(max_ns),
-        "halo_factor": float(sum(len(v) for v in vids)) / nv,
+        "vid": vid, "pc_index": pc_index,
+        "max_a": int(bytes_a.max()), "max_b": int(bytes_b.max()), "max_ns": int(ns.max()),
+        "halo_factor": float(nvt.sum()) / nv,
         "max_neighbours": int(nn.max()),
     }
 
