@@ -49,6 +49,7 @@ PRELUDE = r"""
 #define __restrict__
 struct double2 { double x, y; };
 struct uint4 { unsigned x, y, z, w; };
+struct uint2 { unsigned x, y; };
 #else
 #define SPFEM_DEVICE static __device__ __forceinline__
 #endif
@@ -212,44 +213,31 @@ struct SpfemFanArgs {
     const int *desc;              /* 8 ints per tile: off16, bytes A, bytes B, nr, ns, nvt */
     const unsigned char *blob;
     double *values;
-    int max_a, max_b, max_ns;
+    int max_a, max_b, max_ns, prefetch;
 };
 template <int MAXN>
 SPFEM_DEVICE void @NAME@_fan_row(const SpfemArgs &P, const double2 *__restrict__ pc2,
-                                 const SpfemFanRow *__restrict__ rows, const int row,
-                                 double *__restrict__ sV, int *__restrict__ sG)
+                                 const unsigned char *__restrict__ rec, const int nr,
+                                 const int row, double *__restrict__ sV, int *__restrict__ sG)
 {
-    /* the row record in registers (48 bytes; 32 bytes for the <= 8 neighbour
-       layout); fields are extracted with shifts                                */
-    unsigned w[12];
-    int g0, s0, nfan, posdiag;
-    bool closed;
-    if (MAXN <= 8) {
-        const uint4 *rp = reinterpret_cast<const uint4 *>(
-            reinterpret_cast<const unsigned char *>(rows) + (size_t)32 * row);
-        const uint4 r0 = rp[0], r1 = rp[1];
-        /* words 2..5 neighbours, 8..9 positions (same slots as the wide layout) */
-        w[0] = r0.x; w[1] = r0.y; w[2] = r0.z; w[3] = r0.w;
-        w[4] = r1.x; w[5] = r1.y; w[8] = r1.z; w[9] = r1.w;
-        g0 = (int)w[0];
-        s0 = (int)(w[1] & 0xffffu);
-        nfan = (int)((w[1] >> 16) & 0xfu);
-        closed = ((w[1] >> 20) & 0xfu) != 0u;
-        posdiag = (int)((w[1] >> 24) & 0xffu);
-    } else {
-        const uint4 *rp = reinterpret_cast<const uint4 *>(rows + row);
-        const uint4 r0 = rp[0], r1 = rp[1], r2 = rp[2];
-        w[0] = r0.x; w[1] = r0.y; w[2] = r0.z; w[3] = r0.w;
-        w[4] = r1.x; w[5] = r1.y; w[6] = r1.z; w[7] = r1.w;
-        w[8] = r2.x; w[9] = r2.y; w[10] = r2.z; w[11] = r2.w;
-        g0 = (int)w[0];
-        s0 = (int)(w[1] & 0xffffu);
-        nfan = (int)((w[1] >> 16) & 0xffu);
-        closed = ((w[1] >> 24) & 0xffu) != 0u;
-        posdiag = (int)(w[11] & 0xffu);
+    /* row record planes -> registers; 16-bit neighbour ids extracted with shifts */
+    unsigned w[8];
+    {
+        const uint4 h = reinterpret_cast<const uint4 *>(rec)[row];
+        w[0] = h.x; w[1] = h.y; w[2] = h.z; w[3] = h.w;
+        if (MAXN <= 8) {
+            const uint2 n1 = reinterpret_cast<const uint2 *>(rec + (size_t)16 * nr)[row];
+            w[4] = n1.x; w[5] = n1.y; w[6] = 0u; w[7] = 0u;
+        } else {
+            const uint4 n1 = reinterpret_cast<const uint4 *>(rec + (size_t)16 * nr)[row];
+            w[4] = n1.x; w[5] = n1.y; w[6] = n1.z; w[7] = n1.w;
+        }
     }
 #define SPFEM_NBR(q) ((w[2 + ((q) >> 1)] >> (16 * ((q) & 1))) & 0xffffu)
-#define SPFEM_POS(q) ((w[8 + ((q) >> 2)] >> (8 * ((q) & 3))) & 0xffu)
+    const int gd = (int)w[0];                    /* CSR position - tile slot, of the row */
+    const int s0 = (int)(w[1] & 0xffffu);
+    const int nfan = (int)((w[1] >> 16) & 0xffu);
+    const bool closed = ((w[1] >> 24) & 0xffu) != 0u;
     const double2 cr = pc2[row];                 /* rows are the first vertices of a tile */
     const int nn = nfan + (closed ? 0 : 1);      /* ring neighbours */
     double acc[MAXN + 1];
@@ -276,48 +264,54 @@ SPFEM_DEVICE void @NAME@_fan_row(const SpfemArgs &P, const double2 *__restrict__
         for (int q = 1; q < MAXN + 1; ++q) if (q == nfan) wrap = acc[q];
         acc[0] += wrap;
     }
-    sV[s0 + posdiag] = diag;
-    sG[s0 + posdiag] = g0 + posdiag;
+    /* staged in RING order (slot s0 = diagonal, s0 + 1 + q = neighbour q): the
+       lanes of a warp write with a fixed stride, free of bank conflicts; the
+       store phase maps CSR order to ring order with one byte per slot          */
+    sV[s0] = diag;
+    sG[s0] = gd;
 #pragma unroll
     for (int q = 0; q < MAXN; ++q) {
         if (q >= nn) break;
-        const int ps = (int)SPFEM_POS(q);
-        sV[s0 + ps] = acc[q];
-        sG[s0 + ps] = g0 + ps;
+        sV[s0 + 1 + q] = acc[q];
+        sG[s0 + 1 + q] = gd;
     }
 #undef SPFEM_NBR
-#undef SPFEM_POS
 }
 #ifndef SPFEM_HOST
 template <int MAXN>
 static __device__ __forceinline__ void @NAME@_fan_tile(const SpfemFanArgs &T)
 {
     extern __shared__ __align__(128) unsigned char spfem_smem_raw[];
-    unsigned char *sA = spfem_smem_raw;
-    unsigned char *sB = sA + T.max_a;
-    double *sV = (double *)(sB + T.max_b);
+    unsigned char *sA = spfem_smem_raw;                       /* the tile's blob */
+    double *sV = (double *)(sA + T.max_a);
     unsigned long long *bars = (unsigned long long *)(sV + T.max_ns);
     int *sG = (int *)(bars + 2);
     const int *d = T.desc + 8 * (size_t)blockIdx.x;
-    const int bytes_a = d[1], bytes_b = d[2], nr = d[3], ns = d[4];
+    const int bytes_a = d[1], bytes_b = d[2], nr = d[3], ns = d[4], bytes_c = d[6];
     if (nr == 0) return;
     if (threadIdx.x == 0) {
         spfem_mbar_init(&bars[0], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        const unsigned char *src = T.blob + (size_t)(unsigned)d[0] * 16;
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
-                     ::"r"(spfem_smem(&bars[0])), "r"((unsigned)(bytes_a + bytes_b)) : "memory");
-        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                     ::"r"(spfem_smem(sA)), "l"(src), "r"((unsigned)bytes_a), "r"(spfem_smem(&bars[0])) : "memory");
-        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                     ::"r"(spfem_smem(sB)), "l"(src + bytes_a), "r"((unsigned)bytes_b), "r"(spfem_smem(&bars[0])) : "memory");
+        spfem_bulk_load(sA, T.blob + (size_t)(unsigned)d[0] * 16,
+                        (unsigned)(bytes_a + bytes_b + bytes_c), &bars[0]);
+        /* pull the blob of a tile that will start a few waves later into L2, so
+           its own TMA load does not pay the DRAM latency                       */
+        const long long tp = (long long)blockIdx.x + T.prefetch;
+        if (T.prefetch > 0 && tp < (long long)gridDim.x) {
+            const int *dp = T.desc + 8 * (size_t)tp;
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;"
+                         ::"l"(T.blob + (size_t)(unsigned)dp[0] * 16),
+                           "r"((unsigned)(dp[1] + dp[2] + dp[6])) : "memory");
+        }
     }
     __syncthreads();
     spfem_mbar_wait(&bars[0], 0);
     for (int row = threadIdx.x; row < nr; row += blockDim.x)
-        @NAME@_fan_row<MAXN>(T.base, (const double2 *)sA, (const SpfemFanRow *)sB, row, sV, sG);
+        @NAME@_fan_row<MAXN>(T.base, (const double2 *)sA, sA + bytes_a, nr, row, sV, sG);
     __syncthreads();
-    for (int s = threadIdx.x; s < ns; s += blockDim.x) T.values[sG[s]] = sV[s];
+    const signed char *dl = (const signed char *)(sA + bytes_a + bytes_b);
+    for (int s = threadIdx.x; s < ns; s += blockDim.x)
+        T.values[sG[s] + s] = sV[s + (int)dl[s]];
 }
 /* two instantiations: meshes whose vertices have at most 8 ring neighbours
    (fewer registers, higher occupancy) and the general case (<= 12)         */
@@ -335,12 +329,14 @@ extern "C" void @NAME@_fan_host(const SpfemFanArgs *T, int ntiles, double *sV, i
     for (int t = 0; t < ntiles; ++t) {
         const int *d = T->desc + 8 * (size_t)t;
         const unsigned char *src = T->blob + (size_t)(unsigned)d[0] * 16;
-        for (int row = 0; row < d[3]; ++row)
+        for (int row = 0; row < d[3]; ++row) {
             if (maxn <= 8)
-                @NAME@_fan_row<8>(T->base, (const double2 *)src, (const SpfemFanRow *)(src + d[1]), row, sV, sG);
+                @NAME@_fan_row<8>(T->base, (const double2 *)src, src + d[1], d[3], row, sV, sG);
             else
-                @NAME@_fan_row<12>(T->base, (const double2 *)src, (const SpfemFanRow *)(src + d[1]), row, sV, sG);
-        for (int s = 0; s < d[4]; ++s) T->values[sG[s]] = sV[s];
+                @NAME@_fan_row<12>(T->base, (const double2 *)src, src + d[1], d[3], row, sV, sG);
+        }
+        const signed char *dl = (const signed char *)(src + d[1] + d[2]);
+        for (int s = 0; s < d[4]; ++s) T->values[sG[s] + s] = sV[s + (int)dl[s]];
     }
 }
 #endif

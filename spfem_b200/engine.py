@@ -327,8 +327,10 @@ class FanPrepared(Prepared):
         fa.blob = fp["blob"].data_ptr()
         fa.values = self.values.data_ptr()
         fa.max_a, fa.max_b, fa.max_ns = fp["max_a"], fp["max_b"], fp["max_ns"]
+        # L2 prefetch distance in tiles (about two waves of resident CTAs ahead)
+        fa.prefetch = int(os.environ.get("SPFEM_FAN_PREFETCH", "2400"))
         self.fargs = fa
-        self.smem = fp["max_a"] + fp["max_b"] + 12 * fp["max_ns"] + 64
+        self.smem = fp["max_a"] + 12 * fp["max_ns"] + 64
         from . import codegen
         self.threads = codegen.FAN_THREADS
         self.n_launches = 1

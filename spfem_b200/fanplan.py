@@ -12,13 +12,17 @@ module builds, once per mesh (host NumPy; set-up, not the hot path):
   mesh's own topology (``t2f`` / ``f2t``),
 * tiles of ``R`` Morton-consecutive rows with their tile-local vertex numbering
   (the rows themselves first, then the halo vertices),
-* one 16-byte aligned blob per tile: section A = interleaved ``(x, y)``
-  coordinates of the tile's vertices, section B = one 48-byte record per row
-  (``SpfemFanRow``: CSR position, tile slot offset, fan size, open/closed ring,
-  ring neighbours as tile-local ids, CSR position of every neighbour).
+* one 16-byte aligned blob per tile (brought into shared memory by one TMA
+  bulk copy): section A = interleaved ``(x, y)`` coordinates of the tile's
+  vertices; section B = the row records as planes (structure of arrays, so the
+  threads of a warp read consecutive 16 / 8 byte words): plane 0 =
+  ``{g0 - s0, s0 | nfan << 16 | closed << 24, nbr0..3}``, plane 1 = further
+  ring neighbours (tile-local vertex ids, 16 bit); section C = one signed byte
+  per tile slot: where (relative to the slot) the kernel's ring-ordered
+  staging holds the value of that CSR slot.
 
 Descriptor per tile (int32 x 8): blob offset / 16, bytes A, bytes B, rows,
-slots, vertices, 0, 0.
+slots, vertices, bytes C, 0.
 """
 import numpy as np
 
@@ -204,34 +208,53 @@ def build_fan_plan(mesh, indptr, indices, rows_per_tile=256):
     out = ok & ~inside
     hidx = np.searchsorted(uh, tl[out] * nv + nbr[out])
     loc[out] = nr[tl[out]] + (hidx - h0[tl[out]])
-    # row records
-    rec = np.zeros(nv, dtype=rdt)
+    # row records, as planes
     lens = rowlen[rows]
     ns = np.bincount(tile_of_row, weights=lens, minlength=ntiles).astype(np.int64)
     cl = np.cumsum(lens) - lens
-    rec["g0"] = indptr[rows]
-    rec["s0"] = cl - cl[r0[tile_of_row]]
-    psl = np.where(ok, pos12[:W, rows], 0).T
-    if compact:
-        rec["nfc"] = nfan[rows] | (closed[rows].astype(np.int64) << 4)
-    else:
-        rec["nfan"] = nfan[rows]
-        rec["closed"] = closed[rows]
-    rec["nbr"] = loc.T
-    rec["pos"] = psl
-    rec["posdiag"] = dpos[rows]
+    s0 = cl - cl[r0[tile_of_row]]
+    head = np.zeros((nv, 2), dtype=np.int64)
+    head[:, 0] = indptr[rows] - s0                       # CSR position minus tile slot
+    head[:, 1] = s0 | (nfan[rows] << 16) | (closed[rows].astype(np.int64) << 24)
+    nb16 = loc.T.astype(np.uint16)                         # (nv, W) tile-local neighbour ids
+    plane0 = np.zeros((nv, 16), dtype=np.uint8)
+    plane0[:, :8] = head.astype(np.int32).view(np.uint8).reshape(nv, 8)
+    plane0[:, 8:] = nb16[:, :4].copy().view(np.uint8).reshape(nv, 8)
+    w1 = 8 if compact else 16                              # bytes per row in plane 1
+    plane1 = np.zeros((nv, w1), dtype=np.uint8)
+    plane1[:, :2 * (W - 4)] = nb16[:, 4:].copy().view(np.uint8).reshape(nv, 2 * (W - 4))
+    # section C: ring-ordered staging -> CSR order.  Ring position 0 = diagonal,
+    # 1 + q = q-th ring neighbour.
+    nslots = int(lens.sum())
+    slot_row = np.repeat(np.arange(nv), lens)              # (row order) row of every tile slot
+    slot_j = np.arange(nslots) - cl[slot_row]              # CSR position inside the row
+    ringpos = np.zeros(nslots, dtype=np.int64)             # ring position of CSR slot j
+    psl = np.where(ok, pos12[:W, rows], -1)                # (W, nv) CSR position of neighbour q
+    qq, rr = np.nonzero(psl >= 0)
+    ringpos[cl[rr] + psl[qq, rr]] = 1 + qq
+    ringpos[cl + dpos[rows]] = 0
+    delta = (ringpos - slot_j).astype(np.int8)
     # blob layout
     bytes_a = (nvt * 16 + 15) // 16 * 16
-    bytes_b = nr * rdt.itemsize
-    tb = bytes_a + bytes_b
+    bytes_p0 = nr * 16
+    bytes_p1 = (nr * w1 + 15) // 16 * 16
+    bytes_b = bytes_p0 + bytes_p1
+    bytes_c = (ns + 15) // 16 * 16
+    tb = bytes_a + bytes_b + bytes_c
     off = np.cumsum(tb) - tb
     total = int(tb.sum())
     blob = np.zeros(total, dtype=np.uint8)
-    dest = (off + bytes_a)[tile_of_row] + rdt.itemsize * row_local
-    blob[dest[:, None] + np.arange(rdt.itemsize)[None, :]] = rec.view(np.uint8).reshape(nv, rdt.itemsize)
+    d0 = (off + bytes_a)[tile_of_row] + 16 * row_local
+    blob[d0[:, None] + np.arange(16)[None, :]] = plane0
+    d1 = (off + bytes_a + bytes_p0)[tile_of_row] + w1 * row_local
+    blob[d1[:, None] + np.arange(w1)[None, :]] = plane1
+    slot_tile = tile_of_row[slot_row]
+    s_first = np.cumsum(ns) - ns
+    blob[(off + bytes_a + bytes_b)[slot_tile] + (np.arange(nslots) - s_first[slot_tile])] = \
+        delta.view(np.uint8)
     desc = np.zeros((ntiles, 8), dtype=np.int64)
     desc[:, 0], desc[:, 1], desc[:, 2] = off // 16, bytes_a, bytes_b
-    desc[:, 3], desc[:, 4], desc[:, 5] = nr, ns, nvt
+    desc[:, 3], desc[:, 4], desc[:, 5], desc[:, 6] = nr, ns, nvt, bytes_c
     if desc.max() > 2 ** 31 - 1:
         raise FanPlanError("fan plan offsets exceed 32 bits")
     # tile vertex lists: the rows first, then the halo vertices
@@ -243,7 +266,7 @@ def build_fan_plan(mesh, indptr, indices, rows_per_tile=256):
         "ntiles": ntiles, "rows_per_tile": R,
         "desc": desc.astype(np.int32), "blob": blob,
         "vid": vid, "pc_index": pc_index,
-        "max_a": int(bytes_a.max()), "max_b": int(bytes_b.max()), "max_ns": int(ns.max()),
+        "max_a": int(tb.max()), "max_b": 0, "max_ns": int(ns.max()),
         "halo_factor": float(nvt.sum()) / nv,
         "max_neighbours": int(nn.max()),
     }

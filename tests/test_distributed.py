@@ -25,6 +25,10 @@ def test_partitioned_assembly_matches_reference(world):
            "--master-port", str(_free_port()),
            os.path.join(HERE, "dist_worker.py")]
     env = dict(os.environ, OMP_NUM_THREADS="1")
-    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
+    for attempt in range(2):                     # (a rendezvous port can be taken: retry once)
+        cmd[cmd.index("--master-port") + 1] = str(_free_port())
+        out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
+        if out.returncode == 0:
+            break
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
     assert out.stdout.count("dist ok") == 7 and out.stdout.count("strip ok") == 3, out.stdout
