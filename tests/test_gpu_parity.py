@@ -201,3 +201,47 @@ def test_vertex_fan_wide_records():
     assert type(prep).__name__ == "FanPrepared" and prep.fp["max_neighbours"] == 10
     prep.launch()
     cases.compare_csr(prep.result(), asm_oracle.iasm(m, "TriP1", cases.lap2))
+
+
+def test_empty_and_ragged_inputs():
+    """Empty element / facet subsets give all-zero results of the right shape;
+    boolean masks and unsorted, repeated index lists behave like the reference
+    (every listed element is integrated once per occurrence)."""
+    import spfem_b200 as sp
+    from spfem_b200.assembly import AssemblerElement
+    import asm_oracle
+    m = sp.MeshTri()
+    m.refine(3)
+    a = AssemblerElement(m, sp.ElementTriP1())
+    A = a.iasm(cases.lap2, tind=np.zeros(0, dtype=np.int64))
+    assert A.shape == (81, 81) and A.nnz == 0 and A.indptr.dtype == np.int32
+    f = a.iasm(cases.load1, tind=np.zeros(0, dtype=np.int64))
+    assert f.shape == (81,) and not f.any()
+    B = a.fasm(cases.bnd_mass, find=np.zeros(0, dtype=np.int64))
+    assert B.shape == (81, 81) and B.nnz == 0
+    tind = np.array([5, 3, 3, 100, 7])
+    cases.compare_csr(a.iasm(cases.mass, tind=tind),
+                      asm_oracle.iasm(m, "TriP1", cases.mass, tind=tind))
+    mask = np.zeros(m.t.shape[1], dtype=bool)
+    mask[::5] = True
+    cases.compare_csr(a.iasm(cases.mass, tind=mask),
+                      asm_oracle.iasm(m, "TriP1", cases.mass, tind=np.nonzero(mask)[0]))
+
+
+def test_intorder_variants_and_quadrature_limits():
+    import spfem_b200 as sp
+    from spfem_b200.assembly import AssemblerElement
+    import asm_oracle
+    m = sp.MeshTri()
+    m.refine(2)
+    a = AssemblerElement(m, sp.ElementTriP2())
+    for order in (1, 2, 7, 12, 19):
+        cases.compare_csr(a.iasm(cases.mass_x2, intorder=order),
+                          asm_oracle.iasm(m, "TriP2", cases.mass_x2, intorder=order))
+    with pytest.raises(NotImplementedError):
+        a.iasm(cases.mass, intorder=20)
+    mt = sp.MeshTet()
+    mt.refine(1)
+    at = AssemblerElement(mt, sp.ElementTetP1())
+    with pytest.raises(NotImplementedError):
+        at.iasm(cases.mass, intorder=5)
