@@ -48,6 +48,8 @@ typedef struct SpfemArgs {
     double *out;             /* local entries out[entry*ldo + k*ldk]              */
     long long ldk;           /* 1: entry-major planes; Nu*Nv (with ldo = 1):       */
                              /* element-major local matrices                        */
+    const int *perm;         /* optional: entry id -> position in slot-sorted order */
+                             /* (out[perm[entry*ldo + k]]), see spfem_reduce_sorted */
 } SpfemArgs;
 
 int         spfem_abi_version(void);
@@ -113,6 +115,11 @@ int spfem_pattern_fill(const void *d_ws, long long n_entries,
 int spfem_reduce(const double *d_local, const int *d_cptr,
                  const int *d_contrib, long long nslots, double *d_values,
                  void *stream);
+
+/* Same sum for local entries that the element kernel already wrote in slot-sorted
+ * order (SpfemArgs.perm): d_values[s] = sum d_sorted[cptr[s] .. cptr[s+1]).      */
+int spfem_reduce_sorted(const double *d_sorted, const int *d_cptr, long long nslots,
+                        double *d_values, void *stream);
 
 /* ---- bank-conflict-free schedule of the fused kernel's row reductions ------
  * Set-up step of the tile plan (spfem_b200/tileplan.py).  For every group of

@@ -31,6 +31,7 @@ class SpfemArgs(C.Structure):
         ("lf1", C.c_void_p),
         ("out", C.c_void_p),
         ("ldk", C.c_longlong),
+        ("perm", C.c_void_p),
     ]
 
 
@@ -84,6 +85,8 @@ SYMBOLS = {
                                      C.c_void_p, C.c_void_p, C.c_void_p]),
     "spfem_reduce": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p,
                                C.c_longlong, C.c_void_p, C.c_void_p]),
+    "spfem_reduce_sorted": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p,
+                                      C.c_void_p]),
     "spfem_schedule_rows": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                       C.c_void_p, C.c_void_p, C.c_longlong, C.c_int,
                                       C.c_int, C.c_int, C.c_void_p, C.c_void_p,

@@ -70,6 +70,7 @@ struct SpfemArgs {
     const int *lf1;           /* facet kernels: local facet index inside e1     */
     double *out;              /* out[entry*ldo + k*ldk]                         */
     long long ldk;
+    const int *perm;          /* optional: entry id -> slot-sorted position     */
 };
 """
 
@@ -771,7 +772,7 @@ def generate_interior(spec, name="spfem_elem"):
         body.append("{ const double val = %s;" % expr)
         body.append("  if (TILED) { out[(long long)%d * ldo + k] = val; } else {" % u)
         for idx in idxs:
-            body.append("    out[(long long)%d * ldo + k] = val;" % idx)
+            body.append("    SPFEM_PUT(%d, val);" % idx)
         body.append("  } }")
     spec.alias = alias
     spec.n_unique = len(order_u)
@@ -788,6 +789,10 @@ def generate_interior(spec, name="spfem_elem"):
     src = [PRELUDE, DEVICE_HELPERS]
     src.append("#define SPFEM_NENTRIES %d" % spec.n_entries)
     src.append("#define SPFEM_NUNIQUE %d" % spec.n_unique)
+    # store of one local entry in the two-kernel route: entry-major position, or
+    # (P.perm) its position in slot-sorted order
+    src.append("#define SPFEM_PUT(idx, val) do { const long long a_ = (long long)(idx) * ldo + k; "
+               "out[P.perm ? (long long)P.perm[a_] : a_] = (val); } while (0)")
     # body<TILED>(P, e, vt, ldv, ev, pc, ldpc, out, ldo, k): local matrix of
     # element e whose vertex ids are vt[r*ldv + ev]  ->  out[idx*ldo + k]
     # (TILED: only the distinct values, out[alias*ldo + k])

@@ -156,6 +156,19 @@ k_reduce(const double *__restrict__ local, const int *__restrict__ cptr,
     values[s] = acc;
 }
 
+// values[s] = sum of a contiguous run of slot-sorted local entries.
+__global__ void __launch_bounds__(256)
+k_reduce_sorted(const double *__restrict__ sorted, const int *__restrict__ cptr,
+                long long nslots, double *__restrict__ values)
+{
+    long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= nslots) return;
+    int b = cptr[s], e = cptr[s + 1];
+    double acc = 0.0;
+    for (int k = b; k < e; ++k) acc += sorted[k];
+    values[s] = acc;
+}
+
 __device__ __forceinline__ unsigned long long spread2(unsigned long long x)
 {   // 32 bits -> every second bit
     x &= 0xffffffffull;
@@ -742,6 +755,17 @@ int spfem_schedule_rows(const int *idx, const unsigned char *endf,
         return 0;
     }
     k_schedule<<<grid_for(ngroups, 64), 64, 0, (cudaStream_t)stream>>>(a);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+int spfem_reduce_sorted(const double *d_sorted, const int *d_cptr, long long nslots,
+                        double *d_values, void *stream)
+{
+    if (nslots <= 0) return 0;
+    const int B = 256;
+    k_reduce_sorted<<<grid_for(nslots, B), B, 0, (cudaStream_t)stream>>>(d_sorted, d_cptr, nslots,
+                                                                     d_values);
     CUDA_TRY(cudaGetLastError());
     return 0;
 }

@@ -260,6 +260,10 @@ class Prepared(object):
             cptr, nslots = pat.cptr, pat.nnz
         else:
             cptr, nslots = pat.rowstart, pat.nrows
+        if getattr(self, "sorted_local", False):
+            _lib.check(e.lib.spfem_reduce_sorted(e._ptr(self.local), e._ptr(cptr), nslots,
+                                                 e._ptr(self.values), e._stream()))
+            return
         contrib = getattr(self, "contrib_override", None)
         if contrib is None:
             contrib = pat.contrib
@@ -565,7 +569,21 @@ class Engine(object):
         local = self._empty(max(spec.n_entries * n, 1), torch.float64)
         a.out = local.data_ptr()
         prep = Prepared(self, plan, kernel, a, 128, local, pat, keep=(sel, wt))
-        if os.environ.get("SPFEM_LOCAL_LAYOUT", "entry") == "elem" and spec.n_entries > 1:
+        # entry-major planes + gather reduction measured fastest
+        # (profiles/r01_configs.json); "sorted" and "elem" are kept as options
+        layout = os.environ.get("SPFEM_LOCAL_LAYOUT", "entry")
+        if layout == "sorted" and plan.bilinear and n > 0:
+            # the element kernel scatters every local entry to its position in
+            # slot-sorted order; the reduction then reads contiguous runs
+            pm = getattr(pat, "_perm_sorted", None)
+            if pm is None:
+                pm = torch.empty_like(pat.contrib)
+                pm[pat.contrib.long()] = torch.arange(pat.contrib.numel(), device=self.device,
+                                                     dtype=torch.int32)
+                pat._perm_sorted = pm
+            a.perm = pm.data_ptr()
+            prep.sorted_local = True
+        elif layout == "elem" and spec.n_entries > 1:
             # element-major local matrices: the gathers of neighbouring CSR slots
             # hit the same few 32-byte sectors
             a.ldo, a.ldk = 1, spec.n_entries

@@ -123,6 +123,7 @@ def test_both_assembly_paths(name, mode, monkeypatch):
     both reproduce the reference."""
     if mode == "unfused":
         monkeypatch.setenv("SPFEM_FUSED", "0")
+        monkeypatch.setenv("SPFEM_LOCAL_LAYOUT", "entry")
     else:
         monkeypatch.setenv("SPFEM_TILE_E", "32")
         monkeypatch.setenv("SPFEM_FUSED", "force")   # bypass the "is it worth it" heuristic
@@ -141,6 +142,7 @@ def test_element_major_local_layout(name, monkeypatch):
     """Two-kernel route with element-major local matrices (ldk = Nu*Nv)."""
     monkeypatch.setenv("SPFEM_FUSED", "0")
     monkeypatch.setenv("SPFEM_LOCAL_LAYOUT", "elem")
+    monkeypatch.setenv("SPFEM_FAN", "0")
     case = cases.BY_NAME[name]
     asm = util.assembler_for(case)
     prep = asm.prepare_iasm(case.form)
@@ -245,3 +247,20 @@ def test_intorder_variants_and_quadrature_limits():
     at = AssemblerElement(mt, sp.ElementTetP1())
     with pytest.raises(NotImplementedError):
         at.iasm(cases.mass, intorder=5)
+
+
+@pytest.mark.parametrize("name", ["trip1_lap_r6", "vecp2_elasticity", "tetp2_lap", "stokes_b",
+                                  "trip1_tind", "q2_lap"])
+def test_sorted_local_layout(name, monkeypatch):
+    """Two-kernel route, optional layout: the element kernel scatters the local
+    entries into slot-sorted order (SpfemArgs.perm), spfem_reduce_sorted sums
+    contiguous runs (measured slower than the gather; kept as an option)."""
+    monkeypatch.setenv("SPFEM_FUSED", "0")
+    monkeypatch.setenv("SPFEM_LOCAL_LAYOUT", "sorted")
+    case = cases.BY_NAME[name]
+    asm = util.assembler_for(case)
+    kw = cases.case_inputs(case, asm.mesh, asm.dofnum_u.N)
+    prep = asm.prepare_iasm(case.form, **kw)
+    assert prep.n_launches == 2 and getattr(prep, "sorted_local", False)
+    prep.launch()
+    util.check(prep.result(), util.golden(case))

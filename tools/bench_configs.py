@@ -70,9 +70,9 @@ def main():
             a = AssemblerElement(m, e_u, e_v)
         nt, nv, dim = m.t.shape[1], m.p.shape[1], m.p.shape[0]
         res = {"config": name, "nt": nt}
-        for mode in ("fused", "two_kernel", "two_kernel_elem"):
+        for mode in ("fused", "two_kernel", "two_kernel_sorted"):
             os.environ["SPFEM_FUSED"] = "1" if mode == "fused" else "0"
-            os.environ["SPFEM_LOCAL_LAYOUT"] = "elem" if mode == "two_kernel_elem" else "entry"
+            os.environ["SPFEM_LOCAL_LAYOUT"] = "sorted" if mode == "two_kernel_sorted" else "entry"
             a._engine = None
             t0 = time.perf_counter()
             prep = a.prepare_iasm(form)
