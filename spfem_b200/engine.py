@@ -174,58 +174,67 @@ def _host_copy(arr):
     return out
 
 
-_STAGING = {}
+class _PinnedPool(object):
+    """Recycling pool of pinned host buffers for results that are handed to the
+    caller.  ``take`` returns a NumPy array backed by a pinned tensor; when the
+    array is garbage collected its buffer goes back to the pool (weakref
+    finalizer), so a loop that drops the previous result re-uses the same pinned
+    block: device-to-host copies run at PCIe speed straight into the memory the
+    caller owns, with no staging copy and no repeated page-locking."""
+
+    def __init__(self, max_cached_bytes=2 << 30):
+        self.free = {}            # (dtype, capacity) -> [tensor, ...]
+        self.cached = 0
+        self.max_cached = max_cached_bytes
+
+    def take(self, torch_dtype, n):
+        import torch
+        import weakref
+        cap = max(int(n), 1)
+        if n > (1 << 20):
+            cap = -(-int(n) // (1 << 20)) * (1 << 20)        # round up to 1 Mi elements
+        key = (torch_dtype, cap)
+        lst = self.free.get(key)
+        if lst:
+            buf = lst.pop()
+            self.cached -= buf.numel() * buf.element_size()
+        else:
+            buf = torch.empty(cap, dtype=torch_dtype, pin_memory=True)
+        # the finalizer hangs on the array that wraps the whole buffer: every view
+        # the caller (or SciPy) derives keeps that array alive through ``.base``
+        full = buf.numpy()
+        weakref.finalize(full, self._release, key, buf)
+        return full[:n], buf
+
+    def _release(self, key, buf):
+        nbytes = buf.numel() * buf.element_size()
+        if self.cached + nbytes <= self.max_cached:
+            self.free.setdefault(key, []).append(buf)
+            self.cached += nbytes
 
 
-def _staging(dtype, n):
-    """Persistent pinned staging buffer (grown on demand, never handed out)."""
-    import torch
-    buf = _STAGING.get(dtype)
-    if buf is None or buf.numel() < n:
-        buf = torch.empty(int(n * 1.25) + 1024, dtype=dtype, pin_memory=True)
-        _STAGING[dtype] = buf
-    return buf
+_PINNED = _PinnedPool()
 
 
 def _to_host_begin(t, nchunks=8):
-    """Start the chunked asynchronous device-to-host copy of a 1-D tensor into
-    the pinned staging buffer; returns a handle for :func:`_to_host_finish`."""
+    """Start the asynchronous device-to-host copy of a 1-D tensor into a pinned
+    buffer from the recycling pool; returns a handle for :func:`_to_host_finish`."""
     import torch
     n = t.numel()
-    out = np.empty(n, dtype=torch.empty(0, dtype=t.dtype).numpy().dtype)
     if n == 0:
-        return out, None, None, None
-    stage = _staging(t.dtype, n)
-    parts = _chunks(n, max(1, min(nchunks, n // (1 << 20) + 1)))
-    events = []
-    for lo, hi in parts:
-        stage[lo:hi].copy_(t[lo:hi], non_blocking=True)
-        ev = torch.cuda.Event()
-        ev.record()
-        events.append(ev)
-    return out, stage.numpy(), parts, events
+        return np.empty(0, dtype=torch.empty(0, dtype=t.dtype).numpy().dtype), None
+    arr, buf = _PINNED.take(t.dtype, n)
+    buf[:n].copy_(t, non_blocking=True)
+    ev = torch.cuda.Event()
+    ev.record()
+    return arr, ev
 
 
 def _to_host_finish(handle):
-    """Worker threads wait for each chunk's event and move it from the staging
-    buffer into the fresh (pageable) result array."""
-    out, stage_np, parts, events = handle
-    if parts is None:
-        return out
-
-    def work(i):
-        lo, hi = parts[i]
-        events[i].synchronize()
-        out[lo:hi] = stage_np[lo:hi]
-    global _POOL
-    if len(parts) == 1:
-        work(0)
-    else:
-        if _POOL is None:
-            from concurrent.futures import ThreadPoolExecutor
-            _POOL = ThreadPoolExecutor(max_workers=8)
-        list(_POOL.map(work, range(len(parts))))
-    return out
+    arr, ev = handle
+    if ev is not None:
+        ev.synchronize()
+    return arr
 
 
 def _to_host(t):
