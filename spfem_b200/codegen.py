@@ -812,7 +812,7 @@ def generate_interior(spec, name="spfem_elem"):
         src += ["    " + ln for ln in core]
         src.append("}")
         src.append(FAN_KERNEL.replace("@NAME@", name).replace("@FANTHREADS@", str(FAN_THREADS))
-                   .replace("@FANMINB8@", os.environ.get("SPFEM_FAN_MINB8", "8"))
+                   .replace("@FANMINB8@", os.environ.get("SPFEM_FAN_MINB8", "7"))
                    .replace("@FANMINB@", os.environ.get("SPFEM_FAN_MINB", "6"))
                    .replace("@A00@", str(alias[0])).replace("@A10@", str(alias[3]))
                    .replace("@A20@", str(alias[6])))
