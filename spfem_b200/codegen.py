@@ -198,17 +198,12 @@ extern "C" __global__ void __launch_bounds__(@THREADS@, @MINB@) @NAME@_tile(cons
 # three vertices -- redundant flops instead of shared-memory traffic) and keeps
 # one accumulator per ring neighbour: slot (r, n_q) receives exactly the two
 # triangles that share the edge, in a fixed order.  No local matrices in shared
-# memory, no contribution lists, no atomics.  Per-row record (48 B, fanplan.py):
-#   g0 CSR position of the row | s0 tile slot offset | nfan | closed |
-#   ring neighbours (tile-local vertex ids) | CSR position of each neighbour
+# memory, no contribution lists, no atomics.  Per-row record (fanplan.py):
+#   plane 0 {g0 - s0, s0 | nfan << 16 | closed << 24, neighbours 0..3}, plane 1
+#   further ring neighbours (16-bit tile-local vertex ids); plus one byte per
+#   slot mapping CSR order to the ring order of the staging buffer
 FAN_THREADS = int(os.environ.get("SPFEM_FAN_T", "128"))
 FAN_KERNEL = r"""
-struct SpfemFanRow {
-    int g0; unsigned short s0; unsigned char nfan, closed;
-    unsigned short nbr[12];
-    unsigned char pos[12];
-    unsigned char posdiag, pad[3];
-};
 struct SpfemFanArgs {
     SpfemArgs base;
     const int *desc;              /* 8 ints per tile: off16, bytes A, bytes B, nr, ns, nvt */

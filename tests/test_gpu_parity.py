@@ -264,3 +264,35 @@ def test_sorted_local_layout(name, monkeypatch):
     assert prep.n_launches == 2 and getattr(prep, "sorted_local", False)
     prep.launch()
     util.check(prep.result(), util.golden(case))
+
+
+def test_full_size_config2_properties(monkeypatch):
+    """BASELINE configs[1] at full size (MeshTri.refine(11), 8 388 608
+    triangles): size-independent properties, and two independent kernels (the
+    vertex-fan kernel and the two-kernel route with its radix-sorted
+    contribution lists) agree on every one of the 29 372 417 CSR values."""
+    import spfem_b200 as sp
+    from spfem_b200.assembly import AssemblerElement
+    m = sp.MeshTri()
+    m.refine(11)
+    nv, ne, nt = m.p.shape[1], m.facets.shape[1], m.t.shape[1]
+    assert nt == 8388608 and nv == 4198401
+    a = AssemblerElement(m, sp.ElementTriP1())
+    prep = a.prepare_iasm(cases.lap2)
+    assert type(prep).__name__ == "FanPrepared"
+    prep.launch()
+    K = prep.result()
+    M = a.iasm(cases.mass)
+    assert K.nnz == nv + 2 * ne == 29372417 and K.indices.dtype == np.int32
+    assert np.array_equal(K.indptr, M.indptr) and np.array_equal(K.indices, M.indices)
+    assert np.max(np.abs(K.dot(np.ones(nv)))) < 1e-9          # constants are in the kernel
+    assert abs(M.sum() - 1.0) < 1e-11                          # area of the unit square
+    assert abs(M.dot(m.p[0]).sum() - 0.5) < 1e-11              # first moment
+    d = K - K.T
+    assert abs(d).max() < 1e-12
+    monkeypatch.setenv("SPFEM_FUSED", "0")
+    a2 = AssemblerElement(m, sp.ElementTriP1())
+    K2 = a2.iasm(cases.lap2)
+    assert np.array_equal(K.indptr, K2.indptr) and np.array_equal(K.indices, K2.indices)
+    scale = np.abs(K2.data).max()
+    assert np.max(np.abs(K.data - K2.data)) <= 1e-12 * scale
