@@ -85,6 +85,8 @@ SYMBOLS = {
                                      C.c_void_p, C.c_void_p, C.c_void_p]),
     "spfem_reduce": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p,
                                C.c_longlong, C.c_void_p, C.c_void_p]),
+    "spfem_reduce_rows": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                    C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p]),
     "spfem_reduce_sorted": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p,
                                       C.c_void_p]),
     "spfem_schedule_rows": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,

@@ -156,6 +156,26 @@ k_reduce(const double *__restrict__ local, const int *__restrict__ cptr,
     values[s] = acc;
 }
 
+// Thread per CSR row, rows visited in spatial order (see spfem_reduce_rows).
+__global__ void __launch_bounds__(256)
+k_reduce_rows(const double *__restrict__ local, const int *__restrict__ indptr,
+              const int *__restrict__ cptr, const int *__restrict__ contrib,
+              const int *__restrict__ row_order, long long nrows,
+              double *__restrict__ values)
+{
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nrows) return;
+    const int r = row_order[i];
+    const int s1 = indptr[r + 1];
+    int k = cptr[indptr[r]];
+    for (int s = indptr[r]; s < s1; ++s) {
+        const int e = cptr[s + 1];
+        double acc = 0.0;
+        for (; k < e; ++k) acc += local[contrib[k]];
+        values[s] = acc;
+    }
+}
+
 // values[s] = sum of a contiguous run of slot-sorted local entries.
 __global__ void __launch_bounds__(256)
 k_reduce_sorted(const double *__restrict__ sorted, const int *__restrict__ cptr,
@@ -755,6 +775,18 @@ int spfem_schedule_rows(const int *idx, const unsigned char *endf,
         return 0;
     }
     k_schedule<<<grid_for(ngroups, 64), 64, 0, (cudaStream_t)stream>>>(a);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+int spfem_reduce_rows(const double *d_local, const int *d_indptr, const int *d_cptr,
+                      const int *d_contrib, const int *d_row_order, long long nrows,
+                      double *d_values, void *stream)
+{
+    if (nrows <= 0) return 0;
+    const int B = 256;
+    k_reduce_rows<<<grid_for(nrows, B), B, 0, (cudaStream_t)stream>>>(
+        d_local, d_indptr, d_cptr, d_contrib, d_row_order, nrows, d_values);
     CUDA_TRY(cudaGetLastError());
     return 0;
 }

@@ -269,6 +269,13 @@ class Prepared(object):
             cptr, nslots = pat.cptr, pat.nnz
         else:
             cptr, nslots = pat.rowstart, pat.nrows
+        ro = getattr(self, "row_order", None)
+        if ro is not None:
+            _lib.check(e.lib.spfem_reduce_rows(e._ptr(self.local), e._ptr(pat.indptr),
+                                               e._ptr(pat.cptr), e._ptr(pat.contrib),
+                                               e._ptr(ro), pat.nrows,
+                                               e._ptr(self.values), e._stream()))
+            return
         if getattr(self, "sorted_local", False):
             _lib.check(e.lib.spfem_reduce_sorted(e._ptr(self.local), e._ptr(cptr), nslots,
                                                  e._ptr(self.values), e._stream()))
@@ -581,7 +588,23 @@ class Engine(object):
         # entry-major planes + gather reduction measured fastest
         # (profiles/r01_configs.json); "sorted" and "elem" are kept as options
         layout = os.environ.get("SPFEM_LOCAL_LAYOUT", "entry")
-        if layout == "sorted" and plan.bilinear and n > 0:
+        if (layout == "rows" and plan.bilinear and tind is None and n > 0
+                and pat.indptr.dtype == torch.int32):
+            # reduction by rows in the spatial order of the elements
+            ro = getattr(pat, "_row_order", None)
+            if ro is None:
+                c = pat.contrib.long()
+                counts = (pat.cptr[1:] - pat.cptr[:-1]).long()
+                slot_of_c = torch.repeat_interleave(
+                    torch.arange(pat.nnz, device=self.device), counts)
+                rowlen = (pat.indptr[1:] - pat.indptr[:-1]).long()
+                row_of_slot = torch.repeat_interleave(
+                    torch.arange(pat.nrows, device=self.device), rowlen)
+                minpos = torch.full((pat.nrows,), n, dtype=torch.int64, device=self.device)
+                minpos.scatter_reduce_(0, row_of_slot[slot_of_c], c % n, reduce="amin")
+                ro = pat._row_order = torch.argsort(minpos, stable=True).to(torch.int32)
+            prep.row_order = ro
+        elif layout == "sorted" and plan.bilinear and n > 0:
             # the element kernel scatters every local entry to its position in
             # slot-sorted order; the reduction then reads contiguous runs
             pm = getattr(pat, "_perm_sorted", None)

@@ -296,3 +296,17 @@ def test_full_size_config2_properties(monkeypatch):
     assert np.array_equal(K.indptr, K2.indptr) and np.array_equal(K.indices, K2.indices)
     scale = np.abs(K2.data).max()
     assert np.max(np.abs(K.data - K2.data)) <= 1e-12 * scale
+
+
+@pytest.mark.parametrize("name", ["trip1_lap_r6", "vecp2_elasticity", "tetp2_lap", "stokes_b",
+                                  "q2_lap"])
+def test_row_ordered_reduction(name, monkeypatch):
+    """Two-kernel route with the row-ordered reduction (spfem_reduce_rows)."""
+    monkeypatch.setenv("SPFEM_FUSED", "0")
+    monkeypatch.setenv("SPFEM_LOCAL_LAYOUT", "rows")
+    case = cases.BY_NAME[name]
+    asm = util.assembler_for(case)
+    prep = asm.prepare_iasm(case.form)
+    assert prep.n_launches == 2 and getattr(prep, "row_order", None) is not None
+    prep.launch()
+    util.check(prep.result(), util.golden(case))

@@ -51,6 +51,7 @@ CONFIGS = [
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default=None)
+    ap.add_argument("--only", default=None, help="substring of the configuration name")
     args = ap.parse_args()
     peak = 6558.1
     pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -58,6 +59,8 @@ def main():
         peak = float(json.load(open(pk))["hbm_gbs"])
     out = []
     for name, mesh, ref, eu, ncu, ev, ncv, form, C in CONFIGS:
+        if args.only and args.only not in name:
+            continue
         m = getattr(sp, mesh)()
         m.refine(ref)
         e_u = getattr(sp.element, "Element" + eu)()
@@ -70,9 +73,9 @@ def main():
             a = AssemblerElement(m, e_u, e_v)
         nt, nv, dim = m.t.shape[1], m.p.shape[1], m.p.shape[0]
         res = {"config": name, "nt": nt}
-        for mode in ("fused", "two_kernel", "two_kernel_sorted"):
+        for mode in ("fused", "two_kernel", "two_kernel_rows"):
             os.environ["SPFEM_FUSED"] = "1" if mode == "fused" else "0"
-            os.environ["SPFEM_LOCAL_LAYOUT"] = "sorted" if mode == "two_kernel_sorted" else "entry"
+            os.environ["SPFEM_LOCAL_LAYOUT"] = "rows" if mode == "two_kernel_rows" else "entry"
             a._engine = None
             t0 = time.perf_counter()
             prep = a.prepare_iasm(form)
