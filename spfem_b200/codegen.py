@@ -216,24 +216,29 @@ SPFEM_DEVICE void @NAME@_fan_row(const SpfemArgs &P, const double2 *__restrict__
                                  const unsigned char *__restrict__ rec, const int nr,
                                  const int row, double *__restrict__ sV, int *__restrict__ sG)
 {
-    /* row record planes -> registers; 16-bit neighbour ids extracted with shifts */
-    unsigned w[8];
+    /* row record planes -> registers; neighbour ids (16 bit) and CSR positions
+       (8 bit) are extracted with shifts                                        */
+    unsigned w[8], pw[3];
     {
         const uint4 h = reinterpret_cast<const uint4 *>(rec)[row];
         w[0] = h.x; w[1] = h.y; w[2] = h.z; w[3] = h.w;
+        const uint4 n1 = reinterpret_cast<const uint4 *>(rec + (size_t)16 * nr)[row];
         if (MAXN <= 8) {
-            const uint2 n1 = reinterpret_cast<const uint2 *>(rec + (size_t)16 * nr)[row];
             w[4] = n1.x; w[5] = n1.y; w[6] = 0u; w[7] = 0u;
+            pw[0] = n1.z; pw[1] = n1.w; pw[2] = 0u;
         } else {
-            const uint4 n1 = reinterpret_cast<const uint4 *>(rec + (size_t)16 * nr)[row];
+            const uint4 n2 = reinterpret_cast<const uint4 *>(rec + (size_t)32 * nr)[row];
             w[4] = n1.x; w[5] = n1.y; w[6] = n1.z; w[7] = n1.w;
+            pw[0] = n2.x; pw[1] = n2.y; pw[2] = n2.z;
         }
     }
 #define SPFEM_NBR(q) ((w[2 + ((q) >> 1)] >> (16 * ((q) & 1))) & 0xffffu)
-    const int gd = (int)w[0];                    /* CSR position - tile slot, of the row */
+#define SPFEM_POS(q) ((pw[(q) >> 2] >> (8 * ((q) & 3))) & 0xffu)
+    const int g0 = (int)w[0];                    /* CSR position of the row */
     const int s0 = (int)(w[1] & 0xffffu);
-    const int nfan = (int)((w[1] >> 16) & 0xffu);
-    const bool closed = ((w[1] >> 24) & 0xffu) != 0u;
+    const int nfan = (int)((w[1] >> 16) & 0xfu);
+    const bool closed = ((w[1] >> 20) & 0x1u) != 0u;
+    const int posdiag = (int)((w[1] >> 24) & 0xffu);
     const double2 cr = pc2[row];                 /* rows are the first vertices of a tile */
     const int nn = nfan + (closed ? 0 : 1);      /* ring neighbours */
     double acc[MAXN + 1];
@@ -261,16 +266,18 @@ SPFEM_DEVICE void @NAME@_fan_row(const SpfemArgs &P, const double2 *__restrict__
         acc[0] += wrap;
     }
     /* staged in RING order (slot s0 = diagonal, s0 + 1 + q = neighbour q): the
-       lanes of a warp write with a fixed stride, free of bank conflicts; the
-       store phase maps CSR order to ring order with one byte per slot          */
+       lanes of a warp write with a fixed stride, free of bank conflicts; next to
+       every value goes its CSR position, so the store phase is two conflict-free
+       shared loads and one global store per slot                               */
     sV[s0] = diag;
-    sG[s0] = gd;
+    sG[s0] = g0 + posdiag;
 #pragma unroll
     for (int q = 0; q < MAXN; ++q) {
         if (q >= nn) break;
         sV[s0 + 1 + q] = acc[q];
-        sG[s0 + 1 + q] = gd;
+        sG[s0 + 1 + q] = g0 + (int)SPFEM_POS(q);
     }
+#undef SPFEM_POS
 #undef SPFEM_NBR
 }
 #ifndef SPFEM_HOST
@@ -283,13 +290,13 @@ static __device__ __forceinline__ void @NAME@_fan_tile(const SpfemFanArgs &T)
     unsigned long long *bars = (unsigned long long *)(sV + T.max_ns);
     int *sG = (int *)(bars + 2);
     const int *d = T.desc + 8 * (size_t)blockIdx.x;
-    const int bytes_a = d[1], bytes_b = d[2], nr = d[3], ns = d[4], bytes_c = d[6];
+    const int bytes_a = d[1], bytes_b = d[2], nr = d[3], ns = d[4];
     if (nr == 0) return;
     if (threadIdx.x == 0) {
         spfem_mbar_init(&bars[0], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         spfem_bulk_load(sA, T.blob + (size_t)(unsigned)d[0] * 16,
-                        (unsigned)(bytes_a + bytes_b + bytes_c), &bars[0]);
+                        (unsigned)(bytes_a + bytes_b), &bars[0]);
         /* pull the blob of a tile that will start a few waves later into L2, so
            its own TMA load does not pay the DRAM latency                       */
         const long long tp = (long long)blockIdx.x + T.prefetch;
@@ -297,7 +304,7 @@ static __device__ __forceinline__ void @NAME@_fan_tile(const SpfemFanArgs &T)
             const int *dp = T.desc + 8 * (size_t)tp;
             asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;"
                          ::"l"(T.blob + (size_t)(unsigned)dp[0] * 16),
-                           "r"((unsigned)(dp[1] + dp[2] + dp[6])) : "memory");
+                           "r"((unsigned)(dp[1] + dp[2])) : "memory");
         }
     }
     __syncthreads();
@@ -305,9 +312,9 @@ static __device__ __forceinline__ void @NAME@_fan_tile(const SpfemFanArgs &T)
     for (int row = threadIdx.x; row < nr; row += blockDim.x)
         @NAME@_fan_row<MAXN>(T.base, (const double2 *)sA, sA + bytes_a, nr, row, sV, sG);
     __syncthreads();
-    const signed char *dl = (const signed char *)(sA + bytes_a + bytes_b);
-    for (int s = threadIdx.x; s < ns; s += blockDim.x)
-        T.values[sG[s] + s] = sV[s + (int)dl[s]];
+    /* every slot of the tile exactly once; a warp covers the CSR rows of its
+       threads, so its stores fill whole 32-byte sectors                        */
+    for (int s = threadIdx.x; s < ns; s += blockDim.x) T.values[sG[s]] = sV[s];
 }
 /* two instantiations: meshes whose vertices have at most 8 ring neighbours
    (fewer registers, higher occupancy) and the general case (<= 12)         */
@@ -331,8 +338,7 @@ extern "C" void @NAME@_fan_host(const SpfemFanArgs *T, int ntiles, double *sV, i
             else
                 @NAME@_fan_row<12>(T->base, (const double2 *)src, src + d[1], d[3], row, sV, sG);
         }
-        const signed char *dl = (const signed char *)(src + d[1] + d[2]);
-        for (int s = 0; s < d[4]; ++s) T->values[sG[s] + s] = sV[s + (int)dl[s]];
+        for (int s = 0; s < d[4]; ++s) T->values[sG[s]] = sV[s];
     }
 }
 #endif

@@ -15,14 +15,14 @@ module builds, once per mesh (host NumPy; set-up, not the hot path):
 * one 16-byte aligned blob per tile (brought into shared memory by one TMA
   bulk copy): section A = interleaved ``(x, y)`` coordinates of the tile's
   vertices; section B = the row records as planes (structure of arrays, so the
-  threads of a warp read consecutive 16 / 8 byte words): plane 0 =
-  ``{g0 - s0, s0 | nfan << 16 | closed << 24, nbr0..3}``, plane 1 = further
-  ring neighbours (tile-local vertex ids, 16 bit); section C = one signed byte
-  per tile slot: where (relative to the slot) the kernel's ring-ordered
-  staging holds the value of that CSR slot.
+  threads of a warp read consecutive 16 byte words): plane 0 =
+  ``{g0, s0 | nfan << 16 | closed << 20 | posdiag << 24, nbr0..3}``, plane 1 =
+  ``{nbr4..7, pos0..7}`` (<= 8 neighbours) or ``{nbr4..11}`` + plane 2 =
+  ``{pos0..11}``: ring neighbours as 16-bit tile-local vertex ids and the CSR
+  position (inside the row) of every neighbour as bytes.
 
 Descriptor per tile (int32 x 8): blob offset / 16, bytes A, bytes B, rows,
-slots, vertices, bytes C, 0.
+slots, vertices, 0, 0.
 """
 import numpy as np
 
@@ -214,47 +214,38 @@ def build_fan_plan(mesh, indptr, indices, rows_per_tile=256):
     cl = np.cumsum(lens) - lens
     s0 = cl - cl[r0[tile_of_row]]
     head = np.zeros((nv, 2), dtype=np.int64)
-    head[:, 0] = indptr[rows] - s0                       # CSR position minus tile slot
-    head[:, 1] = s0 | (nfan[rows] << 16) | (closed[rows].astype(np.int64) << 24)
+    head[:, 0] = indptr[rows]                              # CSR position of the row
+    head[:, 1] = (s0 | (nfan[rows] << 16) | (closed[rows].astype(np.int64) << 20)
+                  | (dpos[rows] << 24))
     nb16 = loc.T.astype(np.uint16)                         # (nv, W) tile-local neighbour ids
+    pos8 = np.where(ok, pos12[:W, rows], 0).T.astype(np.uint8)   # (nv, W) CSR positions
     plane0 = np.zeros((nv, 16), dtype=np.uint8)
     plane0[:, :8] = head.astype(np.int32).view(np.uint8).reshape(nv, 8)
     plane0[:, 8:] = nb16[:, :4].copy().view(np.uint8).reshape(nv, 8)
-    w1 = 8 if compact else 16                              # bytes per row in plane 1
-    plane1 = np.zeros((nv, w1), dtype=np.uint8)
-    plane1[:, :2 * (W - 4)] = nb16[:, 4:].copy().view(np.uint8).reshape(nv, 2 * (W - 4))
-    # section C: ring-ordered staging -> CSR order.  Ring position 0 = diagonal,
-    # 1 + q = q-th ring neighbour.
-    nslots = int(lens.sum())
-    slot_row = np.repeat(np.arange(nv), lens)              # (row order) row of every tile slot
-    slot_j = np.arange(nslots) - cl[slot_row]              # CSR position inside the row
-    ringpos = np.zeros(nslots, dtype=np.int64)             # ring position of CSR slot j
-    psl = np.where(ok, pos12[:W, rows], -1)                # (W, nv) CSR position of neighbour q
-    qq, rr = np.nonzero(psl >= 0)
-    ringpos[cl[rr] + psl[qq, rr]] = 1 + qq
-    ringpos[cl + dpos[rows]] = 0
-    delta = (ringpos - slot_j).astype(np.int8)
+    planes = [plane0]
+    if compact:
+        p1 = np.zeros((nv, 16), dtype=np.uint8)
+        p1[:, :8] = nb16[:, 4:8].copy().view(np.uint8).reshape(nv, 8)
+        p1[:, 8:] = pos8[:, :8]
+        planes.append(p1)
+    else:
+        p1 = nb16[:, 4:12].copy().view(np.uint8).reshape(nv, 16)
+        p2 = np.zeros((nv, 16), dtype=np.uint8)
+        p2[:, :12] = pos8[:, :12]
+        planes += [p1, p2]
     # blob layout
     bytes_a = (nvt * 16 + 15) // 16 * 16
-    bytes_p0 = nr * 16
-    bytes_p1 = (nr * w1 + 15) // 16 * 16
-    bytes_b = bytes_p0 + bytes_p1
-    bytes_c = (ns + 15) // 16 * 16
-    tb = bytes_a + bytes_b + bytes_c
+    bytes_b = nr * 16 * len(planes)
+    tb = bytes_a + bytes_b
     off = np.cumsum(tb) - tb
     total = int(tb.sum())
     blob = np.zeros(total, dtype=np.uint8)
-    d0 = (off + bytes_a)[tile_of_row] + 16 * row_local
-    blob[d0[:, None] + np.arange(16)[None, :]] = plane0
-    d1 = (off + bytes_a + bytes_p0)[tile_of_row] + w1 * row_local
-    blob[d1[:, None] + np.arange(w1)[None, :]] = plane1
-    slot_tile = tile_of_row[slot_row]
-    s_first = np.cumsum(ns) - ns
-    blob[(off + bytes_a + bytes_b)[slot_tile] + (np.arange(nslots) - s_first[slot_tile])] = \
-        delta.view(np.uint8)
+    for k, pl in enumerate(planes):
+        dk = (off + bytes_a + k * nr * 16)[tile_of_row] + 16 * row_local
+        blob[dk[:, None] + np.arange(16)[None, :]] = pl
     desc = np.zeros((ntiles, 8), dtype=np.int64)
     desc[:, 0], desc[:, 1], desc[:, 2] = off // 16, bytes_a, bytes_b
-    desc[:, 3], desc[:, 4], desc[:, 5], desc[:, 6] = nr, ns, nvt, bytes_c
+    desc[:, 3], desc[:, 4], desc[:, 5] = nr, ns, nvt
     if desc.max() > 2 ** 31 - 1:
         raise FanPlanError("fan plan offsets exceed 32 bits")
     # tile vertex lists: the rows first, then the halo vertices
