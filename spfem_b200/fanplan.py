@@ -206,8 +206,14 @@ def build_fan_plan(mesh, indptr, indices, rows_per_tile=256):
     loc = np.zeros(nbr.shape, dtype=np.int64)
     loc[inside] = local_of_vertex[nbr[inside]]
     out = ok & ~inside
+    # halo vertices are numbered along mesh lines too (y, then x) so that the
+    # q-th neighbours of consecutive rows are consecutive in shared memory
+    hv = uh % nv
+    hord = np.lexsort((p[0][hv], p[1][hv], h_tile))
+    hrank = np.empty(len(uh), dtype=np.int64)
+    hrank[hord] = np.arange(len(uh))
     hidx = np.searchsorted(uh, tl[out] * nv + nbr[out])
-    loc[out] = nr[tl[out]] + (hidx - h0[tl[out]])
+    loc[out] = nr[tl[out]] + (hrank[hidx] - h0[tl[out]])
     # row records, as planes
     lens = rowlen[rows]
     ns = np.bincount(tile_of_row, weights=lens, minlength=ntiles).astype(np.int64)
@@ -249,9 +255,9 @@ def build_fan_plan(mesh, indptr, indices, rows_per_tile=256):
     if desc.max() > 2 ** 31 - 1:
         raise FanPlanError("fan plan offsets exceed 32 bits")
     # tile vertex lists: the rows first, then the halo vertices
-    vid = np.concatenate((rows, uh % nv))
+    vid = np.concatenate((rows, hv))
     vtile = np.concatenate((tile_of_row, h_tile))
-    vloc = np.concatenate((row_local, nr[h_tile] + np.arange(len(uh)) - h0[h_tile]))
+    vloc = np.concatenate((row_local, nr[h_tile] + hrank - h0[h_tile]))
     pc_index = off[vtile] // 8 + 2 * vloc
     return {
         "ntiles": ntiles, "rows_per_tile": R,
