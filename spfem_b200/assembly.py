@@ -125,6 +125,7 @@ class AssemblerElement(Assembler):
             self.elem_v = elem_v
             self.dofnum_v = Dofnum(mesh, elem_v)
         self._engine = None        # device state, created on first assembly
+        self._pou = None
         self.last_stats = {}
 
     # ------------------------------------------------------------------
@@ -332,6 +333,70 @@ class AssemblerElement(Assembler):
         benchmarks) and ``result()`` fetches it like :meth:`iasm`."""
         plan = self.plan_iasm(form, intorder=intorder, interp=interp)
         return self._get_engine().prepare_interior(plan, tind, interp)
+
+    # ------------------------------------------------------------------
+    # error norms (spfem/assembly.py:1353-1485) on top of the device path
+    # ------------------------------------------------------------------
+    def _unit_assembler(self):
+        """Assembler with a partition-of-unity element on the same mesh: the sum
+        of the load vector of ``g * v`` is the integral of ``g``."""
+        if getattr(self, "_pou", None) is None:
+            elem = {"tri": _element.ElementTriP1, "tet": _element.ElementTetP1,
+                    "quad": _element.ElementQ1}.get(self.mesh.refdom)
+            if elem is None:
+                raise NotImplementedError("error norms on this mesh type")
+            self._pou = AssemblerElement(self.mesh, elem())
+        return self._pou
+
+    def L2error(self, uh, exact, intorder=None):
+        """Global L2 error ``||exact - uh||_0`` through the identity
+        ``(u,u) + (uh,uh) - 2 (u,uh)`` (spfem/assembly.py:1353-1402).  ``exact``
+        is called with the coordinate dict ``x`` of form arguments."""
+        if self.elem_u.maxdeg != self.elem_v.maxdeg:
+            raise NotImplementedError("elem_u.maxdeg must be elem_v.maxdeg "
+                                      "when computing errors!")
+        if intorder is None:
+            intorder = 2 * self.elem_u.maxdeg
+
+        def uv(u, v):
+            return u * v
+
+        def fv(v, x):
+            return exact(x) * v
+
+        def ff(v, x):
+            return exact(x) ** 2 * v
+        M = self.iasm(uv)
+        f = self.iasm(fv)
+        uu = float(np.sum(self._unit_assembler().iasm(ff, intorder=intorder)))
+        return np.sqrt(uu + np.dot(uh, M.dot(uh)) - 2. * np.dot(uh, f))
+
+    def H1error(self, uh, dexact, intorder=None):
+        """Global H1 seminorm error (spfem/assembly.py:1404-1485); ``dexact`` is
+        a dict of callables (one per direction), each called with ``x``."""
+        if self.elem_u.maxdeg != self.elem_v.maxdeg:
+            raise NotImplementedError("elem_u.maxdeg must be elem_v.maxdeg "
+                                      "when computing errors!")
+        if intorder is None:
+            intorder = 2 * self.elem_u.maxdeg
+        dim = self.mesh.p.shape[0]
+        if dim not in (2, 3):
+            raise NotImplementedError("AssemblerElement.H1error not "
+                                      "implemented for current domain "
+                                      "dimension!")
+
+        def uv(du, dv):
+            return sum(du[k] * dv[k] for k in range(dim))
+
+        def fv(dv, x):
+            return sum(dexact[k](x) * dv[k] for k in range(dim))
+
+        def ff(v, x):
+            return sum(dexact[k](x) ** 2 for k in range(dim)) * v
+        M = self.iasm(uv)
+        f = self.iasm(fv)
+        uu = float(np.sum(self._unit_assembler().iasm(ff, intorder=intorder)))
+        return np.sqrt(uu + np.dot(uh, M.dot(uh)) - 2. * np.dot(uh, f))
 
     def fasm(self, form, find=None, interior=False, intorder=None,
              normals=True, interp=None):

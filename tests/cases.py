@@ -135,7 +135,8 @@ def _interp_vec(n, seed=0):
 class Case(object):
     def __init__(self, name, mesh, refine, eu, form, kind="iasm", ncu=1,
                  ev=None, ncv=1, interp_key=None, tind_step=None,
-                 find_step=None, **kw):
+                 find_step=None, oracle=True, **kw):
+        self.oracle = oracle      # False: element not in the oracle, golden only
         self.name, self.mesh, self.refine = name, mesh, refine
         self.eu, self.ev, self.ncu, self.ncv = eu, ev, ncu, ncv
         self.form, self.kind, self.kw = form, kind, kw
@@ -182,6 +183,14 @@ CASES = [
     Case("f_tetp2_jump", "MeshTet", 1, "TetP2", jump, kind="fasm", interior=True),
     Case("f_q1_bnd", "MeshQuad", 3, "Q1", q_bnd, kind="fasm", normals=False),
     Case("f_q2_lin", "MeshQuad", 2, "Q2", q_bnd_lin, kind="fasm", normals=False),
+    # elements outside the oracle's six: discontinuous P1, MINI, P0 (golden only)
+    Case("tridg1_lap", "MeshTri", 2, "TriDG1", lap2, oracle=False),
+    Case("f_tridg1_sipg", "MeshTri", 2, "TriDG1", sipg, kind="fasm", interior=True, oracle=False),
+    Case("trimini_lap", "MeshTri", 2, "TriMini", lap2, oracle=False),
+    Case("trimini_mass", "MeshTri", 2, "TriMini", mass, oracle=False),
+    Case("trip0_mass", "MeshTri", 2, "TriP0", mass, oracle=False),
+    Case("stokes_b_p0", "MeshTri", 2, "TriP2", stokes_b, ncu=2, ev="TriP0", ncv=1, oracle=False),
+    Case("tetp0_mass", "MeshTet", 1, "TetP0", mass, oracle=False),
 ]
 BY_NAME = {c.name: c for c in CASES}
 
@@ -227,3 +236,28 @@ def compare_vec(a, b, rtol=1e-12):
     err = np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300)
     assert err <= rtol, "max relative error %.3e" % err
     return float(err)
+
+
+def exact_fun(dim):
+    """Smooth exact solution and its gradient (callables of the ``x`` dict)."""
+    if dim == 2:
+        ex = lambda x: np.sin(np.pi * x[0]) * np.cos(0.5 * x[1]) + x[0] * x[1]
+        dex = {0: lambda x: np.pi * np.cos(np.pi * x[0]) * np.cos(0.5 * x[1]) + x[1],
+               1: lambda x: -0.5 * np.sin(np.pi * x[0]) * np.sin(0.5 * x[1]) + x[0]}
+    else:
+        ex = lambda x: np.sin(x[0]) * x[1] + np.exp(0.3 * x[2])
+        dex = {0: lambda x: np.cos(x[0]) * x[1], 1: lambda x: np.sin(x[0]) + 0 * x[1],
+               2: lambda x: 0.3 * np.exp(0.3 * x[2])}
+    return ex, dex
+
+
+def nodal_values(mesh, asm, ex):
+    """A discrete function: the exact solution at the vertices, mid-entity
+    averages for the remaining DOFs (any fixed vector works for the test)."""
+    N = asm.dofnum_u.N
+    uh = np.zeros(N)
+    nv = mesh.p.shape[1]
+    uh[:nv] = ex({k: mesh.p[k] for k in range(mesh.p.shape[0])})
+    if N > nv:
+        uh[nv:] = 0.5 * np.cos(np.arange(N - nv))
+    return uh

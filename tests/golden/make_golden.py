@@ -29,7 +29,10 @@ import cases  # noqa: E402
 
 
 def ref_element(name, ncomp):
-    e = getattr(relem, "Element" + name)()
+    if name == "TriDG1":
+        e = relem.ElementTriDG(relem.ElementTriP1())
+    else:
+        e = getattr(relem, "Element" + name)()
     return relem.ElementH1Vec(e) if ncomp > 1 else e
 
 
@@ -62,6 +65,22 @@ def main():
     import spfem.utils as rutils
     x = rutils.direct(A, b, I=m.interior_nodes())
     print("test_asm.py:163 max(x) =", repr(np.max(x)), "(reference pins 0.073614737354524146)")
+    # error norms of nodal interpolants (spfem/assembly.py:1353-1485)
+    import json
+    norms = {}
+    for mname, ename, ref, dim in (("MeshTri", "TriP1", 4, 2), ("MeshTri", "TriP2", 3, 2),
+                                   ("MeshTet", "TetP1", 2, 3), ("MeshQuad", "Q1", 3, 2)):
+        m = getattr(rmesh, mname)()
+        m.refine(ref)
+        a = rasm.AssemblerElement(m, ref_element(ename, 1))
+        ex, dex = cases.exact_fun(dim)
+        N = a.dofnum_u.N
+        uh = cases.nodal_values(m, a, ex)
+        norms[mname + "_" + ename] = {"L2": float(a.L2error(uh, ex)),
+                                      "H1": float(a.H1error(uh, dex))}
+        print("norms", mname, ename, norms[mname + "_" + ename])
+    with open(os.path.join(HERE, "error_norms.json"), "w") as fh:
+        json.dump(norms, fh, indent=1)
 
 
 if __name__ == "__main__":

@@ -310,3 +310,22 @@ def test_row_ordered_reduction(name, monkeypatch):
     assert prep.n_launches == 2 and getattr(prep, "row_order", None) is not None
     prep.launch()
     util.check(prep.result(), util.golden(case))
+
+
+@pytest.mark.parametrize("mname,ename,ref,dim", [("MeshTri", "TriP1", 4, 2), ("MeshTri", "TriP2", 3, 2),
+                                                ("MeshTet", "TetP1", 2, 3), ("MeshQuad", "Q1", 3, 2)])
+def test_error_norms_match_reference(mname, ename, ref, dim):
+    """L2error / H1error (spfem/assembly.py:1353-1485) through the device path
+    against values computed by the reference itself (tests/golden/error_norms.json)."""
+    import json
+    import os
+    import spfem_b200 as sp
+    from spfem_b200.assembly import AssemblerElement
+    gold = json.load(open(os.path.join(util.GOLDEN, "error_norms.json")))[mname + "_" + ename]
+    m = getattr(sp, mname)()
+    m.refine(ref)
+    a = AssemblerElement(m, util.element(ename, 1))
+    ex, dex = cases.exact_fun(dim)
+    uh = cases.nodal_values(m, a, ex)
+    assert abs(a.L2error(uh, ex) - gold["L2"]) <= 1e-9 * max(gold["L2"], 1e-3)
+    assert abs(a.H1error(uh, dex) - gold["H1"]) <= 1e-9 * max(gold["H1"], 1e-3)

@@ -11,7 +11,7 @@ import util
 import asm_oracle
 
 
-@pytest.mark.parametrize("case", cases.CASES, ids=lambda c: c.name)
+@pytest.mark.parametrize("case", [c for c in cases.CASES if c.oracle], ids=lambda c: c.name)
 def test_oracle_matches_reference_output(case):
     util.check(util.oracle_run(case), util.golden(case))
 

@@ -23,7 +23,10 @@ def mesh_for(case):
 
 
 def element(name, ncomp):
-    e = getattr(sp.element, "Element" + name)()
+    if name == "TriDG1":
+        e = sp.element.ElementTriDG(sp.element.ElementTriP1())
+    else:
+        e = getattr(sp.element, "Element" + name)()
     return sp.ElementH1Vec(e) if ncomp > 1 else e
 
 
