@@ -348,6 +348,44 @@ class AssemblerElement(Assembler):
             self._pou = AssemblerElement(self.mesh, elem())
         return self._pou
 
+    def inorm(self, form, interp, intorder=None):
+        """Element-wise squared L2 norms ``int_K form(u, du, x, h)^2`` of
+        interpolated solution vectors (spfem/assembly.py:1273-1351; a posteriori
+        estimators).  ``u`` / ``du`` are the dicts of interpolated fields and
+        their gradients.  Returns an array with one value per element."""
+        if not isinstance(interp, dict):
+            raise Exception("The input solution vector(s) must be in a "
+                            "dictionary! Pass e.g. {0:u} instead of u.")
+        mesh = self.mesh
+        if intorder is None:
+            intorder = 2 * self.elem_u.maxdeg
+        names = _argnames(form)
+        wkeys = self._check_interp(interp)
+        X, W = get_quadrature(mesh.refdom, intorder)
+        dim = mesh.p.shape[0]
+        bu, ncu, _, _ = self._elem_info()
+        if ncu != 1:
+            raise NotImplementedError("inorm: scalar elements only")
+        quad = mesh.refdom == "quad"
+        absdet = Coef.sym("absdetq", True) if quad else Coef.sym("absdet")
+        h = Form.coef(Coef.sym("hq", True)) if quad else Form.coef(Coef.sym("h"))
+        x = {k: Form.coef(Coef.sym("x%d" % k, True)) for k in range(dim)}
+        w = {key: Form.coef(Coef.sym("w%d" % s, True)) for s, key in enumerate(wkeys)}
+        dw = {key: {a: Form.coef(Coef.sym("dw%d_%d" % (s, a), True)) for a in range(dim)}
+              for s, key in enumerate(wkeys)}
+        val = call_form(form, names, {'u': w, 'du': dw, 'x': x, 'h': h})
+        val = Form.coef(val.pure("inorm form"))
+        # one constant "test function" per element: the entry is the integral
+        from .tracer import NONE
+        integrand = val * val * Form.coef(absdet)
+        blocks = {(0, 0): Form({(NONE, 0): integrand.pure()})}
+        ones = [np.ones((1, len(W)))]
+        spec = codegen.InteriorSpec(mesh.refdom, dim, False, bu.nbfun_ref(), 1, 1, 1,
+                                    blocks, X, W, self._tables(bu, X), ones, nw=len(wkeys))
+        src = codegen.generate_interior(spec, "spfem_elem")
+        plan = _Plan("functional", spec, src, "spfem_elem", False, wkeys)
+        return self._get_engine().run_functional(plan, interp)
+
     def L2error(self, uh, exact, intorder=None):
         """Global L2 error ``||exact - uh||_0`` through the identity
         ``(u,u) + (uh,uh) - 2 (u,uh)`` (spfem/assembly.py:1353-1402).  ``exact``

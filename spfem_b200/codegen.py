@@ -717,15 +717,29 @@ def generate_interior(spec, name="spfem_elem"):
     # interpolated fields w[k] = sum_j interp[k][t_dof_u[j, e]] phi_j(X_q)
     #                                          (spfem/assembly.py:955-959)
     for s in range(spec.nw):
-        if not any(("w%d" % s) == nm for nm in syms):
+        use_w = ("w%d" % s) in syms
+        use_dw = any(("dw%d_%d" % (s, a)) in syms for a in range(dim))
+        if not (use_w or use_dw):
             continue
         for j in range(spec.nbu):
             body.append("const double wc%d_%d = P.interp[%d][P.tdof_u[%d * P.ldd + e]];"
                         % (s, j, s, j))
         for q in range(nq):
-            terms = ["wc%d_%d * %s" % (s, j, lit(spec.tab_u[0][j][q]))
-                     for j in range(spec.nbu)]
-            body.append("const double w%d_%d = 0.0 + %s;" % (s, q, " + ".join(terms)))
+            if use_w:
+                terms = ["wc%d_%d * %s" % (s, j, lit(spec.tab_u[0][j][q]))
+                         for j in range(spec.nbu)]
+                body.append("const double w%d_%d = 0.0 + %s;" % (s, q, " + ".join(terms)))
+            if use_dw:
+                # gradient of the interpolated field: DF^{-T} applied to the
+                # reference gradient sum_j c_j dphi_j(X_q)  (inorm, assembly.py:1340-1346)
+                for l in range(dim):
+                    terms = ["wc%d_%d * %s" % (s, j, lit(spec.tab_u[1 + l][j][q]))
+                             for j in range(spec.nbu)]
+                    body.append("const double gw%d_%d_%d = 0.0 + %s;" % (s, l, q, " + ".join(terms)))
+                for a in range(dim):
+                    inv = (lambda l: "iJ_%d%d_%d" % (l, a, q)) if quad else (lambda l: "iA_%d%d" % (l, a))
+                    body.append("const double dw%d_%d_%d = %s;" % (
+                        s, a, q, " + ".join("%s * gw%d_%d_%d" % (inv(l), s, l, q) for l in range(dim))))
 
     def symname(nm, scope):
         if nm.startswith("iA"):
@@ -781,7 +795,7 @@ def generate_interior(spec, name="spfem_elem"):
     # coefficients): the same computation with the vertex coordinates passed in
     spec.fan_ok = (spec.refdom == "tri" and spec.bilinear and spec.ncu == 1 and spec.ncv == 1
                    and spec.nbu == 3 and spec.nbv == 3
-                   and not any(nm[0] in "xw" for nm in syms))
+                   and not any(nm[0] in "xwd" for nm in syms))
     core = []
     if spec.fan_ok:
         core = (affine_geometry(dim, fast_inverse=True, coords_given=True)

@@ -715,6 +715,29 @@ class Engine(object):
         values = prep.launch()
         return self._finish(values, prep.pattern, plan.bilinear, to_host)
 
+    def run_functional(self, plan, interp):
+        """One value per element (``inorm``): the generated kernel writes a single
+        entry per element; the result is returned in the mesh's element order."""
+        torch, lib = self.torch, self.lib
+        kernel = get_kernel(plan.source, plan.name)
+        n = self.nt
+        out = self._empty(max(n, 1), torch.float64)
+        wt = self._interp_tensors(plan, interp)
+        a = _lib.SpfemArgs()
+        a.n, a.ldo, a.ldk = n, n, 1
+        a.t, a.ldt = self.t.data_ptr(), self.t.shape[1]
+        a.p, a.ldp = self.p.data_ptr(), self.p.shape[1]
+        a.tdof_u, a.ldd = self.tdof_u.data_ptr(), self.tdof_u.shape[1]
+        for s, w in enumerate(wt):
+            a.interp[s] = w.data_ptr()
+        a.out = out.data_ptr()
+        _lib.check(lib.spfem_launch(kernel, C.byref(a), 128, self._stream()))
+        if self.perm is not None:
+            res = torch.empty_like(out)
+            res[self.perm_l] = out
+            out = res
+        return _to_host(out)
+
     def run_facet(self, plan, find, interior, interp=None, to_host=True):
         torch, lib, asm = self.torch, self.lib, self.asm
         spec = plan.spec

@@ -261,3 +261,15 @@ def nodal_values(mesh, asm, ex):
     if N > nv:
         uh[nv:] = 0.5 * np.cos(np.arange(N - nv))
     return uh
+
+
+def inorm_form(u, du, x, h):
+    # residual-estimator like: h * (f + something of the discrete solution).
+    # One interpolated field only: with several keys the reference aliases all
+    # ``w[k]`` to one array (``w[k] = zero`` followed by in-place ``+=``,
+    # spfem/assembly.py:1334-1346), which is not reproduced here.
+    return h * (np.sin(x[0]) + u[0] * x[1]) + du[0][0] - 2.0 * du[0][1]
+
+
+INORM_CASES = [("MeshTri", "TriP1", 3), ("MeshTri", "TriP2", 2), ("MeshTet", "TetP2", 1),
+               ("MeshQuad", "Q2", 2)]

@@ -79,6 +79,19 @@ def main():
         norms[mname + "_" + ename] = {"L2": float(a.L2error(uh, ex)),
                                       "H1": float(a.H1error(uh, dex))}
         print("norms", mname, ename, norms[mname + "_" + ename])
+    # element-wise norms (spfem/assembly.py:1273-1351)
+    for mname, ename, ref in cases.INORM_CASES:
+        m = getattr(rmesh, mname)()
+        m.refine(ref)
+        a = rasm.AssemblerElement(m, ref_element(ename, 1))
+        N = a.dofnum_u.N
+        interp = {0: cases._interp_vec(N, 3)}
+        if m.p.shape[0] == 3:
+            val = a.inorm(lambda u, du, x, h: cases.inorm_form(u, du, x, h) + du[0][2], interp)
+        else:
+            val = a.inorm(cases.inorm_form, interp)
+        np.savez_compressed(os.path.join(HERE, "inorm_%s_%s.npz" % (mname, ename)), data=val)
+        print("inorm", mname, ename, val.shape, float(val.sum()))
     with open(os.path.join(HERE, "error_norms.json"), "w") as fh:
         json.dump(norms, fh, indent=1)
 

@@ -158,3 +158,21 @@ def fan_iasm(asm, form, rows_per_tile=64):
     out = ref.copy()
     out.data = values
     return out, fp
+
+
+def inorm(asm, form, interp, intorder=None):
+    """Host emulation of ``AssemblerElement.inorm`` (per-element values)."""
+    import types
+    captured = {}
+
+    class _Eng(object):
+        def run_functional(self, plan, interp_):
+            captured["plan"] = plan
+            return None
+    saved = asm._engine
+    asm._engine = _Eng()
+    try:
+        asm.inorm(form, interp, intorder=intorder)
+    finally:
+        asm._engine = saved
+    return run_interior(asm, captured["plan"], None, interp)[0]
