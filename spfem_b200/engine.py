@@ -638,20 +638,17 @@ class Engine(object):
                 or asm.dofnum_u.t_dof.shape != mesh.t.shape
                 or not np.array_equal(asm.dofnum_u.t_dof, mesh.t)):
             return None
-        from .fanplan import build_fan_plan, FanPlanError
+        from .fanplan import FanPlanError
+        from .fanplan_torch import build_fan_plan
         from .tileplan import fill_coordinates
         t0 = time.perf_counter()
-        indptr, indices = pat.host()
+        dev64 = lambda arr: torch.from_numpy(np.ascontiguousarray(arr, dtype=np.int64)).to(self.device)
         try:
-            hp = build_fan_plan(mesh, indptr, indices,
+            fp = build_fan_plan(torch, self.p, dev64(mesh.t), dev64(mesh.t2f), dev64(mesh.f2t),
+                                pat.indptr, pat.indices,
                                 int(os.environ.get("SPFEM_FAN_ROWS", "128")))
         except FanPlanError:
             return None
-        fp = dict(hp)
-        fp["desc"] = torch.from_numpy(hp["desc"]).to(self.device).contiguous()
-        fp["blob"] = torch.from_numpy(hp["blob"]).to(self.device)
-        fp["vid"] = torch.from_numpy(hp["vid"]).to(self.device)
-        fp["pc_index"] = torch.from_numpy(hp["pc_index"]).to(self.device)
         fp["pc_stride"] = 1
         fp["dim"] = 2
         fill_coordinates(fp, self.p)

@@ -87,3 +87,34 @@ def test_fan_kernel_wide_records():
     out, fp = hostemu.fan_iasm(asm, cases.lap2, rows_per_tile=16)
     assert fp["max_neighbours"] == 10
     cases.compare_csr(out, hostemu.iasm(asm, cases.lap2))
+
+
+@pytest.mark.parametrize("which", ["refined", "wheel", "jiggled"])
+def test_torch_plan_is_byte_identical(which):
+    """The device-side plan builder (PyTorch index ops; run here on CPU tensors)
+    produces exactly the blob / descriptors of the NumPy reference builder."""
+    import torch
+    from spfem_b200 import fanplan_torch
+    if which == "refined":
+        m = sp.MeshTri()
+        m.refine(4)
+    elif which == "wheel":
+        m = _wheel_mesh(10, 2)
+    else:
+        m = sp.MeshTri(initmesh="symmetric")
+        m.refine(3)
+        I = m.interior_nodes()
+        m.p[:, I] += 0.01 * np.random.default_rng(1).standard_normal((2, len(I)))
+    asm = AssemblerElement(m, sp.ElementTriP1())
+    A = hostemu.iasm(asm, cases.mass)
+    a = build_fan_plan(m, A.indptr, A.indices, 32)
+    T = lambda x: torch.from_numpy(np.ascontiguousarray(x))
+    b = fanplan_torch.build_fan_plan(torch, T(m.p), T(m.t.astype(np.int64)), T(m.t2f.astype(np.int64)),
+                                     T(m.f2t.astype(np.int64)), T(A.indptr.astype(np.int64)),
+                                     T(A.indices.astype(np.int64)), 32)
+    assert np.array_equal(a["desc"], b["desc"].numpy())
+    assert np.array_equal(a["blob"], b["blob"].numpy())
+    assert np.array_equal(a["vid"], b["vid"].numpy())
+    assert np.array_equal(a["pc_index"], b["pc_index"].numpy())
+    for k in ("ntiles", "max_a", "max_ns", "max_neighbours"):
+        assert a[k] == b[k]
