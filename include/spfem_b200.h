@@ -124,6 +124,15 @@ int spfem_reduce_rows(const double *d_local, const int *d_indptr, const int *d_c
                       const int *d_contrib, const int *d_row_order, long long nrows,
                       double *d_values, void *stream);
 
+/* Re-ordered variant: the caller lists the CSR slots in any order it likes
+ * (spfem_b200/engine.py: rows in the spatial order of the elements, so the
+ * gathers of one thread block stay inside a narrow window of d_local that lives
+ * in L2) with d_cptr / d_contrib laid out in THAT order; the s-th listed slot is
+ * CSR position d_dest[s]:  d_values[d_dest[s]] = sum d_local[contrib[k]].       */
+int spfem_reduce_scatter(const double *d_local, const int *d_cptr, const int *d_contrib,
+                         long long nslots, const int *d_dest, double *d_values,
+                         void *stream);
+
 /* Same sum for local entries that the element kernel already wrote in slot-sorted
  * order (SpfemArgs.perm): d_values[s] = sum d_sorted[cptr[s] .. cptr[s+1]).      */
 int spfem_reduce_sorted(const double *d_sorted, const int *d_cptr, long long nslots,

@@ -41,7 +41,7 @@ class SpfemTileArgs(C.Structure):
         ("base", SpfemArgs),
         ("desc", C.c_void_p), ("blob", C.c_void_p), ("values", C.c_void_p),
         ("ldl", C.c_int), ("max_a", C.c_int), ("max_b", C.c_int),
-        ("max_ns", C.c_int), ("max_nr", C.c_int),
+        ("max_ns", C.c_int), ("max_nr", C.c_int), ("mode", C.c_int),
     ]
 
 
@@ -87,6 +87,8 @@ SYMBOLS = {
                                C.c_longlong, C.c_void_p, C.c_void_p]),
     "spfem_reduce_rows": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                     C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p]),
+    "spfem_reduce_scatter": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong,
+                                       C.c_void_p, C.c_void_p, C.c_void_p]),
     "spfem_reduce_sorted": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p,
                                       C.c_void_p]),
     "spfem_schedule_rows": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,

@@ -123,7 +123,9 @@ struct SpfemTileArgs {
     double *values;               /* CSR values                                   */
     int ldl;                      /* leading dimension of the smem tile           */
     int max_a, max_b;             /* smem bytes reserved for blob sections A / B  */
-    int max_ns, max_nr;           /* largest slot / row count of a tile           */
+    int max_ns, max_nr;           /* largest slot / row count of a tile; max_ns = 0:
+                                     no staging buffer, values stored from phase B1 */
+    int mode;                     /* 0: thread per owned row, 1: thread per CSR slot */
 };
 extern "C" __global__ void __launch_bounds__(@THREADS@, @MINB@) @NAME@_tile(const SpfemTileArgs T)
 {
@@ -153,9 +155,17 @@ extern "C" __global__ void __launch_bounds__(@THREADS@, @MINB@) @NAME@_tile(cons
     const unsigned short *vt = (const unsigned short *)sA;   /* tile-local vertex ids */
     const double *pc = (const double *)(sA + d[12]);          /* tile-local coordinates */
     const long long ldpc = d[11];
-    for (int el = threadIdx.x; el < ne; el += blockDim.x)
-        @NAME@_body<true>(T.base, @ELEM@, vt, (long long)ne_pad, (long long)el, pc, ldpc,
-                          sL, (long long)ldl, (long long)el);
+    /* SPFEM_NPART threads per element, each computing every NPART-th distinct
+       local value (large local matrices: keeps all threads of the CTA busy); the
+       part index is uniform inside a warp                                       */
+    const int ne32 = (ne + 31) & ~31;
+    for (int w = threadIdx.x; w < ne32 * SPFEM_NPART; w += blockDim.x) {
+        const int part = w / ne32, el = w - part * ne32;
+        if (el >= ne) continue;
+        switch (part) {
+@CASES@
+        }
+    }
     /* phase B1: one thread per owned row walks the row's contribution list
        (bit 15 of an entry = last contribution of a CSR slot) and adds in list
        order -- fixed order => bitwise reproducible.  The lists are scheduled
@@ -165,7 +175,29 @@ extern "C" __global__ void __launch_bounds__(@THREADS@, @MINB@) @NAME@_tile(cons
     spfem_mbar_wait(&bars[1], 0);
     const int2 *rinfo = (const int2 *)sB;      /* {gdelta, s_start | k_start<<16} */
     const unsigned short *cb = (const unsigned short *)(sB + d[8]);
+    const unsigned char *pm = (const unsigned char *)(sB + d[6]);   /* slot order -> CSR order */
+    const bool direct = T.max_ns == 0;           /* no staging buffer: store from B1 */
     __syncthreads();
+    if (T.mode == 1) {
+        /* phase B, slot-parallel: one thread per CSR slot of the tile (slots in
+           CSR order, so a warp stores runs of consecutive values); the first two
+           contributions are fetched together, longer lists finish in a loop --
+           always in list order => bitwise reproducible                         */
+        const int *gd = (const int *)sB;
+        const unsigned short *soff = (const unsigned short *)(sB + d[6]);
+        const unsigned short *srow = (const unsigned short *)(sB + d[7]);
+#pragma unroll 2
+        for (int s = threadIdx.x; s < ns; s += blockDim.x) {
+            const unsigned k0 = soff[s], k1 = soff[s + 1];
+            const unsigned c0 = cb[k0], c1 = cb[k0 + 1];
+            const int g = gd[srow[s]] + s;
+            double acc = sL[c0];
+            if (k0 + 1 < k1) acc += sL[c1];
+            for (unsigned k = k0 + 2; k < k1; ++k) acc += sL[cb[k]];
+            T.values[g] = acc;
+        }
+        return;
+    }
     for (int row = threadIdx.x; row < nr; row += blockDim.x) {
         const int2 ri = rinfo[row];
         unsigned s = (unsigned)ri.y & 0xffffu;
@@ -179,13 +211,17 @@ extern "C" __global__ void __launch_bounds__(@THREADS@, @MINB@) @NAME@_tile(cons
                 c = cb[k++];
                 acc += sL[c & 0x7fffu];
             } while (!(c & 0x8000u));
-            sV[s] = acc;
-            sG[s] = g0;
+            if (direct) {
+                T.values[g0 + (int)pm[s]] = acc;
+            } else {
+                sV[s] = acc;
+                sG[s] = g0;
+            }
         }
     }
+    if (direct) return;
     __syncthreads();
     /* phase B2: coalesced store of the tile's CSR values */
-    const unsigned char *pm = (const unsigned char *)(sB + d[6]);   /* slot order -> CSR order */
     for (int s = threadIdx.x; s < ns; s += blockDim.x)
         T.values[sG[s] + (int)pm[s]] = sV[s];
 }
@@ -782,15 +818,23 @@ def generate_interior(spec, name="spfem_elem"):
             order_u.append(gkey)
         groups[gkey][2].append(idx)
         alias[idx] = groups[gkey][0]
+    # threads per element in the tile kernel's phase A (distinct values dealt
+    # round-robin to the parts)
+    npart = int(os.environ.get("SPFEM_TILE_NPART", "0"))
+    if npart <= 0:
+        npart = 1 if len(order_u) <= 24 else 2
+    spec.npart = npart
     for gkey in order_u:
         u, expr, idxs = groups[gkey]
-        body.append("{ const double val = %s;" % expr)
+        body.append("if (PART < 0 || PART == %d) { const double val = %s;" % (u % npart, expr))
         body.append("  if (TILED) { out[(long long)%d * ldo + k] = val; } else {" % u)
         for idx in idxs:
             body.append("    SPFEM_PUT(%d, val);" % idx)
         body.append("  } }")
     spec.alias = alias
     spec.n_unique = len(order_u)
+    # multiply-adds per element (cost estimate: is recomputing halo elements cheap?)
+    spec.n_terms = sum(groups[g][1].count(" * ") for g in order_u) + len(em.lines)
     # Vertex-fan variant (TriP1-like: one DOF per vertex, element-constant
     # coefficients): the same computation with the vertex coordinates passed in
     spec.fan_ok = (spec.refdom == "tri" and spec.bilinear and spec.ncu == 1 and spec.ncv == 1
@@ -804,6 +848,7 @@ def generate_interior(spec, name="spfem_elem"):
     src = [PRELUDE, DEVICE_HELPERS]
     src.append("#define SPFEM_NENTRIES %d" % spec.n_entries)
     src.append("#define SPFEM_NUNIQUE %d" % spec.n_unique)
+    src.append("#define SPFEM_NPART %d" % spec.npart)
     # store of one local entry in the two-kernel route: entry-major position, or
     # (P.perm) its position in slot-sorted order
     src.append("#define SPFEM_PUT(idx, val) do { const long long a_ = (long long)(idx) * ldo + k; "
@@ -811,7 +856,8 @@ def generate_interior(spec, name="spfem_elem"):
     # body<TILED>(P, e, vt, ldv, ev, pc, ldpc, out, ldo, k): local matrix of
     # element e whose vertex ids are vt[r*ldv + ev]  ->  out[idx*ldo + k]
     # (TILED: only the distinct values, out[alias*ldo + k])
-    src.append("template <bool TILED, typename VT, typename OUT>")
+    # (PART >= 0: only the distinct values of that part; PART < 0: all)
+    src.append("template <bool TILED, int PART, typename VT, typename OUT>")
     src.append("SPFEM_DEVICE void %s_body(const SpfemArgs &P, const long long e, "
                "const VT *__restrict__ vt, const long long ldv, const long long ev, "
                "const double *__restrict__ pc, const long long ldpc, "
@@ -823,7 +869,7 @@ def generate_interior(spec, name="spfem_elem"):
         src.append("SPFEM_DEVICE void %s_core(const SpfemArgs &P, const double X_0_0, "
                    "const double X_1_0, const double X_0_1, const double X_1_1, "
                    "const double X_0_2, const double X_1_2, double *__restrict__ out)\n{" % name)
-        src.append("    const bool TILED = true; const long long ldo = 1, k = 0;")
+        src.append("    const bool TILED = true; const int PART = -1; const long long ldo = 1, k = 0;")
         src += ["    " + ln for ln in core]
         src.append("}")
         src.append(FAN_KERNEL.replace("@NAME@", name).replace("@FANTHREADS@", str(FAN_THREADS))
@@ -836,20 +882,24 @@ def generate_interior(spec, name="spfem_elem"):
     src.append("    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;")
     src.append("    if (k >= P.n) return;")
     src.append("    const long long e = P.sel ? (long long)P.sel[k] : k;")
-    src.append("    %s_body<false>(P, e, P.t, P.ldt, e, P.p, P.ldp, P.out, P.ldo, k * P.ldk);" % name)
+    src.append("    %s_body<false, -1>(P, e, P.t, P.ldt, e, P.p, P.ldp, P.out, P.ldo, k * P.ldk);" % name)
     src.append("}")
     if spec.bilinear:
         nve = 4 if quad else dim + 1
         # element id (only needed for the interp gathers through P.tdof_u)
         elem = "(long long)((const int *)(sA + d[13]))[el]" if spec.nw > 0 else "0LL"
-        src.append(TILE_KERNEL.replace("@NAME@", name).replace("@ELEM@", elem)
+        cases = "\n".join(
+            "        case %d: %s_body<true, %d>(T.base, %s, vt, (long long)ne_pad, (long long)el, "
+            "pc, ldpc, sL, (long long)ldl, (long long)el); break;" % (c, name, c, elem)
+            for c in range(spec.npart))
+        src.append(TILE_KERNEL.replace("@CASES@", cases).replace("@NAME@", name)
                    .replace("@THREADS@", str(TILE_THREADS))
                    .replace("@MINB@", os.environ.get("SPFEM_TILE_MINB", "1")))
     src.append("#else")
     src.append('extern "C" void %s_host(const SpfemArgs *P)\n{' % name)
     src.append("    for (long long k = 0; k < P->n; ++k) {")
     src.append("        const long long e = P->sel ? (long long)P->sel[k] : k;")
-    src.append("        %s_body<false>(*P, e, P->t, P->ldt, e, P->p, P->ldp, P->out, P->ldo, k * P->ldk);" % name)
+    src.append("        %s_body<false, -1>(*P, e, P->t, P->ldt, e, P->p, P->ldp, P->out, P->ldo, k * P->ldk);" % name)
     src.append("    }")
     src.append("}")
     src.append("#endif")

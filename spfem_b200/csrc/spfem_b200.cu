@@ -176,6 +176,22 @@ k_reduce_rows(const double *__restrict__ local, const int *__restrict__ indptr,
     }
 }
 
+// values[dest[s]] = sum of the local entries listed for the s-th slot of a
+// re-ordered slot list (see spfem_reduce_scatter).
+__global__ void __launch_bounds__(256)
+k_reduce_scatter(const double *__restrict__ local, const int *__restrict__ cptr,
+                 const int *__restrict__ contrib, long long nslots,
+                 const int *__restrict__ dest, double *__restrict__ values)
+{
+    long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= nslots) return;
+    int b = cptr[s], e = cptr[s + 1];
+    const int d = dest[s];
+    double acc = 0.0;
+    for (int k = b; k < e; ++k) acc += local[contrib[k]];
+    values[d] = acc;
+}
+
 // values[s] = sum of a contiguous run of slot-sorted local entries.
 __global__ void __launch_bounds__(256)
 k_reduce_sorted(const double *__restrict__ sorted, const int *__restrict__ cptr,
@@ -787,6 +803,17 @@ int spfem_reduce_rows(const double *d_local, const int *d_indptr, const int *d_c
     const int B = 256;
     k_reduce_rows<<<grid_for(nrows, B), B, 0, (cudaStream_t)stream>>>(
         d_local, d_indptr, d_cptr, d_contrib, d_row_order, nrows, d_values);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+int spfem_reduce_scatter(const double *d_local, const int *d_cptr, const int *d_contrib,
+                         long long nslots, const int *d_dest, double *d_values, void *stream)
+{
+    if (nslots <= 0) return 0;
+    const int B = 256;
+    k_reduce_scatter<<<grid_for(nslots, B), B, 0, (cudaStream_t)stream>>>(
+        d_local, d_cptr, d_contrib, nslots, d_dest, d_values);
     CUDA_TRY(cudaGetLastError());
     return 0;
 }

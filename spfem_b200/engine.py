@@ -27,11 +27,12 @@ from . import _lib
 from .codegen import source_key
 
 
-def tile_smem_bytes(nent, tp):
-    """Dynamic shared memory of the tile kernel (layout in codegen.TILE_KERNEL)."""
+def tile_smem_bytes(nent, tp, direct=False):
+    """Dynamic shared memory of the tile kernel (layout in codegen.TILE_KERNEL);
+    ``direct``: without the staging buffer of the coalesced store phase."""
     sl = (8 * (nent * tp["ldl"] + 16) + 15) // 16 * 16
-    return (sl + tp["max_bytes_a"] + tp["max_bytes_b"] + 8 * tp["max_ns"] + 16
-            + 4 * tp["max_ns"] + 16)
+    stage = 0 if direct else 12 * tp["max_ns"]
+    return sl + tp["max_bytes_a"] + tp["max_bytes_b"] + stage + 32
 
 
 def codegen_tile_threads():
@@ -276,6 +277,13 @@ class Prepared(object):
                                                e._ptr(ro), pat.nrows,
                                                e._ptr(self.values), e._stream()))
             return
+        sp = getattr(self, "spatial", None)
+        if sp is not None:
+            dest, cptr2, contrib2 = sp
+            _lib.check(e.lib.spfem_reduce_scatter(e._ptr(self.local), e._ptr(cptr2),
+                                                  e._ptr(contrib2), pat.nnz, e._ptr(dest),
+                                                  e._ptr(self.values), e._stream()))
+            return
         if getattr(self, "sorted_local", False):
             _lib.check(e.lib.spfem_reduce_sorted(e._ptr(self.local), e._ptr(cptr), nslots,
                                                  e._ptr(self.values), e._stream()))
@@ -313,13 +321,22 @@ class TiledPrepared(Prepared):
         ta.ldl = tp["ldl"]
         ta.max_a = tp["max_bytes_a"]
         ta.max_b = tp["max_bytes_b"]
-        ta.max_ns = tp["max_ns"]
+        self.direct = bool(tp.get("direct", False))
+        ta.mode = 1 if tp.get("mode") == "slots" else 0
+        ta.max_ns = 0 if self.direct else tp["max_ns"]
         ta.max_nr = tp["max_nr"]
         self.targs = ta
-        self.smem = tile_smem_bytes(plan.spec.n_unique, tp)
-        # threads per CTA: enough for one element / one owned row per thread
-        need = max(tp["max_ne"], tp["max_nr"])
+        self.smem = tile_smem_bytes(plan.spec.n_unique, tp, self.direct)
+        # threads per CTA: enough for one element part / one owned row per thread
+        need = max((tp["max_ne"] + 31) // 32 * 32 * getattr(plan.spec, "npart", 1),
+                   tp["max_nr"])
         self.threads = int(min(codegen_tile_threads(), max(64, (need + 31) // 32 * 32)))
+        if ta.mode == 1:
+            # slot-parallel phase: 256 threads measured best while two or more
+            # CTAs share an SM; a tile that fills the SM alone takes the maximum
+            self.threads = 256 if self.smem <= 113 * 1024 else codegen_tile_threads()
+        if os.environ.get("SPFEM_TILE_THREADS"):
+            self.threads = int(os.environ["SPFEM_TILE_THREADS"])
         self.n_launches = 1
 
     def launch(self):
@@ -578,7 +595,8 @@ class Engine(object):
                 return FanPrepared(self, plan, kernel, fk, a, pat, fp)
         tp = None
         if tind is None and plan.bilinear and self.fused:
-            tp = self.tile_plan(pat, n, spec.n_entries, spec.nw > 0, tuple(spec.alias))
+            tp = self.tile_plan(pat, n, spec.n_entries, spec.nw > 0, tuple(spec.alias),
+                                getattr(spec, "n_terms", 0))
         if tp is not None:
             tk = get_kernel(plan.source, plan.name + "_tile")
             return TiledPrepared(self, plan, kernel, tk, a, None, pat, tp, keep=(wt,))
@@ -604,6 +622,9 @@ class Engine(object):
                 minpos.scatter_reduce_(0, row_of_slot[slot_of_c], c % n, reduce="amin")
                 ro = pat._row_order = torch.argsort(minpos, stable=True).to(torch.int32)
             prep.row_order = ro
+        elif (layout == "spatial" and plan.bilinear and tind is None and n > 0
+                and pat.indptr.dtype == torch.int32):
+            prep.spatial = self.spatial_slots(pat, n)
         elif layout == "sorted" and plan.bilinear and n > 0:
             # the element kernel scatters every local entry to its position in
             # slot-sorted order; the reduction then reads contiguous runs
@@ -625,6 +646,36 @@ class Engine(object):
                 ce = pat._contrib_elem = ((c % n) * spec.n_entries + c // n).to(torch.int32)
             prep.contrib_override = ce
         return prep
+
+    def spatial_slots(self, pat, n):
+        """CSR slots re-listed row by row in the spatial (Morton) order of the
+        elements -- key of a row = its first element -- with the contribution
+        lists laid out in that order (``spfem_reduce_scatter``).  Cached on the
+        pattern.  Returns ``(dest, cptr2, contrib2)``."""
+        sp = getattr(pat, "_spatial", None)
+        if sp is not None:
+            return sp
+        torch, dev = self.torch, self.device
+        cptr = pat.cptr.long()
+        counts = cptr[1:] - cptr[:-1]
+        ar = torch.arange(pat.nnz, device=dev)
+        slot_of_c = torch.repeat_interleave(ar, counts)
+        row_of_slot = torch.repeat_interleave(torch.arange(pat.nrows, device=dev),
+                                              (pat.indptr[1:] - pat.indptr[:-1]).long())
+        first = torch.full((pat.nrows,), n, dtype=torch.int64, device=dev)
+        first.scatter_reduce_(0, row_of_slot[slot_of_c], pat.contrib.long() % n, reduce="amin")
+        del slot_of_c
+        order = torch.argsort(first[row_of_slot], stable=True)
+        del row_of_slot, first
+        c2 = counts[order]
+        cptr2 = torch.zeros(pat.nnz + 1, dtype=torch.int64, device=dev)
+        torch.cumsum(c2, 0, out=cptr2[1:])
+        new_slot = torch.repeat_interleave(ar, c2)
+        src = cptr[order][new_slot] + (torch.arange(new_slot.numel(), device=dev)
+                                       - cptr2[:-1][new_slot])
+        contrib2 = pat.contrib[src].contiguous()
+        sp = pat._spatial = (order.to(torch.int32), cptr2.to(torch.int32), contrib2)
+        return sp
 
     def fan_plan(self, pat):
         """Plan of the vertex-fan kernel for ``pat`` (cached on the pattern), or
@@ -658,44 +709,71 @@ class Engine(object):
         pat._fan_plan = fp
         return fp
 
-    def tile_plan(self, pat, n, nent, with_el=False, alias=None):
+    def tile_plan(self, pat, n, nent, with_el=False, alias=None, n_terms=0):
         """Tile plan of the fused kernel for ``pat`` (cached on the pattern);
         ``None`` if a tile does not fit in shared memory / 16-bit indices."""
         cache = getattr(pat, "_tile_plans", None)
         if cache is None:
             cache = pat._tile_plans = {}
-        ckey = (nent, with_el, alias)
+        ckey = (nent, with_el, alias, os.environ.get("SPFEM_TILE_MODE", "slots"),
+                os.environ.get("SPFEM_TILE_E", "0"), os.environ.get("SPFEM_TILE_DIRECT", "auto"))
         nuniq = (max(alias) + 1) if alias else nent
         if ckey in cache:
             return cache[ckey]
         from .tileplan import build_tile_plan
-        threads = codegen_tile_threads()
-        E = int(os.environ.get("SPFEM_TILE_E", "0"))
-        if E <= 0:
-            # about one element per thread, and the local matrices of a tile
-            # within ~64 KB of shared memory
-            E = min(int(threads / 1.15), (64 * 1024) // (8 * nuniq)) // 32 * 32
-            E = max(E, 32)
+        mode = os.environ.get("SPFEM_TILE_MODE", "slots")
+        want_direct = os.environ.get("SPFEM_TILE_DIRECT", "auto")
+        if mode == "slots":
+            want_direct = "1"          # slot-parallel stores are coalesced as they are
+        limit = 220 * 1024
+        force = os.environ.get("SPFEM_FUSED", "1") == "force"
+        E_env = int(os.environ.get("SPFEM_TILE_E", "0"))
+        if E_env > 0:
+            cands = [E_env]
+            while cands[-1] > 16:
+                cands.append(max(16, cands[-1] * 3 // 4 // 16 * 16))
+        elif mode == "slots":
+            # measured (profiles/r01_configs.json): three to four CTAs per SM
+            # (<= 56 KB each) but at least 64 elements per tile
+            cands = [384, 256, 160, 96, 64, 48, 32, 16]
+        else:
+            threads = codegen_tile_threads()
+            E0 = max(32, min(int(threads / 1.15), (64 * 1024) // (8 * nuniq)) // 32 * 32)
+            cands = [E0]
+            while cands[-1] > 16:
+                cands.append(max(16, cands[-1] * 3 // 4 // 16 * 16))
         tp = None
         t0 = time.perf_counter()
-        while E >= 16:
+        for E in cands:
+            if E_env <= 0 and mode == "slots" and E > 64 and 8 * nuniq * (1.3 * E + 32) > 56 * 1024:
+                continue                # cannot fit the preferred footprint
             try:
                 tp = build_tile_plan(self.torch, pat.indptr, pat.cptr, pat.contrib,
                                      n, nent, E, self.t, with_el=with_el,
                                      dim=self.p.shape[0], alias=alias,
                                      schedule={"0": False, "full": "full"}.get(
-                                         os.environ.get("SPFEM_SCHEDULE", "inslot"), "inslot"))
+                                         os.environ.get("SPFEM_SCHEDULE", "inslot"), "inslot"),
+                                     mode=mode)
             except ValueError:
                 tp = None
-            if tp is not None and tile_smem_bytes(nuniq, tp) <= 220 * 1024:
+                continue
+            staged = tile_smem_bytes(nuniq, tp)
+            direct = tile_smem_bytes(nuniq, tp, True)
+            if want_direct == "1" or (want_direct == "auto" and staged > limit):
+                tp["direct"], smem = True, direct
+            else:
+                tp["direct"], smem = False, staged
+            if smem > limit:
+                tp = None
+                continue
+            if E_env > 0 or mode != "slots" or smem <= 56 * 1024 or E <= 64:
                 break
             tp = None
-            E //= 2
-        # the fused kernel pays off while the halo stays thin and the local
-        # matrix is small (measured: profiles/r01_configs.json); otherwise the
-        # two-kernel route is faster
-        if tp is not None and os.environ.get("SPFEM_FUSED", "1") != "force":
-            if tp["halo_factor"] > 1.35 or nuniq > 40:
+        # the fused kernel pays off while recomputing the halo elements is cheap
+        # (multiply-adds per element x halo factor; measured: profiles/r01_configs.json:
+        # per-point geometry of the Q2 element -> two-kernel route)
+        if tp is not None and not force:
+            if n_terms * tp["halo_factor"] > 1500:
                 tp = None
         if tp is not None:
             from .tileplan import fill_coordinates

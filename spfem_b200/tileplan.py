@@ -48,10 +48,28 @@ def _pad(x, m):
     return (x + m - 1) // m * m
 
 
+def _wrap16(torch, x):
+    """Unsigned 16-bit values stored through an int16 view."""
+    return torch.where(x >= 32768, x - 65536, x).to(torch.int16)
+
+
 def build_tile_plan(torch, indptr, cptr, contrib, n, nent, E, vt, with_el=True, dim=2,
-                    alias=None, schedule="inslot"):
+                    alias=None, schedule="inslot", mode="rows"):
     """All tensor arguments live on one device.  ``vt``: int32 ``(nve, n)``
-    vertex table in device element order.  Returns a dict of tensors/ints."""
+    vertex table in device element order.  Returns a dict of tensors/ints.
+
+    ``mode="rows"``: section B as described above (one thread per owned row).
+    ``mode="slots"``: one thread per CSR slot (large local matrices: many short
+    independent sums instead of few long serial ones); section B is then
+
+      gdelta int32  [nr]     CSR position of the row's first slot minus its tile
+                             slot index (tile slots are in CSR order)
+      soff   uint16 [ns+1]   start of every slot's contributions in ``contrib``
+      srow   uint16 [ns]     owned-row index of the slot
+      contrib uint16 [nc+1]  shared-memory index of a contribution
+
+    with descriptor entries 6 / 7 / 8 = byte offsets of soff / srow / contrib."""
+    slots_mode = mode == "slots"
     dev = indptr.device
     i64 = torch.int64
     N = indptr.numel() - 1
@@ -77,7 +95,7 @@ def build_tile_plan(torch, indptr, cptr, contrib, n, nent, E, vt, with_el=True, 
     # rows of a regular mesh then finish their slots at the same steps, so the
     # lanes of a warp leave the inner accumulation loop together
     csr_pos = ar_nnz - indptr[row_of_slot]           # position of the slot inside its row
-    if int(csr_pos.max().item()) > 255 or int(counts.max().item()) > 65535:
+    if slots_mode or int(csr_pos.max().item()) > 255 or int(counts.max().item()) > 65535:
         within = ar_nnz                               # very long rows: keep CSR order
     else:
         within = torch.argsort((row_of_slot << 32) | ((65535 - counts) << 16) | csr_pos)
@@ -140,7 +158,7 @@ def build_tile_plan(torch, indptr, cptr, contrib, n, nent, E, vt, with_el=True, 
     sched_len = torch.zeros(n_rows_tot, dtype=torch.int32, device=dev)
     out_idx = out_perm = None
     stride = 0
-    if schedule and n_rows_tot and max_slots <= 255:
+    if schedule and n_rows_tot and max_slots <= 255 and not slots_mode:
         from . import _lib
         import ctypes as C
         lib = _lib.load()
@@ -243,10 +261,20 @@ def build_tile_plan(torch, indptr, cptr, contrib, n, nent, E, vt, with_el=True, 
     off_el = nve * ne_pad * 2
     off_pc = off_el + (ne_pad * 4 if with_el else 0)
     bytes_a = off_pc + dim * nvt_pad * 8
-    off_rowbase = torch.zeros_like(nr)
-    off_cptr = ((nr + 1) * 8 + 15) // 16 * 16          # = offset of the perm section
-    off_contrib = off_cptr + (ns + 15) // 16 * 16
-    bytes_b = off_contrib + (nc * 2 + 15) // 16 * 16
+    if slots_mode:
+        nc = torch.bincount(tile_c, minlength=ntiles)[:ntiles]
+        c0 = torch.cumsum(nc, 0) - nc
+        if int(nc.max().item()) > 65535 or int(nr.max().item()) > 65535:
+            raise ValueError("more than 65535 contributions / rows in one tile")
+        off_cptr = (nr * 4 + 15) // 16 * 16                  # soff
+        off_rowbase = off_cptr + ((ns + 1) * 2 + 15) // 16 * 16   # srow
+        off_contrib = off_rowbase + (ns * 2 + 15) // 16 * 16
+        bytes_b = off_contrib + ((nc + 1) * 2 + 15) // 16 * 16
+    else:
+        off_rowbase = torch.zeros_like(nr)
+        off_cptr = ((nr + 1) * 8 + 15) // 16 * 16          # = offset of the perm section
+        off_contrib = off_cptr + (ns + 15) // 16 * 16
+        bytes_b = off_contrib + (nc * 2 + 15) // 16 * 16
     tile_bytes = bytes_a + bytes_b
     blob_off = torch.cumsum(tile_bytes, 0) - tile_bytes
     total = int(tile_bytes.sum().item())
@@ -277,16 +305,28 @@ def build_tile_plan(torch, indptr, cptr, contrib, n, nent, E, vt, with_el=True, 
     bbase = blob_off + bytes_a
     hrow_local = heads_cum[hidx] - 1 - r0[tile_sorted[hidx]]
     slot_local = ar_nnz - s0[tile_sorted]
-    ri_base = (bbase // 4)[tile_sorted[hidx]] + 2 * hrow_local
-    b32[ri_base] = gdelta.to(torch.int32)
-    packed = slot_local[hidx] + (kstart_local << 16)
-    b32[ri_base + 1] = torch.where(packed >= 2 ** 31, packed - 2 ** 32, packed).to(torch.int32)
-    # terminating entry of every tile: {0, ns | nc << 16}
-    endp = ns + (nc << 16)
-    b32[(bbase // 4) + 2 * nr + 1] = torch.where(endp >= 2 ** 31, endp - 2 ** 32, endp).to(torch.int32)
-    cb_base = ((bbase + off_contrib) // 2)
-    b16[cb_base[ent_tile] + (row_k0[ent_row] + ent_t - c0[ent_tile])] = ent_val.to(torch.int16)
-    blob[(bbase + off_cptr)[tile_sorted] + slot_local] = perm8.to(torch.uint8)
+    if slots_mode:
+        b32[(bbase // 4)[tile_sorted[hidx]] + hrow_local] = gdelta.to(torch.int32)
+        cstart = torch.cumsum(counts_s, 0) - counts_s        # first contribution of every slot
+        b16[((bbase + off_cptr) // 2)[tile_sorted] + slot_local] = \
+            _wrap16(torch, cstart - c0[tile_sorted])
+        b16[((bbase + off_cptr) // 2) + ns] = _wrap16(torch, nc)
+        b16[((bbase + off_rowbase) // 2)[tile_sorted] + slot_local] = \
+            _wrap16(torch, heads_cum - 1 - r0[tile_sorted])
+        cb_base = ((bbase + off_contrib) // 2)
+        ar_c = torch.arange(contrib16.numel(), device=dev)
+        b16[cb_base[tile_c] + (ar_c - c0[tile_c])] = contrib16.to(torch.int16)
+    else:
+        ri_base = (bbase // 4)[tile_sorted[hidx]] + 2 * hrow_local
+        b32[ri_base] = gdelta.to(torch.int32)
+        packed = slot_local[hidx] + (kstart_local << 16)
+        b32[ri_base + 1] = torch.where(packed >= 2 ** 31, packed - 2 ** 32, packed).to(torch.int32)
+        # terminating entry of every tile: {0, ns | nc << 16}
+        endp = ns + (nc << 16)
+        b32[(bbase // 4) + 2 * nr + 1] = torch.where(endp >= 2 ** 31, endp - 2 ** 32, endp).to(torch.int32)
+        cb_base = ((bbase + off_contrib) // 2)
+        b16[cb_base[ent_tile] + (row_k0[ent_row] + ent_t - c0[ent_tile])] = ent_val.to(torch.int16)
+        blob[(bbase + off_cptr)[tile_sorted] + slot_local] = perm8.to(torch.uint8)
     z = torch.zeros_like(ne)
     desc = torch.stack([blob_off // 16, bytes_a, bytes_b, ne, ne_pad, ns, off_cptr,
                         off_rowbase, off_contrib, nr, nc, nvt_pad, off_pc,
@@ -294,7 +334,7 @@ def build_tile_plan(torch, indptr, cptr, contrib, n, nent, E, vt, with_el=True, 
     if int(desc.max().item()) > 2 ** 31 - 1:
         raise ValueError("tile plan offsets exceed 32 bits")
     return {
-        "ntiles": ntiles, "ldl": ldl, "E": E, "nve": nve, "nuniq": nent,
+        "ntiles": ntiles, "ldl": ldl, "E": E, "nve": nve, "nuniq": nent, "mode": mode,
         "desc": desc.to(torch.int32).contiguous(),
         "blob": blob,
         "max_bytes_a": int(bytes_a.max().item()),
@@ -326,12 +366,25 @@ def emulate(plan, local, nnz):
     for ti, (off16, ba, bb, ne, ne_pad, ns, o_cp, o_rb, o_cb, nr, nc, *_r) in enumerate(desc):
         B = blob[off16 * 16 + ba: off16 * 16 + ba + bb]
         elems = all_elems[e0s[ti]: e0s[ti] + ne]
-        rinfo = B[:(nr + 1) * 8].view(np.int32).astype(np.int64).reshape(nr + 1, 2)
-        perm = B[o_cp:o_cp + ns].astype(np.int64)
-        contrib = B[o_cb:o_cb + 2 * nc].view(np.uint16).astype(np.int64)
         sLz = np.zeros(nent * ldl + 16)
         for idx in range(nent):
             sLz[idx * ldl: idx * ldl + ne] = local[idx, elems]
+        if plan.get("mode") == "slots":
+            gd = B[:nr * 4].view(np.int32).astype(np.int64)
+            soff = B[o_cp:o_cp + 2 * (ns + 1)].view(np.uint16).astype(np.int64)
+            srow = B[o_rb:o_rb + 2 * ns].view(np.uint16).astype(np.int64)
+            contrib = B[o_cb:o_cb + 2 * nc].view(np.uint16).astype(np.int64)
+            for sl in range(ns):
+                acc = 0.0
+                for kk in range(soff[sl], soff[sl + 1]):
+                    acc += sLz[contrib[kk]]
+                g = gd[srow[sl]] + sl
+                values[g] = acc
+                written[g] += 1
+            continue
+        rinfo = B[:(nr + 1) * 8].view(np.int32).astype(np.int64).reshape(nr + 1, 2)
+        perm = B[o_cp:o_cp + ns].astype(np.int64)
+        contrib = B[o_cb:o_cb + 2 * nc].view(np.uint16).astype(np.int64)
         for row in range(nr):
             packed = rinfo[row, 1] & 0xffffffff
             kend = (rinfo[row + 1, 1] & 0xffffffff) >> 16

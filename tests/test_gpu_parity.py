@@ -116,7 +116,7 @@ def test_device_resident_result():
 @pytest.mark.parametrize("name", ["trip1_lap_r6", "trip2_lap", "vecp2_elasticity",
                                   "stokes_b", "tetp2_lap", "q2_lap",
                                   "trip1_interp_mass", "trip1_mass_x2"])
-@pytest.mark.parametrize("mode", ["unfused", "small_tiles"])
+@pytest.mark.parametrize("mode", ["unfused", "small_tiles", "slot_parallel", "direct_store"])
 def test_both_assembly_paths(name, mode, monkeypatch):
     """The two-kernel path (local matrices in HBM + gather reduction) and the
     fused tile kernel with many small tiles (exercises halos and row ownership)
@@ -126,6 +126,14 @@ def test_both_assembly_paths(name, mode, monkeypatch):
         monkeypatch.setenv("SPFEM_LOCAL_LAYOUT", "entry")
     else:
         monkeypatch.setenv("SPFEM_TILE_E", "32")
+        if mode == "slot_parallel":                 # one thread per CSR slot in phase B
+            monkeypatch.setenv("SPFEM_TILE_MODE", "slots")
+        elif mode == "direct_store":                # row-owner threads store without staging
+            monkeypatch.setenv("SPFEM_TILE_MODE", "rows")
+            monkeypatch.setenv("SPFEM_TILE_DIRECT", "1")
+        else:
+            monkeypatch.setenv("SPFEM_TILE_MODE", "rows")
+            monkeypatch.setenv("SPFEM_TILE_DIRECT", "0")
         monkeypatch.setenv("SPFEM_FUSED", "force")   # bypass the "is it worth it" heuristic
         monkeypatch.setenv("SPFEM_FAN", "0")         # (the tile kernel, not the vertex-fan kernel)
     case = cases.BY_NAME[name]
@@ -308,6 +316,21 @@ def test_row_ordered_reduction(name, monkeypatch):
     asm = util.assembler_for(case)
     prep = asm.prepare_iasm(case.form)
     assert prep.n_launches == 2 and getattr(prep, "row_order", None) is not None
+    prep.launch()
+    util.check(prep.result(), util.golden(case))
+
+
+@pytest.mark.parametrize("name", ["trip1_lap_r6", "vecp2_elasticity", "tetp2_lap", "stokes_b",
+                                  "q2_lap"])
+def test_spatially_ordered_reduction(name, monkeypatch):
+    """Two-kernel route with the slots re-listed in the spatial order of the
+    elements (spfem_reduce_scatter)."""
+    monkeypatch.setenv("SPFEM_FUSED", "0")
+    monkeypatch.setenv("SPFEM_LOCAL_LAYOUT", "spatial")
+    case = cases.BY_NAME[name]
+    asm = util.assembler_for(case)
+    prep = asm.prepare_iasm(case.form)
+    assert prep.n_launches == 2 and getattr(prep, "spatial", None) is not None
     prep.launch()
     util.check(prep.result(), util.golden(case))
 

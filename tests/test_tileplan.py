@@ -95,3 +95,11 @@ def test_tile_plan_reproduces_assembly(name, E):
     v1, w1 = emulate(tp1, uniq, nnz)
     assert np.all(w1 == 1) and np.max(np.abs(v1 - ref.data)) <= 1e-12 * scale
     assert tp1["list_growth"] < 1.06
+    # slot-parallel section B (one thread per CSR slot)
+    tp2 = build_tile_plan(torch, torch.from_numpy(indptr), torch.from_numpy(cptr),
+                          torch.from_numpy(contrib), n, plan.spec.n_entries, E,
+                          torch.from_numpy(vt), dim=asm.mesh.p.shape[0],
+                          alias=plan.spec.alias, mode="slots")
+    v2, w2 = emulate(tp2, uniq, nnz)
+    assert np.all(w2 == 1) and np.max(np.abs(v2 - ref.data)) <= 1e-12 * scale
+    assert tp2["halo_factor"] == tp1["halo_factor"]

@@ -52,6 +52,11 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default=None)
     ap.add_argument("--only", default=None, help="substring of the configuration name")
+    ap.add_argument("--modes", default="fused,two_kernel,two_kernel_spatial")
+    ap.add_argument("--force", action="store_true",
+                    help="fused tile kernel even where the heuristic prefers two kernels")
+    ap.add_argument("--refine-delta", type=int, default=0, dest="dref",
+                    help="added to every configuration's refinement level")
     args = ap.parse_args()
     peak = 6558.1
     pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -59,10 +64,10 @@ def main():
         peak = float(json.load(open(pk))["hbm_gbs"])
     out = []
     for name, mesh, ref, eu, ncu, ev, ncv, form, C in CONFIGS:
-        if args.only and args.only not in name:
+        if args.only and not any(name.startswith(o) for o in args.only.split(",")):
             continue
         m = getattr(sp, mesh)()
-        m.refine(ref)
+        m.refine(ref + args.dref)
         e_u = getattr(sp.element, "Element" + eu)()
         e_u = sp.ElementH1Vec(e_u) if ncu > 1 else e_u
         if ev is None and ncv == ncu:
@@ -73,9 +78,9 @@ def main():
             a = AssemblerElement(m, e_u, e_v)
         nt, nv, dim = m.t.shape[1], m.p.shape[1], m.p.shape[0]
         res = {"config": name, "nt": nt}
-        for mode in ("fused", "two_kernel", "two_kernel_rows"):
-            os.environ["SPFEM_FUSED"] = "1" if mode == "fused" else "0"
-            os.environ["SPFEM_LOCAL_LAYOUT"] = "rows" if mode == "two_kernel_rows" else "entry"
+        for mode in args.modes.split(","):
+            os.environ["SPFEM_FUSED"] = ("force" if args.force else "1") if mode == "fused" else "0"
+            os.environ["SPFEM_LOCAL_LAYOUT"] = "spatial" if mode == "two_kernel_spatial" else "entry"
             a._engine = None
             t0 = time.perf_counter()
             prep = a.prepare_iasm(form)
@@ -94,7 +99,10 @@ def main():
             res[mode + "_frac_of_hbm_peak"] = round(balg / (ms * 1e-3) / 1e9 / peak, 4)
             if mode == "fused":
                 res["tile"] = {"E": prep.tp["E"], "ldl": prep.tp["ldl"], "threads": prep.threads,
-                               "halo": round(prep.tp["halo_factor"], 3), "smem": prep.smem}
+                               "halo": round(prep.tp["halo_factor"], 3), "smem": prep.smem,
+                               "direct": bool(prep.tp.get("direct", False)),
+                               "mode": prep.tp.get("mode", "rows"),
+                               "npart": getattr(prep.plan.spec, "npart", 1)}
             del prep
             torch.cuda.empty_cache()
         print(json.dumps(res))
