@@ -386,6 +386,62 @@ class AssemblerElement(Assembler):
         plan = _Plan("functional", spec, src, "spfem_elem", False, wkeys)
         return self._get_engine().run_functional(plan, interp)
 
+    def fnorm(self, form, interp, intorder=None, interior=False, normals=True):
+        """Facet-wise squared L2 norms ``int_F form(...)^2`` of interpolated
+        solution vectors (spfem/assembly.py:1185-1271): boundary facets with
+        ``form(u, du, x, n, t, h)``, interior facets with
+        ``form(u1, u2, du1, du2, x, n, t, h)``.  Returns ``(values, find)``."""
+        mesh = self.mesh
+        find = mesh.interior_facets() if interior else mesh.boundary_facets()
+        if not isinstance(interp, dict):
+            raise Exception("The input solution vector(s) must be in a "
+                            "dictionary! Pass e.g. {0:u} instead of u.")
+        if intorder is None:
+            intorder = 2 * self.elem_u.maxdeg
+        names = _argnames(form)
+        if ('u1' in names or 'du1' in names) and not interior:
+            raise Exception("The supplied form contains u1 although "
+                            "no interior=True is given.")
+        wkeys = self._check_interp(interp)
+        X, W = get_quadrature(mesh.brefdom, intorder)
+        X = np.atleast_2d(X)
+        dim = mesh.p.shape[0]
+        if mesh.refdom not in ("tri", "tet"):
+            raise NotImplementedError("fnorm: unsupported reference domain %r"
+                                      % (mesh.refdom,))
+        bu, ncu, _, _ = self._elem_info()
+        if ncu != 1:
+            raise NotImplementedError("fnorm: scalar elements only")
+        x = {k: Form.coef(Coef.sym("x%d" % k, True)) for k in range(dim)}
+        h = Form.coef(Coef.sym("hf", True))
+        n = ({k: Form.coef(Coef.sym("n%d" % k, True)) for k in range(dim)}
+             if normals else {})
+        t = ({k: Form.coef(Coef.sym("t%d" % k, True)) for k in range(2)}
+             if normals and dim == 2 else {})
+
+        def fields(tag):
+            w = {key: Form.coef(Coef.sym("w%d%s" % (s, tag), True))
+                 for s, key in enumerate(wkeys)}
+            dw = {key: {a: Form.coef(Coef.sym("dw%d%s_%d" % (s, tag, a), True))
+                        for a in range(dim)} for s, key in enumerate(wkeys)}
+            return w, dw
+        w1, dw1 = fields("")
+        avail = {'x': x, 'n': n, 't': t, 'h': h}
+        if interior:
+            w2, dw2 = fields("b")
+            avail.update({'u1': w1, 'u2': w2, 'du1': dw1, 'du2': dw2})
+        else:
+            avail.update({'u': w1, 'du': dw1})
+        val = Form.coef(call_form(form, names, avail).pure("fnorm form"))
+        from .tracer import NONE
+        blocks = [{(0, 0): Form({(NONE, NONE): (val * val).pure()})}]
+        spec = codegen.FacetSpec(mesh.refdom, dim, False, interior, bu.nbfun_ref(), 1, 1, 1,
+                                 blocks, [(1, 1)], X, W, bu.polys(), bu.polys(),
+                                 normals=normals, nw=len(wkeys), functional=True)
+        src = codegen.generate_facet(spec, "spfem_facet")
+        plan = _Plan("facet_functional", spec, src, "spfem_facet", False, wkeys)
+        return self._get_engine().run_facet_functional(plan, np.asarray(find), interp), find
+
     def L2error(self, uh, exact, intorder=None):
         """Global L2 error ``||exact - uh||_0`` through the identity
         ``(u,u) + (uh,uh) - 2 (u,uh)`` (spfem/assembly.py:1353-1402).  ``exact``

@@ -125,14 +125,36 @@ struct SpfemTileArgs {
     int max_a, max_b;             /* smem bytes reserved for blob sections A / B  */
     int max_ns, max_nr;           /* largest slot / row count of a tile; max_ns = 0:
                                      no staging buffer, values stored from phase B1 */
-    int mode;                     /* 0: thread per owned row, 1: thread per CSR slot */
+    int mode;                     /* 0: thread per owned row, 1: thread per CSR slot,
+                                     2: thread per slot + packed local values     */
+    int store;                    /* doubles reserved for the local values        */
+};
+/* Packed shared-memory image of one element's local values (tileplan.py,
+   mode "compact"): only the values whose mask bit is set are stored, value u at
+   base[number of set bits below u].  The element body writes through
+   out[u] = val, u a literal after inlining.                                   */
+struct SpfemPacked {
+    double *base;
+    unsigned m[SPFEM_NMASK];
+    int pre[SPFEM_NMASK];
+    struct Ref {
+        double *p; bool on;
+        __device__ __forceinline__ void operator=(const double v) const { if (on) *p = v; }
+    };
+    __device__ __forceinline__ Ref operator[](const long long u) const {
+        const int w = (int)(u >> 5), b = (int)(u & 31);
+        Ref r;
+        r.on = ((m[w] >> b) & 1u) != 0u;
+        r.p = base + pre[w] + __popc(m[w] & ((1u << b) - 1u));
+        return r;
+    }
 };
 extern "C" __global__ void __launch_bounds__(@THREADS@, @MINB@) @NAME@_tile(const SpfemTileArgs T)
 {
     extern __shared__ __align__(128) unsigned char spfem_smem_raw[];
     const int ldl = T.ldl;
     double *sL = (double *)spfem_smem_raw;
-    unsigned char *sA = spfem_smem_raw + (((size_t)8 * (SPFEM_NUNIQUE * ldl + 16) + 15) & ~(size_t)15);
+    unsigned char *sA = spfem_smem_raw + (((size_t)8 * T.store + 15) & ~(size_t)15);
     unsigned char *sB = sA + T.max_a;
     double *sV = (double *)(sB + T.max_b);
     unsigned long long *bars = (unsigned long long *)(sV + T.max_ns);
@@ -140,7 +162,8 @@ extern "C" __global__ void __launch_bounds__(@THREADS@, @MINB@) @NAME@_tile(cons
     const int *d = T.desc + 16 * (size_t)blockIdx.x;
     const int bytes_a = d[1], bytes_b = d[2], ne = d[3], ne_pad = d[4], ns = d[5], nr = d[9];
     if (ne == 0 || ns == 0) return;
-    if (threadIdx.x < 16) sL[SPFEM_NUNIQUE * ldl + threadIdx.x] = 0.0;   /* idle-step targets */
+    if (T.mode == 0 && threadIdx.x < 16)
+        sL[SPFEM_NUNIQUE * ldl + threadIdx.x] = 0.0;          /* idle-step targets */
     if (threadIdx.x == 0) {
         spfem_mbar_init(&bars[0], 1);
         spfem_mbar_init(&bars[1], 1);
@@ -159,11 +182,32 @@ extern "C" __global__ void __launch_bounds__(@THREADS@, @MINB@) @NAME@_tile(cons
        local value (large local matrices: keeps all threads of the CTA busy); the
        part index is uniform inside a warp                                       */
     const int ne32 = (ne + 31) & ~31;
-    for (int w = threadIdx.x; w < ne32 * SPFEM_NPART; w += blockDim.x) {
-        const int part = w / ne32, el = w - part * ne32;
-        if (el >= ne) continue;
-        switch (part) {
+    if (T.mode == 2) {
+        const int *sbase = (const int *)(sA + d[15]);
+        const unsigned *smask = (const unsigned *)(sbase + ne_pad);
+        for (int w = threadIdx.x; w < ne32 * SPFEM_NPART; w += blockDim.x) {
+            const int part = w / ne32, el = w - part * ne32;
+            if (el >= ne) continue;
+            SpfemPacked po;
+            po.base = sL + sbase[el];
+            int below = 0;
+#pragma unroll
+            for (int q = 0; q < SPFEM_NMASK; ++q) {
+                po.m[q] = smask[q * ne_pad + el];
+                po.pre[q] = below;
+                below += __popc(po.m[q]);
+            }
+            switch (part) {
+@PCASES@
+            }
+        }
+    } else {
+        for (int w = threadIdx.x; w < ne32 * SPFEM_NPART; w += blockDim.x) {
+            const int part = w / ne32, el = w - part * ne32;
+            if (el >= ne) continue;
+            switch (part) {
 @CASES@
+            }
         }
     }
     /* phase B1: one thread per owned row walks the row's contribution list
@@ -178,19 +222,30 @@ extern "C" __global__ void __launch_bounds__(@THREADS@, @MINB@) @NAME@_tile(cons
     const unsigned char *pm = (const unsigned char *)(sB + d[6]);   /* slot order -> CSR order */
     const bool direct = T.max_ns == 0;           /* no staging buffer: store from B1 */
     __syncthreads();
-    if (T.mode == 1) {
+    if (T.mode != 0) {
         /* phase B, slot-parallel: one thread per CSR slot of the tile (slots in
            CSR order, so a warp stores runs of consecutive values); the first two
            contributions are fetched together, longer lists finish in a loop --
            always in list order => bitwise reproducible                         */
         const int *gd = (const int *)sB;
-        const unsigned short *soff = (const unsigned short *)(sB + d[6]);
-        const unsigned short *srow = (const unsigned short *)(sB + d[7]);
-#pragma unroll 2
-        for (int s = threadIdx.x; s < ns; s += blockDim.x) {
-            const unsigned k0 = soff[s], k1 = soff[s + 1];
+        const uint2 *chk = (const uint2 *)(sB + d[6]);     /* {row flags, row | first << 16} */
+        const unsigned char *cnt8 = sB + d[7];             /* contributions per slot */
+        const unsigned lane = threadIdx.x & 31u;
+        for (int sb = (int)(threadIdx.x - lane); sb < ns; sb += blockDim.x) {
+            const int s = sb + (int)lane;
+            const unsigned cnt = s < ns ? (unsigned)cnt8[s] : 0u;
+            unsigned incl = cnt;                           /* warp prefix sum of the counts */
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned up = __shfl_up_sync(0xffffffffu, incl, o);
+                if ((int)lane >= o) incl += up;
+            }
+            if (s >= ns) continue;
+            const uint2 ck = chk[s >> 5];
+            const unsigned k0 = (ck.y >> 16) + incl - cnt, k1 = k0 + cnt;
+            const int row = (int)(ck.y & 0xffffu) - 1 + __popc(ck.x & (0xffffffffu >> (31u - lane)));
             const unsigned c0 = cb[k0], c1 = cb[k0 + 1];
-            const int g = gd[srow[s]] + s;
+            const int g = gd[row] + s;
             double acc = sL[c0];
             if (k0 + 1 < k1) acc += sL[c1];
             for (unsigned k = k0 + 2; k < k1; ++k) acc += sL[cb[k]];
@@ -849,6 +904,7 @@ def generate_interior(spec, name="spfem_elem"):
     src.append("#define SPFEM_NENTRIES %d" % spec.n_entries)
     src.append("#define SPFEM_NUNIQUE %d" % spec.n_unique)
     src.append("#define SPFEM_NPART %d" % spec.npart)
+    src.append("#define SPFEM_NMASK %d" % ((spec.n_unique + 31) // 32))
     # store of one local entry in the two-kernel route: entry-major position, or
     # (P.perm) its position in slot-sorted order
     src.append("#define SPFEM_PUT(idx, val) do { const long long a_ = (long long)(idx) * ldo + k; "
@@ -861,7 +917,7 @@ def generate_interior(spec, name="spfem_elem"):
     src.append("SPFEM_DEVICE void %s_body(const SpfemArgs &P, const long long e, "
                "const VT *__restrict__ vt, const long long ldv, const long long ev, "
                "const double *__restrict__ pc, const long long ldpc, "
-               "OUT *__restrict__ out, const long long ldo, const long long k)\n{" % name)
+               "OUT out, const long long ldo, const long long k)\n{" % name)
     src += ["    " + ln for ln in body]
     src.append("}")
     if spec.fan_ok:
@@ -892,7 +948,12 @@ def generate_interior(spec, name="spfem_elem"):
             "        case %d: %s_body<true, %d>(T.base, %s, vt, (long long)ne_pad, (long long)el, "
             "pc, ldpc, sL, (long long)ldl, (long long)el); break;" % (c, name, c, elem)
             for c in range(spec.npart))
-        src.append(TILE_KERNEL.replace("@CASES@", cases).replace("@NAME@", name)
+        pcases = "\n".join(
+            "            case %d: %s_body<true, %d>(T.base, %s, vt, (long long)ne_pad, (long long)el, "
+            "pc, ldpc, po, 1LL, 0LL); break;" % (c, name, c, elem)
+            for c in range(spec.npart))
+        src.append(TILE_KERNEL.replace("@CASES@", cases).replace("@PCASES@", pcases)
+                   .replace("@NAME@", name)
                    .replace("@THREADS@", str(TILE_THREADS))
                    .replace("@MINB@", os.environ.get("SPFEM_TILE_MINB", "1")))
     src.append("#else")
@@ -916,7 +977,11 @@ class FacetSpec(object):
     ``{(cu, cv): Form}``."""
 
     def __init__(self, refdom, dim, bilinear, interior, nbu, nbv, ncu, ncv,
-                 blocks, sides, X, W, polys_u, polys_v, normals=True, nw=0):
+                 blocks, sides, X, W, polys_u, polys_v, normals=True, nw=0,
+                 functional=False):
+        # functional: one value per facet (fnorm) -- no test functions, and the
+        # interpolated fields exist on both sides of an interior facet
+        self.functional = functional
         self.refdom, self.dim, self.bilinear = refdom, dim, bilinear
         self.interior = interior
         self.nbu, self.nbv, self.ncu, self.ncv = nbu, nbv, ncu, ncv
@@ -1016,6 +1081,10 @@ def generate_facet(spec, name="spfem_facet"):
         A("const double nlen = sqrt(%s);" % acc)
         for k in range(dim):
             A("const double n%d = %s;" % (k, _div("nn_%d" % k, "nlen")))
+        if dim == 2 and ("t0" in syms or "t1" in syms):
+            # tangent t = (-n_1, n_0)            (spfem/assembly.py:1239-1241)
+            A("const double t0 = -n1;")
+            A("const double t1 = n0;")
     A("double acc[%d];" % (len(spec.blocks) * spec.n_entries))
     A("for (int z = 0; z < %d; ++z) acc[z] = 0.0;" % (len(spec.blocks) * spec.n_entries))
     A("const double XQ[%d][%d] = {%s};" % (
@@ -1071,6 +1140,8 @@ def generate_facet(spec, name="spfem_facet"):
                                                  (spec.polys_v, spec.nbv, "pv"))):
             if side == 0 and not spec.bilinear and spec.nw == 0:
                 continue
+            if side == 1 and getattr(spec, "functional", False):
+                continue
             P_, dP_ = polys
             A("  double %s%d[%d][%d];" % (tag, s, NA, nb))
             for j in range(nb):
@@ -1078,21 +1149,29 @@ def generate_facet(spec, name="spfem_facet"):
                 for l in range(dim):
                     A("  %s%d[%d][%d] = %s;" % (tag, s, 1 + l, j,
                                                 dP_[j][l].c_expr(ynames)))
-    # interpolated w / dw on side 1           (spfem/assembly.py:1076-1089)
+    # interpolated w / dw on side 1           (spfem/assembly.py:1076-1089);
+    # fnorm also interpolates on side 2 (w<k>b, dw<k>b_<a>; assembly.py:1244-1262)
     for sl in range(spec.nw):
-        if ("w%d" % sl) in syms or any(("dw%d_%d" % (sl, a)) in syms for a in range(dim)):
-            A("  double w%d = 0.0;" % sl)
+        for s_, tag in ((1, ""), (2, "b")):
+            if s_ > nsides:
+                continue
+            if not (("w%d%s" % (sl, tag)) in syms
+                    or any(("dw%d%s_%d" % (sl, tag, a)) in syms for a in range(dim))):
+                continue
+            A("  double w%d%s = 0.0;" % (sl, tag))
             for a in range(dim):
-                A("  double dw%d_%d = 0.0;" % (sl, a))
+                A("  double dw%d%s_%d = 0.0;" % (sl, tag, a))
             A("  for (int j = 0; j < %d; ++j) {" % spec.nbu)
-            A("    const double cf = P.interp[%d][P.tdof_u[j * P.ldd + el1]];" % sl)
-            A("    w%d += cf * pu1[0][j];" % sl)
+            A("    const double cf = P.interp[%d][P.tdof_u[j * P.ldd + el%d]];" % (sl, s_))
+            A("    w%d%s += cf * pu%d[0][j];" % (sl, tag, s_))
             for a in range(dim):
                 if quad:
-                    g = " + ".join("iJ1[%d][%d] * pu1[%d][j]" % (l, a, 1 + l) for l in range(dim))
+                    g = " + ".join("iJ%d[%d][%d] * pu%d[%d][j]" % (s_, l, a, s_, 1 + l)
+                                   for l in range(dim))
                 else:
-                    g = " + ".join("iA1_%d%d * pu1[%d][j]" % (l, a, 1 + l) for l in range(dim))
-                A("    dw%d_%d += cf * (%s);" % (sl, a, g))
+                    g = " + ".join("iA%d_%d%d * pu%d[%d][j]" % (s_, l, a, s_, 1 + l)
+                                   for l in range(dim))
+                A("    dw%d%s_%d += cf * (%s);" % (sl, tag, a, g))
             A("  }")
 
     def symname(nm, scope):

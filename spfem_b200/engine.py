@@ -27,10 +27,17 @@ from . import _lib
 from .codegen import source_key
 
 
+def tile_store(nent, tp):
+    """Doubles of shared memory reserved for a tile's local values."""
+    if tp.get("mode") == "compact":
+        return tp["max_store"] + 2
+    return nent * tp["ldl"] + 16
+
+
 def tile_smem_bytes(nent, tp, direct=False):
     """Dynamic shared memory of the tile kernel (layout in codegen.TILE_KERNEL);
     ``direct``: without the staging buffer of the coalesced store phase."""
-    sl = (8 * (nent * tp["ldl"] + 16) + 15) // 16 * 16
+    sl = (8 * tile_store(nent, tp) + 15) // 16 * 16
     stage = 0 if direct else 12 * tp["max_ns"]
     return sl + tp["max_bytes_a"] + tp["max_bytes_b"] + stage + 32
 
@@ -322,7 +329,8 @@ class TiledPrepared(Prepared):
         ta.max_a = tp["max_bytes_a"]
         ta.max_b = tp["max_bytes_b"]
         self.direct = bool(tp.get("direct", False))
-        ta.mode = 1 if tp.get("mode") == "slots" else 0
+        ta.mode = {"slots": 1, "compact": 2}.get(tp.get("mode"), 0)
+        ta.store = tile_store(plan.spec.n_unique, tp)
         ta.max_ns = 0 if self.direct else tp["max_ns"]
         ta.max_nr = tp["max_nr"]
         self.targs = ta
@@ -331,7 +339,7 @@ class TiledPrepared(Prepared):
         need = max((tp["max_ne"] + 31) // 32 * 32 * getattr(plan.spec, "npart", 1),
                    tp["max_nr"])
         self.threads = int(min(codegen_tile_threads(), max(64, (need + 31) // 32 * 32)))
-        if ta.mode == 1:
+        if ta.mode != 0:
             # slot-parallel phase: 256 threads measured best while two or more
             # CTAs share an SM; a tile that fills the SM alone takes the maximum
             self.threads = 256 if self.smem <= 113 * 1024 else codegen_tile_threads()
@@ -723,7 +731,7 @@ class Engine(object):
         from .tileplan import build_tile_plan
         mode = os.environ.get("SPFEM_TILE_MODE", "slots")
         want_direct = os.environ.get("SPFEM_TILE_DIRECT", "auto")
-        if mode == "slots":
+        if mode != "rows":
             want_direct = "1"          # slot-parallel stores are coalesced as they are
         limit = 220 * 1024
         force = os.environ.get("SPFEM_FUSED", "1") == "force"
@@ -732,7 +740,7 @@ class Engine(object):
             cands = [E_env]
             while cands[-1] > 16:
                 cands.append(max(16, cands[-1] * 3 // 4 // 16 * 16))
-        elif mode == "slots":
+        elif mode != "rows":
             # measured (profiles/r01_configs.json): three to four CTAs per SM
             # (<= 56 KB each) but at least 64 elements per tile
             cands = [384, 256, 160, 96, 64, 48, 32, 16]
@@ -766,7 +774,7 @@ class Engine(object):
             if smem > limit:
                 tp = None
                 continue
-            if E_env > 0 or mode != "slots" or smem <= 56 * 1024 or E <= 64:
+            if E_env > 0 or mode == "rows" or smem <= 56 * 1024 or E <= 64:
                 break
             tp = None
         # the fused kernel pays off while recomputing the halo elements is cheap
@@ -846,6 +854,32 @@ class Engine(object):
                         keep=(fv_d, e1_d, e2_d, lf_d, wt))
         values = prep.launch()
         return self._finish(values, pat, plan.bilinear, to_host)
+
+    def run_facet_functional(self, plan, find, interp):
+        """One value per facet (``fnorm``): the generated facet kernel has a
+        single accumulator; no pattern, no reduction."""
+        torch, asm = self.torch, self.asm
+        kernel = get_kernel(plan.source, plan.name)
+        n = int(find.shape[0])
+        fv, e1, e2, lf1 = asm.facet_tables(find)
+        fv_d = self._dev(fv, np.int32)
+        e1_d = self._elements(e1).to(torch.int32)
+        e2_d = self._elements(e2).to(torch.int32)
+        lf_d = self._dev(lf1, np.int32)
+        out = self._empty(max(n, 1), torch.float64)
+        wt = self._interp_tensors(plan, interp)
+        a = _lib.SpfemArgs()
+        a.n, a.ldo, a.ldk = n, n, 1
+        a.t, a.ldt = self.t.data_ptr(), self.t.shape[1]
+        a.p, a.ldp = self.p.data_ptr(), self.p.shape[1]
+        a.tdof_u, a.ldd = self.tdof_u.data_ptr(), self.tdof_u.shape[1]
+        for s, w in enumerate(wt):
+            a.interp[s] = w.data_ptr()
+        a.fv, a.e1, a.e2, a.lf1 = (fv_d.data_ptr(), e1_d.data_ptr(),
+                                   e2_d.data_ptr(), lf_d.data_ptr())
+        a.out = out.data_ptr()
+        _lib.check(self.lib.spfem_launch(kernel, C.byref(a), 64, self._stream()))
+        return _to_host(out[:n])
 
     def _finish(self, values, pat, bilinear, to_host):
         asm = self.asm

@@ -48,6 +48,11 @@ def _pad(x, m):
     return (x + m - 1) // m * m
 
 
+def _wrap32(torch, x):
+    """Unsigned 32-bit values stored through an int32 view."""
+    return torch.where(x >= 2 ** 31, x - 2 ** 32, x).to(torch.int32)
+
+
 def _wrap16(torch, x):
     """Unsigned 16-bit values stored through an int16 view."""
     return torch.where(x >= 32768, x - 65536, x).to(torch.int16)
@@ -64,12 +69,27 @@ def build_tile_plan(torch, indptr, cptr, contrib, n, nent, E, vt, with_el=True, 
 
       gdelta int32  [nr]     CSR position of the row's first slot minus its tile
                              slot index (tile slots are in CSR order)
-      soff   uint16 [ns+1]   start of every slot's contributions in ``contrib``
-      srow   uint16 [ns]     owned-row index of the slot
+      chunk  uint32x2 [ceil(ns/32)]  per 32 slots (= one warp step): bit l of
+                             word 0 set if slot l starts a new row; word 1 =
+                             (row of slot 0 - its flag + 1) | first contribution << 16
+      count  uint8  [ns]     contributions of the slot (prefix-summed by the warp)
       contrib uint16 [nc+1]  shared-memory index of a contribution
 
-    with descriptor entries 6 / 7 / 8 = byte offsets of soff / srow / contrib."""
-    slots_mode = mode == "slots"
+    with descriptor entries 6 / 7 / 8 = byte offsets of chunk / count / contrib.
+
+    ``mode="compact"``: slot-parallel, and shared memory holds only the local
+    values that some owned slot really reads (a halo element shares one vertex,
+    edge or face with the tile's rows, i.e. a fraction of its local matrix --
+    in 3-D the halo is several times the tile): per tile element a bit mask
+    over the distinct values and the offset of its packed values,
+
+      sbase  int32  [ne_pad]      offset of the element's first stored value
+      smask  uint32 [W][ne_pad]   W = ceil(nuniq / 32) mask words
+
+    appended to section A (descriptor entry 15 = byte offset of sbase); value
+    ``u`` of element ``el`` lives at ``sbase[el] + popcount(mask bits below u)``."""
+    slots_mode = mode in ("slots", "compact")
+    compact = mode == "compact"
     dev = indptr.device
     i64 = torch.int64
     N = indptr.numel() - 1
@@ -120,13 +140,33 @@ def build_tile_plan(torch, indptr, cptr, contrib, n, nent, E, vt, with_el=True, 
     eloc = inv - e0[tile_c]
     ne_max = int(ne.max().item())
     ldl = _pad(ne_max, 32) + 1           # odd: consecutive idx rows shift banks
-    if nent * ldl > 65535:
+    if nent * ldl > 65535 and not compact:
         raise ValueError("tile too large for 16-bit shared-memory indices")
     if alias is not None:
         # aliased local entries share one shared-memory value (codegen)
         ij_s = torch.as_tensor(alias, dtype=i64, device=dev)[ij_s]
         nent = int(max(alias)) + 1
-    contrib16 = ij_s * ldl + eloc
+    max_store, W, smask, sbase = 0, (nent + 31) // 32, None, None
+    if compact:
+        nte = elems.numel()
+        te = e0[tile_c] + eloc                         # tile element of every contribution
+        upair, pinv = torch.unique(te * nent + ij_s, return_inverse=True)
+        pte, pu = upair // nent, upair % nent          # sorted by (tile element, value)
+        cnt = torch.bincount(pte, minlength=nte)
+        cum = torch.cumsum(cnt, 0) - cnt               # first pair of every tile element
+        tile_pair0 = cum[e0]                           # first pair of every tile
+        sbase = cum - tile_pair0[tile_of_u]
+        contrib16 = (torch.arange(upair.numel(), device=dev) - tile_pair0[tile_of_u[pte]])[pinv]
+        store = torch.zeros(ntiles, dtype=i64, device=dev)
+        store.scatter_add_(0, tile_of_u, cnt)
+        max_store = int(store.max().item())
+        if max_store > 65535:
+            raise ValueError("tile too large for 16-bit shared-memory indices")
+        smask = torch.zeros(W * nte, dtype=i64, device=dev)
+        smask.scatter_add_(0, (pu >> 5) * nte + pte, torch.ones_like(pu) << (pu & 31))
+        smask = smask.reshape(W, nte)
+    else:
+        contrib16 = ij_s * ldl + eloc
     counts_s = counts[slot_order]
     rows_s = row_of_slot[slot_order]
     head = torch.ones(nnz, dtype=i64, device=dev)
@@ -261,14 +301,20 @@ def build_tile_plan(torch, indptr, cptr, contrib, n, nent, E, vt, with_el=True, 
     off_el = nve * ne_pad * 2
     off_pc = off_el + (ne_pad * 4 if with_el else 0)
     bytes_a = off_pc + dim * nvt_pad * 8
+    off_base = torch.zeros_like(ne)
+    if compact:
+        off_base = bytes_a
+        bytes_a = (off_base + (1 + W) * 4 * ne_pad + 15) // 16 * 16
     if slots_mode:
         nc = torch.bincount(tile_c, minlength=ntiles)[:ntiles]
         c0 = torch.cumsum(nc, 0) - nc
         if int(nc.max().item()) > 65535 or int(nr.max().item()) > 65535:
             raise ValueError("more than 65535 contributions / rows in one tile")
-        off_cptr = (nr * 4 + 15) // 16 * 16                  # soff
-        off_rowbase = off_cptr + ((ns + 1) * 2 + 15) // 16 * 16   # srow
-        off_contrib = off_rowbase + (ns * 2 + 15) // 16 * 16
+        if int(counts_s.max().item()) > 255:
+            raise ValueError("more than 255 contributions to one CSR slot")
+        off_cptr = (nr * 4 + 15) // 16 * 16                  # chunk words
+        off_rowbase = off_cptr + (nchunk * 8 + 15) // 16 * 16     # contribution counts
+        off_contrib = off_rowbase + (ns + 15) // 16 * 16
         bytes_b = off_contrib + ((nc + 1) * 2 + 15) // 16 * 16
     else:
         off_rowbase = torch.zeros_like(nr)
@@ -291,6 +337,11 @@ def build_tile_plan(torch, indptr, cptr, contrib, n, nent, E, vt, with_el=True, 
         b16[base16 + r * npad_u + el_local] = vloc[r].to(torch.int16)
     if with_el:
         b32[((blob_off + off_el) // 4)[tile_of_u] + el_local] = elems.to(torch.int32)
+    if compact:
+        bb = ((blob_off + off_base) // 4)[tile_of_u]
+        b32[bb + el_local] = sbase.to(torch.int32)
+        for w in range(W):
+            b32[bb + (1 + w) * npad_u + el_local] = _wrap32(torch, smask[w])
     # destination (in float64 units) of coordinate d of every tile vertex:
     # pc_index + d * pc_stride
     v_local = torch.arange(vid.numel(), device=dev) - v0[tile_of_v]
@@ -308,11 +359,15 @@ def build_tile_plan(torch, indptr, cptr, contrib, n, nent, E, vt, with_el=True, 
     if slots_mode:
         b32[(bbase // 4)[tile_sorted[hidx]] + hrow_local] = gdelta.to(torch.int32)
         cstart = torch.cumsum(counts_s, 0) - counts_s        # first contribution of every slot
-        b16[((bbase + off_cptr) // 2)[tile_sorted] + slot_local] = \
-            _wrap16(torch, cstart - c0[tile_sorted])
-        b16[((bbase + off_cptr) // 2) + ns] = _wrap16(torch, nc)
-        b16[((bbase + off_rowbase) // 2)[tile_sorted] + slot_local] = \
-            _wrap16(torch, heads_cum - 1 - r0[tile_sorted])
+        # per chunk of 32 slots: {row-start flags, (row of the first slot - its flag
+        # + 1) | first contribution << 16}; per slot: number of contributions
+        flags = torch.zeros(tot_chunks, dtype=i64, device=dev)
+        flags.scatter_add_(0, rb0[tile_sorted] + slot_local // 32, head << (slot_local & 31))
+        word1 = rowbase + ((cstart[spos] - c0[chunk_tile]) << 16)
+        cw = ((bbase + off_cptr) // 4)[chunk_tile] + 2 * chunk_idx
+        b32[cw] = _wrap32(torch, flags)
+        b32[cw + 1] = _wrap32(torch, word1)
+        blob[(bbase + off_rowbase)[tile_sorted] + slot_local] = counts_s.to(torch.uint8)
         cb_base = ((bbase + off_contrib) // 2)
         ar_c = torch.arange(contrib16.numel(), device=dev)
         b16[cb_base[tile_c] + (ar_c - c0[tile_c])] = contrib16.to(torch.int16)
@@ -330,11 +385,12 @@ def build_tile_plan(torch, indptr, cptr, contrib, n, nent, E, vt, with_el=True, 
     z = torch.zeros_like(ne)
     desc = torch.stack([blob_off // 16, bytes_a, bytes_b, ne, ne_pad, ns, off_cptr,
                         off_rowbase, off_contrib, nr, nc, nvt_pad, off_pc,
-                        off_el if with_el else z - 1, nvt, z], 1)
+                        off_el if with_el else z - 1, nvt, off_base], 1)
     if int(desc.max().item()) > 2 ** 31 - 1:
         raise ValueError("tile plan offsets exceed 32 bits")
     return {
         "ntiles": ntiles, "ldl": ldl, "E": E, "nve": nve, "nuniq": nent, "mode": mode,
+        "max_store": max_store, "W": W,
         "desc": desc.to(torch.int32).contiguous(),
         "blob": blob,
         "max_bytes_a": int(bytes_a.max().item()),
@@ -366,19 +422,36 @@ def emulate(plan, local, nnz):
     for ti, (off16, ba, bb, ne, ne_pad, ns, o_cp, o_rb, o_cb, nr, nc, *_r) in enumerate(desc):
         B = blob[off16 * 16 + ba: off16 * 16 + ba + bb]
         elems = all_elems[e0s[ti]: e0s[ti] + ne]
-        sLz = np.zeros(nent * ldl + 16)
-        for idx in range(nent):
-            sLz[idx * ldl: idx * ldl + ne] = local[idx, elems]
-        if plan.get("mode") == "slots":
+        if plan.get("mode") == "compact":
+            A = blob[off16 * 16: off16 * 16 + ba]
+            ob, W = _r[4], plan["W"]
+            sb = A[ob: ob + 4 * ne_pad].view(np.int32).astype(np.int64)
+            sm = A[ob + 4 * ne_pad: ob + 4 * (1 + W) * ne_pad].view(np.uint32).reshape(W, ne_pad)
+            sLz = np.full(plan["max_store"], np.nan)
+            for el in range(ne):
+                pos = sb[el]
+                for u in range(nent):
+                    if (int(sm[u >> 5, el]) >> (u & 31)) & 1:
+                        sLz[pos] = local[u, elems[el]]
+                        pos += 1
+        else:
+            sLz = np.zeros(nent * ldl + 16)
+            for idx in range(nent):
+                sLz[idx * ldl: idx * ldl + ne] = local[idx, elems]
+        if plan.get("mode") in ("slots", "compact"):
             gd = B[:nr * 4].view(np.int32).astype(np.int64)
-            soff = B[o_cp:o_cp + 2 * (ns + 1)].view(np.uint16).astype(np.int64)
-            srow = B[o_rb:o_rb + 2 * ns].view(np.uint16).astype(np.int64)
+            nch = (ns + 31) // 32
+            chk = B[o_cp:o_cp + 8 * nch].view(np.uint32).astype(np.int64).reshape(nch, 2)
+            cnt = B[o_rb:o_rb + ns].astype(np.int64)
             contrib = B[o_cb:o_cb + 2 * nc].view(np.uint16).astype(np.int64)
             for sl in range(ns):
+                ch, lane = sl >> 5, sl & 31
+                k0 = (chk[ch, 1] >> 16) + cnt[32 * ch: sl].sum()
+                row = (chk[ch, 1] & 0xffff) - 1 + bin(chk[ch, 0] & (0xffffffff >> (31 - lane))).count("1")
                 acc = 0.0
-                for kk in range(soff[sl], soff[sl + 1]):
+                for kk in range(k0, k0 + cnt[sl]):
                     acc += sLz[contrib[kk]]
-                g = gd[srow[sl]] + sl
+                g = gd[row] + sl
                 values[g] = acc
                 written[g] += 1
             continue

@@ -271,5 +271,22 @@ def inorm_form(u, du, x, h):
     return h * (np.sin(x[0]) + u[0] * x[1]) + du[0][0] - 2.0 * du[0][1]
 
 
+def fnorm_boundary_form(u, du, x, n, t, h):
+    # Neumann-residual like (a posteriori estimators): normal / tangential
+    # derivatives of the interpolated solution on boundary facets
+    val = h * (u[0] * x[0] + sum(du[0][k] * n[k] for k in range(len(x))))
+    if len(t) > 0:
+        val = val + du[0][0] * t[0] + du[0][1] * t[1]
+    return val
+
+
+def fnorm_interior_form(u1, u2, du1, du2, x, n, t, h):
+    # jump of the normal derivative across interior facets
+    jump = sum((du1[0][k] - du2[0][k]) * n[k] for k in range(len(x)))
+    return h * jump + u1[0] - 0.5 * u2[0] + x[0]
+
+
+FNORM_CASES = [("MeshTri", "TriP1", 3), ("MeshTri", "TriP2", 2), ("MeshTet", "TetP1", 1),
+               ("MeshTet", "TetP2", 1)]
 INORM_CASES = [("MeshTri", "TriP1", 3), ("MeshTri", "TriP2", 2), ("MeshTet", "TetP2", 1),
                ("MeshQuad", "Q2", 2)]

@@ -92,6 +92,17 @@ def main():
             val = a.inorm(cases.inorm_form, interp)
         np.savez_compressed(os.path.join(HERE, "inorm_%s_%s.npz" % (mname, ename)), data=val)
         print("inorm", mname, ename, val.shape, float(val.sum()))
+    # facet-wise norms (spfem/assembly.py:1185-1271)
+    for mname, ename, ref in cases.FNORM_CASES:
+        m = getattr(rmesh, mname)()
+        m.refine(ref)
+        a = rasm.AssemblerElement(m, ref_element(ename, 1))
+        interp = {0: cases._interp_vec(a.dofnum_u.N, 3)}
+        vb, fb = a.fnorm(cases.fnorm_boundary_form, interp)
+        vi, fi = a.fnorm(cases.fnorm_interior_form, interp, interior=True)
+        np.savez_compressed(os.path.join(HERE, "fnorm_%s_%s.npz" % (mname, ename)),
+                            boundary=vb, boundary_find=fb, interior=vi, interior_find=fi)
+        print("fnorm", mname, ename, vb.shape, float(vb.sum()), vi.shape, float(vi.sum()))
     with open(os.path.join(HERE, "error_norms.json"), "w") as fh:
         json.dump(norms, fh, indent=1)
 

@@ -176,3 +176,45 @@ def inorm(asm, form, interp, intorder=None):
     finally:
         asm._engine = saved
     return run_interior(asm, captured["plan"], None, interp)[0]
+
+
+def fnorm(asm, form, interp, intorder=None, interior=False, normals=True):
+    """Host emulation of ``AssemblerElement.fnorm`` (per-facet values)."""
+    captured = {}
+
+    class _Eng(object):
+        def run_facet_functional(self, plan, find, interp_):
+            captured["plan"], captured["find"] = plan, find
+            return None
+    saved = asm._engine
+    asm._engine = _Eng()
+    try:
+        asm.fnorm(form, interp, intorder=intorder, interior=interior, normals=normals)
+    finally:
+        asm._engine = saved
+    plan, find = captured["plan"], captured["find"]
+    mesh = asm.mesh
+    fv, e1, e2, lf1 = asm.facet_tables(find)
+    n = len(find)
+    t = np.ascontiguousarray(mesh.t, dtype=np.int32)
+    p = np.ascontiguousarray(mesh.p, dtype=np.float64)
+    tdu = np.ascontiguousarray(asm.dofnum_u.t_dof, dtype=np.int32)
+    fv = np.ascontiguousarray(fv, dtype=np.int32)
+    e1 = np.ascontiguousarray(e1, dtype=np.int32)
+    e2 = np.ascontiguousarray(e2, dtype=np.int32)
+    lf1 = np.ascontiguousarray(lf1, dtype=np.int32)
+    out = np.zeros(n)
+    a = SpfemArgs()
+    a.n, a.ldo, a.ldk = n, n, 1
+    a.t, a.ldt = _ptr(t), t.shape[1]
+    a.p, a.ldp = _ptr(p), p.shape[1]
+    a.tdof_u, a.ldd = _ptr(tdu), tdu.shape[1]
+    keep = []
+    for s, key in enumerate(plan.wkeys):
+        arr = np.ascontiguousarray(interp[key], dtype=np.float64)
+        keep.append(arr)
+        a.interp[s] = arr.ctypes.data
+    a.fv, a.e1, a.e2, a.lf1 = _ptr(fv), _ptr(e1), _ptr(e2), _ptr(lf1)
+    a.out = _ptr(out)
+    compile_host(plan)(C.byref(a))
+    return out, find

@@ -103,3 +103,12 @@ def test_tile_plan_reproduces_assembly(name, E):
     v2, w2 = emulate(tp2, uniq, nnz)
     assert np.all(w2 == 1) and np.max(np.abs(v2 - ref.data)) <= 1e-12 * scale
     assert tp2["halo_factor"] == tp1["halo_factor"]
+    # ... with packed storage of the halo elements' values
+    tp3 = build_tile_plan(torch, torch.from_numpy(indptr), torch.from_numpy(cptr),
+                          torch.from_numpy(contrib), n, plan.spec.n_entries, E,
+                          torch.from_numpy(vt), dim=asm.mesh.p.shape[0],
+                          alias=plan.spec.alias, mode="compact")
+    v3, w3 = emulate(tp3, uniq, nnz)
+    assert np.all(w3 == 1) and np.max(np.abs(v3 - ref.data)) <= 1e-12 * scale
+    assert tp3["max_store"] < plan.spec.n_unique * tp3["ldl"]
+    print(name, "dense", plan.spec.n_unique * tp3["ldl"], "compact", tp3["max_store"])
