@@ -94,6 +94,10 @@ def patch_source(name, text):
                             "mid = np.arange(self.t.shape[1]) + np.max(t2f) + 1")
         text = text.replace("np.issubdtype(self.t[0, 0], int)",
                             "np.issubdtype(self.t.dtype, np.integer)")
+    if name == "element.py":
+        # Python 2 integer division (SURVEY.md 8(c) patch 7): ElementTriPp's
+        # interior DOF count and AbstractElementTriPp's
+        text = text.replace("(p-1)*(p-2)/2", "(p-1)*(p-2)//2")
     if name == "utils.py":
         text = text.replace("sp.vstack(map(sp.hstack, block))",
                             "sp.vstack(list(map(sp.hstack, block)))")

@@ -49,6 +49,19 @@ class Poly(object):
                 out[e] = out.get(e, 0) + c1 * c2
         return Poly(out, self.nvar)
 
+    def __add__(self, other):
+        out = dict(self.terms)
+        for e, c in other.terms.items():
+            out[e] = out.get(e, 0) + c
+        return Poly(out, self.nvar)
+
+    def __sub__(self, other):
+        return self + other.scale(-1)
+
+    def scale(self, c):
+        c = Fraction(c)
+        return Poly({e: v * c for e, v in self.terms.items()}, self.nvar)
+
     def is_constant(self):
         return all(sum(e) == 0 for e in self.terms)
 
@@ -356,6 +369,65 @@ class ElementTriMini(ElementH1):
     maxdeg = 3
     _polys = list(ElementTriP1._polys) + [
         ElementTriP1._polys[0] * ElementTriP1._polys[1] * ElementTriP1._polys[2]]
+
+
+class ElementTriPp(ElementH1):
+    """Hierarchical p-basis on triangles (spfem/element.py:623-764): vertex
+    functions, ``p-1`` edge functions ``phi_a phi_b iP_j(phi_b - phi_a)`` per
+    edge (integrated Legendre polynomials, edges in the mesh's local order
+    (0,1), (1,2), (0,2)) and ``(p-1)(p-2)/2`` interior functions
+    ``bubble * B_i``.  As in the reference, for ``p > 3`` the ``B_i`` are the
+    first ``nbdofs(p-3)`` functions of this very basis.  The polynomials are
+    built with exact rational coefficients from the same recurrences."""
+    dim = 2
+
+    def __init__(self, p):
+        p = int(p)
+        self.p = p
+        self.maxdeg = p
+        self.n_dofs = 1
+        self.f_dofs = max(p - 1, 0)
+        self.i_dofs = max((p - 1) * (p - 2) // 2, 0)
+        self.nbdofs = 3 * self.n_dofs + 3 * self.f_dofs + self.i_dofs
+        self._polys = self._build(p)
+
+    @staticmethod
+    def _intleg(eta, n):
+        """Integrated Legendre polynomials ``iP_0 .. `` in the linear polynomial
+        ``eta`` (spfem/element.py:638-663 with its argument ``n`` = p - 2)."""
+        n = n + 1
+        one = Poly({(0, 0): 1}, 2)
+        P = {0: one}
+        if n > 1:
+            P[1] = eta
+        for i in range(1, n):
+            P[i + 1] = (eta * P[i]).scale(Fraction(2 * i + 1, i + 1)) - P[i - 1].scale(Fraction(i, i + 1))
+        iP = {0: one}
+        if n > 1:
+            iP[1] = eta
+        for i in range(1, n - 1):
+            iP[i + 1] = (P[i + 1] - P[i - 1]).scale(Fraction(1, 2 * i + 1))
+        return [iP[k] for k in range(len(iP))]
+
+    @classmethod
+    def _build(cls, p):
+        phi = list(ElementTriP1._polys)
+        out = list(phi)
+        if p > 1:
+            for a, b in ((0, 1), (1, 2), (0, 2)):
+                for Pj in cls._intleg(phi[b] - phi[a], p - 2):
+                    out.append(phi[a] * phi[b] * Pj)
+        if p > 2:
+            if p > 3:
+                pm3 = p - 3
+                N = 3 + 3 * max(pm3 - 1, 0) + max((pm3 - 1) * (pm3 - 2) // 2, 0)
+                B = out[:N]
+            else:
+                B = [Poly({(0, 0): 1}, 2)]
+            bubble = phi[0] * phi[1] * phi[2]
+            for Bi in B:
+                out.append(bubble * Bi)
+        return out
 
 
 class ElementTriDG(ElementH1):

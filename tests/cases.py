@@ -191,6 +191,10 @@ CASES = [
     Case("trip0_mass", "MeshTri", 2, "TriP0", mass, oracle=False),
     Case("stokes_b_p0", "MeshTri", 2, "TriP2", stokes_b, ncu=2, ev="TriP0", ncv=1, oracle=False),
     Case("tetp0_mass", "MeshTet", 1, "TetP0", mass, oracle=False),
+    # hierarchical p-element (spfem/element.py:623-764)
+    Case("tripp3_lap", "MeshTri", 2, "TriPp3", lap2, oracle=False),
+    Case("tripp4_mass", "MeshTri", 1, "TriPp4", mass, oracle=False),
+    Case("tripp3_load", "MeshTri", 2, "TriPp3", load_sin_h, oracle=False),
 ]
 BY_NAME = {c.name: c for c in CASES}
 

@@ -31,6 +31,8 @@ import cases  # noqa: E402
 def ref_element(name, ncomp):
     if name == "TriDG1":
         e = relem.ElementTriDG(relem.ElementTriP1())
+    elif name.startswith("TriPp"):
+        e = relem.ElementTriPp(int(name[5:]))
     else:
         e = getattr(relem, "Element" + name)()
     return relem.ElementH1Vec(e) if ncomp > 1 else e

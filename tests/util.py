@@ -25,6 +25,8 @@ def mesh_for(case):
 def element(name, ncomp):
     if name == "TriDG1":
         e = sp.element.ElementTriDG(sp.element.ElementTriP1())
+    elif name.startswith("TriPp"):
+        e = sp.element.ElementTriPp(int(name[5:]))
     else:
         e = getattr(sp.element, "Element" + name)()
     return sp.ElementH1Vec(e) if ncomp > 1 else e
