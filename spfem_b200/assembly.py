@@ -27,7 +27,7 @@ from scipy.sparse import csr_matrix
 from . import mesh as _mesh
 from . import element as _element
 from .quadrature import get_quadrature
-from .tracer import (Coef, Form, TraceError, basis_args, zero_like, call_form)
+from .tracer import (Coef, Form, TraceError, basis_args, hdiv_args, zero_like, call_form)
 from . import codegen
 
 __all__ = ["Assembler", "AssemblerElement", "Dofnum", "TraceError"]
@@ -179,13 +179,21 @@ class AssemblerElement(Assembler):
         x = {k: Form.coef(Coef.sym("x%d" % k, True)) for k in range(dim)}
         w = {key: Form.coef(Coef.sym("w%d" % s, True))
              for s, key in enumerate(wkeys)}
+        hdiv_u, hdiv_v = getattr(bu, "hdiv", False), getattr(bv, "hdiv", False)
+        if hdiv_u or hdiv_v:
+            if quad or dim != 2:
+                raise NotImplementedError("H(div) elements: affine triangles only")
+            df = {k: {l: Coef.sym("A_%d%d" % (k, l)) for l in range(dim)} for k in range(dim)}
+            rdet = Coef.op("div", Coef.const(1.0), Coef.sym("detA"))
         blocks = {}
         for cu in range(ncu if bilinear else 1):
             for cv in range(ncv):
-                v, dv = basis_args(ncv, cv, 1, dim, invdf)
+                v, dv = (hdiv_args(1, dim, df, rdet) if hdiv_v
+                         else basis_args(ncv, cv, 1, dim, invdf))
                 avail = {'v': v, 'dv': dv, 'x': x, 'w': w, 'h': h}
                 if bilinear:
-                    u, du = basis_args(ncu, cu, 0, dim, invdf)
+                    u, du = (hdiv_args(0, dim, df, rdet) if hdiv_u
+                             else basis_args(ncu, cu, 0, dim, invdf))
                     avail['u'] = u
                     avail['du'] = du
                 f = call_form(form, names, avail)

@@ -371,6 +371,57 @@ class ElementTriMini(ElementH1):
         ElementTriP1._polys[0] * ElementTriP1._polys[1] * ElementTriP1._polys[2]]
 
 
+class ElementHdiv(Element):
+    """H(div)-conforming elements (spfem/element.py:404-425): the reference
+    basis ``(phi_hat, div phi_hat)`` is pushed forward with the contravariant
+    Piola map ``u = DF phi_hat / detDF``, ``div u = div phi_hat / detDF``
+    (signed determinant).  ``_vec[i]`` are the component polynomials and
+    ``_div[i]`` the divergence of local basis function ``i``."""
+    hdiv = True
+    _vec = ()
+    _div = ()
+
+    def polys(self):
+        """Table slot 0 holds the divergence, slots ``1 + l`` component ``l``
+        (the slots an H1 element uses for the value and its derivatives)."""
+        return list(self._div), [list(v) for v in self._vec]
+
+    def nbfun_ref(self):
+        return len(self._vec)
+
+    def lbasis(self, X, i):
+        i = int(i)
+        xs = _coords(X, self.dim)
+        return ({k: self._vec[i][k](*xs) for k in range(self.dim)},
+                self._div[i](*xs))
+
+    def gbasis(self, mapping, X, i, tind):
+        if isinstance(X, dict):
+            raise NotImplementedError("Calling ElementHdiv gbasis with dict not implemented!")
+        x = {k: X[k, :] for k in range(self.dim)}
+        phi, dphi = self.lbasis(x, i)
+        DF = mapping.DF(X, tind)
+        detDF = mapping.detDF(X, tind)
+        u = {k: (DF[k][0] * phi[0] + DF[k][1] * phi[1]) / detDF for k in range(2)}
+        return u, dphi / detDF
+
+
+def _p2(terms):
+    return Poly(terms, 2)
+
+
+class ElementTriRT0(ElementHdiv):
+    """Lowest order Raviart-Thomas element on triangles, one DOF per facet
+    (spfem/element.py:427-452)."""
+    maxdeg = 1
+    f_dofs = 1
+    dim = 2
+    _vec = ((_p2({(1, 0): 1}), _p2({(0, 1): 1, (0, 0): -1})),
+            (_p2({(1, 0): 1}), _p2({(0, 1): 1})),
+            (_p2({(1, 0): -1, (0, 0): 1}), _p2({(0, 1): -1})))
+    _div = (_p2({(0, 0): 2}), _p2({(0, 0): 2}), _p2({(0, 0): -2}))
+
+
 class ElementTriPp(ElementH1):
     """Hierarchical p-basis on triangles (spfem/element.py:623-764): vertex
     functions, ``p-1`` edge functions ``phi_a phi_b iP_j(phi_b - phi_a)`` per

@@ -485,6 +485,23 @@ def basis_args(elem_ncomp, comp, side, dim, invdf):
     return val, grad
 
 
+def hdiv_args(side, dim, df, rdet):
+    """``(u, div u)`` proxies of an H(div) basis function under the Piola map
+    (spfem/element.py:407-425): ``u[k] = sum_l DF[k][l] phi_hat_l / detDF`` as a
+    real dict, ``du = div phi_hat / detDF``.  Table slot 0 is the reference
+    divergence, slot ``1 + l`` component ``l`` (``ElementHdiv.polys``);
+    ``df[k][l]`` and ``rdet`` (= 1/detDF) are coefficient nodes."""
+    val = {}
+    for k in range(dim):
+        terms = {}
+        for l in range(dim):
+            key = (1 + l, NONE) if side == 0 else (NONE, 1 + l)
+            terms[key] = Coef.op("mul", df[k][l], rdet)
+        val[k] = Form(terms)
+    div = Form({((0, NONE) if side == 0 else (NONE, 0)): rdet})
+    return val, div
+
+
 def zero_like(elem_ncomp, dim):
     """The all-zero ``(value, gradient)`` pair used for the "other side" of an
     interior facet (spfem/assembly.py:1108-1111)."""

@@ -22,6 +22,14 @@ def mass(u, v):
     return u * v
 
 
+def rt0_sigtau(u, v):
+    return u[0] * v[0] + u[1] * v[1]
+
+
+def rt0_divsigv(du, v):
+    return du * v
+
+
 def load1(v):
     return 1.0 * v
 
@@ -191,6 +199,9 @@ CASES = [
     Case("trip0_mass", "MeshTri", 2, "TriP0", mass, oracle=False),
     Case("stokes_b_p0", "MeshTri", 2, "TriP2", stokes_b, ncu=2, ev="TriP0", ncv=1, oracle=False),
     Case("tetp0_mass", "MeshTet", 1, "TetP0", mass, oracle=False),
+    # Raviart-Thomas (Piola map; the mixed Poisson blocks of test_module.py:18-77)
+    Case("rt0_sigtau", "MeshTri", 2, "TriRT0", rt0_sigtau, oracle=False),
+    Case("rt0_div_p0", "MeshTri", 2, "TriRT0", rt0_divsigv, ev="P0", oracle=False),
     # hierarchical p-element (spfem/element.py:623-764)
     Case("tripp3_lap", "MeshTri", 2, "TriPp3", lap2, oracle=False),
     Case("tripp4_mass", "MeshTri", 1, "TriPp4", mass, oracle=False),

@@ -355,3 +355,38 @@ def test_error_norms_match_reference(mname, ename, ref, dim):
     uh = cases.nodal_values(m, a, ex)
     assert abs(a.L2error(uh, ex) - gold["L2"]) <= 1e-9 * max(gold["L2"], 1e-3)
     assert abs(a.H1error(uh, dex) - gold["H1"]) <= 1e-9 * max(gold["H1"], 1e-3)
+
+
+def test_rt0_mixed_poisson_convergence():
+    """The reference's ``RT0Test`` (spfem/test_module.py:18-77): mixed Poisson
+    with Raviart-Thomas fluxes and piecewise constants, L2 convergence rate of
+    the scalar unknown between 0.95 and 1.15."""
+    import scipy.sparse as spsp
+    from scipy.sparse.linalg import spsolve
+    import spfem_b200 as sp
+    from spfem_b200.assembly import AssemblerElement
+    mesh = sp.MeshTri()
+    mesh.refine(2)
+
+    def fv(v, x):
+        return 2 * np.pi ** 2 * np.sin(np.pi * x[0]) * np.sin(np.pi * x[1]) * v
+
+    def exact(x):
+        return np.sin(np.pi * x[0]) * np.sin(np.pi * x[1])
+    hs, errs = [], []
+    for _ in range(1, 4):
+        mesh.refine()
+        a = AssemblerElement(mesh, sp.element.ElementTriRT0())
+        b = AssemblerElement(mesh, sp.element.ElementTriRT0(), sp.element.ElementP0())
+        c = AssemblerElement(mesh, sp.element.ElementP0())
+        A = a.iasm(cases.rt0_sigtau)
+        B = b.iasm(cases.rt0_divsigv)
+        C = c.iasm(lambda u, v: u * v)
+        f = c.iasm(fv)
+        K = spsp.vstack((spsp.hstack((-A, -B.T)), spsp.hstack((-B, 0 * C)))).tocsr()
+        u = spsolve(K, np.hstack((np.zeros(A.shape[0]), f)))
+        Iu = np.arange(C.shape[0], dtype=np.int64) + A.shape[0]
+        hs.append(mesh.param())
+        errs.append(c.L2error(u[Iu], exact))
+    rate = np.polyfit(np.log10(hs), np.log10(errs), 1)[0]
+    assert 0.95 <= rate <= 1.15
