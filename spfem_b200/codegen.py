@@ -228,24 +228,13 @@ extern "C" __global__ void __launch_bounds__(@THREADS@, @MINB@) @NAME@_tile(cons
            contributions are fetched together, longer lists finish in a loop --
            always in list order => bitwise reproducible                         */
         const int *gd = (const int *)sB;
-        const uint2 *chk = (const uint2 *)(sB + d[6]);     /* {row flags, row | first << 16} */
-        const unsigned char *cnt8 = sB + d[7];             /* contributions per slot */
-        const unsigned lane = threadIdx.x & 31u;
-        for (int sb = (int)(threadIdx.x - lane); sb < ns; sb += blockDim.x) {
-            const int s = sb + (int)lane;
-            const unsigned cnt = s < ns ? (unsigned)cnt8[s] : 0u;
-            unsigned incl = cnt;                           /* warp prefix sum of the counts */
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const unsigned up = __shfl_up_sync(0xffffffffu, incl, o);
-                if ((int)lane >= o) incl += up;
-            }
-            if (s >= ns) continue;
-            const uint2 ck = chk[s >> 5];
-            const unsigned k0 = (ck.y >> 16) + incl - cnt, k1 = k0 + cnt;
-            const int row = (int)(ck.y & 0xffffu) - 1 + __popc(ck.x & (0xffffffffu >> (31u - lane)));
+        const unsigned short *soff = (const unsigned short *)(sB + d[6]);
+        const unsigned short *srow = (const unsigned short *)(sB + d[7]);
+#pragma unroll 2
+        for (int s = threadIdx.x; s < ns; s += blockDim.x) {
+            const unsigned k0 = soff[s], k1 = soff[s + 1];
             const unsigned c0 = cb[k0], c1 = cb[k0 + 1];
-            const int g = gd[row] + s;
+            const int g = gd[srow[s]] + s;
             double acc = sL[c0];
             if (k0 + 1 < k1) acc += sL[c1];
             for (unsigned k = k0 + 2; k < k1; ++k) acc += sL[cb[k]];

@@ -723,13 +723,18 @@ class Engine(object):
         cache = getattr(pat, "_tile_plans", None)
         if cache is None:
             cache = pat._tile_plans = {}
-        ckey = (nent, with_el, alias, os.environ.get("SPFEM_TILE_MODE", "slots"),
+        ckey = (nent, with_el, alias, os.environ.get("SPFEM_TILE_MODE", "auto"),
                 os.environ.get("SPFEM_TILE_E", "0"), os.environ.get("SPFEM_TILE_DIRECT", "auto"))
         nuniq = (max(alias) + 1) if alias else nent
         if ckey in cache:
             return cache[ckey]
         from .tileplan import build_tile_plan
-        mode = os.environ.get("SPFEM_TILE_MODE", "slots")
+        mode = os.environ.get("SPFEM_TILE_MODE", "auto")
+        if mode == "auto":
+            # 3-D meshes: the halo is 2-3 x the tile, keep only the values that are
+            # read (measured: TetP2 17 %, TetP1 12 % faster); 2-D: dense image
+            mode = "compact" if self.p.shape[0] == 3 else "slots"
+        prefer = (96 if mode == "compact" else 56) * 1024
         want_direct = os.environ.get("SPFEM_TILE_DIRECT", "auto")
         if mode != "rows":
             want_direct = "1"          # slot-parallel stores are coalesced as they are
@@ -753,7 +758,7 @@ class Engine(object):
         tp = None
         t0 = time.perf_counter()
         for E in cands:
-            if E_env <= 0 and mode == "slots" and E > 64 and 8 * nuniq * (1.3 * E + 32) > 56 * 1024:
+            if E_env <= 0 and mode == "slots" and E > 64 and 8 * nuniq * (1.3 * E + 32) > prefer:
                 continue                # cannot fit the preferred footprint
             try:
                 tp = build_tile_plan(self.torch, pat.indptr, pat.cptr, pat.contrib,
@@ -774,7 +779,7 @@ class Engine(object):
             if smem > limit:
                 tp = None
                 continue
-            if E_env > 0 or mode == "rows" or smem <= 56 * 1024 or E <= 64:
+            if E_env > 0 or mode == "rows" or smem <= prefer or E <= 64:
                 break
             tp = None
         # the fused kernel pays off while recomputing the halo elements is cheap
