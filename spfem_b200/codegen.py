@@ -128,6 +128,7 @@ struct SpfemTileArgs {
     int mode;                     /* 0: thread per owned row, 1: thread per CSR slot,
                                      2: thread per slot + packed local values     */
     int store;                    /* doubles reserved for the local values        */
+    int prefetch;                 /* L2 prefetch distance in tiles (0 = off)      */
 };
 /* Packed shared-memory image of one element's local values (tileplan.py,
    mode "compact"): only the values whose mask bit is set are stored, value u at
@@ -171,6 +172,14 @@ extern "C" __global__ void __launch_bounds__(@THREADS@, @MINB@) @NAME@_tile(cons
         const unsigned char *src = T.blob + (size_t)(unsigned)d[0] * 16;
         spfem_bulk_load(sA, src, (unsigned)bytes_a, &bars[0]);
         spfem_bulk_load(sB, src + bytes_a, (unsigned)bytes_b, &bars[1]);
+        /* pull the blob of a tile that starts a few waves later into L2 */
+        const long long tp = (long long)blockIdx.x + T.prefetch;
+        if (T.prefetch > 0 && tp < (long long)gridDim.x) {
+            const int *dp = T.desc + 16 * (size_t)tp;
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;"
+                         ::"l"(T.blob + (size_t)(unsigned)dp[0] * 16),
+                           "r"((unsigned)(dp[1] + dp[2])) : "memory");
+        }
     }
     __syncthreads();
     /* phase A: local matrices -> sL */

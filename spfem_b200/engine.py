@@ -331,6 +331,7 @@ class TiledPrepared(Prepared):
         self.direct = bool(tp.get("direct", False))
         ta.mode = {"slots": 1, "compact": 2}.get(tp.get("mode"), 0)
         ta.store = tile_store(plan.spec.n_unique, tp)
+        ta.prefetch = int(os.environ.get("SPFEM_TILE_PREFETCH", "300"))   # about one wave ahead
         ta.max_ns = 0 if self.direct else tp["max_ns"]
         ta.max_nr = tp["max_nr"]
         self.targs = ta

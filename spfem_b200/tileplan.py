@@ -74,9 +74,11 @@ def build_tile_plan(torch, indptr, cptr, contrib, n, nent, E, vt, with_el=True, 
       contrib uint16 [nc+1]  shared-memory index of a contribution
 
     with descriptor entries 6 / 7 / 8 = byte offsets of soff / srow / contrib.
-    (A packed variant -- row-start bit flags and 8-bit counts prefix-summed by
-    the warp, 1.25 instead of 4 bytes per slot -- was measured 20-40 % slower:
-    this phase is bound by instruction latency, not by the blob's bytes.)
+    (Measured alternatives: row-start bit flags and 8-bit counts prefix-summed
+    by the warp, 1.25 instead of 4 bytes per slot -- 20-40 % slower, the phase is
+    bound by instruction latency, not by the blob's bytes; one 64-bit record per
+    slot {CSR position, first contribution, start of the rest} -- fewer loads
+    but 8 bytes per slot of shared memory, one CTA less per SM: 0-35 % slower.)
 
     ``mode="compact"``: slot-parallel, and shared memory holds only the local
     values that some owned slot really reads (a halo element shares one vertex,

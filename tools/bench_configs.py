@@ -39,6 +39,7 @@ def measure(prep, steps=20):
 
 CONFIGS = [
     ("TriP1 laplace", "MeshTri", 10, "TriP1", 1, None, 1, cases.lap2, 3),
+    ("TriP1 load vector", "MeshTri", 10, "TriP1", 1, None, 1, cases.load1, 3),
     ("TriP2 laplace", "MeshTri", 9, "TriP2", 1, None, 1, cases.lap2, 6),
     ("vecP2 elasticity", "MeshTri", 9, "TriP2", 2, None, 2, cases.elasticity, 6),
     ("Stokes B (P1 x vecP2)", "MeshTri", 9, "TriP2", 2, "TriP1", 1, cases.stokes_b, 6),
@@ -90,7 +91,7 @@ def main():
                 res["fused_ms"] = None
                 continue
             ms = measure(prep)
-            nnz = prep.pattern.nnz
+            nnz = prep.pattern.nnz if prep.plan.bilinear else prep.pattern.nrows
             balg = 4 * C * nt + 8 * dim * nv + 8 * nnz
             res["nnz"] = nnz
             res["B_alg_per_elem"] = round(balg / nt, 1)
