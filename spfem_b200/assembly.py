@@ -21,6 +21,7 @@ reference's.  What happens inside is not:
 There is no CPU fallback: without the CUDA library / a GPU the calls raise.
 """
 import inspect
+import os
 import numpy as np
 from scipy.sparse import csr_matrix
 
@@ -327,7 +328,67 @@ class AssemblerElement(Assembler):
         ``du``.  Returns a CSR matrix of shape ``(dofnum_v.N, dofnum_u.N)`` or
         a vector of length ``dofnum_v.N``."""
         plan = self.plan_iasm(form, intorder=intorder, interp=interp)
+        chunks = self._chunks_needed(plan, tind)
+        if chunks > 1:
+            return self._iasm_chunked(form, plan, intorder, interp, chunks)
         return self._get_engine().run_interior(plan, tind, interp)
+
+    # -- meshes beyond one pattern call -----------------------------------
+    def _chunks_needed(self, plan, tind):
+        """Number of element chunks so that one chunk (with its halo) stays
+        below the limit of local entries per pattern call (2^31 - 1;
+        ``SPFEM_MAX_ENTRIES`` lowers it for the tests)."""
+        limit = int(os.environ.get("SPFEM_MAX_ENTRIES", str(2 ** 31 - 1)))
+        nt = self.mesh.t.shape[1] if tind is None else len(np.atleast_1d(tind))
+        n_ent = plan.spec.n_entries * nt
+        if n_ent <= limit:
+            return 1
+        if tind is not None:
+            raise NotImplementedError("tind subsets with more than %d local entries" % limit)
+        return int(np.ceil(1.4 * n_ent / limit))
+
+    def _iasm_chunked(self, form, plan, intorder, interp, chunks, assemble=None):
+        """Assemble chunk by chunk on one GPU: Morton blocks of elements, every
+        global row owned by the lowest chunk touching it, a chunk's local mesh =
+        its block plus the halo elements of its rows (the multi-GPU partition of
+        ``distributed.py`` run sequentially).  Owned rows are complete after their
+        chunk, so the global CSR is the union of the owned rows; pattern and index
+        width are those of the single call (SciPy's rule on the *total* number of
+        local entries)."""
+        from .distributed import partition_global, DistResult
+        from .engine import scipy_index_dtype
+        from scipy.sparse import coo_matrix
+        ev = None if self.elem_v is self.elem_u else self.elem_v
+        limit = int(os.environ.get("SPFEM_MAX_ENTRIES", str(2 ** 31 - 1)))
+        rows, cols, vals = [], [], []
+        r = 0
+        while r < chunks:
+            part = partition_global(self.mesh, self.elem_u, ev, chunks, r)
+            if plan.spec.n_entries * part.mesh.t.shape[1] > limit:
+                chunks, r, rows, cols, vals = 2 * chunks, 0, [], [], []   # halo thicker than assumed
+                continue
+            loc = AssemblerElement(part.mesh, self.elem_u, ev)
+            li = None if interp is None else {k: np.asarray(v)[part.l2g_u]
+                                              for k, v in interp.items()}
+            if assemble is not None:
+                A = assemble(loc, form, intorder=intorder, interp=li)
+            else:
+                A = loc.iasm(form, intorder=intorder, interp=li)
+                loc._engine = None                      # release the chunk's device memory
+            tr = DistResult(A, part, plan.bilinear, None).owned_triplets()
+            rows.append(tr[0]); cols.append(tr[1]); vals.append(tr[2])
+            r += 1
+        rows, cols, vals = np.concatenate(rows), np.concatenate(cols), np.concatenate(vals)
+        Nv, Nu = self.dofnum_v.N, self.dofnum_u.N
+        if not plan.bilinear:
+            out = np.zeros(Nv)
+            out[rows] = vals
+            return out
+        A = coo_matrix((vals, (rows, cols)), shape=(Nv, Nu)).tocsr()
+        idt = scipy_index_dtype(plan.spec.n_entries * self.mesh.t.shape[1], Nv, Nu)
+        A.indices = A.indices.astype(idt, copy=False)
+        A.indptr = A.indptr.astype(idt, copy=False)
+        return A
 
     def iasm_device(self, form, intorder=None, tind=None, interp=None):
         """Like :meth:`iasm` but leaves the result on the GPU

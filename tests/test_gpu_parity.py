@@ -390,3 +390,17 @@ def test_rt0_mixed_poisson_convergence():
         errs.append(c.L2error(u[Iu], exact))
     rate = np.polyfit(np.log10(hs), np.log10(errs), 1)[0]
     assert 0.95 <= rate <= 1.15
+
+
+@pytest.mark.parametrize("name", ["trip1_lap_r6", "tetp2_lap", "vecp2_elasticity", "stokes_b",
+                                  "trip1_load"])
+def test_chunked_assembly_beyond_one_pattern_call(name, monkeypatch):
+    """``iasm`` on a mesh with more local entries than one pattern call takes
+    (limit lowered through SPFEM_MAX_ENTRIES): element chunks on one GPU, same
+    matrix and pattern as the single call."""
+    case = cases.BY_NAME[name]
+    asm = util.assembler_for(case)
+    plan = asm.plan_iasm(case.form)
+    monkeypatch.setenv("SPFEM_MAX_ENTRIES", str(plan.spec.n_entries * asm.mesh.t.shape[1] // 3))
+    assert asm._chunks_needed(plan, None) >= 4
+    util.check(asm.iasm(case.form), util.golden(case))

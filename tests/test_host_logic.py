@@ -129,3 +129,26 @@ def test_tensor_mode_precontracts_quadrature():
     assert plan.spec.n_entries == 9 and plan.spec.n_unique == 6
     assert plan.spec.alias[1] == plan.spec.alias[3]          # A[0,1] == A[1,0]
     assert a.plan_iasm(cases.mass).spec.n_unique <= 6
+
+
+@pytest.mark.parametrize("name", ["trip1_lap_r6", "tetp2_lap", "vecp2_elasticity", "stokes_b",
+                                  "trip1_load"])
+def test_chunked_assembly_matches_single_call(name, monkeypatch):
+    """Meshes with more local entries than one pattern call takes are assembled
+    chunk by chunk (AssemblerElement._iasm_chunked); the union of the owned rows
+    is the reference matrix, pattern included (generated kernels on the host)."""
+    import hostemu
+    case = cases.BY_NAME[name] if name in cases.BY_NAME else None
+    if case is None:
+        pytest.skip("no such case")
+    asm = util.assembler_for(case)
+    plan = asm.plan_iasm(case.form)
+    n_ent = plan.spec.n_entries * asm.mesh.t.shape[1]
+    monkeypatch.setenv("SPFEM_MAX_ENTRIES", str(n_ent // 3))
+    chunks = asm._chunks_needed(plan, None)
+    assert chunks >= 4
+    out = asm._iasm_chunked(case.form, plan, None, None, chunks,
+                            assemble=lambda loc, form, **kw: hostemu.iasm(loc, form, **kw))
+    util.check(out, util.golden(case))
+    monkeypatch.setenv("SPFEM_MAX_ENTRIES", str(2 ** 31 - 1))
+    assert asm._chunks_needed(plan, None) == 1
