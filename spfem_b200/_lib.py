@@ -42,7 +42,7 @@ class SpfemTileArgs(C.Structure):
         ("desc", C.c_void_p), ("blob", C.c_void_p), ("values", C.c_void_p),
         ("ldl", C.c_int), ("max_a", C.c_int), ("max_b", C.c_int),
         ("max_ns", C.c_int), ("max_nr", C.c_int), ("mode", C.c_int),
-        ("store", C.c_int), ("prefetch", C.c_int),
+        ("store", C.c_int), ("prefetch", C.c_int), ("sorted", C.c_int),
     ]
 
 

@@ -129,6 +129,8 @@ struct SpfemTileArgs {
                                      2: thread per slot + packed local values     */
     int store;                    /* doubles reserved for the local values        */
     int prefetch;                 /* L2 prefetch distance in tiles (0 = off)      */
+    int sorted;                   /* slot-parallel phase: tile slots sorted by their
+                                     number of contributions (uniform warps)      */
 };
 /* Packed shared-memory image of one element's local values (tileplan.py,
    mode "compact"): only the values whose mask bit is set are stored, value u at
@@ -243,7 +245,8 @@ extern "C" __global__ void __launch_bounds__(@THREADS@, @MINB@) @NAME@_tile(cons
         for (int s = threadIdx.x; s < ns; s += blockDim.x) {
             const unsigned k0 = soff[s], k1 = soff[s + 1];
             const unsigned c0 = cb[k0], c1 = cb[k0 + 1];
-            const int g = gd[srow[s]] + s;
+            /* sorted: slots ordered by contribution count, CSR position per slot */
+            const int g = T.sorted ? gd[s] : gd[srow[s]] + s;
             double acc = sL[c0];
             if (k0 + 1 < k1) acc += sL[c1];
             for (unsigned k = k0 + 2; k < k1; ++k) acc += sL[cb[k]];

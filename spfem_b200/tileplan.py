@@ -59,7 +59,8 @@ def _wrap16(torch, x):
 
 
 def build_tile_plan(torch, indptr, cptr, contrib, n, nent, E, vt, with_el=True, dim=2,
-                    alias=None, schedule="inslot", mode="rows"):
+                    alias=None, schedule="inslot", mode="rows", owner_rule="lowest",
+                    sort_slots=False):
     """All tensor arguments live on one device.  ``vt``: int32 ``(nve, n)``
     vertex table in device element order.  Returns a dict of tensors/ints.
 
@@ -93,6 +94,12 @@ def build_tile_plan(torch, indptr, cptr, contrib, n, nent, E, vt, with_el=True, 
     ``u`` of element ``el`` lives at ``sbase[el] + popcount(mask bits below u)``."""
     slots_mode = mode in ("slots", "compact")
     compact = mode == "compact"
+    # sort_slots (slot-parallel modes): a tile's slots ordered by descending
+    # number of contributions, so the 32 slots of a warp step have (nearly) the
+    # same trip count -- on 3-D meshes the counts range from 1 to ~24 inside one
+    # row and a warp otherwise runs at the pace of its longest slot.  The CSR
+    # position then comes per slot (``gpos`` int32 [ns] replaces gdelta + srow).
+    sort_slots = bool(sort_slots) and slots_mode
     dev = indptr.device
     i64 = torch.int64
     N = indptr.numel() - 1
@@ -111,14 +118,27 @@ def build_tile_plan(torch, indptr, cptr, contrib, n, nent, E, vt, with_el=True, 
     k = contrib % n
     ij = contrib // n
     row_of_c = row_of_slot[slot_of_c]
-    owner = torch.full((N,), ntiles, dtype=i64, device=dev)
-    owner.scatter_reduce_(0, row_of_c, k // E, reduce="amin")
+    if owner_rule == "most":
+        # the tile holding most of the row's contributions (ties: the lowest):
+        # fewer elements outside the tile have to be recomputed for its rows
+        pair, cnt = torch.unique(row_of_c * ntiles + k // E, return_counts=True)
+        prow, ptile = pair // ntiles, pair % ntiles
+        best = torch.zeros(N, dtype=i64, device=dev)
+        best.scatter_reduce_(0, prow, cnt, reduce="amax")
+        cand = torch.where(cnt == best[prow], ptile, torch.full_like(ptile, ntiles))
+        owner = torch.full((N,), ntiles, dtype=i64, device=dev)
+        owner.scatter_reduce_(0, prow, cand, reduce="amin")
+    else:
+        owner = torch.full((N,), ntiles, dtype=i64, device=dev)
+        owner.scatter_reduce_(0, row_of_c, k // E, reduce="amin")
     tile_of_slot = owner[row_of_slot]
     # slots in (tile, row, descending contribution count, CSR position) order:
     # rows of a regular mesh then finish their slots at the same steps, so the
     # lanes of a warp leave the inner accumulation loop together
     csr_pos = ar_nnz - indptr[row_of_slot]           # position of the slot inside its row
-    if slots_mode or int(csr_pos.max().item()) > 255 or int(counts.max().item()) > 65535:
+    if sort_slots:
+        within = torch.argsort(((65535 - counts.clamp(max=65535)) << 40) | ar_nnz)
+    elif slots_mode or int(csr_pos.max().item()) > 255 or int(counts.max().item()) > 65535:
         within = ar_nnz                               # very long rows: keep CSR order
     else:
         within = torch.argsort((row_of_slot << 32) | ((65535 - counts) << 16) | csr_pos)
@@ -311,11 +331,16 @@ def build_tile_plan(torch, indptr, cptr, contrib, n, nent, E, vt, with_el=True, 
     if slots_mode:
         nc = torch.bincount(tile_c, minlength=ntiles)[:ntiles]
         c0 = torch.cumsum(nc, 0) - nc
-        if int(nc.max().item()) > 65535 or int(nr.max().item()) > 65535:
+        if int(nc.max().item()) > 65535 or (not sort_slots and int(nr.max().item()) > 65535):
             raise ValueError("more than 65535 contributions / rows in one tile")
-        off_cptr = (nr * 4 + 15) // 16 * 16                  # soff
-        off_rowbase = off_cptr + ((ns + 1) * 2 + 15) // 16 * 16   # srow
-        off_contrib = off_rowbase + (ns * 2 + 15) // 16 * 16
+        if sort_slots:
+            off_cptr = (ns * 4 + 15) // 16 * 16              # soff (behind gpos)
+            off_rowbase = torch.zeros_like(nr)
+            off_contrib = off_cptr + ((ns + 1) * 2 + 15) // 16 * 16
+        else:
+            off_cptr = (nr * 4 + 15) // 16 * 16                  # soff
+            off_rowbase = off_cptr + ((ns + 1) * 2 + 15) // 16 * 16   # srow
+            off_contrib = off_rowbase + (ns * 2 + 15) // 16 * 16
         bytes_b = off_contrib + ((nc + 1) * 2 + 15) // 16 * 16
     else:
         off_rowbase = torch.zeros_like(nr)
@@ -358,13 +383,17 @@ def build_tile_plan(torch, indptr, cptr, contrib, n, nent, E, vt, with_el=True, 
     hrow_local = heads_cum[hidx] - 1 - r0[tile_sorted[hidx]]
     slot_local = ar_nnz - s0[tile_sorted]
     if slots_mode:
-        b32[(bbase // 4)[tile_sorted[hidx]] + hrow_local] = gdelta.to(torch.int32)
+        if sort_slots:
+            b32[(bbase // 4)[tile_sorted] + slot_local] = slot_order.to(torch.int32)
+        else:
+            b32[(bbase // 4)[tile_sorted[hidx]] + hrow_local] = gdelta.to(torch.int32)
         cstart = torch.cumsum(counts_s, 0) - counts_s        # first contribution of every slot
         b16[((bbase + off_cptr) // 2)[tile_sorted] + slot_local] = \
             _wrap16(torch, cstart - c0[tile_sorted])
         b16[((bbase + off_cptr) // 2) + ns] = _wrap16(torch, nc)
-        b16[((bbase + off_rowbase) // 2)[tile_sorted] + slot_local] = \
-            _wrap16(torch, heads_cum - 1 - r0[tile_sorted])
+        if not sort_slots:
+            b16[((bbase + off_rowbase) // 2)[tile_sorted] + slot_local] = \
+                _wrap16(torch, heads_cum - 1 - r0[tile_sorted])
         cb_base = ((bbase + off_contrib) // 2)
         ar_c = torch.arange(contrib16.numel(), device=dev)
         b16[cb_base[tile_c] + (ar_c - c0[tile_c])] = contrib16.to(torch.int16)
@@ -387,7 +416,7 @@ def build_tile_plan(torch, indptr, cptr, contrib, n, nent, E, vt, with_el=True, 
         raise ValueError("tile plan offsets exceed 32 bits")
     return {
         "ntiles": ntiles, "ldl": ldl, "E": E, "nve": nve, "nuniq": nent, "mode": mode,
-        "max_store": max_store, "W": W,
+        "max_store": max_store, "W": W, "sort_slots": sort_slots,
         "desc": desc.to(torch.int32).contiguous(),
         "blob": blob,
         "max_bytes_a": int(bytes_a.max().item()),
@@ -436,7 +465,8 @@ def emulate(plan, local, nnz):
             for idx in range(nent):
                 sLz[idx * ldl: idx * ldl + ne] = local[idx, elems]
         if plan.get("mode") in ("slots", "compact"):
-            gd = B[:nr * 4].view(np.int32).astype(np.int64)
+            srt = plan.get("sort_slots", False)
+            gd = B[:(ns if srt else nr) * 4].view(np.int32).astype(np.int64)
             soff = B[o_cp:o_cp + 2 * (ns + 1)].view(np.uint16).astype(np.int64)
             srow = B[o_rb:o_rb + 2 * ns].view(np.uint16).astype(np.int64)
             contrib = B[o_cb:o_cb + 2 * nc].view(np.uint16).astype(np.int64)
@@ -444,7 +474,7 @@ def emulate(plan, local, nnz):
                 acc = 0.0
                 for kk in range(soff[sl], soff[sl + 1]):
                     acc += sLz[contrib[kk]]
-                g = gd[srow[sl]] + sl
+                g = gd[sl] if srt else gd[srow[sl]] + sl
                 values[g] = acc
                 written[g] += 1
             continue

@@ -117,7 +117,7 @@ def test_device_resident_result():
                                   "stokes_b", "tetp2_lap", "q2_lap",
                                   "trip1_interp_mass", "trip1_mass_x2"])
 @pytest.mark.parametrize("mode", ["unfused", "small_tiles", "slot_parallel", "direct_store",
-                                  "packed_values"])
+                                  "packed_values", "sorted_slots"])
 def test_both_assembly_paths(name, mode, monkeypatch):
     """The two-kernel path (local matrices in HBM + gather reduction) and the
     fused tile kernel with many small tiles (exercises halos and row ownership)
@@ -127,10 +127,14 @@ def test_both_assembly_paths(name, mode, monkeypatch):
         monkeypatch.setenv("SPFEM_LOCAL_LAYOUT", "entry")
     else:
         monkeypatch.setenv("SPFEM_TILE_E", "32")
+        monkeypatch.setenv("SPFEM_TILE_SORT", "0")
         if mode == "slot_parallel":                 # one thread per CSR slot in phase B
             monkeypatch.setenv("SPFEM_TILE_MODE", "slots")
         elif mode == "packed_values":               # ... and only the values that are read
             monkeypatch.setenv("SPFEM_TILE_MODE", "compact")
+        elif mode == "sorted_slots":                # ... slots ordered by contribution count
+            monkeypatch.setenv("SPFEM_TILE_MODE", "compact")
+            monkeypatch.setenv("SPFEM_TILE_SORT", "1")
         elif mode == "direct_store":                # row-owner threads store without staging
             monkeypatch.setenv("SPFEM_TILE_MODE", "rows")
             monkeypatch.setenv("SPFEM_TILE_DIRECT", "1")

@@ -112,3 +112,11 @@ def test_tile_plan_reproduces_assembly(name, E):
     assert np.all(w3 == 1) and np.max(np.abs(v3 - ref.data)) <= 1e-12 * scale
     assert tp3["max_store"] < plan.spec.n_unique * tp3["ldl"]
     print(name, "dense", plan.spec.n_unique * tp3["ldl"], "compact", tp3["max_store"])
+    # ... and the slots of a tile ordered by their number of contributions
+    for md in ("slots", "compact"):
+        tp4 = build_tile_plan(torch, torch.from_numpy(indptr), torch.from_numpy(cptr),
+                              torch.from_numpy(contrib), n, plan.spec.n_entries, E,
+                              torch.from_numpy(vt), dim=asm.mesh.p.shape[0],
+                              alias=plan.spec.alias, mode=md, sort_slots=True)
+        v4, w4 = emulate(tp4, uniq, nnz)
+        assert np.all(w4 == 1) and np.max(np.abs(v4 - ref.data)) <= 1e-12 * scale
