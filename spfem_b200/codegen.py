@@ -941,7 +941,7 @@ def generate_interior(spec, name="spfem_elem"):
     src.append("    const long long e = P.sel ? (long long)P.sel[k] : k;")
     src.append("    %s_body<false, -1>(P, e, P.t, P.ldt, e, P.p, P.ldp, P.out, P.ldo, k * P.ldk);" % name)
     src.append("}")
-    if spec.bilinear:
+    if True:    # bilinear forms and load vectors alike (a vector = one CSR slot per row)
         nve = 4 if quad else dim + 1
         # element id (only needed for the interp gathers through P.tdof_u)
         elem = "(long long)((const int *)(sA + d[13]))[el]" if spec.nw > 0 else "0LL"

@@ -461,11 +461,11 @@ class Engine(object):
 
         def cp_t(lo, hi):
             pt[:, lo:hi] = ht[:, lo:hi]      # int64 -> int32 on the fly
-        # (staging in chunks pipelined with the DMA was measured slower: the host
-        # side, not the 168 MB over PCIe, is the longer part)
+        # (finer chunks pipelined with the DMA were measured slower: the host side,
+        # not the 168 MB over PCIe, is the longer part)
         _parallel(cp_p, hp.shape[1], 1 << 19)
-        _parallel(cp_t, ht.shape[1], 1 << 19)
         self.p = self._pin_p.to(self.device, non_blocking=True)
+        _parallel(cp_t, ht.shape[1], 1 << 19)     # staged while p is on the wire
         t32 = self._pin_t.to(self.device, non_blocking=True)
         self._h2d_done = torch.cuda.Event()
         self._h2d_done.record()
@@ -623,6 +623,15 @@ class Engine(object):
         if tind is None and plan.bilinear and self.fused:
             tp = self.tile_plan(pat, n, spec.n_entries, spec.nw > 0, tuple(spec.alias),
                                 getattr(spec, "n_terms", 0))
+        elif (tind is None and self.fused and n > 0
+              and os.environ.get("SPFEM_TILE_LINEAR", "1") != "0"):
+            # load vector = a matrix with one CSR slot per row: same tile kernel
+            rs = pat.rowstart
+            if int((rs[1:] - rs[:-1]).min().item()) > 0:       # every DOF is touched
+                tp = self.tile_plan(pat, n, spec.n_entries, spec.nw > 0, tuple(spec.alias),
+                                    getattr(spec, "n_terms", 0),
+                                    indptr=torch.arange(pat.nrows + 1, dtype=torch.int32,
+                                                        device=self.device), cptr=rs)
         if tp is not None:
             tk = get_kernel(plan.source, plan.name + "_tile")
             return TiledPrepared(self, plan, kernel, tk, a, None, pat, tp, keep=(wt,))
@@ -735,7 +744,8 @@ class Engine(object):
         pat._fan_plan = fp
         return fp
 
-    def tile_plan(self, pat, n, nent, with_el=False, alias=None, n_terms=0):
+    def tile_plan(self, pat, n, nent, with_el=False, alias=None, n_terms=0,
+                  indptr=None, cptr=None):
         """Tile plan of the fused kernel for ``pat`` (cached on the pattern);
         ``None`` if a tile does not fit in shared memory / 16-bit indices."""
         cache = getattr(pat, "_tile_plans", None)
@@ -785,7 +795,8 @@ class Engine(object):
             if E_env <= 0 and mode == "slots" and E > 64 and 8 * nuniq * (1.3 * E + 32) > prefer:
                 continue                # cannot fit the preferred footprint
             try:
-                tp = build_tile_plan(self.torch, pat.indptr, pat.cptr, pat.contrib,
+                tp = build_tile_plan(self.torch, pat.indptr if indptr is None else indptr,
+                                     pat.cptr if cptr is None else cptr, pat.contrib,
                                      n, nent, E, self.t, with_el=with_el,
                                      dim=self.p.shape[0], alias=alias,
                                      schedule={"0": False, "full": "full"}.get(
