@@ -16,8 +16,9 @@ CSR pattern are derived from them:
 
 The topology is built with one shared routine (packed 64-bit keys + one sort)
 instead of the reference's structured-view ``np.unique`` calls; the resulting
-integer arrays are identical (checked against the reference in
-``tests/test_mesh_host.py`` and the golden fixtures).
+integer arrays are identical (the golden fixtures of the reference pin the DOF
+numbering derived from them; ``tests/test_mesh_host.py`` checks the device
+builder against this one).
 Plotting / adaptive refinement / mesh IO are out of scope.
 """
 import numpy as np
@@ -54,6 +55,58 @@ def _facet_to_element(t2f, nf):
     f2t[1] = order[stop] % nt
     f2t[1, f2t[0] == f2t[1]] = -1
     return f2t
+
+
+# ---------------------------------------------------------------------------
+# device restatement of the two topology builders: same
+# numbering as the NumPy versions above, bit for bit -- ``torch.unique`` on the
+# packed vertex tuples is the lexicographic ``np.unique``, the stable argsort /
+# searchsorted pair is the reference's first / last occurrence rule.  The
+# tensors may live on the CPU (that is how tests/test_mesh_host.py checks them).
+# ---------------------------------------------------------------------------
+def _entity_table_torch(torch, t, local_tuples, nv):
+    k = len(local_tuples[0])
+    if float(nv) ** k >= 2.0 ** 62:
+        raise ValueError("vertex tuples do not fit a 64-bit key")
+    blocks = [torch.sort(t[list(loc), :], dim=0).values for loc in local_tuples]
+    allc = torch.cat(blocks, 1)
+    key = allc[0].clone()
+    for r in range(1, k):
+        key = key * nv + allc[r]
+    ukey, inverse = torch.unique(key, return_inverse=True)
+    rows = []
+    for r in range(k):
+        rows.append((ukey // (nv ** (k - 1 - r))) % nv)
+    return torch.stack(rows, 0), inverse.reshape(len(local_tuples), t.shape[1])
+
+
+def _facet_to_element_torch(torch, t2f, nf):
+    nloc, nt = t2f.shape
+    flat = t2f.reshape(-1)
+    order = torch.argsort(flat, stable=True)
+    sorted_f = flat[order]
+    ar = torch.arange(nf, device=t2f.device)
+    start = torch.searchsorted(sorted_f, ar, right=False)
+    stop = torch.searchsorted(sorted_f, ar, right=True) - 1
+    f0 = order[start] % nt
+    f1 = order[stop] % nt
+    f1 = torch.where(f0 == f1, torch.full_like(f1, -1), f1)
+    return torch.stack((f0, f1), 0)
+
+
+def _device_topology_wanted(nt):
+    """Large meshes build their topology tables on the GPU when there is one
+    (``SPFEM_DEVICE_TOPOLOGY=0`` keeps the NumPy path, ``=1`` forces the device
+    path for any size)."""
+    import os
+    mode = os.environ.get("SPFEM_DEVICE_TOPOLOGY", "auto")
+    if mode == "0" or (mode == "auto" and nt < (1 << 17)):
+        return False
+    try:
+        import torch
+    except ImportError:
+        return False
+    return torch.cuda.is_available()
 
 
 class Mesh(object):
@@ -132,10 +185,26 @@ class Mesh(object):
         return uniq, inverse.reshape((len(local_tuples), nt))
 
     def _build_mappings(self):
+        if _device_topology_wanted(self.t.shape[1]):
+            return self._build_mappings_device()
         if self._local_edges:
             self.edges, self.t2e = self._entity_table(self._local_edges)
         self.facets, self.t2f = self._entity_table(self._local_facets)
         self.f2t = _facet_to_element(self.t2f, self.facets.shape[1])
+
+    def _build_mappings_device(self, device=None):
+        """The same tables built with sort / unique on the GPU and copied back
+        (the mesh classes keep NumPy arrays, like the reference)."""
+        import torch
+        dev = torch.device("cuda", torch.cuda.current_device()) if device is None else device
+        t = torch.from_numpy(np.ascontiguousarray(self.t, dtype=np.int64)).to(dev)
+        nv = max(self.p.shape[1], int(t.max().item()) + 1)
+        if self._local_edges:
+            e, t2e = _entity_table_torch(torch, t, self._local_edges, nv)
+            self.edges, self.t2e = e.cpu().numpy(), t2e.cpu().numpy()
+        f, t2f = _entity_table_torch(torch, t, self._local_facets, nv)
+        f2t = _facet_to_element_torch(torch, t2f, f.shape[1])
+        self.facets, self.t2f, self.f2t = f.cpu().numpy(), t2f.cpu().numpy(), f2t.cpu().numpy()
 
     # -- queries shared by the 2-D / 3-D meshes -----------------------------
     def boundary_facets(self):
