@@ -241,16 +241,19 @@ extern "C" __global__ void __launch_bounds__(@THREADS@, @MINB@) @NAME@_tile(cons
         const int *gd = (const int *)sB;
         const unsigned short *soff = (const unsigned short *)(sB + d[6]);
         const unsigned short *srow = (const unsigned short *)(sB + d[7]);
-#pragma unroll 2
+        double *__restrict__ vals = T.values;
+        const bool srt = T.sorted != 0;
+#pragma unroll @BUNROLL@
         for (int s = threadIdx.x; s < ns; s += blockDim.x) {
             const unsigned k0 = soff[s], k1 = soff[s + 1];
             const unsigned c0 = cb[k0], c1 = cb[k0 + 1];
             /* sorted: slots ordered by contribution count, CSR position per slot */
-            const int g = T.sorted ? gd[s] : gd[srow[s]] + s;
+            const int g = srt ? gd[s] : gd[srow[s]] + s;
             double acc = sL[c0];
             if (k0 + 1 < k1) acc += sL[c1];
+#pragma unroll @TUNROLL@
             for (unsigned k = k0 + 2; k < k1; ++k) acc += sL[cb[k]];
-            T.values[g] = acc;
+            vals[g] = acc;
         }
         return;
     }
@@ -955,6 +958,8 @@ def generate_interior(spec, name="spfem_elem"):
             for c in range(spec.npart))
         src.append(TILE_KERNEL.replace("@CASES@", cases).replace("@PCASES@", pcases)
                    .replace("@NAME@", name)
+                   .replace("@BUNROLL@", os.environ.get("SPFEM_TILE_BUNROLL", "2"))
+                   .replace("@TUNROLL@", os.environ.get("SPFEM_TILE_TUNROLL", "4"))
                    .replace("@THREADS@", str(TILE_THREADS))
                    .replace("@MINB@", os.environ.get("SPFEM_TILE_MINB", "1")))
     src.append("#else")
