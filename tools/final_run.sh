@@ -6,7 +6,7 @@ python bench.py > gpurun_out/r01_final_bench.json 2> gpurun_out/r01_final_bench.
 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/r01_final_reference.json 2>&1
 CMD="python bench.py --steps 3 --warmup 3 --no-cpu-baseline --e2e-steps 1"
 $CMD > gpurun_out/plain_final.log 2>&1 &&
-ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv \
+ncu --metrics gpu__time_duration.sum --clock-control none -c 8000 --csv \
     --log-file gpurun_out/r01_final_launches.csv $CMD > gpurun_out/ncu_launches.log 2>&1
 $CMD > gpurun_out/plain_final2.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:fan8 -s 8 -c 2 \
