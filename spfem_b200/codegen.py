@@ -174,7 +174,11 @@ extern "C" __global__ void __launch_bounds__(@THREADS@, @MINB@) @NAME@_tile(cons
         const unsigned char *src = T.blob + (size_t)(unsigned)d[0] * 16;
         spfem_bulk_load(sA, src, (unsigned)bytes_a, &bars[0]);
         spfem_bulk_load(sB, src + bytes_a, (unsigned)bytes_b, &bars[1]);
-        /* pull the blob of a tile that starts a few waves later into L2 */
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        /* pull the blob of a tile that starts a few waves later into L2 (after the
+           barrier: the descriptor load of that tile must not hold up the CTA)   */
         const long long tp = (long long)blockIdx.x + T.prefetch;
         if (T.prefetch > 0 && tp < (long long)gridDim.x) {
             const int *dp = T.desc + 16 * (size_t)tp;
@@ -183,7 +187,6 @@ extern "C" __global__ void __launch_bounds__(@THREADS@, @MINB@) @NAME@_tile(cons
                            "r"((unsigned)(dp[1] + dp[2])) : "memory");
         }
     }
-    __syncthreads();
     /* phase A: local matrices -> sL */
     spfem_mbar_wait(&bars[0], 0);
     const unsigned short *vt = (const unsigned short *)sA;   /* tile-local vertex ids */
@@ -392,8 +395,12 @@ static __device__ __forceinline__ void @NAME@_fan_tile(const SpfemFanArgs &T)
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         spfem_bulk_load(sA, T.blob + (size_t)(unsigned)d[0] * 16,
                         (unsigned)(bytes_a + bytes_b), &bars[0]);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
         /* pull the blob of a tile that will start a few waves later into L2, so
-           its own TMA load does not pay the DRAM latency                       */
+           its own TMA load does not pay the DRAM latency (issued after the
+           barrier: the descriptor load of that tile must not hold up this CTA)  */
         const long long tp = (long long)blockIdx.x + T.prefetch;
         if (T.prefetch > 0 && tp < (long long)gridDim.x) {
             const int *dp = T.desc + 8 * (size_t)tp;
@@ -402,7 +409,6 @@ static __device__ __forceinline__ void @NAME@_fan_tile(const SpfemFanArgs &T)
                            "r"((unsigned)(dp[1] + dp[2])) : "memory");
         }
     }
-    __syncthreads();
     spfem_mbar_wait(&bars[0], 0);
     for (int row = threadIdx.x; row < nr; row += blockDim.x)
         @NAME@_fan_row<MAXN>(T.base, (const double2 *)sA, sA + bytes_a, nr, row, sV, sG);
