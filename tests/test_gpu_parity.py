@@ -408,3 +408,20 @@ def test_chunked_assembly_beyond_one_pattern_call(name, monkeypatch):
     monkeypatch.setenv("SPFEM_MAX_ENTRIES", str(plan.spec.n_entries * asm.mesh.t.shape[1] // 3))
     assert asm._chunks_needed(plan, None) >= 4
     util.check(asm.iasm(case.form), util.golden(case))
+
+
+@pytest.mark.parametrize("ename", ["TriP1", "TriP2"])
+def test_tile_kernel_irregular_mesh(ename):
+    """A high-valence vertex (wheel of 40 triangles, refined): the vertex-fan
+    plan declines (> 12 ring neighbours), the element-tile kernel takes over;
+    rows of very different lengths and slots with 1 ... 40 contributions."""
+    import asm_oracle
+    from test_fanplan import _wheel_mesh
+    from spfem_b200.assembly import AssemblerElement
+    mesh = _wheel_mesh(40, 2)
+    a = AssemblerElement(mesh, util.element(ename, 1))
+    prep = a.prepare_iasm(cases.lap2)
+    assert type(prep).__name__ == "TiledPrepared"
+    prep.launch()
+    cases.compare_csr(prep.result(), asm_oracle.iasm(mesh, ename, cases.lap2))
+    cases.compare_vec(a.iasm(cases.load1), asm_oracle.iasm(mesh, ename, cases.load1))

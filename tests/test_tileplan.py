@@ -120,3 +120,37 @@ def test_tile_plan_reproduces_assembly(name, E):
                               alias=plan.spec.alias, mode=md, sort_slots=True)
         v4, w4 = emulate(tp4, uniq, nnz)
         assert np.all(w4 == 1) and np.max(np.abs(v4 - ref.data)) <= 1e-12 * scale
+
+
+@pytest.mark.parametrize("ename", ["TriP1", "TriP2"])
+def test_tile_plan_on_irregular_mesh(ename):
+    """A mesh with a high-valence vertex (wheel of 40 triangles, refined and
+    perturbed): rows of very different lengths, slots with 1 ... 40
+    contributions, through every slot-parallel variant of the plan."""
+    import spfem_b200 as sp
+    from spfem_b200.assembly import AssemblerElement
+    from test_fanplan import _wheel_mesh
+    mesh = _wheel_mesh(40, 1)
+    asm = AssemblerElement(mesh, util.element(ename, 1))
+    plan = asm.plan_iasm(cases.lap_mass if hasattr(cases, "lap_mass") else cases.lap2)
+    ref = hostemu.iasm(asm, cases.lap_mass if hasattr(cases, "lap_mass") else cases.lap2)
+    perm = _morton(mesh)
+    local = hostemu.run_interior(asm, plan)[:, perm]
+    tv, tu = asm.dofnum_v.t_dof[:, perm], asm.dofnum_u.t_dof[:, perm]
+    n = tv.shape[1]
+    ukeys, cptr, contrib = _pattern_numpy(tv, tu, asm.dofnum_u.N)
+    nnz = len(ukeys)
+    indptr = np.searchsorted(ukeys // asm.dofnum_u.N, np.arange(asm.dofnum_v.N + 1))
+    vt = np.ascontiguousarray(mesh.t[:, perm], dtype=np.int32)
+    uniq = np.zeros((plan.spec.n_unique, n))
+    uniq[plan.spec.alias, :] = local
+    scale = np.abs(ref.data).max()
+    for md, srt in (("slots", False), ("compact", False), ("slots", True), ("compact", True),
+                    ("rows", False)):
+        tp = build_tile_plan(torch, torch.from_numpy(indptr), torch.from_numpy(cptr),
+                             torch.from_numpy(contrib), n, plan.spec.n_entries, 32,
+                             torch.from_numpy(vt), dim=2, alias=plan.spec.alias,
+                             mode=md, sort_slots=srt)
+        v, w = emulate(tp, uniq, nnz)
+        assert np.all(w == 1), (md, srt)
+        assert np.max(np.abs(v - ref.data)) <= 1e-12 * scale, (md, srt)
