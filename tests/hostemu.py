@@ -30,10 +30,17 @@ def compile_host(plan):
     src = os.path.join(_TMP, key + ".cpp")
     so = os.path.join(_TMP, key + ".so")
     if not os.path.exists(so):
+        # private temporaries + atomic rename: several test processes (gloo ranks,
+        # xdist workers) may compile the same source at the same time
+        tag = "%s.%d" % (key, os.getpid())
+        src = os.path.join(_TMP, tag + ".cpp")
+        tmp_so = os.path.join(_TMP, tag + ".so.tmp")
         with open(src, "w") as fh:
             fh.write(plan.source)
         subprocess.check_call(["g++", "-O1", "-ffp-contract=off", "-DSPFEM_HOST",
-                               "-shared", "-fPIC", "-o", so, src])
+                               "-shared", "-fPIC", "-o", tmp_so, src])
+        os.replace(tmp_so, so)
+        os.remove(src)
     lib = C.CDLL(so)
     fn = getattr(lib, plan.name + "_host")
     fn.argtypes = [C.POINTER(SpfemArgs)]
