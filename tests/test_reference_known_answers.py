@@ -183,3 +183,96 @@ def test_convergence_trip2():               # test_module.py:258-323
 @pytest.mark.parametrize("p", [1, 2, 3])    # test_module.py:325-395 (p = 1, 2 there)
 def test_convergence_tripp(p):
     assert _h_convergence(sp.element.ElementTriPp(p)) >= 0.95 * p
+
+
+@pytest.mark.gpu
+def test_convergence_nitsche():             # test_module.py:475-532
+    """Poisson with Nitsche's method for the Dirichlet condition: boundary forms
+    with normals, the facet size ``h`` and interior gradients."""
+    from scipy.sparse.linalg import spsolve
+    G = lambda x, y: x ** 3 * np.sin(20.0 * y)
+    U = lambda x: G(x[0], x[1])
+    dU = {0: lambda x: 3.0 * x[0] ** 2 * np.sin(20.0 * x[1]),
+          1: lambda x: 20.0 * x[0] ** 3 * np.cos(20.0 * x[1])}
+    gamma = 100
+
+    def uv(u, v, du, dv, x, h, n):
+        return (gamma * 1 / h * u * v - du[0] * n[0] * v - du[1] * n[1] * v
+                - u * dv[0] * n[0] - u * dv[1] * n[1])
+
+    def fv(v, dv, x):
+        return (-6.0 * x[0] * np.sin(20.0 * x[1]) + 400.0 * x[0] ** 3 * np.sin(20.0 * x[1])) * v
+
+    def gv(v, dv, x, h, n):
+        return (G(x[0], x[1]) * v + gamma * 1 / h * G(x[0], x[1]) * v
+                - dv[0] * n[0] * G(x[0], x[1]) - dv[1] * n[1] * G(x[0], x[1]))
+    mesh = sp.MeshTri()
+    mesh.refine(2)
+    hs, errs = [], []
+    for _ in range(4):
+        mesh.refine()
+        a = AssemblerElement(mesh, sp.ElementTriP1())
+        K = a.iasm(lambda du, dv: du[0] * dv[0] + du[1] * dv[1])
+        B = a.fasm(uv, normals=True)
+        f = a.iasm(fv)
+        g = a.fasm(gv, normals=True)
+        x = spsolve((K + B).tocsc(), f + g)
+        hs.append(mesh.param())
+        errs.append(np.sqrt(a.L2error(x, U) ** 2 + a.H1error(x, dU) ** 2))
+    assert np.polyfit(np.log10(hs), np.log10(errs), 1)[0] >= 0.99
+
+
+def _robin_rate(meshes, make_elem, U, dexact, F, G, normals=True):
+    """Energy-norm convergence rate of the Robin problem over ``meshes``."""
+    from scipy.sparse.linalg import spsolve
+    dim = len(dexact)
+    hs, errs = [], []
+    for mesh in meshes:
+        a = AssemblerElement(mesh, make_elem())
+        A = a.iasm(lambda du, dv: sum(du[k] * dv[k] for k in range(dim)))
+        f = a.iasm(lambda v, x: F(*[x[k] for k in range(dim)]) * v)
+        B = a.fasm(lambda u, v: u * v, normals=normals)
+        g = a.fasm(lambda v, x: G(*[x[k] for k in range(dim)]) * v, normals=normals)
+        u = spsolve((A + B).tocsc(), f + g)
+        hs.append(mesh.param())
+        errs.append(np.sqrt(a.L2error(u, U) ** 2 + a.H1error(u, dexact) ** 2))
+    return np.polyfit(np.log10(hs), np.log10(errs), 1)[0]
+
+
+@pytest.mark.gpu
+def test_convergence_tetp2():               # test_module.py:82-157
+    U = lambda x: 1 + x[0] - x[0] ** 2 * x[1] ** 2 + x[0] * x[1] * x[2] ** 3
+    dexact = {0: lambda x: 1 - 2 * x[0] * x[1] ** 2 + x[1] * x[2] ** 3,
+              1: lambda x: -2 * x[0] ** 2 * x[1] + x[0] * x[2] ** 3,
+              2: lambda x: 3 * x[0] * x[1] * x[2] ** 2}
+    F = lambda x, y, z: 2 * x ** 2 + 2 * y ** 2 - 6 * x * y * z
+    G = lambda x, y, z: ((x == 1) * (3 - 3 * y ** 2 + 2 * y * z ** 3) + (x == 0) * (-y * z ** 3)
+                         + (y == 1) * (1 + x - 3 * x ** 2 + 2 * x * z ** 3)
+                         + (y == 0) * (1 + x - x * z ** 3)
+                         + (z == 1) * (1 + x + 4 * x * y - x ** 2 * y ** 2)
+                         + (z == 0) * (1 + x - x ** 2 * y ** 2))
+    meshes = []
+    for itr in range(1, 4):
+        m = sp.MeshTet()
+        m.refine(itr)
+        meshes.append(m)
+    rate = _robin_rate(meshes, sp.ElementTetP2, U, dexact, F, G)
+    assert 1.95 <= rate <= 2.2
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("ename,lo,hi", [("Q1", 0.95, 1.05), ("Q2", 1.95, 2.05)])
+def test_convergence_q1_q2(ename, lo, hi):  # test_module.py:159-256
+    U = lambda x: 1 + x[0] - x[0] ** 2 * x[1] ** 2 + np.exp(x[0])
+    dexact = {0: lambda x: 1 - 2 * x[0] * x[1] ** 2 + np.exp(x[0]),
+              1: lambda x: -2 * x[0] ** 2 * x[1]}
+    F = lambda x, y: 2 * x ** 2 + 2 * y ** 2 - np.exp(x)
+    G = lambda x, y: ((x == 1) * (3 - 3 * y ** 2 + 2 * np.exp(1)) + (x == 0) * 0
+                      + (y == 1) * (1 + x - 3 * x ** 2 + np.exp(x)) + (y == 0) * (1 + x + np.exp(x)))
+    meshes = []
+    m = sp.MeshQuad()
+    for _ in range(3):
+        m.refine()
+        meshes.append(sp.MeshQuad(m.p.copy(), m.t.copy()))
+    rate = _robin_rate(meshes, getattr(sp, "Element" + ename), U, dexact, F, G, normals=False)
+    assert lo <= rate <= hi
