@@ -730,8 +730,11 @@ def interior_terms(spec, drop_tol=1e-15):
             for j in range(nbu):
                 for i in range(spec.nbv):
                     for q in range(nq):
-                        K[j, i, q] = (spec.W[q] * _psi(spec.tab_u, a, j, q)
-                                      * _psi(spec.tab_v, b, i, q))
+                        # the product of the two basis values first: commutative, so
+                        # the transposed entry of a symmetric form gets bit-identical
+                        # constants and is recognised as an alias below
+                        K[j, i, q] = spec.W[q] * (_psi(spec.tab_u, a, j, q)
+                                                  * _psi(spec.tab_v, b, i, q))
             if coef.qdep:
                 scale = np.max(np.abs(K)) if K.size else 0.0
                 for q in range(nq):
