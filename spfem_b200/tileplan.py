@@ -99,7 +99,7 @@ def build_tile_plan(torch, indptr, cptr, contrib, n, nent, E, vt, with_el=True, 
     # same trip count -- on 3-D meshes the counts range from 1 to ~24 inside one
     # row and a warp otherwise runs at the pace of its longest slot.  The CSR
     # position then comes per slot (``gpos`` int32 [ns] replaces gdelta + srow).
-    sort_slots = bool(sort_slots) and slots_mode
+    sort_slots = sort_slots if slots_mode else False
     dev = indptr.device
     i64 = torch.int64
     N = indptr.numel() - 1
@@ -136,7 +136,12 @@ def build_tile_plan(torch, indptr, cptr, contrib, n, nent, E, vt, with_el=True, 
     # rows of a regular mesh then finish their slots at the same steps, so the
     # lanes of a warp leave the inner accumulation loop together
     csr_pos = ar_nnz - indptr[row_of_slot]           # position of the slot inside its row
-    if sort_slots:
+    if sort_slots == "bucket":
+        # coarse classes (<= 2, 3-4, 5-8, > 8 contributions), CSR order inside a
+        # class: most of a warp's stores stay consecutive
+        cls = (counts > 2).to(i64) + (counts > 4).to(i64) + (counts > 8).to(i64)
+        within = torch.argsort(((3 - cls) << 40) | ar_nnz)
+    elif sort_slots:
         within = torch.argsort(((65535 - counts.clamp(max=65535)) << 40) | ar_nnz)
     elif slots_mode or int(csr_pos.max().item()) > 255 or int(counts.max().item()) > 65535:
         within = ar_nnz                               # very long rows: keep CSR order

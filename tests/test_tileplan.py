@@ -113,11 +113,11 @@ def test_tile_plan_reproduces_assembly(name, E):
     assert tp3["max_store"] < plan.spec.n_unique * tp3["ldl"]
     print(name, "dense", plan.spec.n_unique * tp3["ldl"], "compact", tp3["max_store"])
     # ... and the slots of a tile ordered by their number of contributions
-    for md in ("slots", "compact"):
+    for md, srt in (("slots", True), ("compact", True), ("slots", "bucket")):
         tp4 = build_tile_plan(torch, torch.from_numpy(indptr), torch.from_numpy(cptr),
                               torch.from_numpy(contrib), n, plan.spec.n_entries, E,
                               torch.from_numpy(vt), dim=asm.mesh.p.shape[0],
-                              alias=plan.spec.alias, mode=md, sort_slots=True)
+                              alias=plan.spec.alias, mode=md, sort_slots=srt)
         v4, w4 = emulate(tp4, uniq, nnz)
         assert np.all(w4 == 1) and np.max(np.abs(v4 - ref.data)) <= 1e-12 * scale
 
@@ -146,7 +146,7 @@ def test_tile_plan_on_irregular_mesh(ename):
     uniq[plan.spec.alias, :] = local
     scale = np.abs(ref.data).max()
     for md, srt in (("slots", False), ("compact", False), ("slots", True), ("compact", True),
-                    ("rows", False)):
+                    ("slots", "bucket"), ("rows", False)):
         tp = build_tile_plan(torch, torch.from_numpy(indptr), torch.from_numpy(cptr),
                              torch.from_numpy(contrib), n, plan.spec.n_entries, 32,
                              torch.from_numpy(vt), dim=2, alias=plan.spec.alias,
