@@ -23,12 +23,12 @@ There is no CPU fallback: without the CUDA library / a GPU the calls raise.
 import inspect
 import os
 import numpy as np
-from scipy.sparse import csr_matrix
 
 from . import mesh as _mesh
 from . import element as _element
 from .quadrature import get_quadrature
-from .tracer import (Coef, Form, TraceError, basis_args, hdiv_args, zero_like, call_form)
+from .tracer import (Coef, Form, TraceError, basis_args, hdiv_args, zero_like,  # noqa: F401
+                     call_form)
 from . import codegen
 
 __all__ = ["Assembler", "AssemblerElement", "Dofnum", "TraceError"]

@@ -36,7 +36,7 @@ against the oracle without a GPU.
 import hashlib
 import os
 import numpy as np
-from .tracer import Coef, NONE
+from .tracer import NONE
 
 PRELUDE = r"""
 #ifdef SPFEM_HOST

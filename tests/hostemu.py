@@ -169,7 +169,6 @@ def fan_iasm(asm, form, rows_per_tile=64):
 
 def inorm(asm, form, interp, intorder=None):
     """Host emulation of ``AssemblerElement.inorm`` (per-element values)."""
-    import types
     captured = {}
 
     class _Eng(object):

@@ -6,7 +6,6 @@ emulation; ``-m gpu`` runs the whole chain on the device."""
 import numpy as np
 import pytest
 import scipy.sparse as spsp
-import scipy.sparse.linalg as spl
 import torch
 
 import spfem_b200 as sp

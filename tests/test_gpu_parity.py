@@ -4,7 +4,6 @@ C-ABI -> generated sm_100a kernels) against the reference's golden outputs,
 the oracle, and size-independent properties at larger sizes."""
 import numpy as np
 import pytest
-import scipy.sparse.linalg as spl
 
 import cases
 import util

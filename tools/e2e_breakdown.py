@@ -5,7 +5,6 @@ the cached pattern."""
 import os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-import numpy as np
 import torch
 import spfem_b200 as sp
 from spfem_b200.assembly import AssemblerElement
