@@ -273,8 +273,8 @@ def run_gpu_arm(args):
     if fused:
         kname = {"FanPrepared": "spfem_elem_fan", "TiledPrepared": "spfem_elem_tile"}.get(
             type(preps[0]).__name__, "fused")
-        if kname == "spfem_elem_fan" and preps[0].fp["max_neighbours"] <= 8:
-            kname = "spfem_elem_fan8"
+        if kname == "spfem_elem_fan":
+            kname += {"tiny": "8t", "fan8": "8"}.get(preps[0].fp.get("format"), "")
         kernels = {kname + "_ms": float(t_red)}
         t_elem = 0.0
     else:

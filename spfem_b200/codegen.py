@@ -309,17 +309,22 @@ struct SpfemFanArgs {
     double *values;
     int max_a, max_b, max_ns, prefetch;
 };
-template <int MAXN>
+template <int MAXN, bool TINY>
 SPFEM_DEVICE void @NAME@_fan_row(const SpfemArgs &P, const double2 *__restrict__ pc2,
                                  const unsigned char *__restrict__ rec, const int nr,
                                  const int row, double *__restrict__ sV, int *__restrict__ sG)
 {
-    /* row record planes -> registers; neighbour ids (16 bit) and CSR positions
-       (8 bit) are extracted with shifts                                        */
+    /* row record planes -> registers; neighbour ids (16 bit; TINY: 8 bit) and CSR
+       positions (8 bit; TINY: 4 bit) are extracted with shifts                  */
     unsigned w[8], pw[3];
     {
         const uint4 h = reinterpret_cast<const uint4 *>(rec)[row];
         w[0] = h.x; w[1] = h.y; w[2] = h.z; w[3] = h.w;
+        if (TINY) {
+            w[4] = w[5] = w[6] = w[7] = 0u;
+            pw[0] = reinterpret_cast<const unsigned *>(rec + (size_t)16 * nr)[row];
+            pw[1] = pw[2] = 0u;
+        } else {
         const uint4 n1 = reinterpret_cast<const uint4 *>(rec + (size_t)16 * nr)[row];
         if (MAXN <= 8) {
             w[4] = n1.x; w[5] = n1.y; w[6] = 0u; w[7] = 0u;
@@ -329,9 +334,12 @@ SPFEM_DEVICE void @NAME@_fan_row(const SpfemArgs &P, const double2 *__restrict__
             w[4] = n1.x; w[5] = n1.y; w[6] = n1.z; w[7] = n1.w;
             pw[0] = n2.x; pw[1] = n2.y; pw[2] = n2.z;
         }
+        }
     }
-#define SPFEM_NBR(q) ((w[2 + ((q) >> 1)] >> (16 * ((q) & 1))) & 0xffffu)
-#define SPFEM_POS(q) ((pw[(q) >> 2] >> (8 * ((q) & 3))) & 0xffu)
+#define SPFEM_NBR(q) (TINY ? ((w[2 + (((q) & 7) >> 2)] >> (8 * ((q) & 3))) & 0xffu) \
+                           : ((w[2 + ((q) >> 1)] >> (16 * ((q) & 1))) & 0xffffu))
+#define SPFEM_POS(q) (TINY ? ((pw[0] >> (4 * ((q) & 7))) & 0xfu) \
+                           : ((pw[(q) >> 2] >> (8 * ((q) & 3))) & 0xffu))
     const int g0 = (int)w[0];                    /* CSR position of the row */
     const int s0 = (int)(w[1] & 0xffffu);
     const int nfan = (int)((w[1] >> 16) & 0xfu);
@@ -379,7 +387,7 @@ SPFEM_DEVICE void @NAME@_fan_row(const SpfemArgs &P, const double2 *__restrict__
 #undef SPFEM_NBR
 }
 #ifndef SPFEM_HOST
-template <int MAXN>
+template <int MAXN, bool TINY>
 static __device__ __forceinline__ void @NAME@_fan_tile(const SpfemFanArgs &T)
 {
     extern __shared__ __align__(128) unsigned char spfem_smem_raw[];
@@ -411,7 +419,7 @@ static __device__ __forceinline__ void @NAME@_fan_tile(const SpfemFanArgs &T)
     }
     spfem_mbar_wait(&bars[0], 0);
     for (int row = threadIdx.x; row < nr; row += blockDim.x)
-        @NAME@_fan_row<MAXN>(T.base, (const double2 *)sA, sA + bytes_a, nr, row, sV, sG);
+        @NAME@_fan_row<MAXN, TINY>(T.base, (const double2 *)sA, sA + bytes_a, nr, row, sV, sG);
     __syncthreads();
     /* every slot of the tile exactly once; a warp covers the CSR rows of its
        threads, so its stores fill whole 32-byte sectors                        */
@@ -421,11 +429,16 @@ static __device__ __forceinline__ void @NAME@_fan_tile(const SpfemFanArgs &T)
    (fewer registers, higher occupancy) and the general case (<= 12)         */
 extern "C" __global__ void __launch_bounds__(@FANTHREADS@, @FANMINB8@) @NAME@_fan8(const SpfemFanArgs T)
 {
-    @NAME@_fan_tile<8>(T);
+    @NAME@_fan_tile<8, false>(T);
+}
+/* ... and tiles of <= 256 vertices: 20-byte records (8-bit ids, 4-bit positions) */
+extern "C" __global__ void __launch_bounds__(@FANTHREADS@, @FANMINB8@) @NAME@_fan8t(const SpfemFanArgs T)
+{
+    @NAME@_fan_tile<8, true>(T);
 }
 extern "C" __global__ void __launch_bounds__(@FANTHREADS@, @FANMINB@) @NAME@_fan(const SpfemFanArgs T)
 {
-    @NAME@_fan_tile<12>(T);
+    @NAME@_fan_tile<12, false>(T);
 }
 #else
 extern "C" void @NAME@_fan_host(const SpfemFanArgs *T, int ntiles, double *sV, int *sG, int maxn)
@@ -434,10 +447,12 @@ extern "C" void @NAME@_fan_host(const SpfemFanArgs *T, int ntiles, double *sV, i
         const int *d = T->desc + 8 * (size_t)t;
         const unsigned char *src = T->blob + (size_t)(unsigned)d[0] * 16;
         for (int row = 0; row < d[3]; ++row) {
-            if (maxn <= 8)
-                @NAME@_fan_row<8>(T->base, (const double2 *)src, src + d[1], d[3], row, sV, sG);
+            if (maxn > 100)          /* 100 + 8: the 20-byte record format */
+                @NAME@_fan_row<8, true>(T->base, (const double2 *)src, src + d[1], d[3], row, sV, sG);
+            else if (maxn <= 8)
+                @NAME@_fan_row<8, false>(T->base, (const double2 *)src, src + d[1], d[3], row, sV, sG);
             else
-                @NAME@_fan_row<12>(T->base, (const double2 *)src, src + d[1], d[3], row, sV, sG);
+                @NAME@_fan_row<12, false>(T->base, (const double2 *)src, src + d[1], d[3], row, sV, sG);
         }
         for (int s = 0; s < d[4]; ++s) T->values[sG[s]] = sV[s];
     }

@@ -616,8 +616,8 @@ class Engine(object):
                 and os.environ.get("SPFEM_FAN", "1") != "0"):
             fp = self.fan_plan(pat)
             if fp is not None:
-                fk = get_kernel(plan.source, plan.name + (
-                    "_fan8" if fp["max_neighbours"] <= 8 else "_fan"))
+                fk = get_kernel(plan.source, plan.name + {
+                    "tiny": "_fan8t", "fan8": "_fan8"}.get(fp["format"], "_fan"))
                 return FanPrepared(self, plan, kernel, fk, a, pat, fp)
         tp = None
         if tind is None and plan.bilinear and self.fused:
@@ -733,7 +733,8 @@ class Engine(object):
         try:
             fp = build_fan_plan(torch, self.p, dev64(mesh.t), dev64(mesh.t2f), dev64(mesh.f2t),
                                 pat.indptr, pat.indices,
-                                int(os.environ.get("SPFEM_FAN_ROWS", "128")))
+                                int(os.environ.get("SPFEM_FAN_ROWS", "128")),
+                                tiny=os.environ.get("SPFEM_FAN_TINY", "1") != "0")
         except FanPlanError:
             return None
         fp["pc_stride"] = 1

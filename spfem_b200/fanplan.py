@@ -136,7 +136,7 @@ def vertex_rings(mesh):
     return nb, nfan, closed
 
 
-def build_fan_plan(mesh, indptr, indices, rows_per_tile=256):
+def build_fan_plan(mesh, indptr, indices, rows_per_tile=256, tiny=True):
     """Host arrays of the vertex-fan plan for the CSR pattern ``indptr/indices``
     (rows = columns = vertices).  Raises :class:`FanPlanError` if it does not
     apply."""
@@ -225,11 +225,23 @@ def build_fan_plan(mesh, indptr, indices, rows_per_tile=256):
                   | (dpos[rows] << 24))
     nb16 = loc.T.astype(np.uint16)                         # (nv, W) tile-local neighbour ids
     pos8 = np.where(ok, pos12[:W, rows], 0).T.astype(np.uint8)   # (nv, W) CSR positions
+    # "tiny" records (20 bytes per row): 8-bit neighbour ids (tiles of <= 256
+    # vertices) in plane 0, eight 4-bit CSR positions in one extra word
+    tiny = bool(tiny) and compact and int(nvt.max()) <= 256
     plane0 = np.zeros((nv, 16), dtype=np.uint8)
     plane0[:, :8] = head.astype(np.int32).view(np.uint8).reshape(nv, 8)
-    plane0[:, 8:] = nb16[:, :4].copy().view(np.uint8).reshape(nv, 8)
+    nib = None
+    if tiny:
+        plane0[:, 8:] = nb16[:, :8].astype(np.uint8)
+        nib = np.zeros(nv, dtype=np.int64)
+        for q in range(8):
+            nib |= pos8[:, q].astype(np.int64) << (4 * q)
+    else:
+        plane0[:, 8:] = nb16[:, :4].copy().view(np.uint8).reshape(nv, 8)
     planes = [plane0]
-    if compact:
+    if tiny:
+        pass
+    elif compact:
         p1 = np.zeros((nv, 16), dtype=np.uint8)
         p1[:, :8] = nb16[:, 4:8].copy().view(np.uint8).reshape(nv, 8)
         p1[:, 8:] = pos8[:, :8]
@@ -242,6 +254,8 @@ def build_fan_plan(mesh, indptr, indices, rows_per_tile=256):
     # blob layout
     bytes_a = (nvt * 16 + 15) // 16 * 16
     bytes_b = nr * 16 * len(planes)
+    if tiny:
+        bytes_b = bytes_b + (nr * 4 + 15) // 16 * 16
     tb = bytes_a + bytes_b
     off = np.cumsum(tb) - tb
     total = int(tb.sum())
@@ -249,6 +263,9 @@ def build_fan_plan(mesh, indptr, indices, rows_per_tile=256):
     for k, pl in enumerate(planes):
         dk = (off + bytes_a + k * nr * 16)[tile_of_row] + 16 * row_local
         blob[dk[:, None] + np.arange(16)[None, :]] = pl
+    if tiny:
+        dk = ((off + bytes_a + nr * 16)[tile_of_row] + 4 * row_local) // 4
+        blob.view(np.uint32)[dk] = nib.astype(np.uint32)
     desc = np.zeros((ntiles, 8), dtype=np.int64)
     desc[:, 0], desc[:, 1], desc[:, 2] = off // 16, bytes_a, bytes_b
     desc[:, 3], desc[:, 4], desc[:, 5] = nr, ns, nvt
@@ -266,6 +283,7 @@ def build_fan_plan(mesh, indptr, indices, rows_per_tile=256):
         "max_a": int(tb.max()), "max_b": 0, "max_ns": int(ns.max()),
         "halo_factor": float(nvt.sum()) / nv,
         "max_neighbours": int(nn.max()),
+        "format": "tiny" if tiny else ("fan8" if compact else "wide"),
     }
 
 

@@ -108,7 +108,7 @@ def _wrap32(torch, x):
     return torch.where(x >= 2 ** 31, x - 2 ** 32, x).to(torch.int32)
 
 
-def build_fan_plan(torch, p, t, t2f, f2t, indptr, indices, rows_per_tile=128):
+def build_fan_plan(torch, p, t, t2f, f2t, indptr, indices, rows_per_tile=128, tiny=True):
     """Torch version of :func:`fanplan.build_fan_plan`; all tensor arguments on
     one device (int64 topology, float64 coordinates).  Returns the same dict with
     tensors instead of arrays."""
@@ -196,10 +196,22 @@ def build_fan_plan(torch, p, t, t2f, f2t, indptr, indices, rows_per_tile=128):
     def quad(a, b, c, d):
         return _wrap32(torch, a | (b << 8) | (c << 16) | (d << 24))
     z = torch.zeros(nv, dtype=torch.int32, device=dev)
-    plane0 = torch.stack([_wrap32(torch, w0), _wrap32(torch, w1),
-                          pair(nbl[:, 0], nbl[:, 1]), pair(nbl[:, 2], nbl[:, 3])], 1)
+    tiny = bool(tiny) and compact and int(nvt.max()) <= 256
+    nib = None
+    if tiny:
+        plane0 = torch.stack([_wrap32(torch, w0), _wrap32(torch, w1),
+                              quad(nbl[:, 0], nbl[:, 1], nbl[:, 2], nbl[:, 3]),
+                              quad(nbl[:, 4], nbl[:, 5], nbl[:, 6], nbl[:, 7])], 1)
+        nib = torch.zeros(nv, dtype=i64, device=dev)
+        for q in range(8):
+            nib |= psl[:, q] << (4 * q)
+    else:
+        plane0 = torch.stack([_wrap32(torch, w0), _wrap32(torch, w1),
+                              pair(nbl[:, 0], nbl[:, 1]), pair(nbl[:, 2], nbl[:, 3])], 1)
     planes = [plane0]
-    if compact:
+    if tiny:
+        pass
+    elif compact:
         planes.append(torch.stack([pair(nbl[:, 4], nbl[:, 5]), pair(nbl[:, 6], nbl[:, 7]),
                                    quad(psl[:, 0], psl[:, 1], psl[:, 2], psl[:, 3]),
                                    quad(psl[:, 4], psl[:, 5], psl[:, 6], psl[:, 7])], 1))
@@ -211,6 +223,8 @@ def build_fan_plan(torch, p, t, t2f, f2t, indptr, indices, rows_per_tile=128):
                                    quad(psl[:, 8], psl[:, 9], psl[:, 10], psl[:, 11]), z], 1))
     bytes_a = (nvt * 16 + 15) // 16 * 16
     bytes_b = nr * 16 * len(planes)
+    if tiny:
+        bytes_b = bytes_b + (nr * 4 + 15) // 16 * 16
     tb = bytes_a + bytes_b
     off = torch.cumsum(tb, 0) - tb
     total = int(tb.sum())
@@ -219,6 +233,8 @@ def build_fan_plan(torch, p, t, t2f, f2t, indptr, indices, rows_per_tile=128):
     for k, pl in enumerate(planes):
         dk = ((off + bytes_a + k * nr * 16)[tile_of_row] + 16 * row_local) // 4
         blob32[dk[:, None] + a4[None, :]] = pl
+    if tiny:
+        blob32[((off + bytes_a + nr * 16)[tile_of_row] + 4 * row_local) // 4] = _wrap32(torch, nib)
     zt = torch.zeros_like(nr)
     desc = torch.stack([off // 16, bytes_a, bytes_b, nr, ns, nvt, zt, zt], 1)
     if int(desc.max()) > 2 ** 31 - 1:
@@ -234,4 +250,5 @@ def build_fan_plan(torch, p, t, t2f, f2t, indptr, indices, rows_per_tile=128):
         "max_a": int(tb.max()), "max_b": 0, "max_ns": int(ns.max()),
         "halo_factor": float(nvt.sum()) / nv,
         "max_neighbours": int(nn.max()),
+        "format": "tiny" if tiny else ("fan8" if compact else "wide"),
     }

@@ -139,7 +139,7 @@ def fasm(asm, form, find=None, interior=False, intorder=None, normals=True,
                       shape=(asm.dofnum_v.N, 1)).toarray().T[0]
 
 
-def fan_iasm(asm, form, rows_per_tile=64):
+def fan_iasm(asm, form, rows_per_tile=64, tiny=True):
     """Host emulation of the vertex-fan kernel: plan (spfem_b200/fanplan.py) +
     the generated ``<name>_fan_host`` loop; pattern from the plain emulation."""
     from spfem_b200._lib import SpfemFanArgs
@@ -147,7 +147,7 @@ def fan_iasm(asm, form, rows_per_tile=64):
     ref = iasm(asm, form)
     plan = asm.plan_iasm(form)
     assert plan.spec.fan_ok
-    fp = build_fan_plan(asm.mesh, ref.indptr, ref.indices, rows_per_tile)
+    fp = build_fan_plan(asm.mesh, ref.indptr, ref.indices, rows_per_tile, tiny=tiny)
     fill_coordinates_host(fp, asm.mesh.p)
     key = hashlib.sha256(plan.source.encode()).hexdigest()[:20]
     compile_host(plan)
@@ -161,7 +161,8 @@ def fan_iasm(asm, form, rows_per_tile=64):
     a = SpfemFanArgs()
     a.desc, a.blob, a.values = _ptr(fp["desc"]), _ptr(fp["blob"]), _ptr(values)
     a.max_a, a.max_b, a.max_ns = fp["max_a"], fp["max_b"], fp["max_ns"]
-    fn(C.byref(a), fp["ntiles"], _ptr(sV), _ptr(sG), fp["max_neighbours"])
+    fn(C.byref(a), fp["ntiles"], _ptr(sV), _ptr(sG),
+       108 if fp["format"] == "tiny" else fp["max_neighbours"])
     out = ref.copy()
     out.data = values
     return out, fp

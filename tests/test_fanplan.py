@@ -34,11 +34,13 @@ def test_rings_are_vertex_stars():
         assert a[0] * b[1] - a[1] * b[0] > 0
 
 
+@pytest.mark.parametrize("tiny", [True, False])
 @pytest.mark.parametrize("name", ["trip1_lap", "trip1_mass", "trip1_lap_r6"])
-def test_fan_kernel_matches_reference(name):
+def test_fan_kernel_matches_reference(name, tiny):
     case = cases.BY_NAME[name]
     asm = util.assembler_for(case)
-    out, fp = hostemu.fan_iasm(asm, case.form, rows_per_tile=64)
+    out, fp = hostemu.fan_iasm(asm, case.form, rows_per_tile=64, tiny=tiny)
+    assert fp["format"] == ("tiny" if tiny else "fan8")   # 20- / 32-byte row records
     assert not np.isnan(out.data).any()            # every CSR value written
     util.check(out, util.golden(case))
     assert fp["halo_factor"] < 2.0
@@ -89,8 +91,9 @@ def test_fan_kernel_wide_records():
     cases.compare_csr(out, hostemu.iasm(asm, cases.lap2))
 
 
+@pytest.mark.parametrize("tiny", [True, False])
 @pytest.mark.parametrize("which", ["refined", "wheel", "jiggled"])
-def test_torch_plan_is_byte_identical(which):
+def test_torch_plan_is_byte_identical(which, tiny):
     """The device-side plan builder (PyTorch index ops; run here on CPU tensors)
     produces exactly the blob / descriptors of the NumPy reference builder."""
     import torch
@@ -107,11 +110,12 @@ def test_torch_plan_is_byte_identical(which):
         m.p[:, I] += 0.01 * np.random.default_rng(1).standard_normal((2, len(I)))
     asm = AssemblerElement(m, sp.ElementTriP1())
     A = hostemu.iasm(asm, cases.mass)
-    a = build_fan_plan(m, A.indptr, A.indices, 32)
+    a = build_fan_plan(m, A.indptr, A.indices, 32, tiny=tiny)
     T = lambda x: torch.from_numpy(np.ascontiguousarray(x))
     b = fanplan_torch.build_fan_plan(torch, T(m.p), T(m.t.astype(np.int64)), T(m.t2f.astype(np.int64)),
                                      T(m.f2t.astype(np.int64)), T(A.indptr.astype(np.int64)),
-                                     T(A.indices.astype(np.int64)), 32)
+                                     T(A.indices.astype(np.int64)), 32, tiny=tiny)
+    assert a["format"] == b["format"] and (a["format"] == "tiny") == (tiny and which != "wheel")
     assert np.array_equal(a["desc"], b["desc"].numpy())
     assert np.array_equal(a["blob"], b["blob"].numpy())
     assert np.array_equal(a["vid"], b["vid"].numpy())
