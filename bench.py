@@ -56,6 +56,7 @@ class ClockSampler(threading.Thread):
         self.index, self.period = index, period
         self.samples, self.reasons = [], set()
         self.max_mhz = None
+        self.recording = False        # samples count only inside the timed region
         self._stop_evt = threading.Event()
         self.ok = False
         try:
@@ -80,19 +81,22 @@ class ClockSampler(threading.Thread):
         }
         while not self._stop_evt.is_set():
             try:
-                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                mhz = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
                 try:
                     r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
                 except Exception:
                     r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
-                for bit, nm in names.items():
-                    if r & bit:
-                        self.reasons.add(nm)
+                if self.recording:
+                    self.samples.append(mhz)
+                    for bit, nm in names.items():
+                        if r & bit:
+                            self.reasons.add(nm)
             except Exception:
                 pass
             self._stop_evt.wait(self.period)
 
     def stop(self):
+        self.recording = False
         self._stop_evt.set()
         if self.is_alive():
             self.join(timeout=2)
@@ -239,12 +243,15 @@ def run_gpu_arm(args):
             torch.cuda.synchronize()
 
     # ---- device-resident steps -------------------------------------------
+    # the sampler thread starts before the warm-up (the first NVML queries of a
+    # process can take tens of ms) and records only inside the timed region
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for _ in range(max(args.warmup, 3)):
         for p in preps:
             p.launch()
     barrier()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
+    sampler.recording = True
     fused = all(p.n_launches == 1 for p in preps)
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(1 + 2 * len(preps))]
           for _ in range(args.steps)]
