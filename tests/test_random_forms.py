@@ -111,3 +111,53 @@ def test_random_form_host(ename, k, bilinear, with_w, seed):
 @pytest.mark.parametrize("ename,k,bilinear,with_w,seed", _cases())
 def test_random_form_cuda(ename, k, bilinear, with_w, seed):
     _run(ename, bilinear, with_w, seed, True)
+
+
+# ---------------------------------------------------------------------------
+# boundary facet forms: the same idea with normals and the facet size
+# ---------------------------------------------------------------------------
+def _random_facet_form(rng, dim, bilinear):
+    terms = []
+    for _ in range(int(rng.integers(1, 4))):
+        c, _t = _coefficient(rng, dim, False)
+        tu = int(rng.integers(dim + 1))
+        tv = int(rng.integers(dim + 1))
+        kn = int(rng.integers(dim))                # multiply by a normal component
+        terms.append((c, tu, tv, kn))
+
+    def pick(val, grad, t):
+        return val if t == 0 else grad[t - 1]
+    if bilinear:
+        def form(u, v, du, dv, x, h, n):
+            return sum(c(x, h, None) * n[kn] * pick(u, du, tu) * pick(v, dv, tv)
+                       for c, tu, tv, kn in terms)
+    else:
+        def form(v, dv, x, h, n):
+            return sum(c(x, h, None) * n[kn] * pick(v, dv, tv) for c, tu, tv, kn in terms)
+    return form
+
+
+def _facet_cases():
+    rng = np.random.default_rng(777)
+    return [(en, bool(k % 2 == 0), int(rng.integers(1 << 30)))
+            for en in ("TriP1", "TriP2", "TetP1") for k in range(2)]
+
+
+def _run_facet(ename, bilinear, seed, device):
+    mesh = MESHES[ename]()
+    form = _random_facet_form(np.random.default_rng(seed), mesh.p.shape[0], bilinear)
+    a = AssemblerElement(mesh, getattr(sp, "Element" + ename)())
+    ref = asm_oracle.fasm(mesh, ename, form, normals=True)
+    got = a.fasm(form, normals=True) if device else hostemu.fasm(a, form, normals=True)
+    (cases.compare_csr if bilinear else cases.compare_vec)(got, ref)
+
+
+@pytest.mark.parametrize("ename,bilinear,seed", _facet_cases())
+def test_random_facet_form_host(ename, bilinear, seed):
+    _run_facet(ename, bilinear, seed, False)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("ename,bilinear,seed", _facet_cases())
+def test_random_facet_form_cuda(ename, bilinear, seed):
+    _run_facet(ename, bilinear, seed, True)
