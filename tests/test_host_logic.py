@@ -132,7 +132,7 @@ def test_tensor_mode_precontracts_quadrature():
 
 
 @pytest.mark.parametrize("name", ["trip1_lap_r6", "tetp2_lap", "vecp2_elasticity", "stokes_b",
-                                  "trip1_load"])
+                                  "trip1_load", "trip1_interp_mass", "trip1_interp_load"])
 def test_chunked_assembly_matches_single_call(name, monkeypatch):
     """Meshes with more local entries than one pattern call takes are assembled
     chunk by chunk (AssemblerElement._iasm_chunked); the union of the owned rows
@@ -142,12 +142,14 @@ def test_chunked_assembly_matches_single_call(name, monkeypatch):
     if case is None:
         pytest.skip("no such case")
     asm = util.assembler_for(case)
-    plan = asm.plan_iasm(case.form)
+    kw = cases.case_inputs(case, asm.mesh, asm.dofnum_u.N)
+    interp = kw.get("interp")                    # interpolated fields follow the chunks' DOFs
+    plan = asm.plan_iasm(case.form, interp=interp)
     n_ent = plan.spec.n_entries * asm.mesh.t.shape[1]
     monkeypatch.setenv("SPFEM_MAX_ENTRIES", str(n_ent // 3))
     chunks = asm._chunks_needed(plan, None)
     assert chunks >= 4
-    out = asm._iasm_chunked(case.form, plan, None, None, chunks,
+    out = asm._iasm_chunked(case.form, plan, None, interp, chunks,
                             assemble=lambda loc, form, **kw: hostemu.iasm(loc, form, **kw))
     util.check(out, util.golden(case))
     monkeypatch.setenv("SPFEM_MAX_ENTRIES", str(2 ** 31 - 1))
