@@ -161,3 +161,33 @@ def test_random_facet_form_host(ename, bilinear, seed):
 @pytest.mark.parametrize("ename,bilinear,seed", _facet_cases())
 def test_random_facet_form_cuda(ename, bilinear, seed):
     _run_facet(ename, bilinear, seed, True)
+
+
+# ---------------------------------------------------------------------------
+# vector elements (ElementH1Vec): random bilinear forms in the components
+# ---------------------------------------------------------------------------
+def _random_vector_form(rng, dim):
+    terms = []
+    for _ in range(int(rng.integers(2, 5))):
+        c, _t = _coefficient(rng, dim, False)
+        cu, cv = int(rng.integers(dim)), int(rng.integers(dim))
+        tu, tv = int(rng.integers(dim + 1)), int(rng.integers(dim + 1))
+        terms.append((c, cu, cv, tu, tv))
+
+    def pick(val, grad, comp, t):
+        return val[comp] if t == 0 else grad[comp][t - 1]
+
+    def form(u, v, du, dv, x, h):
+        return sum(c(x, h, None) * pick(u, du, cu, tu) * pick(v, dv, cv, tv)
+                   for c, cu, cv, tu, tv in terms)
+    return form
+
+
+@pytest.mark.parametrize("ename,seed", [("TriP1", 11), ("TriP2", 12), ("TetP1", 13), ("TriP1", 14)])
+def test_random_vector_form_host(ename, seed):
+    mesh = MESHES[ename]()
+    dim = mesh.p.shape[0]
+    form = _random_vector_form(np.random.default_rng(seed), dim)
+    a = AssemblerElement(mesh, sp.ElementH1Vec(getattr(sp, "Element" + ename)()))
+    ref = asm_oracle.iasm(mesh, ename, form, ncomp_u=dim, ncomp_v=dim)
+    cases.compare_csr(hostemu.iasm(a, form), ref)
