@@ -191,3 +191,34 @@ def test_random_vector_form_host(ename, seed):
     a = AssemblerElement(mesh, sp.ElementH1Vec(getattr(sp, "Element" + ename)()))
     ref = asm_oracle.iasm(mesh, ename, form, ncomp_u=dim, ncomp_v=dim)
     cases.compare_csr(hostemu.iasm(a, form), ref)
+
+
+# ---------------------------------------------------------------------------
+# interior facets: two-sided forms (u1, u2, v1, v2, du1, ...) as used for DG / jumps
+# ---------------------------------------------------------------------------
+def _random_interior_form(rng, dim):
+    terms = []
+    for _ in range(int(rng.integers(2, 5))):
+        c, _t = _coefficient(rng, dim, False)
+        su, sv = int(rng.integers(2)), int(rng.integers(2))     # side of trial / test
+        tu, tv = int(rng.integers(dim + 1)), int(rng.integers(dim + 1))
+        kn = int(rng.integers(dim))
+        terms.append((c, su, sv, tu, tv, kn))
+
+    def pick(val, grad, t):
+        return val if t == 0 else grad[t - 1]
+
+    def form(u1, u2, v1, v2, du1, du2, dv1, dv2, x, h, n):
+        U, V, dU, dV = (u1, u2), (v1, v2), (du1, du2), (dv1, dv2)
+        return sum(c(x, h, None) * n[kn] * pick(U[su], dU[su], tu) * pick(V[sv], dV[sv], tv)
+                   for c, su, sv, tu, tv, kn in terms)
+    return form
+
+
+@pytest.mark.parametrize("ename,seed", [("TriP1", 21), ("TriP2", 22), ("TetP1", 23)])
+def test_random_interior_facet_form_host(ename, seed):
+    mesh = MESHES[ename]()
+    form = _random_interior_form(np.random.default_rng(seed), mesh.p.shape[0])
+    a = AssemblerElement(mesh, getattr(sp, "Element" + ename)())
+    ref = asm_oracle.fasm(mesh, ename, form, interior=True, normals=True)
+    cases.compare_csr(hostemu.fasm(a, form, interior=True, normals=True), ref)
