@@ -7,7 +7,8 @@ from .mesh import Mesh, MeshTri, MeshTet, MeshQuad, MeshLine
 from .element import (Element, ElementH1, ElementH1Vec, ElementTriP1,
                       ElementTriP2, ElementTetP1, ElementTetP2, ElementQ1,
                       ElementQ2, ElementTriP0, ElementP0, ElementTetP0,
-                      ElementTriMini, ElementTriDG, ElementTetDG)
+                      ElementTriMini, ElementTriDG, ElementTetDG, ElementTriPp,
+                      ElementHdiv, ElementTriRT0)
 from .utils import direct, stack, const_cell, cell_shape
 
 __version__ = "0.1.0"
