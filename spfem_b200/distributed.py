@@ -9,7 +9,10 @@ its block **plus the halo elements that touch rows it owns** (an O(surface)
 layer that the neighbouring rank computes as well), so every owned row is
 complete after the rank's own fused kernel:
 
-* no data-path collective, no partial sums crossing NVLink,
+* no data-path collective, no partial sums crossing NVLink (``mode="halo"``,
+  the default; ``mode="exchange"`` is the north star's alternative: own block
+  only, ghost-row partial sums sent to the owners in one ``all_to_all`` and
+  added in fixed rank order, see :class:`InterfaceExchange`),
 * the summation order inside a CSR slot is fixed by the local contribution
   lists => bitwise reproducible for a given partition,
 * the global ``indptr/indices`` are exactly the single-GPU pattern: ownership
@@ -52,14 +55,22 @@ class LocalPart(object):
     """A rank's share of the mesh: the local mesh (own block + halo), the maps
     from local to global DOFs and the mask of owned test DOFs (rows)."""
 
-    def __init__(self, mesh, l2g_u, l2g_v, owned_v, N_u, N_v, n_own_elements):
+    def __init__(self, mesh, l2g_u, l2g_v, owned_v, N_u, N_v, n_own_elements,
+                 owner_v=None):
         self.mesh, self.l2g_u, self.l2g_v = mesh, l2g_u, l2g_v
         self.owned_v, self.N_u, self.N_v = owned_v, N_u, N_v
         self.n_own_elements = n_own_elements
+        # owning rank of every local test DOF (needed by the interface exchange)
+        self.owner_v = owner_v
 
 
-def partition_global(mesh, elem_u, elem_v, world, rank):
-    """Split the replicated global ``mesh`` for ``rank`` of ``world``."""
+def partition_global(mesh, elem_u, elem_v, world, rank, halo=True):
+    """Split the replicated global ``mesh`` for ``rank`` of ``world``.
+
+    ``halo=True``: own block + the elements touching owned rows (owned rows are
+    complete locally).  ``halo=False``: the own block only; rows that the rank
+    touches but does not own carry partial sums that :class:`InterfaceExchange`
+    sends to their owners."""
     nt = mesh.t.shape[1]
     perm = morton_order_host(mesh)
     rank_of_elem = np.empty(nt, dtype=np.int64)
@@ -70,7 +81,10 @@ def partition_global(mesh, elem_u, elem_v, world, rank):
     dn_v = dn_u if elem_v is None or elem_v is elem_u else Dofnum(mesh, elem_v)
     owner_v = np.full(dn_v.N, world, dtype=np.int64)
     np.minimum.at(owner_v, dn_v.t_dof, rank_of_elem[None, :])
-    mine = (owner_v[dn_v.t_dof] == rank).any(axis=0)
+    if halo:
+        mine = (owner_v[dn_v.t_dof] == rank).any(axis=0)
+    else:
+        mine = rank_of_elem == rank
     elems = np.nonzero(mine)[0]
     verts = np.unique(mesh.t[:, elems])
     t_loc = np.searchsorted(verts, mesh.t[:, elems])
@@ -85,7 +99,8 @@ def partition_global(mesh, elem_u, elem_v, world, rank):
         l2g_v[ldn_v.t_dof] = dn_v.t_dof[:, elems]
     owned = owner_v[l2g_v] == rank
     return LocalPart(local, l2g_u, l2g_v, owned, dn_u.N, dn_v.N,
-                     int(np.sum(rank_of_elem[elems] == rank)))
+                     int(np.sum(rank_of_elem[elems] == rank)),
+                     owner_v=owner_v[l2g_v])
 
 
 def strip_part(rank, world, refine, unit=None):
@@ -216,6 +231,134 @@ class DistResult(object):
         return out
 
 
+def _local_tensors(loc, bilinear):
+    """(row ids, column ids, values) of a rank-local result as torch tensors on
+    the device the values live on (``engine.DeviceCSR`` / device vector on the
+    GPU, SciPy / NumPy objects in the CPU tests)."""
+    import torch
+    if bilinear:
+        if hasattr(loc, "pattern"):                       # engine.DeviceCSR
+            indptr, indices, values = loc.pattern.indptr, loc.pattern.indices, loc.values
+        else:
+            A = loc.tocsr()
+            indptr = torch.from_numpy(A.indptr.astype(np.int64))
+            indices = torch.from_numpy(A.indices.astype(np.int64))
+            values = torch.from_numpy(np.ascontiguousarray(A.data, dtype=np.float64))
+        indptr = indptr.to(torch.int64)
+        counts = indptr[1:] - indptr[:-1]
+        rows = torch.repeat_interleave(
+            torch.arange(counts.numel(), device=values.device, dtype=torch.int64), counts)
+        return rows, indices.to(torch.int64), values
+    v = loc if isinstance(loc, torch.Tensor) else torch.from_numpy(
+        np.ascontiguousarray(loc, dtype=np.float64))
+    rows = torch.arange(v.numel(), device=v.device, dtype=torch.int64)
+    return rows, None, v                  # (a vector: one global column, id 0)
+
+
+class InterfaceExchange(object):
+    """The north star's exchange step for a ``halo=False`` partition: every rank
+    assembles its own element block only; the partial sums of rows it touches
+    but does not own ("ghost rows") travel to the owning rank in ONE
+    ``all_to_all_single`` (NCCL over NVLink on GPUs, gloo in the CPU tests) and
+    the owner adds them **in fixed rank order** -- its own values first, then
+    the senders in ascending rank -- so the result is reproducible run to run.
+
+    Built once per (partition, local pattern): the sorted (global row, global
+    column) keys of the ghost entries are exchanged, the owner forms the union
+    pattern of its rows (an interface row also has columns that only the
+    neighbour's elements produce) and every later call moves fp64 values only:
+    one gather into the send buffer, one collective, one indexed add per
+    sending rank (the indices inside one add are unique: no atomics race).
+    Interface volume is O(surface) of the block, so the step is latency bound;
+    it is not fused into the element kernel."""
+
+    def __init__(self, part, rows, cols, group=None, rank=None, world=None):
+        import torch
+        import torch.distributed as dist
+        self.group = group
+        self.rank = dist.get_rank(group) if rank is None else rank
+        self.world = dist.get_world_size(group) if world is None else world
+        dev = rows.device
+        self.device = dev
+        ncols = max(int(part.N_u), 1) if cols is not None else 1
+        self.ncols = ncols
+        l2g_v = torch.from_numpy(np.ascontiguousarray(part.l2g_v, dtype=np.int64)).to(dev)
+        l2g_u = torch.from_numpy(np.ascontiguousarray(part.l2g_u, dtype=np.int64)).to(dev)
+        owner = torch.from_numpy(np.ascontiguousarray(part.owner_v, dtype=np.int64)).to(dev)
+        key = l2g_v[rows] * ncols
+        if cols is not None:
+            key = key + l2g_u[cols]
+        own = owner[rows]
+        # ---- my ghost entries, grouped by destination, sorted by key inside
+        ghost = torch.nonzero(own != self.rank).reshape(-1)
+        order = torch.argsort(own[ghost] * (int(part.N_v) * ncols + 1) + key[ghost])
+        self.send_idx = ghost[order]
+        send_keys = key[self.send_idx].contiguous()
+        send_counts = torch.bincount(own[self.send_idx], minlength=self.world)[:self.world]
+        recv_counts = torch.empty_like(send_counts)
+        dist.all_to_all_single(recv_counts, send_counts, group=group)
+        self.send_splits = [int(x) for x in send_counts.tolist()]
+        self.recv_splits = [int(x) for x in recv_counts.tolist()]
+        recv_keys = torch.empty(sum(self.recv_splits), dtype=torch.int64, device=dev)
+        dist.all_to_all_single(recv_keys, send_keys, self.recv_splits, self.send_splits,
+                               group=group)
+        # ---- union pattern of the owned rows
+        self.own_idx = torch.nonzero(own == self.rank).reshape(-1)
+        own_keys = key[self.own_idx]
+        self.keys = torch.unique(torch.cat((own_keys, recv_keys)))      # sorted
+        self.pos_own = torch.searchsorted(self.keys, own_keys)
+        self.pos_recv = torch.searchsorted(self.keys, recv_keys)
+        self.nnz = int(self.keys.numel())
+        self.rows = torch.div(self.keys, ncols, rounding_mode="floor")
+        self.cols = self.keys - self.rows * ncols
+        self.interface_entries = int(self.send_idx.numel())
+
+    def reduce(self, values):
+        """Owned-row values (aligned with ``self.rows/self.cols``) from the
+        rank-local ``values`` (aligned with the local pattern)."""
+        import torch
+        import torch.distributed as dist
+        send = values.index_select(0, self.send_idx)
+        recv = torch.empty(sum(self.recv_splits), dtype=values.dtype, device=values.device)
+        dist.all_to_all_single(recv, send, self.recv_splits, self.send_splits,
+                               group=self.group)
+        out = torch.zeros(self.nnz, dtype=values.dtype, device=values.device)
+        out.index_copy_(0, self.pos_own, values.index_select(0, self.own_idx))
+        lo = 0
+        for s in range(self.world):                       # fixed rank order
+            n = self.recv_splits[s]
+            if n:
+                out.index_add_(0, self.pos_recv[lo:lo + n], recv[lo:lo + n])
+            lo += n
+        return out
+
+
+class ExchangedResult(object):
+    """Row-distributed result after the interface exchange: the owned rows with
+    *global* row / column ids (sorted by row, then column) and their values on
+    the rank's device.  ``csr()`` gives the rank's row slice as device CSR
+    arrays; ``gather`` collects the global host object like
+    :meth:`DistResult.gather`."""
+
+    def __init__(self, xchg, values, part, bilinear, group):
+        self.xchg, self.values, self.part = xchg, values, part
+        self.bilinear, self.group = bilinear, group
+
+    def csr(self):
+        """(owned global row ids, indptr over them, global column ids, values)."""
+        import torch
+        urows, counts = torch.unique_consecutive(self.xchg.rows, return_counts=True)
+        indptr = torch.zeros(urows.numel() + 1, dtype=torch.int64, device=urows.device)
+        indptr[1:] = torch.cumsum(counts, 0)
+        return urows, indptr, self.xchg.cols, self.values
+
+    def owned_triplets(self):
+        return (self.xchg.rows.cpu().numpy(), self.xchg.cols.cpu().numpy(),
+                self.values.cpu().numpy())
+
+    gather = DistResult.gather
+
+
 class DistributedAssembler(object):
     """``AssemblerElement`` over an element-partitioned mesh, one rank per GPU.
 
@@ -226,15 +369,22 @@ class DistributedAssembler(object):
     signatures and return a :class:`DistResult`."""
 
     def __init__(self, mesh, elem_u, elem_v=None, group=None, part=None,
-                 rank=None, world=None, assemble=None):
+                 rank=None, world=None, assemble=None, mode="halo"):
         import torch.distributed as dist
+        if mode not in ("halo", "exchange"):
+            raise ValueError("mode must be 'halo' or 'exchange'")
+        self.mode = mode
+        self._xchg = {}
         if world is None:
             world = dist.get_world_size(group) if dist.is_initialized() else 1
         if rank is None:
             rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.rank, self.world, self.group = rank, world, group
         self.part = part if part is not None else partition_global(
-            mesh, elem_u, elem_v, world, rank)
+            mesh, elem_u, elem_v, world, rank, halo=(mode == "halo"))
+        if mode == "exchange" and self.part.owner_v is None:
+            raise ValueError("mode='exchange' needs a partition with owner_v "
+                             "(partition_global(..., halo=False))")
         self.local = AssemblerElement(self.part.mesh, elem_u, elem_v)
         self._assemble = assemble
 
@@ -248,7 +398,23 @@ class DistributedAssembler(object):
             loc = self.local.iasm(form, intorder=intorder, interp=interp)
         else:
             loc = self.local.iasm_device(form, intorder=intorder, interp=interp)
+        if self.mode == "exchange":
+            return self._exchange(loc, bilinear)
         return DistResult(loc, self.part, bilinear, self.group)
+
+    def _exchange(self, loc, bilinear):
+        """Send the ghost rows' partial sums to their owners (one collective)."""
+        rows, cols, values = _local_tensors(loc, bilinear)
+        # one exchange plan per local pattern (the pattern object is cached by
+        # the engine per (row table, column table); host results: per shape/nnz)
+        pkey = (bilinear, id(getattr(loc, "pattern", None)), int(values.numel()))
+        hit = self._xchg.get(pkey)
+        if hit is None:                # (the pattern is kept alive with its plan)
+            hit = self._xchg[pkey] = (InterfaceExchange(
+                self.part, rows, cols, self.group, self.rank, self.world),
+                getattr(loc, "pattern", None))
+        x = hit[0]
+        return ExchangedResult(x, x.reduce(values), self.part, bilinear, self.group)
 
     def prepare_iasm(self, form, intorder=None):
         """Staged local assembly (see ``AssemblerElement.prepare_iasm``)."""
