@@ -103,7 +103,7 @@ def partition_global(mesh, elem_u, elem_v, world, rank, halo=True):
                      owner_v=owner_v[l2g_v])
 
 
-def strip_part(rank, world, refine, unit=None):
+def strip_part(rank, world, refine, unit=None, halo=True):
     """Rank ``rank``'s part of the weak-scaling mesh: ``world`` copies of the
     unit-square mesh ``MeshTri().refine(refine)`` glued side by side along x
     (copy r = unit mesh translated by (r, 0); the vertices on x = r+1 are
@@ -114,7 +114,9 @@ def strip_part(rank, world, refine, unit=None):
     ``r*(nv - nb) + c(v) + (nb if r > 0 ... )`` -- see ``gid`` below.  Ownership
     follows the general rule (lowest rank touching the row): rank r owns every
     vertex of its copy except its left edge.  The halo is the layer of copy
-    r+1's elements touching x = r+1."""
+    r+1's elements touching x = r+1; ``halo=False`` leaves it out (the part for
+    ``DistributedAssembler(mode="exchange")``: the left-edge rows are ghost
+    rows whose partial sums go to rank r-1)."""
     if unit is None:
         unit = _mesh.MeshTri()
         unit.refine(refine)
@@ -148,7 +150,8 @@ def strip_part(rank, world, refine, unit=None):
 
     N = nv + (world - 1) * (nv - nb)
     # own elements + halo (copy rank+1's elements touching its left edge)
-    halo = np.nonzero(is_left[t].any(axis=0))[0] if rank < world - 1 else np.zeros(0, np.int64)
+    halo = (np.nonzero(is_left[t].any(axis=0))[0] if rank < world - 1 and halo
+            else np.zeros(0, np.int64))
     hv = np.unique(t[:, halo])
     hv_new = hv[~is_left[hv]]                     # halo vertices not on the shared edge
     # local numbering: unit vertices 0..nv-1, then the new halo vertices
@@ -164,9 +167,12 @@ def strip_part(rank, world, refine, unit=None):
                           if len(hv_new) else np.zeros(0, np.int64)))
     owned = np.zeros(p_loc.shape[1], dtype=bool)
     owned[:nv] = True
+    owner = np.full(p_loc.shape[1], rank + 1, dtype=np.int64)   # new halo vertices
+    owner[:nv] = rank
     if rank > 0:
         owned[left] = False
-    return LocalPart(local, l2g, l2g, owned, N, N, t.shape[1])
+        owner[left] = rank - 1
+    return LocalPart(local, l2g, l2g, owned, N, N, t.shape[1], owner_v=owner)
 
 
 def strip_global(world, refine):

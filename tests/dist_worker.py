@@ -85,6 +85,21 @@ def main():
             else:
                 cases.compare_vec(res, ref)
             print("strip ok", form.__name__)
+    # 2b. the strip without halo, through the interface exchange
+    part = strip_part(rank, world, 3, halo=False)
+    assert part.mesh.t.shape[1] == part.n_own_elements
+    da = DistributedAssembler(None, sp.ElementTriP1(), part=part, assemble=host_assemble,
+                              mode="exchange")
+    for form in (cases.lap2, cases.mass, cases.load1):
+        res = da.iasm(form).gather(0)
+        if rank == 0:
+            import asm_oracle
+            ref = asm_oracle.iasm(strip_global(world, 3), "TriP1", form)
+            if hasattr(ref, "indptr"):
+                cases.compare_csr(res, ref)
+            else:
+                cases.compare_vec(res, ref)
+            print("strip exchange ok", form.__name__)
     dist.barrier()
     dist.destroy_process_group()
 
