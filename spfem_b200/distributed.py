@@ -62,6 +62,16 @@ class LocalPart(object):
         self.n_own_elements = n_own_elements
         # owning rank of every local test DOF (needed by the interface exchange)
         self.owner_v = owner_v
+        # local facet ids -> bool "is a boundary facet of the GLOBAL mesh" (the
+        # local mesh also has artificial boundary facets along the cuts)
+        self.on_global_boundary = None
+
+    def global_boundary_facets(self):
+        """Local ids of the facets that lie on the boundary of the global mesh."""
+        lb = self.mesh.boundary_facets()
+        if self.on_global_boundary is None:
+            raise NotImplementedError("this partition does not know the global boundary")
+        return lb[self.on_global_boundary(self.mesh, lb)]
 
 
 def partition_global(mesh, elem_u, elem_v, world, rank, halo=True):
@@ -98,9 +108,24 @@ def partition_global(mesh, elem_u, elem_v, world, rank, halo=True):
         l2g_v = np.empty(ldn_v.N, dtype=np.int64)
         l2g_v[ldn_v.t_dof] = dn_v.t_dof[:, elems]
     owned = owner_v[l2g_v] == rank
-    return LocalPart(local, l2g_u, l2g_v, owned, dn_u.N, dn_v.N,
+    part = LocalPart(local, l2g_u, l2g_v, owned, dn_u.N, dn_v.N,
                      int(np.sum(rank_of_elem[elems] == rank)),
                      owner_v=owner_v[l2g_v])
+    gb = np.sort(mesh.facets[:, mesh.boundary_facets()], axis=0)
+
+    def on_global_boundary(lmesh, lf):
+        """Match the (sorted, global) vertex tuples of local facets ``lf``
+        against the global boundary facets."""
+        mine = np.sort(verts[lmesh.facets[:, lf]], axis=0)
+        both = np.hstack((gb, mine)).T
+        _, inv = np.unique(both, axis=0, return_inverse=True)
+        inv = inv.reshape(-1)
+        hit = np.zeros(inv.max() + 1, dtype=bool)
+        hit[inv[:gb.shape[1]]] = True
+        return hit[inv[gb.shape[1]:]]
+
+    part.on_global_boundary = on_global_boundary
+    return part
 
 
 def strip_part(rank, world, refine, unit=None, halo=True):
@@ -172,7 +197,17 @@ def strip_part(rank, world, refine, unit=None, halo=True):
     if rank > 0:
         owned[left] = False
         owner[left] = rank - 1
-    return LocalPart(local, l2g, l2g, owned, N, N, t.shape[1], owner_v=owner)
+    part = LocalPart(local, l2g, l2g, owned, N, N, t.shape[1], owner_v=owner)
+
+    def on_global_boundary(lmesh, lf):
+        """A local boundary facet is on the strip's boundary iff its midpoint is
+        on y = 0, y = 1, x = 0 or x = world (the rest are cuts)."""
+        mid = lmesh.p[:, lmesh.facets[:, lf]].mean(axis=1)
+        return ((mid[1] == 0.0) | (mid[1] == 1.0) | (mid[0] == 0.0)
+                | (mid[0] == float(world)))
+
+    part.on_global_boundary = on_global_boundary
+    return part
 
 
 def strip_global(world, refine):
@@ -375,7 +410,8 @@ class DistributedAssembler(object):
     signatures and return a :class:`DistResult`."""
 
     def __init__(self, mesh, elem_u, elem_v=None, group=None, part=None,
-                 rank=None, world=None, assemble=None, mode="halo"):
+                 rank=None, world=None, assemble=None, mode="halo",
+                 assemble_facet=None):
         import torch.distributed as dist
         if mode not in ("halo", "exchange"):
             raise ValueError("mode must be 'halo' or 'exchange'")
@@ -393,6 +429,7 @@ class DistributedAssembler(object):
                              "(partition_global(..., halo=False))")
         self.local = AssemblerElement(self.part.mesh, elem_u, elem_v)
         self._assemble = assemble
+        self._assemble_facet = assemble_facet
 
     def iasm(self, form, intorder=None, interp=None, to_host=False):
         if interp is not None:
@@ -408,12 +445,12 @@ class DistributedAssembler(object):
             return self._exchange(loc, bilinear)
         return DistResult(loc, self.part, bilinear, self.group)
 
-    def _exchange(self, loc, bilinear):
+    def _exchange(self, loc, bilinear, kind="interior"):
         """Send the ghost rows' partial sums to their owners (one collective)."""
         rows, cols, values = _local_tensors(loc, bilinear)
         # one exchange plan per local pattern (the pattern object is cached by
         # the engine per (row table, column table); host results: per shape/nnz)
-        pkey = (bilinear, id(getattr(loc, "pattern", None)), int(values.numel()))
+        pkey = (kind, bilinear, id(getattr(loc, "pattern", None)), int(values.numel()))
         hit = self._xchg.get(pkey)
         if hit is None:                # (the pattern is kept alive with its plan)
             hit = self._xchg[pkey] = (InterfaceExchange(
@@ -421,6 +458,36 @@ class DistributedAssembler(object):
                 getattr(loc, "pattern", None))
         x = hit[0]
         return ExchangedResult(x, x.reduce(values), self.part, bilinear, self.group)
+
+    def fasm(self, form, find=None, interior=False, intorder=None, normals=True,
+             interp=None, to_host=False):
+        """Boundary-facet assembly over the partitioned mesh (the Nitsche terms
+        of BASELINE config 5).  ``find`` is not supported (facet ids are local
+        to a rank): the facets are the rank's share of the *global* boundary --
+        the artificial boundary along the cuts is left out.  Halo mode: a rank
+        assembles the boundary facets of its own and its halo elements, which
+        completes its owned rows; exchange mode: of its own elements only, then
+        the ghost rows travel to their owners.  Interior facets
+        (``interior=True``) would need the element across every cut facet,
+        i.e. a second halo layer: not implemented."""
+        if interior:
+            raise NotImplementedError("interior facets over a partitioned mesh")
+        if find is not None:
+            raise NotImplementedError("find= over a partitioned mesh (facet ids are rank-local)")
+        if interp is not None:
+            interp = {k: np.asarray(v)[self.part.l2g_u] for k, v in interp.items()}
+        lf = self.part.global_boundary_facets()
+        plan = self.local.plan_fasm(form, interior=False, intorder=intorder,
+                                    normals=normals, interp=interp)
+        if self._assemble_facet is not None:    # CPU tests inject the local assembly
+            loc = self._assemble_facet(self.local, form, find=lf, intorder=intorder,
+                                       normals=normals, interp=interp)
+        else:
+            loc = self.local._get_engine().run_facet(plan, np.asarray(lf), False, interp,
+                                                     to_host=to_host)
+        if self.mode == "exchange":
+            return self._exchange(loc, plan.bilinear, kind="facet")
+        return DistResult(loc, self.part, plan.bilinear, self.group)
 
     def prepare_iasm(self, form, intorder=None):
         """Staged local assembly (see ``AssemblerElement.prepare_iasm``)."""

@@ -26,6 +26,11 @@ def host_assemble(asm, form, intorder=None, interp=None):
     return hostemu.iasm(asm, form, intorder=intorder, interp=interp)
 
 
+def host_assemble_facet(asm, form, find=None, intorder=None, normals=True, interp=None):
+    return hostemu.fasm(asm, form, find=find, intorder=intorder, normals=normals,
+                        interp=interp)
+
+
 def main():
     dist.init_process_group("gloo")
     rank, world = dist.get_rank(), dist.get_world_size()
@@ -70,6 +75,23 @@ def main():
         if rank == 0:
             util.check(res, util.golden(case))
             print("xchg ok", name, "world", world)
+    # 1c. boundary-facet forms (the Nitsche terms of config 5) in both modes:
+    #     only the global boundary is assembled, not the cuts
+    for name in ("f_trip1_nitsche", "f_trip1_lin", "f_trip2_nitsche", "f_vecp2_nitsche",
+                 "f_tetp2_bnd", "f_q1_bnd"):
+        case = cases.BY_NAME[name]
+        m = util.mesh_for(case)
+        eu = util.element(case.eu, case.ncu)
+        for mode in ("halo", "exchange"):
+            da = DistributedAssembler(m, eu, None, assemble=host_assemble,
+                                      assemble_facet=host_assemble_facet, mode=mode)
+            nloc = len(da.part.global_boundary_facets())
+            assert nloc <= len(m.boundary_facets())
+            assert mode == "halo" or nloc < len(m.boundary_facets())
+            res = da.fasm(case.form, normals=case.kw.get("normals", True)).gather(0)
+            if rank == 0:
+                util.check(res, util.golden(case))
+                print("facet ok", name, mode, "world", world)
     # 2. weak-scaling strip mesh built per rank, against the oracle on the
     #    explicitly assembled global strip
     part = strip_part(rank, world, 3)
@@ -100,6 +122,18 @@ def main():
             else:
                 cases.compare_vec(res, ref)
             print("strip exchange ok", form.__name__)
+    # 2c. boundary forms on the strip: the cuts x = 1 .. world-1 are not boundary
+    for mode in ("halo", "exchange"):
+        part = strip_part(rank, world, 3, halo=(mode == "halo"))
+        da = DistributedAssembler(None, sp.ElementTriP1(), part=part, mode=mode,
+                                  assemble_facet=host_assemble_facet)
+        for form in (cases.nitsche, cases.bnd_lin):
+            res = da.fasm(form).gather(0)
+            if rank == 0:
+                import asm_oracle
+                ref = asm_oracle.fasm(strip_global(world, 3), "TriP1", form)
+                util.check(res, ref)
+                print("strip facet ok", mode, form.__name__)
     dist.barrier()
     dist.destroy_process_group()
 

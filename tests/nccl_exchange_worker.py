@@ -48,6 +48,16 @@ def main():
                 cases.compare_vec(res, halo)
             print("nccl xchg ok", name, "world", world,
                   "interface entries", r1.xchg.interface_entries)
+    # boundary-facet (Nitsche) terms in both modes
+    for name in ("f_trip2_nitsche", "f_tetp2_bnd"):
+        case = cases.BY_NAME[name]
+        m = util.mesh_for(case)
+        eu = util.element(case.eu, case.ncu)
+        for mode in ("halo", "exchange"):
+            res = DistributedAssembler(m, eu, None, mode=mode).fasm(case.form).gather(0)
+            if rank == 0:
+                util.check(res, util.golden(case))
+                print("nccl facet ok", name, mode)
     dist.barrier()
     dist.destroy_process_group()
 

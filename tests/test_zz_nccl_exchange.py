@@ -33,3 +33,4 @@ def test_interface_exchange_nccl():
                          env=dict(os.environ, OMP_NUM_THREADS="1"))
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
     assert out.stdout.count("nccl xchg ok") == 5, out.stdout
+    assert out.stdout.count("nccl facet ok") == 4, out.stdout
