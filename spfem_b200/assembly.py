@@ -347,25 +347,39 @@ class AssemblerElement(Assembler):
             raise NotImplementedError("tind subsets with more than %d local entries" % limit)
         return int(np.ceil(1.4 * n_ent / limit))
 
-    def _iasm_chunked(self, form, plan, intorder, interp, chunks, assemble=None):
+    def _iasm_chunked(self, form, plan, intorder, interp, chunks, assemble=None,
+                      to_host=True):
         """Assemble chunk by chunk on one GPU: Morton blocks of elements, every
         global row owned by the lowest chunk touching it, a chunk's local mesh =
         its block plus the halo elements of its rows (the multi-GPU partition of
         ``distributed.py`` run sequentially).  Owned rows are complete after their
         chunk, so the global CSR is the union of the owned rows; pattern and index
         width are those of the single call (SciPy's rule on the *total* number of
-        local entries)."""
-        from .distributed import partition_global, DistResult
+        local entries).
+
+        The merge runs on the device: a chunk's owned entries are renumbered to
+        global ids and sorted by (row, column) key there and stay in HBM; the rows
+        of different chunks are disjoint, so once every chunk has reported its
+        row lengths the global ``indptr`` is one prefix sum and each chunk's
+        entries are scattered to ``indptr[row] + position in the row`` -- no
+        global sort, no host-side COO.  One device-to-host copy at the end."""
+        import torch
+        from .distributed import Partitioner, _local_tensors
         from .engine import scipy_index_dtype
-        from scipy.sparse import coo_matrix
+        from scipy.sparse import csr_matrix
         ev = None if self.elem_v is self.elem_u else self.elem_v
         limit = int(os.environ.get("SPFEM_MAX_ENTRIES", str(2 ** 31 - 1)))
-        rows, cols, vals = [], [], []
+        Nv, Nu = self.dofnum_v.N, self.dofnum_u.N
+        bilinear = plan.bilinear
+        pieces = []                 # per chunk: (global rows, their lengths, columns, values)
+        counts = out = None
+        parts = Partitioner(self.mesh, self.elem_u, ev, chunks)
         r = 0
         while r < chunks:
-            part = partition_global(self.mesh, self.elem_u, ev, chunks, r)
+            part = parts.part(r)
             if plan.spec.n_entries * part.mesh.t.shape[1] > limit:
-                chunks, r, rows, cols, vals = 2 * chunks, 0, [], [], []   # halo thicker than assumed
+                chunks, r, pieces, counts, out = 2 * chunks, 0, [], None, None
+                parts = Partitioner(self.mesh, self.elem_u, ev, chunks)   # halo thicker than assumed
                 continue
             loc = AssemblerElement(part.mesh, self.elem_u, ev)
             li = None if interp is None else {k: np.asarray(v)[part.l2g_u]
@@ -373,21 +387,56 @@ class AssemblerElement(Assembler):
             if assemble is not None:
                 A = assemble(loc, form, intorder=intorder, interp=li)
             else:
-                A = loc.iasm(form, intorder=intorder, interp=li)
-                loc._engine = None                      # release the chunk's device memory
-            tr = DistResult(A, part, plan.bilinear, None).owned_triplets()
-            rows.append(tr[0]); cols.append(tr[1]); vals.append(tr[2])
+                A = loc.iasm_device(form, intorder=intorder, interp=li)
+            rows, cols, vals = _local_tensors(A, bilinear)
+            dev = vals.device
+            keep = torch.from_numpy(part.owned_v).to(dev)[rows]
+            grow = torch.from_numpy(np.ascontiguousarray(part.l2g_v, dtype=np.int64)).to(dev)[rows[keep]]
+            vals = vals[keep]
+            if not bilinear:
+                if out is None:
+                    out = torch.zeros(Nv, dtype=torch.float64, device=dev)
+                out[grow] = vals
+            else:
+                gcol = torch.from_numpy(np.ascontiguousarray(part.l2g_u, dtype=np.int64)).to(dev)[cols[keep]]
+                key, order = torch.sort(grow * Nu + gcol)
+                grow = torch.div(key, Nu, rounding_mode="floor")
+                gcol = key - grow * Nu
+                urows, cnt = torch.unique_consecutive(grow, return_counts=True)
+                if counts is None:
+                    counts = torch.zeros(Nv, dtype=torch.int64, device=dev)
+                counts[urows] = cnt                     # (rows of different chunks are disjoint)
+                pieces.append((urows, cnt, gcol, vals[order]))
+                del key, order, grow
+            del A, rows, cols, keep
+            loc._engine = None                          # release the chunk's device memory
             r += 1
-        rows, cols, vals = np.concatenate(rows), np.concatenate(cols), np.concatenate(vals)
-        Nv, Nu = self.dofnum_v.N, self.dofnum_u.N
-        if not plan.bilinear:
-            out = np.zeros(Nv)
-            out[rows] = vals
-            return out
-        A = coo_matrix((vals, (rows, cols)), shape=(Nv, Nu)).tocsr()
+        if not bilinear:
+            return out.cpu().numpy() if to_host else out
         idt = scipy_index_dtype(plan.spec.n_entries * self.mesh.t.shape[1], Nv, Nu)
-        A.indices = A.indices.astype(idt, copy=False)
-        A.indptr = A.indptr.astype(idt, copy=False)
+        tdt = torch.int64 if idt == np.int64 else torch.int32
+        dev = counts.device
+        indptr = torch.zeros(Nv + 1, dtype=torch.int64, device=dev)
+        indptr[1:] = torch.cumsum(counts, 0)
+        nnz = int(indptr[-1])
+        indices = torch.empty(nnz, dtype=tdt, device=dev)
+        data = torch.empty(nnz, dtype=torch.float64, device=dev)
+        while pieces:
+            urows, cnt, gcol, vals = pieces.pop()
+            first = torch.cumsum(cnt, 0) - cnt           # start of each row inside the chunk
+            pos = (torch.arange(gcol.numel(), device=dev, dtype=torch.int64)
+                   + torch.repeat_interleave(indptr[urows] - first, cnt))
+            indices[pos] = gcol.to(tdt)
+            data[pos] = vals
+            del urows, cnt, gcol, vals, first, pos
+        indptr = indptr.to(tdt)
+        if not to_host:
+            return indptr, indices, data
+        A = csr_matrix((Nv, Nu), dtype=np.float64)
+        A.indptr, A.indices, A.data = (indptr.cpu().numpy(), indices.cpu().numpy(),
+                                       data.cpu().numpy())
+        A.has_sorted_indices = True
+        A.has_canonical_format = True
         return A
 
     def iasm_device(self, form, intorder=None, tind=None, interp=None):

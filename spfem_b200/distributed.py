@@ -74,58 +74,83 @@ class LocalPart(object):
         return lb[self.on_global_boundary(self.mesh, lb)]
 
 
+class Partitioner(object):
+    """Element partition of a replicated host mesh into ``world`` Morton blocks.
+    The rank-independent work (Morton order, global DOF numbering, row owners)
+    is done once; :meth:`part` cuts out one rank's :class:`LocalPart` (the
+    chunked single-GPU assembly asks for every part in turn)."""
+
+    def __init__(self, mesh, elem_u, elem_v, world):
+        self.mesh, self.elem_u, self.elem_v, self.world = mesh, elem_u, elem_v, world
+        nt = mesh.t.shape[1]
+        perm = morton_order_host(mesh)
+        self.rank_of_elem = np.empty(nt, dtype=np.int64)
+        bounds = [(nt * r) // world for r in range(world + 1)]
+        for r in range(world):
+            self.rank_of_elem[perm[bounds[r]:bounds[r + 1]]] = r
+        self.dn_u = Dofnum(mesh, elem_u)
+        self.dn_v = (self.dn_u if elem_v is None or elem_v is elem_u
+                     else Dofnum(mesh, elem_v))
+        # a row belongs to the lowest rank touching it: write the ranks in
+        # descending order, the lowest one last
+        self.owner_v = np.full(self.dn_v.N, world, dtype=np.int64)
+        for r in range(world - 1, -1, -1):
+            self.owner_v[self.dn_v.t_dof[:, self.rank_of_elem == r]] = r
+        self._gb = None
+
+    def _global_boundary(self):
+        if self._gb is None:
+            m = self.mesh
+            self._gb = np.sort(m.facets[:, m.boundary_facets()], axis=0)
+        return self._gb
+
+    def part(self, rank, halo=True):
+        """``halo=True``: own block + the elements touching owned rows (owned
+        rows are complete locally).  ``halo=False``: the own block only; rows
+        that the rank touches but does not own carry partial sums that
+        :class:`InterfaceExchange` sends to their owners."""
+        mesh, dn_u, dn_v, owner_v = self.mesh, self.dn_u, self.dn_v, self.owner_v
+        if halo:
+            mine = (owner_v[dn_v.t_dof] == rank).any(axis=0)
+        else:
+            mine = self.rank_of_elem == rank
+        elems = np.nonzero(mine)[0]
+        verts = np.unique(mesh.t[:, elems])
+        t_loc = np.searchsorted(verts, mesh.t[:, elems])
+        local = type(mesh)(np.ascontiguousarray(mesh.p[:, verts]), t_loc, validate=False)
+        ldn_u = Dofnum(local, self.elem_u)
+        ldn_v = ldn_u if dn_v is dn_u else Dofnum(local, self.elem_v)
+        l2g_u = np.empty(ldn_u.N, dtype=np.int64)
+        l2g_u[ldn_u.t_dof] = dn_u.t_dof[:, elems]
+        l2g_v = l2g_u
+        if ldn_v is not ldn_u:
+            l2g_v = np.empty(ldn_v.N, dtype=np.int64)
+            l2g_v[ldn_v.t_dof] = dn_v.t_dof[:, elems]
+        owned = owner_v[l2g_v] == rank
+        part = LocalPart(local, l2g_u, l2g_v, owned, dn_u.N, dn_v.N,
+                         int(np.sum(self.rank_of_elem[elems] == rank)),
+                         owner_v=owner_v[l2g_v])
+
+        def on_global_boundary(lmesh, lf):
+            """Match the (sorted, global) vertex tuples of local facets ``lf``
+            against the global boundary facets."""
+            gb = self._global_boundary()
+            mine = np.sort(verts[lmesh.facets[:, lf]], axis=0)
+            both = np.hstack((gb, mine)).T
+            _, inv = np.unique(both, axis=0, return_inverse=True)
+            inv = inv.reshape(-1)
+            hit = np.zeros(inv.max() + 1, dtype=bool)
+            hit[inv[:gb.shape[1]]] = True
+            return hit[inv[gb.shape[1]:]]
+
+        part.on_global_boundary = on_global_boundary
+        return part
+
+
 def partition_global(mesh, elem_u, elem_v, world, rank, halo=True):
-    """Split the replicated global ``mesh`` for ``rank`` of ``world``.
-
-    ``halo=True``: own block + the elements touching owned rows (owned rows are
-    complete locally).  ``halo=False``: the own block only; rows that the rank
-    touches but does not own carry partial sums that :class:`InterfaceExchange`
-    sends to their owners."""
-    nt = mesh.t.shape[1]
-    perm = morton_order_host(mesh)
-    rank_of_elem = np.empty(nt, dtype=np.int64)
-    bounds = [(nt * r) // world for r in range(world + 1)]
-    for r in range(world):
-        rank_of_elem[perm[bounds[r]:bounds[r + 1]]] = r
-    dn_u = Dofnum(mesh, elem_u)
-    dn_v = dn_u if elem_v is None or elem_v is elem_u else Dofnum(mesh, elem_v)
-    owner_v = np.full(dn_v.N, world, dtype=np.int64)
-    np.minimum.at(owner_v, dn_v.t_dof, rank_of_elem[None, :])
-    if halo:
-        mine = (owner_v[dn_v.t_dof] == rank).any(axis=0)
-    else:
-        mine = rank_of_elem == rank
-    elems = np.nonzero(mine)[0]
-    verts = np.unique(mesh.t[:, elems])
-    t_loc = np.searchsorted(verts, mesh.t[:, elems])
-    local = type(mesh)(np.ascontiguousarray(mesh.p[:, verts]), t_loc, validate=False)
-    ldn_u = Dofnum(local, elem_u)
-    ldn_v = ldn_u if dn_v is dn_u else Dofnum(local, elem_v)
-    l2g_u = np.empty(ldn_u.N, dtype=np.int64)
-    l2g_u[ldn_u.t_dof] = dn_u.t_dof[:, elems]
-    l2g_v = l2g_u
-    if ldn_v is not ldn_u:
-        l2g_v = np.empty(ldn_v.N, dtype=np.int64)
-        l2g_v[ldn_v.t_dof] = dn_v.t_dof[:, elems]
-    owned = owner_v[l2g_v] == rank
-    part = LocalPart(local, l2g_u, l2g_v, owned, dn_u.N, dn_v.N,
-                     int(np.sum(rank_of_elem[elems] == rank)),
-                     owner_v=owner_v[l2g_v])
-    gb = np.sort(mesh.facets[:, mesh.boundary_facets()], axis=0)
-
-    def on_global_boundary(lmesh, lf):
-        """Match the (sorted, global) vertex tuples of local facets ``lf``
-        against the global boundary facets."""
-        mine = np.sort(verts[lmesh.facets[:, lf]], axis=0)
-        both = np.hstack((gb, mine)).T
-        _, inv = np.unique(both, axis=0, return_inverse=True)
-        inv = inv.reshape(-1)
-        hit = np.zeros(inv.max() + 1, dtype=bool)
-        hit[inv[:gb.shape[1]]] = True
-        return hit[inv[gb.shape[1]:]]
-
-    part.on_global_boundary = on_global_boundary
-    return part
+    """Split the replicated global ``mesh`` for ``rank`` of ``world``
+    (see :class:`Partitioner`)."""
+    return Partitioner(mesh, elem_u, elem_v, world).part(rank, halo=halo)
 
 
 def strip_part(rank, world, refine, unit=None, halo=True):
