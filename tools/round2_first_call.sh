@@ -22,18 +22,29 @@ python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.
     > gpurun_out/r02_dist_configs_${mode}_2gpu.json 2> gpurun_out/r02_dist_configs_${mode}.err
 done
 tail -3 gpurun_out/r02_dist_configs_halo_2gpu.json
-# 4. config 3 at (nearly) full size on one GPU through the chunked path:
-#    MeshTri refine(11) vector-P2 = 8.4 M triangles x 144 entries = 1.2e9 (one call);
-#    refine(12) = 33.5 M x 144 = 4.8e9 entries -> chunks, on-device merge
-python - > gpurun_out/r02_chunked_full.log 2>&1 <<'PY'
-import time, sys
+# 4. the chunked path with the on-device merge at a size that is safe for the
+#    host (result: 0.77e9 nonzeros = 12 GB of host arrays): MeshTri refine(11)
+#    vector-P2 elasticity, 8.4 M triangles x 144 = 1.2e9 local entries, limit
+#    lowered so that it runs in >= 3 chunks; compare with the single call.
+#    (refine(12) = 4.8e9 entries needs ~50 GB of host memory for the result:
+#    check `free -g` on the box before trying it.)
+free -g | head -2
+python - > gpurun_out/r02_chunked.log 2>&1 <<'PY'
+import os, time, sys
 sys.path.insert(0, "tests")
+import numpy as np
 import spfem_b200 as sp, cases
 from spfem_b200.assembly import AssemblerElement
-t0 = time.time(); m = sp.MeshTri(); m.refine(12); print("mesh", m.t.shape[1], time.time() - t0, flush=True)
+t0 = time.time(); m = sp.MeshTri(); m.refine(11); print("mesh", m.t.shape[1], time.time() - t0, flush=True)
 a = AssemblerElement(m, sp.ElementH1Vec(sp.ElementTriP2()))
 t0 = time.time(); A = a.iasm(cases.elasticity); dt = time.time() - t0
-print("chunked vecP2 elasticity: nnz", A.nnz, "index dtype", A.indices.dtype, "s", dt,
+print("single call: nnz", A.nnz, "s", dt, flush=True)
+a._engine = None
+os.environ["SPFEM_MAX_ENTRIES"] = str(144 * m.t.shape[1] // 2)
+t0 = time.time(); B = a.iasm(cases.elasticity); dt = time.time() - t0
+print("chunked: nnz", B.nnz, "index dtype", B.indices.dtype, "s", dt,
       "elements/s", m.t.shape[1] / dt, flush=True)
+assert np.array_equal(A.indptr, B.indptr) and np.array_equal(A.indices, B.indices)
+print("max |A - B| / max |A|", float(np.max(np.abs(A.data - B.data)) / np.max(np.abs(A.data))))
 PY
-tail -3 gpurun_out/r02_chunked_full.log
+tail -4 gpurun_out/r02_chunked.log
