@@ -104,15 +104,25 @@ class Partitioner(object):
             self._gb = np.sort(m.facets[:, m.boundary_facets()], axis=0)
         return self._gb
 
-    def part(self, rank, halo=True):
+    def part(self, rank, halo=True, facet_halo=False):
         """``halo=True``: own block + the elements touching owned rows (owned
         rows are complete locally).  ``halo=False``: the own block only; rows
         that the rank touches but does not own carry partial sums that
-        :class:`InterfaceExchange` sends to their owners."""
+        :class:`InterfaceExchange` sends to their owners.  ``facet_halo=True``
+        (with ``halo``) adds the facet neighbours of those elements: an interior
+        facet contributes to the rows of the elements on *both* its sides, so
+        interior-facet forms need the element across every facet of an element
+        that touches an owned row."""
         mesh, dn_u, dn_v, owner_v = self.mesh, self.dn_u, self.dn_v, self.owner_v
         if halo:
             mine = (owner_v[dn_v.t_dof] == rank).any(axis=0)
+            if facet_halo:
+                nb = mesh.f2t[:, mesh.t2f[:, mine].reshape(-1)].reshape(-1)
+                mine = mine.copy()
+                mine[nb[nb >= 0]] = True
         else:
+            if facet_halo:
+                raise NotImplementedError("facet_halo needs halo=True")
             mine = self.rank_of_elem == rank
         elems = np.nonzero(mine)[0]
         verts = np.unique(mesh.t[:, elems])
@@ -147,10 +157,11 @@ class Partitioner(object):
         return part
 
 
-def partition_global(mesh, elem_u, elem_v, world, rank, halo=True):
+def partition_global(mesh, elem_u, elem_v, world, rank, halo=True, facet_halo=False):
     """Split the replicated global ``mesh`` for ``rank`` of ``world``
     (see :class:`Partitioner`)."""
-    return Partitioner(mesh, elem_u, elem_v, world).part(rank, halo=halo)
+    return Partitioner(mesh, elem_u, elem_v, world).part(rank, halo=halo,
+                                                         facet_halo=facet_halo)
 
 
 def strip_part(rank, world, refine, unit=None, halo=True):
@@ -436,7 +447,7 @@ class DistributedAssembler(object):
 
     def __init__(self, mesh, elem_u, elem_v=None, group=None, part=None,
                  rank=None, world=None, assemble=None, mode="halo",
-                 assemble_facet=None):
+                 assemble_facet=None, facet_halo=False):
         import torch.distributed as dist
         if mode not in ("halo", "exchange"):
             raise ValueError("mode must be 'halo' or 'exchange'")
@@ -447,8 +458,10 @@ class DistributedAssembler(object):
         if rank is None:
             rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.rank, self.world, self.group = rank, world, group
+        self.facet_halo = facet_halo
         self.part = part if part is not None else partition_global(
-            mesh, elem_u, elem_v, world, rank, halo=(mode == "halo"))
+            mesh, elem_u, elem_v, world, rank, halo=(mode == "halo"),
+            facet_halo=facet_halo)
         if mode == "exchange" and self.part.owner_v is None:
             raise ValueError("mode='exchange' needs a partition with owner_v "
                              "(partition_global(..., halo=False))")
@@ -492,23 +505,30 @@ class DistributedAssembler(object):
         the artificial boundary along the cuts is left out.  Halo mode: a rank
         assembles the boundary facets of its own and its halo elements, which
         completes its owned rows; exchange mode: of its own elements only, then
-        the ghost rows travel to their owners.  Interior facets
-        (``interior=True``) would need the element across every cut facet,
-        i.e. a second halo layer: not implemented."""
-        if interior:
-            raise NotImplementedError("interior facets over a partitioned mesh")
+        the ghost rows travel to their owners.
+
+        ``interior=True`` (two-sided DG / jump forms): needs the element across
+        every facet of an element that touches an owned row, i.e. a partition
+        built with ``facet_halo=True`` (halo mode); the rank then assembles all
+        interior facets of its local mesh -- the cut facets are boundary facets
+        of the local mesh and belong to the neighbour that has both sides."""
+        if interior and not (self.mode == "halo" and self.facet_halo):
+            raise NotImplementedError(
+                "interior facets over a partitioned mesh need "
+                "DistributedAssembler(..., mode='halo', facet_halo=True)")
         if find is not None:
             raise NotImplementedError("find= over a partitioned mesh (facet ids are rank-local)")
         if interp is not None:
             interp = {k: np.asarray(v)[self.part.l2g_u] for k, v in interp.items()}
-        lf = self.part.global_boundary_facets()
-        plan = self.local.plan_fasm(form, interior=False, intorder=intorder,
+        lf = (self.part.mesh.interior_facets() if interior
+              else self.part.global_boundary_facets())
+        plan = self.local.plan_fasm(form, interior=interior, intorder=intorder,
                                     normals=normals, interp=interp)
         if self._assemble_facet is not None:    # CPU tests inject the local assembly
-            loc = self._assemble_facet(self.local, form, find=lf, intorder=intorder,
-                                       normals=normals, interp=interp)
+            loc = self._assemble_facet(self.local, form, find=lf, interior=interior,
+                                       intorder=intorder, normals=normals, interp=interp)
         else:
-            loc = self.local._get_engine().run_facet(plan, np.asarray(lf), False, interp,
+            loc = self.local._get_engine().run_facet(plan, np.asarray(lf), interior, interp,
                                                      to_host=to_host)
         if self.mode == "exchange":
             return self._exchange(loc, plan.bilinear, kind="facet")

@@ -26,9 +26,10 @@ def host_assemble(asm, form, intorder=None, interp=None):
     return hostemu.iasm(asm, form, intorder=intorder, interp=interp)
 
 
-def host_assemble_facet(asm, form, find=None, intorder=None, normals=True, interp=None):
-    return hostemu.fasm(asm, form, find=find, intorder=intorder, normals=normals,
-                        interp=interp)
+def host_assemble_facet(asm, form, find=None, interior=False, intorder=None,
+                         normals=True, interp=None):
+    return hostemu.fasm(asm, form, find=find, interior=interior, intorder=intorder,
+                        normals=normals, interp=interp)
 
 
 def main():
@@ -92,6 +93,24 @@ def main():
             if rank == 0:
                 util.check(res, util.golden(case))
                 print("facet ok", name, mode, "world", world)
+    # 1d. interior-facet (DG / jump) forms: facet-neighbour halo
+    for name in ("f_trip1_sipg", "f_tridg1_sipg", "f_tetp2_jump"):
+        case = cases.BY_NAME[name]
+        m = util.mesh_for(case)
+        eu = util.element(case.eu, case.ncu)
+        da = DistributedAssembler(m, eu, None, assemble=host_assemble,
+                                  assemble_facet=host_assemble_facet, facet_halo=True)
+        res = da.fasm(case.form, interior=True).gather(0)
+        ia = da.iasm(cases.mass).gather(0)          # interior forms on the wider halo
+        if rank == 0:
+            util.check(res, util.golden(case))
+            print("interior facet ok", name, "world", world)
+        try:
+            DistributedAssembler(m, eu, None, assemble_facet=host_assemble_facet).fasm(
+                case.form, interior=True)
+            raise AssertionError("interior facets without facet_halo must be refused")
+        except NotImplementedError:
+            pass
     # 2. weak-scaling strip mesh built per rank, against the oracle on the
     #    explicitly assembled global strip
     part = strip_part(rank, world, 3)
