@@ -395,20 +395,6 @@ def test_rt0_mixed_poisson_convergence():
     assert 0.95 <= rate <= 1.15
 
 
-@pytest.mark.parametrize("name", ["trip1_lap_r6", "tetp2_lap", "vecp2_elasticity", "stokes_b",
-                                  "trip1_load"])
-def test_chunked_assembly_beyond_one_pattern_call(name, monkeypatch):
-    """``iasm`` on a mesh with more local entries than one pattern call takes
-    (limit lowered through SPFEM_MAX_ENTRIES): element chunks on one GPU, same
-    matrix and pattern as the single call."""
-    case = cases.BY_NAME[name]
-    asm = util.assembler_for(case)
-    plan = asm.plan_iasm(case.form)
-    monkeypatch.setenv("SPFEM_MAX_ENTRIES", str(plan.spec.n_entries * asm.mesh.t.shape[1] // 3))
-    assert asm._chunks_needed(plan, None) >= 4
-    util.check(asm.iasm(case.form), util.golden(case))
-
-
 @pytest.mark.parametrize("ename", ["TriP1", "TriP2"])
 def test_tile_kernel_irregular_mesh(ename):
     """A high-valence vertex (wheel of 40 triangles, refined): the vertex-fan

@@ -7,7 +7,7 @@ mkdir -p gpurun_out
 # 1. the new GPU tests (GPU variants of the restated reference tests, chunked
 #    assembly with the on-device merge, NCCL interface exchange at world 2)
 python -m pytest tests/test_reference_module_tests.py tests/test_zz_nccl_exchange.py \
-    "tests/test_gpu_parity.py::test_chunked_assembly_beyond_one_pattern_call" \
+    tests/test_zz_chunked_gpu.py \
     -m gpu -q > gpurun_out/r02_new_gpu_tests.log 2>&1
 tail -5 gpurun_out/r02_new_gpu_tests.log
 # 2. halo vs exchange on the benchmark strip
