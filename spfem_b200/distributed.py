@@ -282,6 +282,27 @@ class DistResult(object):
         idx = np.nonzero(part.owned_v)[0]
         return (part.l2g_v[idx], np.zeros(len(idx), dtype=np.int64), v[idx])
 
+    def csr(self):
+        """The rank's row slice on its device: (owned global row ids, ascending;
+        ``indptr`` over them; global column ids, sorted inside a row; values) --
+        the same layout as :meth:`ExchangedResult.csr`.  Bilinear forms only."""
+        import torch
+        if not self.bilinear:
+            raise NotImplementedError("csr() of a load vector")
+        part = self.part
+        rows, cols, values = _local_tensors(self.local, True)
+        dev = values.device
+        keep = torch.from_numpy(np.ascontiguousarray(part.owned_v)).to(dev)[rows]
+        l2g_v = torch.from_numpy(np.ascontiguousarray(part.l2g_v, dtype=np.int64)).to(dev)
+        l2g_u = torch.from_numpy(np.ascontiguousarray(part.l2g_u, dtype=np.int64)).to(dev)
+        ncols = max(int(part.N_u), 1)
+        key, order = torch.sort(l2g_v[rows[keep]] * ncols + l2g_u[cols[keep]])
+        grow = torch.div(key, ncols, rounding_mode="floor")
+        urows, counts = torch.unique_consecutive(grow, return_counts=True)
+        indptr = torch.zeros(urows.numel() + 1, dtype=torch.int64, device=dev)
+        indptr[1:] = torch.cumsum(counts, 0)
+        return urows, indptr, key - grow * ncols, values[keep][order]
+
     def gather(self, dst=0):
         """Collect the global matrix / vector on rank ``dst`` (``None`` on the
         other ranks).  Every row is owned by exactly one rank, so no value is

@@ -32,6 +32,24 @@ def host_assemble_facet(asm, form, find=None, interior=False, intorder=None,
                         normals=normals, interp=interp)
 
 
+def check_row_slices(res, full, rank, world):
+    """The device row slices (``csr()``) of all ranks stacked = the gathered matrix."""
+    urows, indptr, cols, vals = res.csr()
+    objs = [None] * world
+    dist.all_gather_object(objs, (urows.numpy(), indptr.numpy(), cols.numpy(), vals.numpy()))
+    if rank != 0:
+        return
+    seen = np.concatenate([o[0] for o in objs])
+    assert len(np.unique(seen)) == len(seen)            # every row on one rank only
+    full = full.tocsr()
+    for ur, ip, cc, vv in objs:
+        for k, r in enumerate(ur):
+            lo, hi = full.indptr[r], full.indptr[r + 1]
+            assert np.array_equal(cc[ip[k]:ip[k + 1]], full.indices[lo:hi])
+            assert np.array_equal(vv[ip[k]:ip[k + 1]], full.data[lo:hi])
+    assert len(seen) == np.count_nonzero(np.diff(full.indptr))
+
+
 def main():
     dist.init_process_group("gloo")
     rank, world = dist.get_rank(), dist.get_world_size()
@@ -46,8 +64,10 @@ def main():
         if not (case.ev is None and case.ncv == case.ncu):
             ev = util.element(case.ev or case.eu, case.ncv)
         da = DistributedAssembler(m, eu, ev, assemble=host_assemble)
-        res = da.iasm(case.form).gather(0)
-        owned = np.array([int(da.part.owned_v.sum())])
+        dres = da.iasm(case.form)
+        res = dres.gather(0)
+        if dres.bilinear:
+            check_row_slices(dres, res, rank, world)
         if rank == 0:
             util.check(res, util.golden(case))
             print("dist ok", name, "world", world)
@@ -73,6 +93,8 @@ def main():
         urows, indptr, cols, vals = r1.csr()
         assert int(indptr[-1]) == vals.numel() == cols.numel()
         res = r1.gather(0)
+        if r1.bilinear:
+            check_row_slices(r1, res, rank, world)
         if rank == 0:
             util.check(res, util.golden(case))
             print("xchg ok", name, "world", world)
