@@ -4,8 +4,10 @@
 #   gpurun --gpus 2 --timeout 1500 -- 'bash tools/round2_first_call.sh'
 set -x
 mkdir -p gpurun_out
-# 1. the new GPU tests (GPU variants of the restated reference tests, chunked
-#    assembly with the on-device merge, NCCL interface exchange at world 2)
+# 1. the new GPU tests (GPU variants of the restated reference tests and chunked
+#    assembly with the on-device merge: these passed on one B200 at the end of
+#    round 1, profiles/r01_late_gpu_tests.log; the NCCL interface exchange at
+#    world 2 has not run on GPUs yet)
 python -m pytest tests/test_reference_module_tests.py tests/test_zz_nccl_exchange.py \
     tests/test_zz_chunked_gpu.py \
     -m gpu -q > gpurun_out/r02_new_gpu_tests.log 2>&1
