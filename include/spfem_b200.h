@@ -168,6 +168,86 @@ int spfem_morton_order(const double *d_p, long long ldp, int dim,
                        const double *h_lo, const double *h_hi, /* bounding box */
                        int *d_perm, void *d_ws, size_t ws_bytes, void *stream);
 
+
+/* ---- tile plan: sparsity pattern + plan of the fused kernel, natively -------
+ * (csrc/spfem_plan.cu).  Builds, for the element range described by the DOF
+ * tables, (i) the CSR structure of SciPy's coo_matrix(...).tocsr()
+ * (spfem/assembly.py:985-986: sorted unique columns per row, explicit zeros
+ * kept) and (ii) the per-tile blobs the generated kernel `<name>_tile` reads
+ * (codegen.TILE_KERNEL): tiles of E consecutive elements, every row owned by
+ * the lowest tile touching it, a tile's element list = its elements + the halo
+ * elements touching its rows.  The work is done in batches of tiles with at
+ * most `batch_cap` contributions each, so the memory in use is bounded by the
+ * batch, not by the mesh (no 2^31 limit on Nu*Nv*nt).  One SpfemPlanBatch = one
+ * launch of the tile kernel.
+ *
+ * Vector elements: with bsv / bsu > 1 the DOF tables are checked for the
+ * interleaved structure dof = bs * scalar_dof + component; if it holds, the
+ * plan is built on the scalar structure and one slot stands for a bsv x bsu
+ * block of CSR values (SpfemPlanOut.bsv / bsu report what was used).
+ *
+ * Memory: every buffer is requested from the caller through `alloc` (tag says
+ * what for; tags starting with "out:" are results whose ownership passes to
+ * the caller, everything else is released through `release` before return).
+ * on_device = 0: the same code on host pointers (tests without a GPU).
+ * Return codes: 0 ok, 2 = a tile does not fit the 16-bit fields (retry with a
+ * smaller E), other = error (spfem_last_error()).                              */
+typedef void *(*spfem_alloc_fn)(void *ctx, size_t bytes, const char *tag);
+typedef void (*spfem_free_fn)(void *ctx, void *ptr);
+
+#define SPFEM_PLAN_MAX_BATCHES 256
+
+typedef struct SpfemPlanIn {
+    const int *rowdof;        /* test DOF table  rowdof[i*ldr + e], device element order */
+    long long ldr;
+    int nloc_v;
+    const int *coldof;        /* trial DOF table (NULL: linear form, one column)      */
+    long long ldc;
+    int nloc_u;
+    long long n;              /* elements                                              */
+    long long nrows, ncols;
+    const int *vt;            /* vertex table vt[r*ldvt + e]                           */
+    long long ldvt;
+    int nve, dim;
+    int bsv, bsu;             /* block sizes to try (components of a vector element)   */
+    const int *alias;         /* [nloc_u*nloc_v] local entry j*nloc_v+i -> distinct    */
+    int nuniq;                /*   local value (scalar plans only), their number       */
+    int E;                    /* elements per tile                                     */
+    int with_el;              /* keep element ids in the blobs (interp gathers)        */
+    int sort_slots;           /* 0: CSR order, 1: by contribution count, 2: coarse classes */
+    int compact;              /* shared memory holds only the local values that are read */
+    const unsigned char *row_mask; /* optional [nrows]: 0 = row is not assembled here  */
+    int index_bytes;          /* 4 or 8: width of indptr / indices                     */
+    long long batch_cap;      /* contributions per batch (0: 2^27)                     */
+} SpfemPlanIn;
+
+typedef struct SpfemPlanBatch {
+    void *desc;               /* int32 [16 * ntiles]                                    */
+    void *blob;               /* bytes, 16-byte aligned sections                        */
+    void *vid;                /* int32 [nvid] global vertex id of every tile vertex     */
+    void *vptr;               /* int64 [ntiles + 1] first tile vertex of every tile     */
+    long long ntiles, blob_bytes, nvid, first_tile, nslots;
+} SpfemPlanBatch;
+
+typedef struct SpfemPlanOut {
+    long long nnz;
+    void *indptr, *indices;   /* index_bytes wide; indices NULL for a linear form       */
+    int nbatches;
+    int ldl;                  /* leading dimension of the shared-memory value image     */
+    int els;                  /* block plans: contribution code = (entry << els) | elem */
+    int bsv, bsu;
+    int max_ne, max_nr, max_ns, max_store, max_bytes_a, max_bytes_b;
+    long long ntiles, n_pairs, n_contrib;
+    SpfemPlanBatch batches[SPFEM_PLAN_MAX_BATCHES];
+} SpfemPlanOut;
+
+int spfem_tileplan_build(const SpfemPlanIn *in, SpfemPlanOut *out, spfem_alloc_fn alloc,
+                         spfem_free_fn release, void *alloc_ctx, int on_device, void *stream);
+/* (Re)writes the tiles' private vertex coordinates from p[k*ldp + v].            */
+int spfem_tileplan_fill_coords(const int *desc, unsigned char *blob, const int *vid,
+                               const long long *vptr, long long ntiles, const double *p,
+                               long long ldp, int dim, int on_device, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

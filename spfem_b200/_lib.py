@@ -15,7 +15,9 @@ LIB_PATH = os.path.join(CSRC, "libspfem_b200.so")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3",
-              "-std=c++17", "-shared", "-Xcompiler", "-fPIC", "-cudart", "static"]
+              "-std=c++17", "--extended-lambda", "-shared", "-Xcompiler", "-fPIC",
+              "-cudart", "static"]
+SOURCES = ["spfem_b200.cu", "spfem_plan.cu"]
 
 
 class SpfemArgs(C.Structure):
@@ -36,13 +38,53 @@ class SpfemArgs(C.Structure):
 
 
 class SpfemTileArgs(C.Structure):
-    """Mirror of ``struct SpfemTileArgs`` (generated source, codegen.TILE_KERNEL)."""
+    """Mirror of ``struct SpfemTileArgs`` (include/spfem_b200.h; the generated
+    source declares the identical struct, codegen.TILE_KERNEL)."""
     _fields_ = [
         ("base", SpfemArgs),
         ("desc", C.c_void_p), ("blob", C.c_void_p), ("values", C.c_void_p),
         ("ldl", C.c_int), ("max_a", C.c_int), ("max_b", C.c_int),
-        ("max_ns", C.c_int), ("max_nr", C.c_int), ("mode", C.c_int),
-        ("store", C.c_int), ("prefetch", C.c_int), ("sorted", C.c_int),
+        ("compact", C.c_int), ("store", C.c_int), ("prefetch", C.c_int),
+        ("sorted", C.c_int), ("els", C.c_int),
+    ]
+
+
+ALLOC_FN = C.CFUNCTYPE(C.c_void_p, C.c_void_p, C.c_size_t, C.c_char_p)
+FREE_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p)
+PLAN_MAX_BATCHES = 256
+
+
+class SpfemPlanIn(C.Structure):
+    """Mirror of ``struct SpfemPlanIn`` (include/spfem_b200.h)."""
+    _fields_ = [
+        ("rowdof", C.c_void_p), ("ldr", C.c_longlong), ("nloc_v", C.c_int),
+        ("coldof", C.c_void_p), ("ldc", C.c_longlong), ("nloc_u", C.c_int),
+        ("n", C.c_longlong), ("nrows", C.c_longlong), ("ncols", C.c_longlong),
+        ("vt", C.c_void_p), ("ldvt", C.c_longlong), ("nve", C.c_int), ("dim", C.c_int),
+        ("bsv", C.c_int), ("bsu", C.c_int),
+        ("alias", C.c_void_p), ("nuniq", C.c_int),
+        ("E", C.c_int), ("with_el", C.c_int), ("sort_slots", C.c_int), ("compact", C.c_int),
+        ("row_mask", C.c_void_p), ("index_bytes", C.c_int), ("batch_cap", C.c_longlong),
+    ]
+
+
+class SpfemPlanBatch(C.Structure):
+    _fields_ = [
+        ("desc", C.c_void_p), ("blob", C.c_void_p), ("vid", C.c_void_p), ("vptr", C.c_void_p),
+        ("ntiles", C.c_longlong), ("blob_bytes", C.c_longlong), ("nvid", C.c_longlong),
+        ("first_tile", C.c_longlong), ("nslots", C.c_longlong),
+    ]
+
+
+class SpfemPlanOut(C.Structure):
+    _fields_ = [
+        ("nnz", C.c_longlong), ("indptr", C.c_void_p), ("indices", C.c_void_p),
+        ("nbatches", C.c_int), ("ldl", C.c_int), ("els", C.c_int),
+        ("bsv", C.c_int), ("bsu", C.c_int),
+        ("max_ne", C.c_int), ("max_nr", C.c_int), ("max_ns", C.c_int), ("max_store", C.c_int),
+        ("max_bytes_a", C.c_int), ("max_bytes_b", C.c_int),
+        ("ntiles", C.c_longlong), ("n_pairs", C.c_longlong), ("n_contrib", C.c_longlong),
+        ("batches", SpfemPlanBatch * PLAN_MAX_BATCHES),
     ]
 
 
@@ -96,6 +138,11 @@ SYMBOLS = {
                                       C.c_void_p, C.c_void_p, C.c_longlong, C.c_int,
                                       C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                       C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "spfem_tileplan_build": (C.c_int, [C.POINTER(SpfemPlanIn), C.POINTER(SpfemPlanOut),
+                                       ALLOC_FN, FREE_FN, C.c_void_p, C.c_int, C.c_void_p]),
+    "spfem_tileplan_fill_coords": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                             C.c_longlong, C.c_void_p, C.c_longlong, C.c_int,
+                                             C.c_int, C.c_void_p]),
     "spfem_morton_ws_bytes": (C.c_size_t, [C.c_longlong]),
     "spfem_morton_order": (C.c_int, [C.c_void_p, C.c_longlong, C.c_int,
                                      C.c_void_p, C.c_longlong, C.c_int,
@@ -113,14 +160,13 @@ class SpfemError(RuntimeError):
 
 def build(force=False, verbose=False):
     """Compile ``csrc/spfem_b200.cu`` into ``csrc/libspfem_b200.so``."""
-    src = os.path.join(CSRC, "spfem_b200.cu")
+    srcs = [os.path.join(CSRC, f) for f in SOURCES]
     hdr = os.path.join(INCLUDE, "spfem_b200.h")
     if (not force and os.path.exists(LIB_PATH)
-            and os.path.getmtime(LIB_PATH) >= max(os.path.getmtime(src),
-                                                  os.path.getmtime(hdr))):
+            and os.path.getmtime(LIB_PATH) >= max(os.path.getmtime(f) for f in srcs + [hdr])):
         return LIB_PATH
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + ["-o", LIB_PATH, src, "-lnvrtc", "-Xlinker",
+    cmd = [nvcc] + NVCC_FLAGS + ["-o", LIB_PATH] + srcs + ["-lnvrtc", "-Xlinker",
                                  "-rpath", "-Xlinker", "/usr/local/cuda/lib64"]
     if verbose:
         print(" ".join(cmd))

@@ -537,6 +537,8 @@ int bits_for(unsigned long long maxval)
 
 } // namespace
 
+void spfem_set_error_(const std::string &msg) { g_err = msg; }
+
 extern "C" {
 
 int spfem_abi_version(void) { return SPFEM_ABI_VERSION; }

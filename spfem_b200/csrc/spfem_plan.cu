@@ -1,0 +1,938 @@
+// spfem_plan -- native builder of the sparsity pattern AND the tile plan of the
+// fused assembly kernel (spfem_b200/codegen.py, TILE_KERNEL), see
+// include/spfem_b200.h "tile plan".
+//
+// Replaces two things of round 1: the global (row, col) sort of all
+// Nu*Nv*nt local entries (spfem_pattern_sort/fill; limited to 2^31-1 entries
+// per call) and the PyTorch index-op tile planner (dozens of int64 temporaries
+// of that size: out of memory at 8 M vector-P2 triangles).  Here the work is
+// tile-local and batched, so memory is bounded by the batch size, not by the
+// mesh:
+//
+//   1. every CSR row gets an owner tile (lowest tile of E Morton-consecutive
+//      elements touching it): integer atomicMin,
+//   2. tile element lists = own elements + halo (elements touching an owned
+//      row): (tile, element) pairs, one radix sort,
+//   3. batches of tiles with <= batch_cap contributions: the contributions
+//      (tile, owned row, column) -> shared-memory cell of the local value are
+//      generated, radix-sorted (stable: fixed summation order) and run-length
+//      encoded PER BATCH; this yields at the same time
+//        * the CSR structure of the owned rows (= the rows of SciPy's
+//          coo_matrix(...).tocsr(), spfem/assembly.py:985-986: sorted unique
+//          columns, explicit zeros kept), and
+//        * the per-tile slot / contribution lists of the kernel's phase B,
+//   4. a prefix sum over the row lengths gives indptr; the column ids are
+//      scattered from tile-major to CSR order and the row positions are patched
+//      into the blobs.
+//
+// Vector elements (ElementH1Vec; DOF = bs * scalar DOF + component, spfem/
+// assembly.py:1499-1550, spfem/element.py:505-546) are planned on the SCALAR
+// structure: one "slot" stands for a bsv x bsu block of CSR values, which
+// divides the plan's size and the kernel's index work by bsv*bsu.
+//
+// Everything runs on the device (CUB sorts / scans + small kernels) or, with
+// on_device = 0, on the host with the same code (tests without a GPU: the
+// lambdas are __host__ __device__).  Memory comes from the caller's allocator
+// callbacks (PyTorch tensors in the Python host layer): no hidden allocation.
+#include "../../include/spfem_b200.h"
+
+#include <cuda_runtime.h>
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+
+#include <algorithm>
+#include <climits>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+void spfem_set_error_(const std::string &msg);   // spfem_b200.cu
+
+namespace spfem_plan {
+
+typedef unsigned long long u64;
+typedef unsigned int u32;
+typedef unsigned short u16;
+typedef long long i64;
+
+struct Err { int code; std::string msg; };
+
+#define PLAN_CK(expr)                                                           \
+    do {                                                                        \
+        cudaError_t _e = (expr);                                                \
+        if (_e != cudaSuccess)                                                  \
+            throw Err{1, std::string(#expr) + ": " + cudaGetErrorString(_e)};   \
+    } while (0)
+
+struct Ctx {
+    bool dev;
+    cudaStream_t st;
+    spfem_alloc_fn alloc;
+    spfem_free_fn release;
+    void *actx;
+    std::vector<void *> scratch;
+    void *tmp = nullptr;          // CUB temporary storage, grown on demand
+    size_t tmp_bytes = 0;
+};
+
+void *raw_alloc(Ctx &c, size_t bytes, const char *tag)
+{
+    void *p = c.alloc(c.actx, bytes ? bytes : 16, tag);
+    if (!p) throw Err{3, std::string("allocation failed: ") + tag};
+    return p;
+}
+
+template <class T> T *scratch(Ctx &c, size_t n, const char *tag)
+{
+    void *p = raw_alloc(c, n * sizeof(T), tag);
+    c.scratch.push_back(p);
+    return (T *)p;
+}
+
+template <class T> T *keep(Ctx &c, size_t n, const char *tag)
+{
+    return (T *)raw_alloc(c, n * sizeof(T), tag);
+}
+
+void drop(Ctx &c, void *p)
+{
+    if (!p) return;
+    for (size_t i = 0; i < c.scratch.size(); ++i)
+        if (c.scratch[i] == p) {
+            c.scratch.erase(c.scratch.begin() + i);
+            c.release(c.actx, p);
+            return;
+        }
+}
+
+void drop_all(Ctx &c)
+{
+    if (c.dev) cudaStreamSynchronize(c.st);
+    for (void *p : c.scratch) c.release(c.actx, p);
+    c.scratch.clear();
+    c.tmp = nullptr;
+    c.tmp_bytes = 0;
+}
+
+void *cub_tmp(Ctx &c, size_t bytes)
+{
+    if (bytes > c.tmp_bytes) {
+        if (c.tmp) { PLAN_CK(cudaStreamSynchronize(c.st)); drop(c, c.tmp); }
+        c.tmp_bytes = bytes + (bytes >> 2) + 256;
+        c.tmp = scratch<char>(c, c.tmp_bytes, "cub");
+    }
+    return c.tmp;
+}
+
+template <class F> __global__ void k_for(i64 n, F f)
+{
+    const i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) f(i);
+}
+
+template <class F> void par_for(Ctx &c, i64 n, F f)
+{
+    if (n <= 0) return;
+    if (c.dev) {
+        k_for<<<(unsigned)((n + 255) / 256), 256, 0, c.st>>>(n, f);
+        PLAN_CK(cudaGetLastError());
+    } else {
+        for (i64 i = 0; i < n; ++i) f(i);
+    }
+}
+
+__host__ __device__ inline void amin(int *p, int v)
+{
+#ifdef __CUDA_ARCH__
+    atomicMin(p, v);
+#else
+    if (v < *p) *p = v;
+#endif
+}
+
+__host__ __device__ inline void amax(int *p, int v)
+{
+#ifdef __CUDA_ARCH__
+    atomicMax(p, v);
+#else
+    if (v > *p) *p = v;
+#endif
+}
+
+__host__ __device__ inline int popc(u32 x)
+{
+#ifdef __CUDA_ARCH__
+    return __popc(x);
+#else
+    return __builtin_popcount(x);
+#endif
+}
+
+template <class T> T get(Ctx &c, const T *p)
+{
+    T v;
+    if (c.dev) {
+        PLAN_CK(cudaMemcpyAsync(&v, p, sizeof(T), cudaMemcpyDeviceToHost, c.st));
+        PLAN_CK(cudaStreamSynchronize(c.st));
+    } else {
+        v = *p;
+    }
+    return v;
+}
+
+template <class T> void to_host(Ctx &c, const T *p, size_t n, std::vector<T> &out)
+{
+    out.resize(n);
+    if (!n) return;
+    if (c.dev) {
+        PLAN_CK(cudaMemcpyAsync(out.data(), p, n * sizeof(T), cudaMemcpyDeviceToHost, c.st));
+        PLAN_CK(cudaStreamSynchronize(c.st));
+    } else {
+        memcpy(out.data(), p, n * sizeof(T));
+    }
+}
+
+template <class T> void fill(Ctx &c, T *p, i64 n, T v)
+{
+    par_for(c, n, [=] __host__ __device__(i64 i) { p[i] = v; });
+}
+
+// out[i] = sum_{k<i} in[k] for i in [0, n]  (out has n + 1 entries)
+void exscan(Ctx &c, const i64 *in, i64 *out, i64 n)
+{
+    if (c.dev) {
+        if (n > 0) {
+            size_t bytes = 0;
+            PLAN_CK(cub::DeviceScan::ExclusiveSum(nullptr, bytes, in, out, n, c.st));
+            void *t = cub_tmp(c, bytes);
+            PLAN_CK(cub::DeviceScan::ExclusiveSum(t, bytes, in, out, n, c.st));
+        }
+        par_for(c, 1, [=] __host__ __device__(i64) {
+            out[n] = n > 0 ? out[n - 1] + in[n - 1] : 0;
+        });
+    } else {
+        i64 acc = 0;
+        for (i64 i = 0; i < n; ++i) { out[i] = acc; acc += in[i]; }
+        out[n] = acc;
+    }
+}
+
+int bits_for(u64 maxval)
+{
+    int b = 1;
+    while (b < 64 && (maxval >> b) != 0ull) ++b;
+    return b;
+}
+
+// stable sort of (key, value) pairs by the low `end_bit` bits of the key; on
+// return `keys` / `vals` point at the sorted data (one of the two buffers)
+void sort_pairs(Ctx &c, u64 *&keys, u64 *&keys_alt, u32 *&vals, u32 *&vals_alt, i64 n, int end_bit)
+{
+    if (n <= 1) return;
+    if (c.dev) {
+        cub::DoubleBuffer<u64> dk(keys, keys_alt);
+        cub::DoubleBuffer<u32> dv(vals, vals_alt);
+        size_t bytes = 0;
+        PLAN_CK(cub::DeviceRadixSort::SortPairs(nullptr, bytes, dk, dv, n, 0, end_bit, c.st));
+        void *t = cub_tmp(c, bytes);
+        PLAN_CK(cub::DeviceRadixSort::SortPairs(t, bytes, dk, dv, n, 0, end_bit, c.st));
+        keys = dk.Current(); keys_alt = dk.Alternate();
+        vals = dv.Current(); vals_alt = dv.Alternate();
+    } else {
+        std::vector<i64> idx(n);
+        for (i64 i = 0; i < n; ++i) idx[i] = i;
+        const u64 *k = keys;
+        std::stable_sort(idx.begin(), idx.end(), [k](i64 a, i64 b) { return k[a] < k[b]; });
+        for (i64 i = 0; i < n; ++i) { keys_alt[i] = keys[idx[i]]; vals_alt[i] = vals[idx[i]]; }
+        std::swap(keys, keys_alt);
+        std::swap(vals, vals_alt);
+    }
+}
+
+void sort_keys(Ctx &c, u64 *&keys, u64 *&keys_alt, i64 n, int end_bit)
+{
+    if (n <= 1) return;
+    if (c.dev) {
+        cub::DoubleBuffer<u64> dk(keys, keys_alt);
+        size_t bytes = 0;
+        PLAN_CK(cub::DeviceRadixSort::SortKeys(nullptr, bytes, dk, n, 0, end_bit, c.st));
+        void *t = cub_tmp(c, bytes);
+        PLAN_CK(cub::DeviceRadixSort::SortKeys(t, bytes, dk, n, 0, end_bit, c.st));
+        keys = dk.Current(); keys_alt = dk.Alternate();
+    } else {
+        std::sort(keys, keys + n);
+    }
+}
+
+// seg[g] = first position p in [0, n) with group(p) >= g, for g in [0, ngroups];
+// group() is non-decreasing over the positions
+template <class G> void boundaries(Ctx &c, i64 n, i64 ngroups, i64 *seg, G group)
+{
+    if (n == 0) { fill<i64>(c, seg, ngroups + 1, 0); return; }
+    par_for(c, n, [=] __host__ __device__(i64 p) {
+        const i64 g = group(p);
+        const i64 gp = p == 0 ? -1 : group(p - 1);
+        for (i64 x = gp + 1; x <= g; ++x) seg[x] = p;
+        if (p == n - 1)
+            for (i64 x = g + 1; x <= ngroups; ++x) seg[x] = n;
+    });
+}
+
+__host__ __device__ inline i64 pad16(i64 x) { return (x + 15) & ~(i64)15; }
+
+struct Geo {                  // scalar structure of the DOF tables
+    const int *rowdof; i64 ldr; int nbv, bsv;
+    const int *coldof; i64 ldc; int nbu, bsu;
+    __host__ __device__ int row(int i, i64 e) const { return rowdof[(i64)(bsv * i) * ldr + e] / bsv; }
+    __host__ __device__ int col(int j, i64 e) const { return coldof ? coldof[(i64)(bsu * j) * ldc + e] / bsu : 0; }
+};
+
+#define MAXLOC 64             // scalar local DOFs per element (rows)
+
+int build(const SpfemPlanIn &in, SpfemPlanOut &out, Ctx &c)
+{
+    memset(&out, 0, sizeof(out));
+    const i64 n = in.n;
+    if (n <= 0) throw Err{1, "tile plan: no elements"};
+    if (in.E <= 0 || in.E > 32767) throw Err{1, "tile plan: bad E"};
+    if (in.nrows <= 0 || in.nrows > INT_MAX || in.ncols > INT_MAX)
+        throw Err{1, "tile plan: row / column count out of range"};
+    int bsv = in.bsv > 0 ? in.bsv : 1, bsu = in.bsu > 0 ? in.bsu : 1;
+    if (!in.coldof) bsu = 1;
+    if (in.nloc_v % bsv || in.nrows % bsv) bsv = 1;
+    if (in.coldof && (in.nloc_u % bsu || in.ncols % bsu)) bsu = 1;
+    if (in.compact) { bsv = 1; bsu = 1; }
+
+    // ---- 0. block structure of the DOF tables ------------------------------
+    if (bsv > 1 || bsu > 1) {
+        int *flag = scratch<int>(c, 2, "flag");
+        fill<int>(c, flag, 2, 1);
+        const int *rd = in.rowdof, *cd = in.coldof;
+        const i64 ldr = in.ldr, ldc = in.ldc;
+        const int nlv = in.nloc_v, nlu = in.nloc_u, bv = bsv, bu = bsu;
+        par_for(c, n, [=] __host__ __device__(i64 e) {
+            bool okv = true, oku = true;
+            for (int i = 0; i < nlv; i += bv) {
+                const int d0 = rd[(i64)i * ldr + e];
+                if (d0 % bv) okv = false;
+                for (int a = 1; a < bv; ++a)
+                    if (rd[(i64)(i + a) * ldr + e] != d0 + a) okv = false;
+            }
+            if (cd)
+                for (int j = 0; j < nlu; j += bu) {
+                    const int d0 = cd[(i64)j * ldc + e];
+                    if (d0 % bu) oku = false;
+                    for (int b = 1; b < bu; ++b)
+                        if (cd[(i64)(j + b) * ldc + e] != d0 + b) oku = false;
+                }
+            if (!okv) flag[0] = 0;
+            if (!oku) flag[1] = 0;
+        });
+        if (!get(c, flag)) bsv = 1;
+        if (!get(c, flag + 1)) bsu = 1;
+        drop(c, flag);
+    }
+    Geo g;
+    g.rowdof = in.rowdof; g.ldr = in.ldr; g.bsv = bsv; g.nbv = in.nloc_v / bsv;
+    g.coldof = in.coldof; g.ldc = in.ldc; g.bsu = bsu; g.nbu = in.coldof ? in.nloc_u / bsu : 1;
+    const int nbv = g.nbv, nbu = g.nbu, nb = bsv * bsu;
+    if (nbv > MAXLOC) throw Err{1, "tile plan: more than 64 scalar test functions per element"};
+    const i64 NR = in.nrows / bsv;
+    const i64 NC = in.coldof ? in.ncols / bsu : 1;
+    const int E = in.E;
+    const i64 ntiles = (n + E - 1) / E;
+    const unsigned char *row_mask = in.row_mask;
+    const int INF = INT_MAX;
+
+    // ---- 1. row owners -------------------------------------------------------
+    int *owner = scratch<int>(c, NR, "owner");
+    fill<int>(c, owner, NR, INF);
+    par_for(c, n * nbv, [=] __host__ __device__(i64 w) {
+        const int i = (int)(w / n);
+        const i64 e = w - (i64)i * n;
+        const int R = g.row(i, e);
+        if (row_mask && !row_mask[(i64)R * bsv]) return;
+        amin(&owner[R], (int)(e / E));
+    });
+
+    // ---- 2. tile element lists: own elements + halo ---------------------------
+    i64 *cnt = scratch<i64>(c, n + 1, "cnt");
+    par_for(c, n, [=] __host__ __device__(i64 e) {
+        int seen[MAXLOC];
+        int ns = 0;
+        for (int i = 0; i < nbv; ++i) {
+            const int o = owner[g.row(i, e)];
+            if (o == INF) continue;
+            bool dup = false;
+            for (int k = 0; k < ns; ++k) dup = dup || seen[k] == o;
+            if (!dup) seen[ns++] = o;
+        }
+        cnt[e] = ns;
+    });
+    i64 *poff = scratch<i64>(c, n + 1, "poff");
+    exscan(c, cnt, poff, n);
+    const i64 P = get(c, poff + n);
+    if (P == 0) throw Err{1, "tile plan: no owned rows"};
+    u64 *pk = scratch<u64>(c, P, "pairs"), *pk2 = scratch<u64>(c, P, "pairs2");
+    par_for(c, n, [=] __host__ __device__(i64 e) {
+        int seen[MAXLOC];
+        int ns = 0;
+        i64 pos = poff[e];
+        for (int i = 0; i < nbv; ++i) {
+            const int o = owner[g.row(i, e)];
+            if (o == INF) continue;
+            bool dup = false;
+            for (int k = 0; k < ns; ++k) dup = dup || seen[k] == o;
+            if (!dup) { seen[ns++] = o; pk[pos++] = (u64)o * (u64)n + (u64)e; }
+        }
+    });
+    drop(c, cnt); drop(c, poff);
+    sort_keys(c, pk, pk2, P, bits_for((u64)ntiles * (u64)n));
+    drop(c, pk2);
+    int *pe = scratch<int>(c, P, "pe"), *pt = scratch<int>(c, P, "pt");
+    {
+        const u64 *k = pk;
+        par_for(c, P, [=] __host__ __device__(i64 q) {
+            const u64 T = k[q] / (u64)n;
+            pt[q] = (int)T;
+            pe[q] = (int)(k[q] - T * (u64)n);
+        });
+    }
+    drop(c, pk);
+    i64 *te_ptr = scratch<i64>(c, ntiles + 1, "te_ptr");
+    boundaries(c, P, ntiles, te_ptr, [=] __host__ __device__(i64 q) { return (i64)pt[q]; });
+    int *mx = scratch<int>(c, 8, "mx");       // running maxima: ne, nr, nc, ns, nvt, store, bytes_a, bytes_b
+    fill<int>(c, mx, 8, 0);
+    par_for(c, ntiles, [=] __host__ __device__(i64 T) { amax(&mx[0], (int)(te_ptr[T + 1] - te_ptr[T])); });
+    const int ne_max = get(c, mx);
+    const int ldl = ((ne_max + 31) / 32) * 32 + 1;
+    int els = 0;
+    while ((1 << els) < ne_max) ++els;
+    const int nsidx = nbv * nbu;
+    const bool compact = in.compact != 0;
+    if (nb > 1) {
+        if (((i64)nsidx << els) > 65536) throw Err{2, "tile too large for 16-bit contribution codes (blocks)"};
+    } else if (!compact) {
+        if ((i64)in.nuniq * ldl > 65535) throw Err{2, "tile too large for 16-bit shared-memory indices"};
+    }
+
+    // ---- 3. contributions per (tile, element) pair ----------------------------
+    i64 *cntc = scratch<i64>(c, P + 1, "cntc");
+    par_for(c, P, [=] __host__ __device__(i64 q) {
+        const int T = pt[q];
+        const i64 e = pe[q];
+        int k = 0;
+        for (int i = 0; i < nbv; ++i) k += owner[g.row(i, e)] == T;
+        cntc[q] = (i64)k * nbu;
+    });
+    i64 *coff = scratch<i64>(c, P + 1, "coff");
+    exscan(c, cntc, coff, P);
+    drop(c, cntc);
+    const i64 n_contrib = get(c, coff + P);
+    // compact mode: which distinct local values of a tile element are read at all
+    const int W = (in.nuniq + 31) / 32;
+    const int *alias = in.alias;
+    u32 *mask = nullptr;
+    i64 *sb = nullptr;
+    if (compact) {
+        mask = scratch<u32>(c, (size_t)P * W, "mask");
+        i64 *pc = scratch<i64>(c, P + 1, "popc");
+        par_for(c, P, [=] __host__ __device__(i64 q) {
+            const int T = pt[q];
+            const i64 e = pe[q];
+            u32 m[32];
+            for (int w = 0; w < W; ++w) m[w] = 0u;
+            for (int i = 0; i < nbv; ++i) {
+                if (owner[g.row(i, e)] != T) continue;
+                for (int j = 0; j < nbu; ++j) {
+                    const int u = alias[j * nbv + i];
+                    m[u >> 5] |= 1u << (u & 31);
+                }
+            }
+            i64 tot = 0;
+            for (int w = 0; w < W; ++w) {
+                mask[(size_t)q * W + w] = m[w];
+                tot += popc(m[w]);
+            }
+            pc[q] = tot;
+        });
+        if (W > 32) throw Err{1, "tile plan: more than 1024 distinct local values"};
+        sb = scratch<i64>(c, P + 1, "sbase");
+        exscan(c, pc, sb, P);
+        drop(c, pc);
+        par_for(c, ntiles, [=] __host__ __device__(i64 T) {
+            amax(&mx[5], (int)(sb[te_ptr[T + 1]] - sb[te_ptr[T]] > INT_MAX ? INT_MAX
+                               : sb[te_ptr[T + 1]] - sb[te_ptr[T]]));
+        });
+        if (get(c, mx + 5) > 65535) throw Err{2, "tile too large for 16-bit shared-memory indices (compact)"};
+    }
+
+    // ---- 4. owned rows of every tile, rank of a row inside its tile ------------
+    u64 *rk = scratch<u64>(c, NR, "rk"), *rk2 = scratch<u64>(c, NR, "rk2");
+    par_for(c, NR, [=] __host__ __device__(i64 R) {
+        const u64 o = owner[R] == INF ? (u64)ntiles : (u64)owner[R];
+        rk[R] = o * (u64)NR + (u64)R;
+    });
+    sort_keys(c, rk, rk2, NR, bits_for((u64)(ntiles + 1) * (u64)NR));
+    drop(c, rk2);
+    i64 *tr_ptr = scratch<i64>(c, ntiles + 2, "tr_ptr");
+    {
+        const u64 *k = rk;
+        boundaries(c, NR, ntiles + 1, tr_ptr, [=] __host__ __device__(i64 p) { return (i64)(k[p] / (u64)NR); });
+    }
+    int *rrank = scratch<int>(c, NR, "rrank");
+    int *rows_sorted = scratch<int>(c, NR, "rows_sorted");
+    {
+        const u64 *k = rk;
+        par_for(c, NR, [=] __host__ __device__(i64 p) {
+            const u64 T = k[p] / (u64)NR;
+            const int R = (int)(k[p] - T * (u64)NR);
+            rows_sorted[p] = R;
+            rrank[R] = (int)(p - tr_ptr[T]);
+        });
+    }
+    drop(c, rk);
+    par_for(c, ntiles, [=] __host__ __device__(i64 T) {
+        amax(&mx[1], (int)(tr_ptr[T + 1] - tr_ptr[T]));
+        const i64 ncT = coff[te_ptr[T + 1]] - coff[te_ptr[T]];
+        amax(&mx[2], (int)(ncT > INT_MAX ? INT_MAX : ncT));
+    });
+    const int nr_max = get(c, mx + 1), nc_max = get(c, mx + 2);
+    if (nr_max > 65535) throw Err{2, "more than 65535 owned rows in one tile"};
+    if (nc_max > 65535) throw Err{2, "more than 65535 contributions in one tile"};
+    const int cbits = bits_for((u64)(NC > 1 ? NC - 1 : 1));
+    const int rbits = bits_for((u64)(nr_max > 1 ? nr_max - 1 : 1));
+    const int tbits = 64 - cbits - rbits;
+    if (tbits < 1) throw Err{1, "tile plan: key does not fit 64 bits"};
+    const i64 max_tiles_batch = tbits >= 40 ? ((i64)1 << 40) : ((i64)1 << tbits);
+
+    // ---- batches ----------------------------------------------------------------
+    std::vector<i64> h_tc;                       // contributions before tile T
+    {
+        i64 *tc = scratch<i64>(c, ntiles + 1, "tc");
+        par_for(c, ntiles + 1, [=] __host__ __device__(i64 T) { tc[T] = coff[te_ptr[T]]; });
+        to_host(c, tc, (size_t)ntiles + 1, h_tc);
+        drop(c, tc);
+    }
+    const i64 cap = in.batch_cap > 0 ? in.batch_cap : ((i64)1 << 27);
+    std::vector<i64> bstart;
+    for (i64 T = 0; T < ntiles;) {
+        bstart.push_back(T);
+        i64 T2 = T + 1;
+        while (T2 < ntiles && T2 - T < max_tiles_batch && h_tc[T2 + 1] - h_tc[T] <= cap) ++T2;
+        T = T2;
+    }
+    bstart.push_back(ntiles);
+    const int nbatch = (int)bstart.size() - 1;
+    if (nbatch > SPFEM_PLAN_MAX_BATCHES) throw Err{1, "tile plan: too many batches (raise batch_cap)"};
+
+    const int sorted = in.sort_slots;
+    const int nve = in.nve, dim = in.dim, with_el = in.with_el;
+    const int *vt = in.vt;
+    const i64 ldvt = in.ldvt;
+    i64 *rowlen = scratch<i64>(c, NR + 1, "rowlen");
+    fill<i64>(c, rowlen, NR + 1, 0);
+
+    struct Pending {             // kept until indptr is known
+        int *cols; i64 nS; i64 *rowfirst; i64 nRb; i64 Ta; i64 *blob_off; i64 *bytes_a;
+    };
+    std::vector<Pending> pend;
+
+    for (int b = 0; b < nbatch; ++b) {
+        const i64 Ta = bstart[b], Tb = bstart[b + 1], nT = Tb - Ta;
+        const i64 qa = get(c, te_ptr + Ta), qb = get(c, te_ptr + Tb), nQ = qb - qa;
+        const i64 ca = h_tc[Ta], nC = h_tc[Tb] - ca;
+        const i64 ra = get(c, tr_ptr + Ta), nRb = get(c, tr_ptr + Tb) - ra;
+        SpfemPlanBatch &B = out.batches[b];
+        B.ntiles = nT;
+        // -- contributions: key (tile, row rank, column), value = shared-memory cell
+        u64 *ck = scratch<u64>(c, nC, "ck"), *ck2 = scratch<u64>(c, nC, "ck2");
+        u32 *cv = scratch<u32>(c, nC, "cv"), *cv2 = scratch<u32>(c, nC, "cv2");
+        par_for(c, nQ, [=] __host__ __device__(i64 qq) {
+            const i64 q = qa + qq;
+            const int T = pt[q];
+            const i64 e = pe[q];
+            const u32 el = (u32)(q - te_ptr[T]);
+            i64 pos = coff[q] - ca;
+            for (int i = 0; i < nbv; ++i) {
+                const int R = g.row(i, e);
+                if (owner[R] != T) continue;
+                const u64 hi = ((u64)(T - Ta) << (rbits + cbits)) | ((u64)rrank[R] << cbits);
+                for (int j = 0; j < nbu; ++j) {
+                    const int sidx = j * nbv + i;
+                    u32 code;
+                    if (nb > 1) {
+                        code = ((u32)sidx << els) | el;
+                    } else if (compact) {
+                        const int u = alias[sidx];
+                        i64 below = sb[q] - sb[te_ptr[T]];
+                        for (int w = 0; w < (u >> 5); ++w) below += popc(mask[(size_t)q * W + w]);
+                        below += popc(mask[(size_t)q * W + (u >> 5)] & ((1u << (u & 31)) - 1u));
+                        code = (u32)below;
+                    } else {
+                        code = (u32)alias[sidx] * (u32)ldl + el;
+                    }
+                    ck[pos] = hi | (u64)g.col(j, e);
+                    cv[pos] = code;
+                    ++pos;
+                }
+            }
+        });
+        sort_pairs(c, ck, ck2, cv, cv2, nC, rbits + cbits + bits_for((u64)(nT > 1 ? nT - 1 : 1)));
+        drop(c, ck2); drop(c, cv2);
+        // -- slots = runs of equal keys
+        i64 *head = scratch<i64>(c, nC + 1, "head");
+        {
+            const u64 *k = ck;
+            par_for(c, nC, [=] __host__ __device__(i64 p) { head[p] = (p == 0 || k[p] != k[p - 1]) ? 1 : 0; });
+        }
+        i64 *sid = scratch<i64>(c, nC + 1, "sid");
+        exscan(c, head, sid, nC);
+        const i64 nS = get(c, sid + nC);
+        u64 *skey = scratch<u64>(c, nS, "skey");
+        i64 *sfc = scratch<i64>(c, nS + 1, "sfc");        // first contribution of every slot
+        {
+            const u64 *k = ck;
+            par_for(c, nC, [=] __host__ __device__(i64 p) {
+                if (head[p]) { skey[sid[p]] = k[p]; sfc[sid[p]] = p; }
+                if (p == nC - 1) sfc[nS] = nC;
+            });
+        }
+        drop(c, head); drop(c, sid); drop(c, ck);
+        // -- per tile / per row structure (slots are in (tile, row rank, column) order)
+        i64 *ts_ptr = scratch<i64>(c, nT + 1, "ts_ptr");
+        boundaries(c, nS, nT, ts_ptr, [=] __host__ __device__(i64 s) { return (i64)(skey[s] >> (rbits + cbits)); });
+        i64 *rowfirst = scratch<i64>(c, nRb + 1, "rowfirst");
+        {
+            const u64 rmask = ((u64)1 << rbits) - 1;
+            boundaries(c, nS, nRb, rowfirst, [=] __host__ __device__(i64 s) {
+                const i64 T = (i64)(skey[s] >> (rbits + cbits));
+                return tr_ptr[Ta + T] - ra + (i64)((skey[s] >> cbits) & rmask);
+            });
+        }
+        par_for(c, nRb, [=] __host__ __device__(i64 r) {
+            rowlen[rows_sorted[ra + r]] = rowfirst[r + 1] - rowfirst[r];
+        });
+        int *cols = scratch<int>(c, nS, "cols");
+        {
+            const u64 cmask = ((u64)1 << cbits) - 1;
+            par_for(c, nS, [=] __host__ __device__(i64 s) { cols[s] = (int)(skey[s] & cmask); });
+        }
+        // -- order of a tile's slots in the kernel (CSR order, or by contribution count)
+        i64 *order = nullptr;                     // kernel slot position -> slot
+        if (sorted) {
+            u64 *ok = scratch<u64>(c, nS, "ok"), *ok2 = scratch<u64>(c, nS, "ok2");
+            u32 *ov = scratch<u32>(c, nS, "ov"), *ov2 = scratch<u32>(c, nS, "ov2");
+            if (nS > (i64)UINT_MAX) throw Err{1, "tile plan: batch has more than 2^32 slots"};
+            par_for(c, nS, [=] __host__ __device__(i64 s) {
+                const u64 T = skey[s] >> (rbits + cbits);
+                i64 cn = sfc[s + 1] - sfc[s];
+                if (cn > 65535) cn = 65535;
+                u64 cls;
+                if (sorted == 2) cls = 3 - ((cn > 2) + (cn > 4) + (cn > 8));
+                else cls = 65535 - (u64)cn;
+                ok[s] = (T << 16) | cls;
+                ov[s] = (u32)s;
+            });
+            sort_pairs(c, ok, ok2, ov, ov2, nS, 16 + bits_for((u64)(nT > 1 ? nT - 1 : 1)));
+            order = scratch<i64>(c, nS, "order");
+            {
+                const u32 *v = ov;
+                par_for(c, nS, [=] __host__ __device__(i64 s) { order[s] = (i64)v[s]; });
+            }
+            drop(c, ok); drop(c, ok2); drop(c, ov); drop(c, ov2);
+        }
+        // start of every kernel slot's contributions inside its tile
+        i64 *kcnt = scratch<i64>(c, nS + 1, "kcnt");
+        par_for(c, nS, [=] __host__ __device__(i64 s) {
+            const i64 so = order ? order[s] : s;
+            kcnt[s] = sfc[so + 1] - sfc[so];
+        });
+        i64 *kofs = scratch<i64>(c, nS + 1, "kofs");
+        exscan(c, kcnt, kofs, nS);
+        drop(c, kcnt);
+        // -- tile-local vertex numbering: unique (tile, vertex) keys
+        const i64 nVK = nQ * nve;
+        u64 *vk = scratch<u64>(c, nVK, "vk"), *vk2 = scratch<u64>(c, nVK, "vk2");
+        par_for(c, nVK, [=] __host__ __device__(i64 w) {
+            const int r = (int)(w / nQ);
+            const i64 q = qa + (w - (i64)r * nQ);
+            vk[w] = ((u64)(pt[q] - Ta) << 32) | (u64)(u32)vt[(i64)r * ldvt + pe[q]];
+        });
+        sort_keys(c, vk, vk2, nVK, 32 + bits_for((u64)(nT > 1 ? nT - 1 : 1)));
+        drop(c, vk2);
+        i64 *vh = scratch<i64>(c, nVK + 1, "vh");
+        {
+            const u64 *k = vk;
+            par_for(c, nVK, [=] __host__ __device__(i64 p) { vh[p] = (p == 0 || k[p] != k[p - 1]) ? 1 : 0; });
+        }
+        i64 *vidx = scratch<i64>(c, nVK + 1, "vidx");
+        exscan(c, vh, vidx, nVK);
+        const i64 nU = get(c, vidx + nVK);
+        u64 *uv = scratch<u64>(c, nU, "uv");
+        {
+            const u64 *k = vk;
+            par_for(c, nVK, [=] __host__ __device__(i64 p) { if (vh[p]) uv[vidx[p]] = k[p]; });
+        }
+        drop(c, vh); drop(c, vidx); drop(c, vk);
+        i64 *vptr = keep<i64>(c, nT + 1, "out:vptr");
+        boundaries(c, nU, nT, vptr, [=] __host__ __device__(i64 p) { return (i64)(uv[p] >> 32); });
+        int *vid = keep<int>(c, nU, "out:vid");
+        par_for(c, nU, [=] __host__ __device__(i64 p) { vid[p] = (int)(uv[p] & 0xffffffffull); });
+        // -- section sizes, blob offsets, descriptors
+        i64 *tbytes = scratch<i64>(c, nT + 1, "tbytes");
+        i64 *bytes_a = scratch<i64>(c, nT, "bytes_a");
+        int *desc = keep<int>(c, 16 * nT, "out:desc");
+        par_for(c, nT, [=] __host__ __device__(i64 t) {
+            const i64 T = Ta + t;
+            const i64 ne = te_ptr[T + 1] - te_ptr[T], ne_pad = (ne + 7) / 8 * 8;
+            const i64 nvt = vptr[t + 1] - vptr[t], nvt_pad = (nvt + 1) / 2 * 2;
+            const i64 nr = tr_ptr[T + 1] - tr_ptr[T];
+            const i64 ns = ts_ptr[t + 1] - ts_ptr[t];
+            const i64 nc = kofs[ts_ptr[t + 1]] - kofs[ts_ptr[t]];
+            const i64 off_el = 2 * nve * ne_pad;
+            const i64 off_pc = pad16(off_el + (with_el ? 4 * ne_pad : 0));
+            i64 ba = off_pc + 8 * dim * nvt_pad;
+            i64 off_base = 0;
+            if (compact) { off_base = ba; ba = pad16(off_base + (1 + W) * 4 * ne_pad); }
+            ba = pad16(ba);
+            const i64 off_rinfo = pad16(8 * nr);
+            const i64 off_soff = off_rinfo + pad16(4 * nr);
+            const i64 off_srow = off_soff + pad16(2 * (ns + 1));
+            const i64 off_spos = off_srow + pad16(2 * ns);
+            const i64 off_contrib = off_spos + (sorted ? pad16(2 * ns) : 0);
+            const i64 bb = off_contrib + pad16(2 * (nc + 1));
+            bytes_a[t] = ba;
+            tbytes[t] = ba + bb;
+            int *d = desc + 16 * t;
+            d[1] = (int)ba; d[2] = (int)bb; d[3] = (int)ne; d[4] = (int)ne_pad; d[5] = (int)ns;
+            d[6] = (int)off_soff; d[7] = (int)off_srow; d[8] = (int)off_contrib; d[9] = (int)nr;
+            d[10] = (int)nc; d[11] = (int)nvt_pad; d[12] = (int)off_pc;
+            d[13] = with_el ? (int)off_el : -1; d[14] = (int)nvt; d[15] = (int)off_base;
+            amax(&mx[3], (int)(ns > INT_MAX ? INT_MAX : ns));
+            amax(&mx[4], (int)(nvt > INT_MAX ? INT_MAX : nvt));
+            amax(&mx[6], (int)ba);
+            amax(&mx[7], (int)(bb > INT_MAX ? INT_MAX : bb));
+        });
+        i64 *blob_off = scratch<i64>(c, nT + 1, "blob_off");
+        exscan(c, tbytes, blob_off, nT);
+        drop(c, tbytes);
+        const i64 blob_bytes = get(c, blob_off + nT);
+        if (get(c, mx + 3) > 65535) throw Err{2, "more than 65535 slots in one tile"};
+        if (get(c, mx + 4) > 65535) throw Err{2, "more than 65535 vertices in one tile"};
+        if (blob_bytes / 16 > INT_MAX) throw Err{1, "tile plan: batch blob exceeds 32 GB (lower batch_cap)"};
+        unsigned char *blob = keep<unsigned char>(c, blob_bytes, "out:blob");
+        if (c.dev) PLAN_CK(cudaMemsetAsync(blob, 0, blob_bytes, c.st));
+        else memset(blob, 0, blob_bytes);
+        par_for(c, nT, [=] __host__ __device__(i64 t) { desc[16 * t] = (int)(blob_off[t] / 16); });
+        // -- section A: tile-local vertex ids, element ids, packed-value masks
+        par_for(c, nQ, [=] __host__ __device__(i64 qq) {
+            const i64 q = qa + qq;
+            const i64 T = pt[q], t = T - Ta;
+            const i64 e = pe[q];
+            const i64 el = q - te_ptr[T];
+            const int *d = desc + 16 * t;
+            unsigned char *A = blob + blob_off[t];
+            u16 *lv = (u16 *)A;
+            const i64 ne_pad = d[4];
+            const u64 *seg = uv + vptr[t];
+            const i64 nvt = vptr[t + 1] - vptr[t];
+            for (int r = 0; r < nve; ++r) {
+                const u64 key = ((u64)t << 32) | (u64)(u32)vt[(i64)r * ldvt + e];
+                i64 lo = 0, hi = nvt;
+                while (lo < hi) { const i64 m = (lo + hi) >> 1; if (seg[m] < key) lo = m + 1; else hi = m; }
+                lv[(i64)r * ne_pad + el] = (u16)lo;
+            }
+            if (with_el) ((int *)(A + d[13]))[el] = (int)e;
+            if (compact) {
+                int *base = (int *)(A + d[15]);
+                base[el] = (int)(sb[q] - sb[te_ptr[T]]);
+                u32 *mw = (u32 *)(base + ne_pad);
+                for (int w = 0; w < W; ++w) mw[(i64)w * ne_pad + el] = mask[(size_t)q * W + w];
+            }
+        });
+        drop(c, uv);
+        // -- section B: rows, slots, contributions
+        par_for(c, nRb, [=] __host__ __device__(i64 r) {
+            // tile of the row: binary search in tr_ptr
+            i64 lo = Ta, hi = Tb;
+            while (hi - lo > 1) { const i64 m = (lo + hi) >> 1; if (tr_ptr[m] - ra <= r) lo = m; else hi = m; }
+            const i64 t = lo - Ta;
+            const i64 rr = r - (tr_ptr[lo] - ra);
+            const int *d = desc + 16 * t;
+            unsigned char *Bs = blob + blob_off[t] + d[1];
+            const i64 L = rowfirst[r + 1] - rowfirst[r];
+            const i64 sfirst = rowfirst[r] - ts_ptr[t];
+            int *rinfo = (int *)(Bs + pad16(8 * (i64)d[9]));
+            rinfo[rr] = (int)(u32)((u64)(sfirst & 0xffff) | ((u64)L << 16));
+        });
+        par_for(c, nS, [=] __host__ __device__(i64 s) {
+            const i64 so = order ? order[s] : s;
+            const i64 t = (i64)(skey[so] >> (rbits + cbits));
+            const int *d = desc + 16 * t;
+            unsigned char *Bs = blob + blob_off[t] + d[1];
+            const i64 sl = s - ts_ptr[t];
+            const i64 ns = d[5];
+            const u64 rmask = ((u64)1 << rbits) - 1;
+            const i64 rr = (i64)((skey[so] >> cbits) & rmask);
+            u16 *soff = (u16 *)(Bs + d[6]);
+            u16 *srow = (u16 *)(Bs + d[7]);
+            const i64 k0 = kofs[s] - kofs[ts_ptr[t]];
+            soff[sl] = (u16)k0;
+            if (sl == ns - 1) soff[ns] = (u16)d[10];
+            srow[sl] = (u16)rr;
+            if (sorted) {
+                u16 *spos = (u16 *)(Bs + d[7] + pad16(2 * ns));
+                const i64 rb = tr_ptr[Ta + t] - ra + rr;
+                spos[sl] = (u16)(so - rowfirst[rb]);
+            }
+            u16 *cb = (u16 *)(Bs + d[8]);
+            const i64 c0 = sfc[so], c1 = sfc[so + 1];
+            for (i64 k = c0; k < c1; ++k) cb[k0 + (k - c0)] = (u16)cv[k];
+        });
+        drop(c, cv); drop(c, skey); drop(c, sfc); drop(c, kofs);
+        if (order) drop(c, order);
+        drop(c, ts_ptr);
+        B.desc = desc; B.blob = blob; B.vid = vid; B.vptr = vptr;
+        B.blob_bytes = blob_bytes; B.nvid = nU; B.first_tile = Ta; B.nslots = nS;
+        pend.push_back(Pending{cols, nS, rowfirst, nRb, Ta, blob_off, bytes_a});
+    }
+
+    // ---- 6. indptr, indices, row positions in the blobs ---------------------------
+    i64 *iptr = scratch<i64>(c, NR + 1, "iptr");
+    exscan(c, rowlen, iptr, NR);
+    const i64 nnz_s = get(c, iptr + NR);
+    const i64 nnz = nnz_s * nb;
+    const int ib = in.index_bytes == 8 ? 8 : 4;
+    if (ib == 4 && nnz > INT_MAX) throw Err{1, "tile plan: nnz exceeds int32 (index_bytes must be 8)"};
+    void *indptr = raw_alloc(c, (size_t)(in.nrows + 1) * ib, "out:indptr");
+    void *indices = in.coldof ? raw_alloc(c, (size_t)(nnz > 0 ? nnz : 1) * ib, "out:indices") : nullptr;
+    const i64 nrows_full = in.nrows;
+    par_for(c, NR + 1, [=] __host__ __device__(i64 R) {
+        if (R == NR) {
+            if (ib == 4) ((int *)indptr)[nrows_full] = (int)nnz; else ((i64 *)indptr)[nrows_full] = nnz;
+            return;
+        }
+        const i64 L = rowlen[R];
+        for (int a = 0; a < bsv; ++a) {
+            const i64 v = nb * iptr[R] + (i64)a * bsu * L;
+            if (ib == 4) ((int *)indptr)[R * bsv + a] = (int)v; else ((i64 *)indptr)[R * bsv + a] = v;
+        }
+    });
+    for (int b = 0; b < nbatch; ++b) {
+        const Pending &pd = pend[b];
+        const SpfemPlanBatch &B = out.batches[b];
+        const i64 Ta = pd.Ta, Tb = Ta + B.ntiles;
+        const i64 ra = get(c, tr_ptr + Ta);
+        const int *desc = (const int *)B.desc;
+        unsigned char *blob = (unsigned char *)B.blob;
+        const i64 *rowfirst = pd.rowfirst, *blob_off = pd.blob_off;
+        const int *cols = pd.cols;
+        const i64 nRb = pd.nRb;
+        par_for(c, nRb, [=] __host__ __device__(i64 r) {
+            i64 lo = Ta, hi = Tb;
+            while (hi - lo > 1) { const i64 m = (lo + hi) >> 1; if (tr_ptr[m] - ra <= r) lo = m; else hi = m; }
+            const i64 t = lo - Ta;
+            const i64 rr = r - (tr_ptr[lo] - ra);
+            const int R = rows_sorted[ra + r];
+            const i64 base = nb * iptr[R];
+            i64 *rbase = (i64 *)(blob + blob_off[t] + desc[16 * t + 1]);
+            rbase[rr] = base;
+            if (!indices) return;
+            const i64 L = rowfirst[r + 1] - rowfirst[r];
+            for (i64 k = 0; k < L; ++k) {
+                const i64 C = cols[rowfirst[r] + k];
+                for (int a = 0; a < bsv; ++a)
+                    for (int bb = 0; bb < bsu; ++bb) {
+                        const i64 pos = base + (i64)a * bsu * L + bsu * k + bb;
+                        if (ib == 4) ((int *)indices)[pos] = (int)(C * bsu + bb);
+                        else ((i64 *)indices)[pos] = C * bsu + bb;
+                    }
+            }
+        });
+    }
+    out.nnz = nnz;
+    out.indptr = indptr;
+    out.indices = indices;
+    out.nbatches = nbatch;
+    out.ldl = ldl;
+    out.els = els;
+    out.bsv = bsv; out.bsu = bsu;
+    out.ntiles = ntiles;
+    out.n_pairs = P;
+    out.n_contrib = n_contrib;
+    out.max_ne = ne_max;
+    out.max_nr = nr_max;
+    out.max_ns = get(c, mx + 3);
+    out.max_store = get(c, mx + 5);
+    out.max_bytes_a = get(c, mx + 6);
+    out.max_bytes_b = get(c, mx + 7);
+    return 0;
+}
+
+} // namespace spfem_plan
+
+extern "C" {
+
+int spfem_tileplan_build(const SpfemPlanIn *in, SpfemPlanOut *out, spfem_alloc_fn alloc,
+                         spfem_free_fn release, void *alloc_ctx, int on_device, void *stream)
+{
+    using namespace spfem_plan;
+    if (!in || !out || !alloc || !release) {
+        spfem_set_error_("spfem_tileplan_build: null argument");
+        return 1;
+    }
+    Ctx c;
+    c.dev = on_device != 0;
+    c.st = (cudaStream_t)stream;
+    c.alloc = alloc; c.release = release; c.actx = alloc_ctx;
+    int rc = 0;
+    try {
+        rc = build(*in, *out, c);
+    } catch (const Err &e) {
+        spfem_set_error_(e.msg);
+        rc = e.code;
+    } catch (const std::exception &e) {
+        spfem_set_error_(std::string("spfem_tileplan_build: ") + e.what());
+        rc = 1;
+    }
+    drop_all(c);
+    return rc;
+}
+
+int spfem_tileplan_fill_coords(const int *desc, unsigned char *blob, const int *vid,
+                               const long long *vptr, long long ntiles, const double *p,
+                               long long ldp, int dim, int on_device, void *stream)
+{
+    using namespace spfem_plan;
+    Ctx c;
+    c.dev = on_device != 0;
+    c.st = (cudaStream_t)stream;
+    c.alloc = nullptr; c.release = nullptr; c.actx = nullptr;
+    if (ntiles <= 0) return 0;
+    try {
+        const i64 total = get(c, vptr + ntiles);
+        // one thread per tile vertex; the tile is found by binary search in vptr
+        par_for(c, total, [=] __host__ __device__(i64 w) {
+            i64 lo = 0, hi = ntiles;
+            while (hi - lo > 1) { const i64 m = (lo + hi) >> 1; if (vptr[m] <= w) lo = m; else hi = m; }
+            const int *d = desc + 16 * lo;
+            double *pc = (double *)(blob + (i64)d[0] * 16 + d[12]);
+            const i64 vl = w - vptr[lo];
+            const i64 v = vid[w];
+            if (dim == 2) {
+                pc[2 * vl] = p[v];
+                pc[2 * vl + 1] = p[ldp + v];
+            } else {
+                for (int k = 0; k < dim; ++k) pc[(i64)k * d[11] + vl] = p[(i64)k * ldp + v];
+            }
+        });
+    } catch (const Err &e) {
+        spfem_set_error_(e.msg);
+        return e.code;
+    }
+    return 0;
+}
+
+} // extern "C"

@@ -1,7 +1,9 @@
 # -*- coding: utf-8 -*-
-"""Tile plan of the fused kernel checked on the CPU: a NumPy emulation of the
-kernel's phase B over the plan must reproduce the reference result and write
-every CSR value exactly once."""
+"""Native pattern + tile-plan builder (csrc/spfem_plan.cu) checked on the CPU:
+``on_device = 0`` runs the same code on host pointers.  The CSR structure must
+equal SciPy's ``coo_matrix(...).tocsr()`` bit for bit, and a NumPy emulation of
+the kernel's phase B over the blobs must reproduce the reference result and
+write every CSR value exactly once."""
 import numpy as np
 import pytest
 import torch
@@ -10,7 +12,7 @@ import cases
 import util
 import hostemu
 from spfem_b200.tileplan import (build_tile_plan, emulate, check_vertex_table,
-                                 fill_coordinates, bank_conflicts)
+                                 fill_coordinates, TileTooLarge)
 
 
 def _morton(mesh):
@@ -26,131 +28,155 @@ def _morton(mesh):
     return np.argsort(key, kind="stable")
 
 
-def _pattern_numpy(rowdof, coldof, ncols):
-    """Host restatement of spfem_pattern_sort/fill (stable sort by (row, col))."""
-    nv, n = rowdof.shape
-    nu = coldof.shape[0]
-    ids = np.arange(nu * nv * n)
-    blk, k = ids // n, ids % n
-    j, i = blk // nv, blk % nv
-    keys = rowdof[i, k].astype(np.int64) * ncols + coldof[j, k]
-    order = np.argsort(keys, kind="stable")
-    ks = keys[order]
-    head = np.ones(len(ks), dtype=bool)
-    head[1:] = ks[1:] != ks[:-1]
-    cptr = np.concatenate((np.nonzero(head)[0], [len(ks)]))
-    return ks[head], cptr, order
+def _ut(spec, bsv, bsu):
+    """Distinct-value ids of the bsv x bsu block of every scalar entry (what
+    codegen emits as SPFEM_UT)."""
+    nbv, nbu = spec.n_rows // bsv, spec.n_cols // bsu
+    ut = np.zeros((nbu * nbv, bsv * bsu), dtype=np.int64)
+    for j in range(nbu):
+        for i in range(nbv):
+            for a in range(bsv):
+                for b in range(bsu):
+                    ut[j * nbv + i, a * bsu + b] = spec.alias[(bsu * j + b) * spec.n_rows
+                                                              + (bsv * i + a)]
+    return ut
+
+
+def _setup(case_or_asm, form):
+    asm = case_or_asm
+    plan = asm.plan_iasm(form)
+    perm = _morton(asm.mesh)
+    local = hostemu.run_interior(asm, plan)[:, perm]
+    tv = np.ascontiguousarray(asm.dofnum_v.t_dof[:, perm], dtype=np.int32)
+    tu = np.ascontiguousarray(asm.dofnum_u.t_dof[:, perm], dtype=np.int32)
+    vt = np.ascontiguousarray(asm.mesh.t[:, perm], dtype=np.int32)
+    uniq = np.zeros((plan.spec.n_unique, local.shape[1]))
+    uniq[plan.spec.alias, :] = local
+    assert np.array_equal(uniq[plan.spec.alias, :], local)   # aliases really are equal
+    return plan, tv, tu, vt, uniq
+
+
+def _build(asm, plan, tv, tu, vt, E, **kw):
+    spec = plan.spec
+    tp = build_tile_plan(torch, torch.from_numpy(tv),
+                         torch.from_numpy(tu) if plan.bilinear else None,
+                         torch.from_numpy(vt), asm.dofnum_v.N,
+                         asm.dofnum_u.N if plan.bilinear else 1, E,
+                         spec.alias, spec.n_unique, asm.mesh.p.shape[0],
+                         with_el=True, **kw)
+    fill_coordinates(tp, torch.from_numpy(np.ascontiguousarray(asm.mesh.p)))
+    return tp
+
+
+VARIANTS = [dict(), dict(sort_slots=1), dict(sort_slots=2), dict(compact=True),
+            dict(compact=True, sort_slots=1), dict(batch_cap=3000),
+            dict(batch_cap=1500, sort_slots=1)]
 
 
 @pytest.mark.parametrize("name,E", [("trip1_lap", 64), ("trip1_lap_r6", 1024),
                                     ("trip2_lap", 32), ("stokes_b", 16),
-                                    ("vecp2_elasticity", 50), ("tetp2_lap", 24)])
-def test_tile_plan_reproduces_assembly(name, E):
+                                    ("vecp2_elasticity", 50), ("tetp2_lap", 24),
+                                    ("vectetp1_mixed", 20)])
+def test_native_plan_reproduces_assembly(name, E):
     case = cases.BY_NAME[name]
     asm = util.assembler_for(case)
-    plan = asm.plan_iasm(case.form)
-    perm = _morton(asm.mesh)
-    local = hostemu.run_interior(asm, plan)[:, perm]
-    tv, tu = asm.dofnum_v.t_dof[:, perm], asm.dofnum_u.t_dof[:, perm]
-    n = tv.shape[1]
-    ukeys, cptr, contrib = _pattern_numpy(tv, tu, asm.dofnum_u.N)
-    nnz = len(ukeys)
-    rows = ukeys // asm.dofnum_u.N
-    indptr = np.searchsorted(rows, np.arange(asm.dofnum_v.N + 1))
-    vt = np.ascontiguousarray(asm.mesh.t[:, perm], dtype=np.int32)
-    tp = build_tile_plan(torch, torch.from_numpy(indptr), torch.from_numpy(cptr),
-                         torch.from_numpy(contrib), n, plan.spec.n_entries, E,
-                         torch.from_numpy(vt), dim=asm.mesh.p.shape[0],
-                         alias=plan.spec.alias, schedule="full")
-    fill_coordinates(tp, torch.from_numpy(np.ascontiguousarray(asm.mesh.p)))
-    assert check_vertex_table(tp, vt, asm.mesh.p)
-    # shared-memory image of the tile kernel: one row per distinct local value
-    uniq = np.zeros((plan.spec.n_unique, local.shape[1]))
-    uniq[plan.spec.alias, :] = local
-    assert np.array_equal(uniq[plan.spec.alias, :], local)   # aliases really are equal
-    values, written = emulate(tp, uniq, nnz)
-    assert np.all(written == 1)
+    plan, tv, tu, vt, uniq = _setup(asm, case.form)
     ref = util.golden(case)
-    assert nnz == ref.nnz
     scale = np.abs(ref.data).max()
-    assert np.max(np.abs(values - ref.data)) <= 1e-12 * scale
-    assert 1.0 <= tp["halo_factor"] < 3.0
-    # the scheduled contribution lists are bank-conflict free
-    assert tp["scheduled_rows"] > 0.9    # very long rows fall back to their CSR order
-    if tp["scheduled_rows"] > 0.99:
-        assert bank_conflicts(tp) < 1.05
-    assert tp["list_growth"] < 2.5
-    tp0 = build_tile_plan(torch, torch.from_numpy(indptr), torch.from_numpy(cptr),
-                          torch.from_numpy(contrib), n, plan.spec.n_entries, E,
-                          torch.from_numpy(vt), dim=asm.mesh.p.shape[0],
-                          alias=plan.spec.alias, schedule=False)
-    v0, w0 = emulate(tp0, uniq, nnz)
-    assert np.all(w0 == 1) and np.max(np.abs(v0 - ref.data)) <= 1e-12 * scale
-    assert bank_conflicts(tp0) > 1.5
-    # default: contributions re-ordered inside their slots only (no list growth)
-    tp1 = build_tile_plan(torch, torch.from_numpy(indptr), torch.from_numpy(cptr),
-                          torch.from_numpy(contrib), n, plan.spec.n_entries, E,
-                          torch.from_numpy(vt), dim=asm.mesh.p.shape[0],
-                          alias=plan.spec.alias, schedule="inslot")
-    v1, w1 = emulate(tp1, uniq, nnz)
-    assert np.all(w1 == 1) and np.max(np.abs(v1 - ref.data)) <= 1e-12 * scale
-    assert tp1["list_growth"] < 1.06
-    # slot-parallel section B (one thread per CSR slot)
-    tp2 = build_tile_plan(torch, torch.from_numpy(indptr), torch.from_numpy(cptr),
-                          torch.from_numpy(contrib), n, plan.spec.n_entries, E,
-                          torch.from_numpy(vt), dim=asm.mesh.p.shape[0],
-                          alias=plan.spec.alias, mode="slots")
-    v2, w2 = emulate(tp2, uniq, nnz)
-    assert np.all(w2 == 1) and np.max(np.abs(v2 - ref.data)) <= 1e-12 * scale
-    assert tp2["halo_factor"] == tp1["halo_factor"]
-    # ... with packed storage of the halo elements' values
-    tp3 = build_tile_plan(torch, torch.from_numpy(indptr), torch.from_numpy(cptr),
-                          torch.from_numpy(contrib), n, plan.spec.n_entries, E,
-                          torch.from_numpy(vt), dim=asm.mesh.p.shape[0],
-                          alias=plan.spec.alias, mode="compact")
-    v3, w3 = emulate(tp3, uniq, nnz)
-    assert np.all(w3 == 1) and np.max(np.abs(v3 - ref.data)) <= 1e-12 * scale
-    assert tp3["max_store"] < plan.spec.n_unique * tp3["ldl"]
-    print(name, "dense", plan.spec.n_unique * tp3["ldl"], "compact", tp3["max_store"])
-    # ... and the slots of a tile ordered by their number of contributions
-    for md, srt in (("slots", True), ("compact", True), ("slots", "bucket")):
-        tp4 = build_tile_plan(torch, torch.from_numpy(indptr), torch.from_numpy(cptr),
-                              torch.from_numpy(contrib), n, plan.spec.n_entries, E,
-                              torch.from_numpy(vt), dim=asm.mesh.p.shape[0],
-                              alias=plan.spec.alias, mode=md, sort_slots=srt)
-        v4, w4 = emulate(tp4, uniq, nnz)
-        assert np.all(w4 == 1) and np.max(np.abs(v4 - ref.data)) <= 1e-12 * scale
+    spec = plan.spec
+    blocks = [(1, 1)]
+    if spec.ncu * spec.ncv > 1:
+        blocks.append((spec.ncv, spec.ncu))
+    for bsv, bsu in blocks:
+        for kw in VARIANTS:
+            if kw.get("compact") and bsv * bsu > 1:
+                continue
+            tp = _build(asm, plan, tv, tu, vt, E, bsv=bsv, bsu=bsu, **kw)
+            assert (tp["bsv"], tp["bsu"]) == (bsv, bsu)
+            if "batch_cap" in kw and tp["n_contrib"] > 2 * kw["batch_cap"]:
+                assert len(tp["batches"]) > 1
+            assert check_vertex_table(tp, vt, asm.mesh.p)
+            # the CSR structure is SciPy's, bit for bit
+            assert tp["nnz"] == ref.nnz
+            assert np.array_equal(tp["indptr"].numpy(), ref.indptr)
+            assert np.array_equal(tp["indices"].numpy(), ref.indices)
+            values, written = emulate(tp, uniq, _ut(spec, bsv, bsu))
+            assert np.all(written == 1), (bsv, bsu, kw)
+            assert np.max(np.abs(values - ref.data)) <= 1e-12 * scale, (bsv, bsu, kw)
+            assert 1.0 <= tp["halo_factor"] < 4.0
+            if kw.get("compact"):
+                assert tp["max_store"] <= spec.n_unique * tp["ldl"]
+
+
+def test_native_plan_int64_indices_and_linear_form():
+    case = cases.BY_NAME["trip2_lap"]
+    asm = util.assembler_for(case)
+    plan, tv, tu, vt, uniq = _setup(asm, case.form)
+    ref = util.golden(case)
+    tp = _build(asm, plan, tv, tu, vt, 32, index_bytes=8)
+    assert tp["indptr"].dtype == torch.int64 and tp["indices"].dtype == torch.int64
+    assert np.array_equal(tp["indptr"].numpy(), ref.indptr)
+    assert np.array_equal(tp["indices"].numpy(), ref.indices)
+    # a load vector = one slot per row
+    asm1 = util.assembler_for(cases.BY_NAME["trip1_lap"])
+    plan, tv, tu, vt, uniq = _setup(asm1, cases.load1)
+    tp = _build(asm1, plan, tv, tu, vt, 64)
+    assert tp["indices"] is None
+    values, written = emulate(tp, uniq)
+    assert np.all(written == 1)
+    ref = hostemu.iasm(asm1, cases.load1)
+    assert np.max(np.abs(values - ref)) <= 1e-12 * np.abs(ref).max()
+
+
+def test_native_plan_row_mask():
+    """Rows that are not assembled here (another rank owns them) get no slots."""
+    case = cases.BY_NAME["trip2_lap"]
+    asm = util.assembler_for(case)
+    plan, tv, tu, vt, uniq = _setup(asm, case.form)
+    ref = util.golden(case)
+    N = asm.dofnum_v.N
+    mask = np.ones(N, dtype=np.uint8)
+    mask[::3] = 0
+    tp = _build(asm, plan, tv, tu, vt, 32, row_mask=torch.from_numpy(mask))
+    indptr = tp["indptr"].numpy()
+    lens = np.diff(indptr)
+    assert np.all(lens[mask == 0] == 0)
+    assert np.array_equal(lens[mask == 1], np.diff(ref.indptr)[mask == 1])
+    values, written = emulate(tp, uniq)
+    assert np.all(written == 1)
+    keep = np.repeat(mask == 1, np.diff(ref.indptr))
+    assert np.array_equal(tp["indices"].numpy(), ref.indices[keep])
+    assert np.max(np.abs(values - ref.data[keep])) <= 1e-12 * np.abs(ref.data).max()
+
+
+def test_native_plan_tile_too_large():
+    import spfem_b200 as sp
+    from spfem_b200.assembly import AssemblerElement
+    m = sp.MeshTet()
+    m.refine(3)
+    asm = AssemblerElement(m, sp.ElementTetP2())
+    plan, tv, tu, vt, uniq = _setup(asm, cases.lap3)
+    with pytest.raises(TileTooLarge):
+        _build(asm, plan, tv, tu, vt, 4096)
 
 
 @pytest.mark.parametrize("ename", ["TriP1", "TriP2"])
-def test_tile_plan_on_irregular_mesh(ename):
+def test_native_plan_on_irregular_mesh(ename):
     """A mesh with a high-valence vertex (wheel of 40 triangles, refined and
     perturbed): rows of very different lengths, slots with 1 ... 40
-    contributions, through every slot-parallel variant of the plan."""
-    import spfem_b200 as sp
+    contributions, through every variant of the plan."""
     from spfem_b200.assembly import AssemblerElement
     from test_fanplan import _wheel_mesh
     mesh = _wheel_mesh(40, 1)
     asm = AssemblerElement(mesh, util.element(ename, 1))
-    plan = asm.plan_iasm(cases.lap_mass if hasattr(cases, "lap_mass") else cases.lap2)
-    ref = hostemu.iasm(asm, cases.lap_mass if hasattr(cases, "lap_mass") else cases.lap2)
-    perm = _morton(mesh)
-    local = hostemu.run_interior(asm, plan)[:, perm]
-    tv, tu = asm.dofnum_v.t_dof[:, perm], asm.dofnum_u.t_dof[:, perm]
-    n = tv.shape[1]
-    ukeys, cptr, contrib = _pattern_numpy(tv, tu, asm.dofnum_u.N)
-    nnz = len(ukeys)
-    indptr = np.searchsorted(ukeys // asm.dofnum_u.N, np.arange(asm.dofnum_v.N + 1))
-    vt = np.ascontiguousarray(mesh.t[:, perm], dtype=np.int32)
-    uniq = np.zeros((plan.spec.n_unique, n))
-    uniq[plan.spec.alias, :] = local
+    form = cases.lap_mass if hasattr(cases, "lap_mass") else cases.lap2
+    plan, tv, tu, vt, uniq = _setup(asm, form)
+    ref = hostemu.iasm(asm, form)
     scale = np.abs(ref.data).max()
-    for md, srt in (("slots", False), ("compact", False), ("slots", True), ("compact", True),
-                    ("slots", "bucket"), ("rows", False)):
-        tp = build_tile_plan(torch, torch.from_numpy(indptr), torch.from_numpy(cptr),
-                             torch.from_numpy(contrib), n, plan.spec.n_entries, 32,
-                             torch.from_numpy(vt), dim=2, alias=plan.spec.alias,
-                             mode=md, sort_slots=srt)
-        v, w = emulate(tp, uniq, nnz)
-        assert np.all(w == 1), (md, srt)
-        assert np.max(np.abs(v - ref.data)) <= 1e-12 * scale, (md, srt)
+    for kw in VARIANTS:
+        tp = _build(asm, plan, tv, tu, vt, 32, **kw)
+        assert np.array_equal(tp["indptr"].numpy(), ref.indptr)
+        assert np.array_equal(tp["indices"].numpy(), ref.indices)
+        v, w = emulate(tp, uniq)
+        assert np.all(w == 1), kw
+        assert np.max(np.abs(v - ref.data)) <= 1e-12 * scale, kw
