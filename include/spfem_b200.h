@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define SPFEM_ABI_VERSION 1
+#define SPFEM_ABI_VERSION 2
 
 /* Argument block of every generated kernel (see spfem_b200/codegen.py; the
  * generated source declares the identical struct). */
@@ -46,11 +46,34 @@ typedef struct SpfemArgs {
     const int *e2;
     const int *lf1;          /* facet kernels: local facet index inside e1        */
     double *out;             /* local entries out[entry*ldo + k*ldk]              */
-    long long ldk;           /* 1: entry-major planes; Nu*Nv (with ldo = 1):       */
-                             /* element-major local matrices                        */
-    const int *perm;         /* optional: entry id -> position in slot-sorted order */
-                             /* (out[perm[entry*ldo + k]]), see spfem_reduce_sorted */
+    long long ldk;           /* stride between items inside an entry plane (1)     */
 } SpfemArgs;
+
+/* Argument block of the fused tile kernel `<name>_tile` (codegen.TILE_KERNEL);
+ * one launch per SpfemPlanBatch of the tile plan (see below). */
+typedef struct SpfemTileArgs {
+    SpfemArgs base;
+    const int *desc;             /* SpfemPlanBatch.desc                              */
+    const unsigned char *blob;   /* SpfemPlanBatch.blob                              */
+    double *values;              /* CSR values                                        */
+    int ldl;                     /* SpfemPlanOut.ldl                                  */
+    int max_a, max_b;            /* SpfemPlanOut.max_bytes_a / max_bytes_b            */
+    int compact;                 /* SpfemPlanIn.compact                               */
+    int store;                   /* doubles of shared memory for the local values:
+                                    nuniq * ldl, or max_store + 2 (compact)           */
+    int prefetch;                /* L2 prefetch distance in tiles (0 = off)           */
+    int sorted;                  /* SpfemPlanIn.sort_slots != 0                       */
+    int els;                     /* SpfemPlanOut.els                                  */
+} SpfemTileArgs;
+
+/* Argument block of the vertex-fan kernels `<name>_fan*` (codegen.FAN_KERNEL). */
+typedef struct SpfemFanArgs {
+    SpfemArgs base;
+    const int *desc;             /* 8 ints per tile: offset/16, bytes A, bytes B, rows, slots, vertices */
+    const unsigned char *blob;
+    double *values;
+    int max_a, max_b, max_ns, prefetch;
+} SpfemFanArgs;
 
 int         spfem_abi_version(void);
 const char *spfem_last_error(void);
@@ -71,8 +94,7 @@ int spfem_module_get_kernel(void *module, const char *name, void **kernel);
 /* Launches a generated kernel: one thread per item, `block` threads per CTA. */
 int spfem_launch(void *kernel, const SpfemArgs *args, int block, void *stream);
 /* Launches the fused tile kernel `<name>_tile` of a generated module: `args`
- * points to a SpfemTileArgs block (declared in the generated source and in
- * spfem_b200/_lib.py), one CTA per tile, `smem_bytes` of dynamic shared memory
+ * points to a SpfemTileArgs / SpfemFanArgs block, one CTA per tile, `smem_bytes` of dynamic shared memory
  * (opt-in above 48 KB is handled here).                                       */
 int spfem_launch_tiled(void *kernel, const void *args, unsigned grid, unsigned block,
                        size_t smem_bytes, void *stream);
@@ -115,49 +137,6 @@ int spfem_pattern_fill(const void *d_ws, long long n_entries,
 int spfem_reduce(const double *d_local, const int *d_cptr,
                  const int *d_contrib, long long nslots, double *d_values,
                  void *stream);
-
-/* Row-ordered variant: thread i handles CSR row d_row_order[i] and sums every slot
- * of that row (slots d_indptr[r] .. d_indptr[r+1]).  With the rows visited in the
- * spatial (Morton) order of the elements, neighbouring threads gather from the same
- * 32-byte sectors of d_local and the L2 hit rate goes up.                         */
-int spfem_reduce_rows(const double *d_local, const int *d_indptr, const int *d_cptr,
-                      const int *d_contrib, const int *d_row_order, long long nrows,
-                      double *d_values, void *stream);
-
-/* Re-ordered variant: the caller lists the CSR slots in any order it likes
- * (spfem_b200/engine.py: rows in the spatial order of the elements, so the
- * gathers of one thread block stay inside a narrow window of d_local that lives
- * in L2) with d_cptr / d_contrib laid out in THAT order; the s-th listed slot is
- * CSR position d_dest[s]:  d_values[d_dest[s]] = sum d_local[contrib[k]].       */
-int spfem_reduce_scatter(const double *d_local, const int *d_cptr, const int *d_contrib,
-                         long long nslots, const int *d_dest, double *d_values,
-                         void *stream);
-
-/* Same sum for local entries that the element kernel already wrote in slot-sorted
- * order (SpfemArgs.perm): d_values[s] = sum d_sorted[cptr[s] .. cptr[s+1]).      */
-int spfem_reduce_sorted(const double *d_sorted, const int *d_cptr, long long nslots,
-                        double *d_values, void *stream);
-
-/* ---- bank-conflict-free schedule of the fused kernel's row reductions ------
- * Set-up step of the tile plan (spfem_b200/tileplan.py).  For every group of
- * <= 16 consecutive owned rows of a tile, re-orders each row's contribution list
- * (idx = shared-memory word index, endf = last contribution of a CSR slot) so
- * that the entries read at the same step by the 16 lanes of a half-warp fall
- * into distinct shared-memory banks; idle steps read one of 16 zero cells at
- * `zero_base`.  out_idx: stride entries per row (bit 15 = slot finished),
- * out_len: scheduled length per row (0 = row group could not be scheduled, keep
- * the original list), out_perm: CSR position (within the row) of the j-th
- * finished slot.  mode 0 = full schedule (slots and contributions in any order,
- * idle steps allowed: conflict free but ~1.4-1.8 x longer lists -- measured
- * slower, kept for reference); mode 1 = keep slot order and list length, only
- * choose the order of the contributions inside each slot (used by default).
- * on_device = 0 runs on the host with host pointers (tests).                   */
-int spfem_schedule_rows(const int *idx, const unsigned char *endf,
-                        const long long *row_first, const int *row_count,
-                        const long long *grp_row0, const int *grp_nrows,
-                        long long ngroups, int stride, int max_slots, int zero_base,
-                        unsigned short *out_idx, int *out_len, unsigned char *out_perm,
-                        int mode, int on_device, void *stream);
 
 /* ---- element ordering -------------------------------------------------------
  * Morton (Z-order) permutation of the elements by centroid: d_perm[k] = index

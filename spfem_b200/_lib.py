@@ -33,7 +33,6 @@ class SpfemArgs(C.Structure):
         ("lf1", C.c_void_p),
         ("out", C.c_void_p),
         ("ldk", C.c_longlong),
-        ("perm", C.c_void_p),
     ]
 
 
@@ -128,16 +127,6 @@ SYMBOLS = {
                                      C.c_void_p, C.c_void_p, C.c_void_p]),
     "spfem_reduce": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p,
                                C.c_longlong, C.c_void_p, C.c_void_p]),
-    "spfem_reduce_rows": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
-                                    C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p]),
-    "spfem_reduce_scatter": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong,
-                                       C.c_void_p, C.c_void_p, C.c_void_p]),
-    "spfem_reduce_sorted": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p,
-                                      C.c_void_p]),
-    "spfem_schedule_rows": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
-                                      C.c_void_p, C.c_void_p, C.c_longlong, C.c_int,
-                                      C.c_int, C.c_int, C.c_void_p, C.c_void_p,
-                                      C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "spfem_tileplan_build": (C.c_int, [C.POINTER(SpfemPlanIn), C.POINTER(SpfemPlanOut),
                                        ALLOC_FN, FREE_FN, C.c_void_p, C.c_int, C.c_void_p]),
     "spfem_tileplan_fill_coords": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
@@ -188,7 +177,7 @@ def load():
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
-    if lib.spfem_abi_version() != 1:
+    if lib.spfem_abi_version() != 2:
         raise SpfemError("libspfem_b200.so ABI version mismatch; rebuild")
     _lib = lib
     return lib

@@ -70,18 +70,20 @@ struct SpfemArgs {
     const int *lf1;           /* facet kernels: local facet index inside e1     */
     double *out;              /* out[entry*ldo + k*ldk]                         */
     long long ldk;
-    const int *perm;          /* optional: entry id -> slot-sorted position     */
 };
 """
 
 # Fused tile kernel: one CTA per tile of (Morton-contiguous) elements plus the
-# halo elements that touch rows the tile owns (tileplan.py).  The per-tile blob
-# (vertex ids, contribution lists, CSR offsets) is brought into shared memory by
-# two TMA bulk copies (cp.async.bulk + mbarrier, SASS UBLKCP).  Phase A: every
-# thread computes one local matrix into shared memory (entry-major,
-# sL[idx*ldl + el]).  Phase B: one thread per CSR slot owned by the tile sums
-# its contributions from shared memory in a fixed order and writes the CSR value
-# exactly once -- no atomics, no partial sums in HBM.
+# halo elements that touch rows the tile owns (tileplan.py; plan built natively by
+# csrc/spfem_plan.cu).  The per-tile blob (vertex ids, coordinates, contribution
+# lists, CSR positions) is brought into shared memory by two TMA bulk copies
+# (cp.async.bulk + mbarrier, SASS UBLKCP).  Phase A: every thread computes one
+# local matrix into shared memory (distinct values only, sL[u*ldl + el]).  Phase
+# B: one thread per slot owned by the tile sums its contributions from shared
+# memory in a fixed order and writes the CSR value(s) exactly once -- no atomics,
+# no partial sums in HBM.  For vector elements (SPFEM_NB = bsv*bsu > 1) a slot
+# is the bsv x bsu block of values of one scalar entry: one index decode serves
+# NB values and the plan is NB times smaller.
 TILE_THREADS = int(os.environ.get("SPFEM_TILE_T", "512"))
 DEVICE_HELPERS = r"""
 #ifndef SPFEM_HOST
@@ -123,17 +125,15 @@ struct SpfemTileArgs {
     double *values;               /* CSR values                                   */
     int ldl;                      /* leading dimension of the smem tile           */
     int max_a, max_b;             /* smem bytes reserved for blob sections A / B  */
-    int max_ns, max_nr;           /* largest slot / row count of a tile; max_ns = 0:
-                                     no staging buffer, values stored from phase B1 */
-    int mode;                     /* 0: thread per owned row, 1: thread per CSR slot,
-                                     2: thread per slot + packed local values     */
+    int compact;                  /* packed local values (per-element bit masks)  */
     int store;                    /* doubles reserved for the local values        */
     int prefetch;                 /* L2 prefetch distance in tiles (0 = off)      */
-    int sorted;                   /* slot-parallel phase: tile slots sorted by their
-                                     number of contributions (uniform warps)      */
+    int sorted;                   /* tile slots ordered by contribution count:
+                                     position inside the row comes from `spos`    */
+    int els;                      /* block plans: contribution = entry << els | element */
 };
-/* Packed shared-memory image of one element's local values (tileplan.py,
-   mode "compact"): only the values whose mask bit is set are stored, value u at
+/* Packed shared-memory image of one element's local values (compact plans):
+   only the values whose mask bit is set are stored, value u at
    base[number of set bits below u].  The element body writes through
    out[u] = val, u a literal after inlining.                                   */
 struct SpfemPacked {
@@ -152,6 +152,10 @@ struct SpfemPacked {
         return r;
     }
 };
+#if SPFEM_NB > 1
+/* distinct-value id of component (a, b) of scalar entry j*nbv + i (block plans) */
+__device__ const unsigned short SPFEM_UT[SPFEM_NSIDX * SPFEM_NB] = {@UT@};
+#endif
 extern "C" __global__ void __launch_bounds__(@THREADS@, @MINB@) @NAME@_tile(const SpfemTileArgs T)
 {
     extern __shared__ __align__(128) unsigned char spfem_smem_raw[];
@@ -159,14 +163,15 @@ extern "C" __global__ void __launch_bounds__(@THREADS@, @MINB@) @NAME@_tile(cons
     double *sL = (double *)spfem_smem_raw;
     unsigned char *sA = spfem_smem_raw + (((size_t)8 * T.store + 15) & ~(size_t)15);
     unsigned char *sB = sA + T.max_a;
-    double *sV = (double *)(sB + T.max_b);
-    unsigned long long *bars = (unsigned long long *)(sV + T.max_ns);
-    int *sG = (int *)(bars + 2);
+    unsigned long long *bars = (unsigned long long *)(sB + T.max_b);
     const int *d = T.desc + 16 * (size_t)blockIdx.x;
     const int bytes_a = d[1], bytes_b = d[2], ne = d[3], ne_pad = d[4], ns = d[5], nr = d[9];
     if (ne == 0 || ns == 0) return;
-    if (T.mode == 0 && threadIdx.x < 16)
-        sL[SPFEM_NUNIQUE * ldl + threadIdx.x] = 0.0;          /* idle-step targets */
+#if SPFEM_NB > 1
+    int *sUT = (int *)(bars + 2);             /* id * ldl, one row of NB ints per entry */
+    for (int i = threadIdx.x; i < SPFEM_NSIDX * SPFEM_NB; i += blockDim.x)
+        sUT[i] = (int)SPFEM_UT[i] * ldl;
+#endif
     if (threadIdx.x == 0) {
         spfem_mbar_init(&bars[0], 1);
         spfem_mbar_init(&bars[1], 1);
@@ -196,7 +201,7 @@ extern "C" __global__ void __launch_bounds__(@THREADS@, @MINB@) @NAME@_tile(cons
        local value (large local matrices: keeps all threads of the CTA busy); the
        part index is uniform inside a warp                                       */
     const int ne32 = (ne + 31) & ~31;
-    if (T.mode == 2) {
+    if (T.compact) {
         const int *sbase = (const int *)(sA + d[15]);
         const unsigned *smask = (const unsigned *)(sbase + ne_pad);
         for (int w = threadIdx.x; w < ne32 * SPFEM_NPART; w += blockDim.x) {
@@ -224,68 +229,70 @@ extern "C" __global__ void __launch_bounds__(@THREADS@, @MINB@) @NAME@_tile(cons
             }
         }
     }
-    /* phase B1: one thread per owned row walks the row's contribution list
-       (bit 15 of an entry = last contribution of a CSR slot) and adds in list
-       order -- fixed order => bitwise reproducible.  The lists are scheduled
-       (spfem_schedule_rows) so that the 16 rows of a half-warp read distinct
-       shared-memory banks in every step.  Finished slot values and the CSR
-       position of their row are staged in shared memory.                      */
+    /* phase B: one thread per slot of the tile's rows (a slot = one CSR value, or
+       the bsv x bsu block of values of a vector element's scalar entry); slots in
+       CSR order, so a warp stores runs of consecutive values.  Contributions are
+       added in list order => bitwise reproducible.                              */
     spfem_mbar_wait(&bars[1], 0);
-    const int2 *rinfo = (const int2 *)sB;      /* {gdelta, s_start | k_start<<16} */
+    __syncthreads();
+    const long long *rbase = (const long long *)sB;
+    const unsigned *rinfo = (const unsigned *)(sB + (((size_t)8 * nr + 15) & ~(size_t)15));
+    const unsigned short *soff = (const unsigned short *)(sB + d[6]);
+    const unsigned short *srow = (const unsigned short *)(sB + d[7]);
+    const unsigned short *spos = (const unsigned short *)(sB + d[7] + (((size_t)2 * ns + 15) & ~(size_t)15));
     const unsigned short *cb = (const unsigned short *)(sB + d[8]);
-    const unsigned char *pm = (const unsigned char *)(sB + d[6]);   /* slot order -> CSR order */
-    const bool direct = T.max_ns == 0;           /* no staging buffer: store from B1 */
-    __syncthreads();
-    if (T.mode != 0) {
-        /* phase B, slot-parallel: one thread per CSR slot of the tile (slots in
-           CSR order, so a warp stores runs of consecutive values); the first two
-           contributions are fetched together, longer lists finish in a loop --
-           always in list order => bitwise reproducible                         */
-        const int *gd = (const int *)sB;
-        const unsigned short *soff = (const unsigned short *)(sB + d[6]);
-        const unsigned short *srow = (const unsigned short *)(sB + d[7]);
-        double *__restrict__ vals = T.values;
-        const bool srt = T.sorted != 0;
+    double *__restrict__ vals = T.values;
+    const bool srt = T.sorted != 0;
+#if SPFEM_NB == 1
 #pragma unroll @BUNROLL@
-        for (int s = threadIdx.x; s < ns; s += blockDim.x) {
-            const unsigned k0 = soff[s], k1 = soff[s + 1];
-            const unsigned c0 = cb[k0], c1 = cb[k0 + 1];
-            /* sorted: slots ordered by contribution count, CSR position per slot */
-            const int g = srt ? gd[s] : gd[srow[s]] + s;
-            double acc = sL[c0];
-            if (k0 + 1 < k1) acc += sL[c1];
+    for (int s = threadIdx.x; s < ns; s += blockDim.x) {
+        const unsigned k0 = soff[s], k1 = soff[s + 1];
+        const unsigned c0 = cb[k0], c1 = cb[k0 + 1];
+        const unsigned r = srow[s];
+        const unsigned info = rinfo[r];
+        const unsigned k = srt ? (unsigned)spos[s] : (unsigned)s - (info & 0xffffu);
+        double acc = sL[c0];
+        if (k0 + 1 < k1) acc += sL[c1];
 #pragma unroll @TUNROLL@
-            for (unsigned k = k0 + 2; k < k1; ++k) acc += sL[cb[k]];
-            vals[g] = acc;
-        }
-        return;
+        for (unsigned kk = k0 + 2; kk < k1; ++kk) acc += sL[cb[kk]];
+        vals[rbase[r] + (long long)k] = acc;
     }
-    for (int row = threadIdx.x; row < nr; row += blockDim.x) {
-        const int2 ri = rinfo[row];
-        unsigned s = (unsigned)ri.y & 0xffffu;
-        const unsigned s_end = (unsigned)rinfo[row + 1].y & 0xffffu;
-        const int g0 = ri.x + (int)s;               /* CSR position of the row's first slot */
-        unsigned k = ((unsigned)ri.y) >> 16;
-        for (; s < s_end; ++s) {                    /* slots, largest first */
-            double acc = 0.0;
-            unsigned c;
-            do {
-                c = cb[k++];
-                acc += sL[c & 0x7fffu];
-            } while (!(c & 0x8000u));
-            if (direct) {
-                T.values[g0 + (int)pm[s]] = acc;
-            } else {
-                sV[s] = acc;
-                sG[s] = g0;
-            }
+#else
+    const unsigned elm = (1u << T.els) - 1u;
+    for (int s = threadIdx.x; s < ns; s += blockDim.x) {
+        const unsigned k0 = soff[s], k1 = soff[s + 1];
+        const unsigned r = srow[s];
+        const unsigned info = rinfo[r];
+        const unsigned L = info >> 16;
+        const unsigned k = srt ? (unsigned)spos[s] : (unsigned)s - (info & 0xffffu);
+        double acc[SPFEM_NB];
+        {
+            const unsigned c = cb[k0];
+            const int *ut = sUT + (c >> T.els) * SPFEM_NB;
+            const double *col = sL + (c & elm);
+#pragma unroll
+            for (int ab = 0; ab < SPFEM_NB; ++ab) acc[ab] = col[ut[ab]];
+        }
+        for (unsigned kk = k0 + 1; kk < k1; ++kk) {
+            const unsigned c = cb[kk];
+            const int *ut = sUT + (c >> T.els) * SPFEM_NB;
+            const double *col = sL + (c & elm);
+#pragma unroll
+            for (int ab = 0; ab < SPFEM_NB; ++ab) acc[ab] += col[ut[ab]];
+        }
+        double *__restrict__ o = vals + rbase[r] + (long long)(SPFEM_BSU * k);
+#pragma unroll
+        for (int a = 0; a < SPFEM_BSV; ++a) {
+#if SPFEM_BSU == 2
+            *reinterpret_cast<double2 *>(o) = make_double2(acc[2 * a], acc[2 * a + 1]);
+#else
+#pragma unroll
+            for (int b = 0; b < SPFEM_BSU; ++b) o[b] = acc[a * SPFEM_BSU + b];
+#endif
+            o += SPFEM_BSU * L;
         }
     }
-    if (direct) return;
-    __syncthreads();
-    /* phase B2: coalesced store of the tile's CSR values */
-    for (int s = threadIdx.x; s < ns; s += blockDim.x)
-        T.values[sG[s] + (int)pm[s]] = sV[s];
+#endif
 }
 """
 
@@ -933,10 +940,22 @@ def generate_interior(spec, name="spfem_elem"):
     src.append("#define SPFEM_NUNIQUE %d" % spec.n_unique)
     src.append("#define SPFEM_NPART %d" % spec.npart)
     src.append("#define SPFEM_NMASK %d" % ((spec.n_unique + 31) // 32))
-    # store of one local entry in the two-kernel route: entry-major position, or
-    # (P.perm) its position in slot-sorted order
-    src.append("#define SPFEM_PUT(idx, val) do { const long long a_ = (long long)(idx) * ldo + k; "
-               "out[P.perm ? (long long)P.perm[a_] : a_] = (val); } while (0)")
+    # block structure of a vector element: bsv x bsu values per scalar entry
+    bsv, bsu = spec.ncv, (spec.ncu if spec.bilinear else 1)
+    nbv_s, nbu_s = spec.n_rows // bsv, spec.n_cols // bsu
+    ut = []
+    for j in range(nbu_s):
+        for i in range(nbv_s):
+            for a_ in range(bsv):
+                for b_ in range(bsu):
+                    ut.append(alias[(bsu * j + b_) * spec.n_rows + (bsv * i + a_)])
+    spec.bsv, spec.bsu, spec.ut = bsv, bsu, ut
+    src.append("#define SPFEM_BSV %d" % bsv)
+    src.append("#define SPFEM_BSU %d" % bsu)
+    src.append("#define SPFEM_NB %d" % (bsv * bsu))
+    src.append("#define SPFEM_NSIDX %d" % (nbv_s * nbu_s))
+    # store of one local entry in the two-kernel route: entry-major planes
+    src.append("#define SPFEM_PUT(idx, val) out[(long long)(idx) * ldo + k] = (val)")
     # body<TILED>(P, e, vt, ldv, ev, pc, ldpc, out, ldo, k): local matrix of
     # element e whose vertex ids are vt[r*ldv + ev]  ->  out[idx*ldo + k]
     # (TILED: only the distinct values, out[alias*ldo + k])
@@ -981,6 +1000,7 @@ def generate_interior(spec, name="spfem_elem"):
             "pc, ldpc, po, 1LL, 0LL); break;" % (c, name, c, elem)
             for c in range(spec.npart))
         src.append(TILE_KERNEL.replace("@CASES@", cases).replace("@PCASES@", pcases)
+                   .replace("@UT@", ", ".join(str(u) for u in ut))
                    .replace("@NAME@", name)
                    .replace("@BUNROLL@", os.environ.get("SPFEM_TILE_BUNROLL", "2"))
                    .replace("@TUNROLL@", os.environ.get("SPFEM_TILE_TUNROLL", "4"))

@@ -156,55 +156,6 @@ k_reduce(const double *__restrict__ local, const int *__restrict__ cptr,
     values[s] = acc;
 }
 
-// Thread per CSR row, rows visited in spatial order (see spfem_reduce_rows).
-__global__ void __launch_bounds__(256)
-k_reduce_rows(const double *__restrict__ local, const int *__restrict__ indptr,
-              const int *__restrict__ cptr, const int *__restrict__ contrib,
-              const int *__restrict__ row_order, long long nrows,
-              double *__restrict__ values)
-{
-    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= nrows) return;
-    const int r = row_order[i];
-    const int s1 = indptr[r + 1];
-    int k = cptr[indptr[r]];
-    for (int s = indptr[r]; s < s1; ++s) {
-        const int e = cptr[s + 1];
-        double acc = 0.0;
-        for (; k < e; ++k) acc += local[contrib[k]];
-        values[s] = acc;
-    }
-}
-
-// values[dest[s]] = sum of the local entries listed for the s-th slot of a
-// re-ordered slot list (see spfem_reduce_scatter).
-__global__ void __launch_bounds__(256)
-k_reduce_scatter(const double *__restrict__ local, const int *__restrict__ cptr,
-                 const int *__restrict__ contrib, long long nslots,
-                 const int *__restrict__ dest, double *__restrict__ values)
-{
-    long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= nslots) return;
-    int b = cptr[s], e = cptr[s + 1];
-    const int d = dest[s];
-    double acc = 0.0;
-    for (int k = b; k < e; ++k) acc += local[contrib[k]];
-    values[d] = acc;
-}
-
-// values[s] = sum of a contiguous run of slot-sorted local entries.
-__global__ void __launch_bounds__(256)
-k_reduce_sorted(const double *__restrict__ sorted, const int *__restrict__ cptr,
-                long long nslots, double *__restrict__ values)
-{
-    long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= nslots) return;
-    int b = cptr[s], e = cptr[s + 1];
-    double acc = 0.0;
-    for (int k = b; k < e; ++k) acc += sorted[k];
-    values[s] = acc;
-}
-
 __device__ __forceinline__ unsigned long long spread2(unsigned long long x)
 {   // 32 bits -> every second bit
     x &= 0xffffffffull;
@@ -254,274 +205,6 @@ __global__ void k_morton_keys(const double *__restrict__ p, long long ldp, int d
     ids[e] = (int)e;
 }
 
-
-// ---- bank-conflict-free schedule of the tile kernel's row reductions -----------
-// Phase B1 of the fused kernel: lane = owned row, step t = the t-th entry of the
-// row's contribution list; the 16 lanes of a half-warp read sL[idx] (8-byte
-// words, 16 banks) in lock step.  For every group of up to 16 consecutive rows
-// of a tile this routine re-orders each row's list so that the entries read at
-// the same step fall into distinct banks: slots may be processed in any order
-// and the contributions of a slot in any order (one register accumulator per
-// lane), lanes without a conflict-free candidate read a zero cell in a free
-// bank.  Greedy, deterministic, typically ~1.5 x the longest list of the group.
-#define SPFEM_SCHED_MAXC 256
-#define SPFEM_SCHED_MAXS 96
-#define SPFEM_SCHED_MAXT 1024
-struct SchedArgs {
-    const int *idx;            // [C] shared-memory index of every contribution
-    const unsigned char *endf; // [C] 1 = last contribution of its CSR slot
-    const long long *row_first;// [R] first contribution of the row
-    const int *row_count;      // [R] number of contributions of the row
-    const long long *grp_row0; // [G] first row of the group
-    const int *grp_nrows;      // [G] rows in the group (<= 16)
-    long long ngroups;
-    int stride;                // output entries reserved per row
-    int max_slots;             // slot-permutation entries reserved per row
-    int zero_base;             // index of the first of 16 zero cells
-    int mode;                  // 0 = full schedule (idle steps), 1 = re-order inside slots only
-    unsigned short *out_idx;   // [R*stride] scheduled entries (bit 15 = slot end)
-    int *out_len;              // [R] scheduled length (0 = could not schedule)
-    unsigned char *out_perm;   // [R*max_slots] CSR position of the j-th finished slot
-};
-
-__host__ __device__ inline void schedule_group(const SchedArgs &a, long long g)
-{
-    const int nrows = a.grp_nrows[g];
-    const long long r0 = a.grp_row0[g];
-    unsigned char done[16][SPFEM_SCHED_MAXC];
-    unsigned char slot_of[16][SPFEM_SCHED_MAXC];
-    short slot_rem[16][SPFEM_SCHED_MAXS];
-    int cnt[16], cur[16], left[16], nfin[16], len[16];
-    bool ok = true;
-    for (int i = 0; i < nrows; ++i) {
-        cnt[i] = a.row_count[r0 + i];
-        if (cnt[i] > SPFEM_SCHED_MAXC) ok = false;
-    }
-    if (ok) {
-        for (int i = 0; i < nrows && ok; ++i) {
-            const long long f = a.row_first[r0 + i];
-            int sidx = 0, rem = 0;
-            for (int c = 0; c < cnt[i]; ++c) {
-                done[i][c] = 0;
-                slot_of[i][c] = (unsigned char)sidx;
-                ++rem;
-                if (a.endf[f + c]) {
-                    if (sidx >= SPFEM_SCHED_MAXS || sidx >= a.max_slots) { ok = false; break; }
-                    slot_rem[i][sidx] = (short)rem;
-                    rem = 0;
-                    ++sidx;
-                }
-            }
-            cur[i] = -1; left[i] = cnt[i]; nfin[i] = 0; len[i] = 0;
-        }
-    }
-    if (!ok) {
-        for (int i = 0; i < nrows; ++i) a.out_len[r0 + i] = 0;
-        return;
-    }
-    int active = 0;
-    for (int i = 0; i < nrows; ++i) active += left[i] > 0;
-    int t = 0;
-    unsigned short usedmask[SPFEM_SCHED_MAXT];
-    while (active > 0) {
-        if (t >= a.stride || t >= SPFEM_SCHED_MAXT) {   // does not fit: give up on this group
-            for (int i = 0; i < nrows; ++i) a.out_len[r0 + i] = 0;
-            return;
-        }
-        unsigned used = 0;
-        int padrow[16], npad = 0;
-        for (int j = 0; j < nrows; ++j) {
-            const int i = (j + t) % nrows;      // rotate the priority
-            if (left[i] == 0) continue;
-            const long long f = a.row_first[r0 + i];
-            int pick = -1;
-            for (int c = 0; c < cnt[i]; ++c) {
-                if (done[i][c]) continue;
-                if (cur[i] >= 0 && slot_of[i][c] != cur[i]) continue;
-                const unsigned bank = (unsigned)a.idx[f + c] & 15u;
-                if (used & (1u << bank)) continue;
-                pick = c;
-                used |= 1u << bank;
-                break;
-            }
-            unsigned short *o = a.out_idx + (r0 + i) * (long long)a.stride;
-            if (pick < 0) {
-                padrow[npad++] = i;
-                continue;
-            }
-            const int sl = slot_of[i][pick];
-            done[i][pick] = 1;
-            --left[i];
-            cur[i] = sl;
-            unsigned short e = (unsigned short)a.idx[f + pick];
-            if (--slot_rem[i][sl] == 0) {
-                e |= 0x8000u;
-                a.out_perm[(r0 + i) * (long long)a.max_slots + nfin[i]] = (unsigned char)sl;
-                ++nfin[i];
-                cur[i] = -1;
-            }
-            o[t] = e;
-            len[i] = t + 1;
-            if (left[i] == 0) --active;
-        }
-        for (int q = 0; q < npad; ++q) {        // idle lanes read a zero cell in a free bank
-            unsigned bank = 0;
-            while (used & (1u << bank)) ++bank;
-            used |= 1u << bank;
-            const int i = padrow[q];
-            const int cell = a.zero_base + (int)((bank + 16u - ((unsigned)a.zero_base & 15u)) & 15u);
-            a.out_idx[(r0 + i) * (long long)a.stride + t] = (unsigned short)cell;
-            len[i] = t + 1;
-        }
-        usedmask[t] = (unsigned short)used;
-        ++t;
-    }
-    // All rows of the group get the same (even) length: lanes that are done keep
-    // reading zero cells in free banks, so the 16 lanes stay in lock step through
-    // the unrolled loop of the kernel and the schedule stays conflict free.
-    int T = (t + 1) & ~1;
-    if (T > a.stride || T > SPFEM_SCHED_MAXT) {
-        for (int i = 0; i < nrows; ++i) a.out_len[r0 + i] = 0;
-        return;
-    }
-    if (T > t) usedmask[t] = 0;
-    for (int i = 0; i < nrows; ++i) {
-        unsigned short *o = a.out_idx + (r0 + i) * (long long)a.stride;
-        for (int q = len[i]; q < T; ++q) {
-            unsigned used = usedmask[q];
-            unsigned bank = 0;
-            while (bank < 15u && (used & (1u << bank))) ++bank;
-            usedmask[q] = (unsigned short)(used | (1u << bank));
-            o[q] = (unsigned short)(a.zero_base
-                                    + (int)((bank + 16u - ((unsigned)a.zero_base & 15u)) & 15u));
-        }
-        a.out_len[r0 + i] = T;
-    }
-}
-
-// mode 1: keep every row's slot order and list length; only the order of the
-// contributions INSIDE a slot is chosen.  The kernel walks the slots of the 16
-// rows of a half-warp round by round (round j = j-th slot of every row, the lanes
-// re-converge after each slot), so step (j, i) reads the i-th entry of slot j of
-// every lane: pick, per lane, the remaining entry whose bank is least loaded.
-__host__ __device__ inline void order_group_inslot(const SchedArgs &a, long long g)
-{
-    const int nrows = a.grp_nrows[g];
-    const long long r0 = a.grp_row0[g];
-    // per row: slot table (start, size) in list order (sizes are non-increasing)
-    short sstart[16][SPFEM_SCHED_MAXS], ssize[16][SPFEM_SCHED_MAXS];
-    unsigned char sdone[16][SPFEM_SCHED_MAXS];
-    int nsl[16], cnt[16], outpos[16], nfin[16], cur[16];
-    bool ok = true;
-    for (int i = 0; i < nrows; ++i) {
-        cnt[i] = a.row_count[r0 + i];
-        if (cnt[i] > a.stride || cnt[i] > 32767) ok = false;
-    }
-    for (int i = 0; i < nrows && ok; ++i) {
-        const long long f = a.row_first[r0 + i];
-        int n = 0, st = 0;
-        for (int c = 0; c < cnt[i]; ++c)
-            if (a.endf[f + c]) {
-                if (n >= SPFEM_SCHED_MAXS || n >= a.max_slots) { ok = false; break; }
-                sstart[i][n] = (short)st;
-                ssize[i][n] = (short)(c + 1 - st);
-                sdone[i][n] = 0;
-                st = c + 1;
-                ++n;
-            }
-        nsl[i] = n; outpos[i] = 0; nfin[i] = 0;
-    }
-    if (!ok) {
-        for (int i = 0; i < nrows; ++i) a.out_len[r0 + i] = 0;
-        return;
-    }
-    unsigned char taken[16][64];
-    for (;;) {
-        // round: every row with slots left processes one slot; the slot is chosen
-        // among the row's remaining slots of the largest remaining size
-        int maxsz = 0, active = 0;
-        for (int i = 0; i < nrows; ++i) {
-            cur[i] = -1;
-            if (nfin[i] >= nsl[i]) continue;
-            ++active;
-            for (int q = 0; q < nsl[i]; ++q)
-                if (!sdone[i][q]) { if (ssize[i][q] > maxsz) maxsz = ssize[i][q]; break; }
-        }
-        if (!active) break;
-        for (int it = 0; it < maxsz; ++it) {
-            unsigned char load[16];
-            for (int b = 0; b < 16; ++b) load[b] = 0;
-            for (int j = 0; j < nrows; ++j) {
-                const int i = (j + it) % nrows;
-                if (nfin[i] >= nsl[i] && cur[i] < 0) continue;
-                const long long f = a.row_first[r0 + i];
-                unsigned short *o = a.out_idx + (r0 + i) * (long long)a.stride;
-                if (it == 0) {
-                    // choose the slot: first undone slot's size class, least loaded bank
-                    int first = 0;
-                    while (sdone[i][first]) ++first;
-                    const int sz0 = ssize[i][first];
-                    int bslot = first, bc = 0, best = 1000;
-                    for (int q = first; q < nsl[i] && ssize[i][q] == sz0; ++q) {
-                        if (sdone[i][q]) continue;
-                        const int lim = sz0 < 64 ? sz0 : 1;
-                        for (int c = 0; c < lim; ++c) {
-                            const int l = load[a.idx[f + sstart[i][q] + c] & 15];
-                            if (l < best) { best = l; bslot = q; bc = c; }
-                        }
-                    }
-                    cur[i] = bslot;
-                    sdone[i][bslot] = 1;
-                    const int sz = ssize[i][bslot];
-                    for (int c = 0; c < sz && c < 64; ++c) taken[i][c] = 0;
-                    int pick = sz > 64 ? 0 : bc;
-                    if (sz <= 64) taken[i][pick] = 1;
-                    const int v = a.idx[f + sstart[i][bslot] + pick];
-                    ++load[v & 15];
-                    unsigned short e = (unsigned short)v;
-                    if (sz == 1) e |= 0x8000u;
-                    o[outpos[i]] = e;
-                } else {
-                    if (cur[i] < 0) continue;
-                    const int q = cur[i];
-                    const int sz = ssize[i][q];
-                    if (it >= sz) continue;
-                    int pick = -1, best = 1000;
-                    if (sz > 64) {
-                        pick = it;
-                    } else {
-                        for (int c = 0; c < sz; ++c) {
-                            if (taken[i][c]) continue;
-                            const int l = load[a.idx[f + sstart[i][q] + c] & 15];
-                            if (l < best) { best = l; pick = c; }
-                        }
-                        taken[i][pick] = 1;
-                    }
-                    const int v = a.idx[f + sstart[i][q] + pick];
-                    ++load[v & 15];
-                    unsigned short e = (unsigned short)v;
-                    if (it == sz - 1) e |= 0x8000u;
-                    o[outpos[i] + it] = e;
-                }
-            }
-        }
-        for (int i = 0; i < nrows; ++i) {
-            if (cur[i] < 0) continue;
-            a.out_perm[(r0 + i) * (long long)a.max_slots + nfin[i]] = (unsigned char)cur[i];
-            outpos[i] += ssize[i][cur[i]];
-            ++nfin[i];
-        }
-    }
-    for (int i = 0; i < nrows; ++i) a.out_len[r0 + i] = cnt[i];
-}
-
-__global__ void k_schedule(SchedArgs a)
-{
-    long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= a.ngroups) return;
-    if (a.mode == 1) order_group_inslot(a, g);
-    else schedule_group(a, g);
-}
 
 inline unsigned grid_for(long long n, int block)
 {
@@ -768,68 +451,6 @@ int spfem_reduce(const double *d_local, const int *d_cptr, const int *d_contrib,
     return 0;
 }
 
-
-int spfem_schedule_rows(const int *idx, const unsigned char *endf,
-                        const long long *row_first, const int *row_count,
-                        const long long *grp_row0, const int *grp_nrows,
-                        long long ngroups, int stride, int max_slots, int zero_base,
-                        unsigned short *out_idx, int *out_len, unsigned char *out_perm,
-                        int mode, int on_device, void *stream)
-{
-    SchedArgs a;
-    a.mode = mode;
-    a.idx = idx; a.endf = endf; a.row_first = row_first; a.row_count = row_count;
-    a.grp_row0 = grp_row0; a.grp_nrows = grp_nrows; a.ngroups = ngroups;
-    a.stride = stride; a.max_slots = max_slots; a.zero_base = zero_base;
-    a.out_idx = out_idx; a.out_len = out_len; a.out_perm = out_perm;
-    if (ngroups <= 0) return 0;
-    if (stride <= 0 || max_slots <= 0 || max_slots > 255)
-        return fail("spfem_schedule_rows: bad stride / max_slots");
-    if (!on_device) {
-        for (long long g = 0; g < ngroups; ++g) {
-            if (mode == 1) order_group_inslot(a, g);
-            else schedule_group(a, g);
-        }
-        return 0;
-    }
-    k_schedule<<<grid_for(ngroups, 64), 64, 0, (cudaStream_t)stream>>>(a);
-    CUDA_TRY(cudaGetLastError());
-    return 0;
-}
-
-int spfem_reduce_rows(const double *d_local, const int *d_indptr, const int *d_cptr,
-                      const int *d_contrib, const int *d_row_order, long long nrows,
-                      double *d_values, void *stream)
-{
-    if (nrows <= 0) return 0;
-    const int B = 256;
-    k_reduce_rows<<<grid_for(nrows, B), B, 0, (cudaStream_t)stream>>>(
-        d_local, d_indptr, d_cptr, d_contrib, d_row_order, nrows, d_values);
-    CUDA_TRY(cudaGetLastError());
-    return 0;
-}
-
-int spfem_reduce_scatter(const double *d_local, const int *d_cptr, const int *d_contrib,
-                         long long nslots, const int *d_dest, double *d_values, void *stream)
-{
-    if (nslots <= 0) return 0;
-    const int B = 256;
-    k_reduce_scatter<<<grid_for(nslots, B), B, 0, (cudaStream_t)stream>>>(
-        d_local, d_cptr, d_contrib, nslots, d_dest, d_values);
-    CUDA_TRY(cudaGetLastError());
-    return 0;
-}
-
-int spfem_reduce_sorted(const double *d_sorted, const int *d_cptr, long long nslots,
-                        double *d_values, void *stream)
-{
-    if (nslots <= 0) return 0;
-    const int B = 256;
-    k_reduce_sorted<<<grid_for(nslots, B), B, 0, (cudaStream_t)stream>>>(d_sorted, d_cptr, nslots,
-                                                                     d_values);
-    CUDA_TRY(cudaGetLastError());
-    return 0;
-}
 
 size_t spfem_morton_ws_bytes(long long nt)
 {

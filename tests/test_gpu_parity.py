@@ -115,54 +115,52 @@ def test_device_resident_result():
 @pytest.mark.parametrize("name", ["trip1_lap_r6", "trip2_lap", "vecp2_elasticity",
                                   "stokes_b", "tetp2_lap", "q2_lap",
                                   "trip1_interp_mass", "trip1_mass_x2"])
-@pytest.mark.parametrize("mode", ["unfused", "small_tiles", "slot_parallel", "direct_store",
-                                  "packed_values", "sorted_slots"])
+@pytest.mark.parametrize("mode", ["unfused", "dense", "dense_sorted", "bucket_sorted",
+                                  "packed_values", "packed_sorted", "scalar_slots",
+                                  "batched"])
 def test_both_assembly_paths(name, mode, monkeypatch):
     """The two-kernel path (local matrices in HBM + gather reduction) and the
-    fused tile kernel with many small tiles (exercises halos and row ownership)
-    both reproduce the reference."""
+    fused tile kernel with many small tiles (exercises halos and row ownership;
+    every variant of the native plan: dense / packed local values, slots in CSR
+    order or ordered by contribution count, block or scalar slots for vector
+    elements, several batches = several launches) reproduce the reference."""
     if mode == "unfused":
         monkeypatch.setenv("SPFEM_FUSED", "0")
-        monkeypatch.setenv("SPFEM_LOCAL_LAYOUT", "entry")
     else:
         monkeypatch.setenv("SPFEM_TILE_E", "32")
         monkeypatch.setenv("SPFEM_TILE_SORT", "0")
-        if mode == "slot_parallel":                 # one thread per CSR slot in phase B
-            monkeypatch.setenv("SPFEM_TILE_MODE", "slots")
-        elif mode == "packed_values":               # ... and only the values that are read
+        monkeypatch.setenv("SPFEM_TILE_MODE", "dense")
+        if mode == "dense_sorted":
+            monkeypatch.setenv("SPFEM_TILE_SORT", "1")
+        elif mode == "bucket_sorted":
+            monkeypatch.setenv("SPFEM_TILE_SORT", "bucket")
+        elif mode == "packed_values":               # only the values that are read
             monkeypatch.setenv("SPFEM_TILE_MODE", "compact")
-        elif mode == "sorted_slots":                # ... slots ordered by contribution count
+        elif mode == "packed_sorted":
             monkeypatch.setenv("SPFEM_TILE_MODE", "compact")
             monkeypatch.setenv("SPFEM_TILE_SORT", "1")
-        elif mode == "direct_store":                # row-owner threads store without staging
-            monkeypatch.setenv("SPFEM_TILE_MODE", "rows")
-            monkeypatch.setenv("SPFEM_TILE_DIRECT", "1")
-        else:
-            monkeypatch.setenv("SPFEM_TILE_MODE", "rows")
-            monkeypatch.setenv("SPFEM_TILE_DIRECT", "0")
+        elif mode == "scalar_slots":                # vector elements without block slots
+            monkeypatch.setenv("SPFEM_TILE_BLOCKS", "0")
+        elif mode == "batched":
+            monkeypatch.setenv("SPFEM_TILE_BATCH", "20000")
         monkeypatch.setenv("SPFEM_FUSED", "force")   # bypass the "is it worth it" heuristic
         monkeypatch.setenv("SPFEM_FAN", "0")         # (the tile kernel, not the vertex-fan kernel)
     case = cases.BY_NAME[name]
     asm = util.assembler_for(case)
     kw = cases.case_inputs(case, asm.mesh, asm.dofnum_u.N)
     prep = asm.prepare_iasm(case.form, **kw)
-    assert prep.n_launches == (2 if mode == "unfused" else 1)
+    if mode == "unfused":
+        assert prep.n_launches == 2
+    else:
+        assert type(prep).__name__ == "TiledPrepared"
+        assert (prep.n_launches > 1) == (mode == "batched")
     prep.launch()
     util.check(prep.result(), util.golden(case))
-
-
-@pytest.mark.parametrize("name", ["trip1_lap_r6", "vecp2_elasticity", "tetp2_lap", "stokes_b"])
-def test_element_major_local_layout(name, monkeypatch):
-    """Two-kernel route with element-major local matrices (ldk = Nu*Nv)."""
-    monkeypatch.setenv("SPFEM_FUSED", "0")
-    monkeypatch.setenv("SPFEM_LOCAL_LAYOUT", "elem")
-    monkeypatch.setenv("SPFEM_FAN", "0")
-    case = cases.BY_NAME[name]
-    asm = util.assembler_for(case)
-    prep = asm.prepare_iasm(case.form)
-    assert prep.n_launches == 2 and prep.args.ldk == prep.plan.spec.n_entries
+    prep.launch()                                   # bitwise reproducible
+    v1 = prep.values.clone()
     prep.launch()
-    util.check(prep.result(), util.golden(case))
+    import torch
+    assert torch.equal(v1, prep.values)
 
 
 @pytest.mark.parametrize("name", ["trip1_lap", "trip1_mass", "trip1_lap_r6"])
@@ -263,23 +261,6 @@ def test_intorder_variants_and_quadrature_limits():
         at.iasm(cases.mass, intorder=5)
 
 
-@pytest.mark.parametrize("name", ["trip1_lap_r6", "vecp2_elasticity", "tetp2_lap", "stokes_b",
-                                  "trip1_tind", "q2_lap"])
-def test_sorted_local_layout(name, monkeypatch):
-    """Two-kernel route, optional layout: the element kernel scatters the local
-    entries into slot-sorted order (SpfemArgs.perm), spfem_reduce_sorted sums
-    contiguous runs (measured slower than the gather; kept as an option)."""
-    monkeypatch.setenv("SPFEM_FUSED", "0")
-    monkeypatch.setenv("SPFEM_LOCAL_LAYOUT", "sorted")
-    case = cases.BY_NAME[name]
-    asm = util.assembler_for(case)
-    kw = cases.case_inputs(case, asm.mesh, asm.dofnum_u.N)
-    prep = asm.prepare_iasm(case.form, **kw)
-    assert prep.n_launches == 2 and getattr(prep, "sorted_local", False)
-    prep.launch()
-    util.check(prep.result(), util.golden(case))
-
-
 def test_full_size_config2_properties(monkeypatch):
     """BASELINE configs[1] at full size (MeshTri.refine(11), 8 388 608
     triangles): size-independent properties, and two independent kernels (the
@@ -310,35 +291,6 @@ def test_full_size_config2_properties(monkeypatch):
     assert np.array_equal(K.indptr, K2.indptr) and np.array_equal(K.indices, K2.indices)
     scale = np.abs(K2.data).max()
     assert np.max(np.abs(K.data - K2.data)) <= 1e-12 * scale
-
-
-@pytest.mark.parametrize("name", ["trip1_lap_r6", "vecp2_elasticity", "tetp2_lap", "stokes_b",
-                                  "q2_lap"])
-def test_row_ordered_reduction(name, monkeypatch):
-    """Two-kernel route with the row-ordered reduction (spfem_reduce_rows)."""
-    monkeypatch.setenv("SPFEM_FUSED", "0")
-    monkeypatch.setenv("SPFEM_LOCAL_LAYOUT", "rows")
-    case = cases.BY_NAME[name]
-    asm = util.assembler_for(case)
-    prep = asm.prepare_iasm(case.form)
-    assert prep.n_launches == 2 and getattr(prep, "row_order", None) is not None
-    prep.launch()
-    util.check(prep.result(), util.golden(case))
-
-
-@pytest.mark.parametrize("name", ["trip1_lap_r6", "vecp2_elasticity", "tetp2_lap", "stokes_b",
-                                  "q2_lap"])
-def test_spatially_ordered_reduction(name, monkeypatch):
-    """Two-kernel route with the slots re-listed in the spatial order of the
-    elements (spfem_reduce_scatter)."""
-    monkeypatch.setenv("SPFEM_FUSED", "0")
-    monkeypatch.setenv("SPFEM_LOCAL_LAYOUT", "spatial")
-    case = cases.BY_NAME[name]
-    asm = util.assembler_for(case)
-    prep = asm.prepare_iasm(case.form)
-    assert prep.n_launches == 2 and getattr(prep, "spatial", None) is not None
-    prep.launch()
-    util.check(prep.result(), util.golden(case))
 
 
 @pytest.mark.parametrize("mname,ename,ref,dim", [("MeshTri", "TriP1", 4, 2), ("MeshTri", "TriP2", 3, 2),

@@ -78,7 +78,12 @@ def run(kind, size):
                frac=round(balg / (ms * 1e-3) / 1e9 / PEAK, 4),
                peak_mem_gb=round(torch.cuda.max_memory_allocated() / 2 ** 30, 2))
     if hasattr(prep, "tp"):
-        res["tile"] = {k: prep.tp.get(k) for k in ("E", "halo_factor", "ntiles", "mode", "blob_bytes")}
+        res["tile"] = {k: prep.tp.get(k) for k in ("E", "halo_factor", "ntiles", "compact", "sort_slots",
+                                                   "blob_bytes", "bsv", "bsu", "ldl", "max_ne",
+                                                   "scratch_peak_bytes")}
+        res["tile"]["batches"] = len(prep.tp.get("batches", [])) or None
+        res["tile"]["smem"] = prep.smem
+        res["tile"]["threads"] = prep.threads
     return res
 
 
