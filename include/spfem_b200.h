@@ -198,6 +198,9 @@ typedef struct SpfemPlanIn {
     const unsigned char *row_mask; /* optional [nrows]: 0 = row is not assembled here  */
     int index_bytes;          /* 4 or 8: width of indptr / indices                     */
     long long batch_cap;      /* contributions per batch (0: 2^27)                     */
+    double split_factor;      /* > 0: tiles whose element list (with halo) exceeds
+                                 split_factor x the median are split (the Morton curve
+                                 jumps; the largest tile sizes every CTA's shared memory) */
 } SpfemPlanIn;
 
 typedef struct SpfemPlanBatch {

@@ -942,6 +942,8 @@ def generate_interior(spec, name="spfem_elem"):
     src.append("#define SPFEM_NMASK %d" % ((spec.n_unique + 31) // 32))
     # block structure of a vector element: bsv x bsu values per scalar entry
     bsv, bsu = spec.ncv, (spec.ncu if spec.bilinear else 1)
+    if os.environ.get("SPFEM_TILE_BLOCKS", "1") == "0":
+        bsv = bsu = 1              # plan every CSR value as its own slot
     nbv_s, nbu_s = spec.n_rows // bsv, spec.n_cols // bsu
     ut = []
     for j in range(nbu_s):

@@ -193,6 +193,17 @@ template <class T> void to_host(Ctx &c, const T *p, size_t n, std::vector<T> &ou
     }
 }
 
+void from_host(Ctx &c, void *dst, const void *src, size_t bytes)
+{
+    if (!bytes) return;
+    if (c.dev) {
+        PLAN_CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c.st));
+        PLAN_CK(cudaStreamSynchronize(c.st));
+    } else {
+        memcpy(dst, src, bytes);
+    }
+}
+
 template <class T> void fill(Ctx &c, T *p, i64 n, T v)
 {
     par_for(c, n, [=] __host__ __device__(i64 i) { p[i] = v; });
@@ -341,67 +352,121 @@ int build(const SpfemPlanIn &in, SpfemPlanOut &out, Ctx &c)
     const i64 NR = in.nrows / bsv;
     const i64 NC = in.coldof ? in.ncols / bsu : 1;
     const int E = in.E;
-    const i64 ntiles = (n + E - 1) / E;
+    i64 ntiles = (n + E - 1) / E;
     const unsigned char *row_mask = in.row_mask;
     const int INF = INT_MAX;
 
-    // ---- 1. row owners -------------------------------------------------------
+    // ---- 1 + 2. tiles, row owners, tile element lists (own elements + halo) ----
+    // Tiles are E consecutive elements; a tile whose element list (with halo) is
+    // far above the median -- the Morton curve jumps at quadrant boundaries, so a
+    // few tiles span distant regions -- is split, because the largest tile sizes
+    // the shared memory of every CTA.
+    std::vector<i64> h_tstart;
+    for (i64 e0 = 0; e0 < n; e0 += E) h_tstart.push_back(e0);
+    h_tstart.push_back(n);
+    int *etile = scratch<int>(c, n, "etile");
     int *owner = scratch<int>(c, NR, "owner");
-    fill<int>(c, owner, NR, INF);
-    par_for(c, n * nbv, [=] __host__ __device__(i64 w) {
-        const int i = (int)(w / n);
-        const i64 e = w - (i64)i * n;
-        const int R = g.row(i, e);
-        if (row_mask && !row_mask[(i64)R * bsv]) return;
-        amin(&owner[R], (int)(e / E));
-    });
-
-    // ---- 2. tile element lists: own elements + halo ---------------------------
-    i64 *cnt = scratch<i64>(c, n + 1, "cnt");
-    par_for(c, n, [=] __host__ __device__(i64 e) {
-        int seen[MAXLOC];
-        int ns = 0;
-        for (int i = 0; i < nbv; ++i) {
-            const int o = owner[g.row(i, e)];
-            if (o == INF) continue;
-            bool dup = false;
-            for (int k = 0; k < ns; ++k) dup = dup || seen[k] == o;
-            if (!dup) seen[ns++] = o;
+    int *pe = nullptr, *pt = nullptr;
+    i64 *te_ptr = nullptr;
+    i64 P = 0;
+    for (int pass = 0;; ++pass) {
+        ntiles = (i64)h_tstart.size() - 1;
+        i64 *tstart = scratch<i64>(c, ntiles + 1, "tstart");
+        from_host(c, tstart, h_tstart.data(), (size_t)(ntiles + 1) * sizeof(i64));
+        {
+            const i64 nt_ = ntiles;
+            par_for(c, n, [=] __host__ __device__(i64 e) {
+                i64 lo = 0, hi = nt_;
+                while (hi - lo > 1) { const i64 m = (lo + hi) >> 1; if (tstart[m] <= e) lo = m; else hi = m; }
+                etile[e] = (int)lo;
+            });
         }
-        cnt[e] = ns;
-    });
-    i64 *poff = scratch<i64>(c, n + 1, "poff");
-    exscan(c, cnt, poff, n);
-    const i64 P = get(c, poff + n);
-    if (P == 0) throw Err{1, "tile plan: no owned rows"};
-    u64 *pk = scratch<u64>(c, P, "pairs"), *pk2 = scratch<u64>(c, P, "pairs2");
-    par_for(c, n, [=] __host__ __device__(i64 e) {
-        int seen[MAXLOC];
-        int ns = 0;
-        i64 pos = poff[e];
-        for (int i = 0; i < nbv; ++i) {
-            const int o = owner[g.row(i, e)];
-            if (o == INF) continue;
-            bool dup = false;
-            for (int k = 0; k < ns; ++k) dup = dup || seen[k] == o;
-            if (!dup) { seen[ns++] = o; pk[pos++] = (u64)o * (u64)n + (u64)e; }
-        }
-    });
-    drop(c, cnt); drop(c, poff);
-    sort_keys(c, pk, pk2, P, bits_for((u64)ntiles * (u64)n));
-    drop(c, pk2);
-    int *pe = scratch<int>(c, P, "pe"), *pt = scratch<int>(c, P, "pt");
-    {
-        const u64 *k = pk;
-        par_for(c, P, [=] __host__ __device__(i64 q) {
-            const u64 T = k[q] / (u64)n;
-            pt[q] = (int)T;
-            pe[q] = (int)(k[q] - T * (u64)n);
+        drop(c, tstart);
+        fill<int>(c, owner, NR, INF);
+        par_for(c, n * nbv, [=] __host__ __device__(i64 w) {
+            const int i = (int)(w / n);
+            const i64 e = w - (i64)i * n;
+            const int R = g.row(i, e);
+            if (row_mask && !row_mask[(i64)R * bsv]) return;
+            amin(&owner[R], etile[e]);
         });
+        i64 *cnt = scratch<i64>(c, n + 1, "cnt");
+        par_for(c, n, [=] __host__ __device__(i64 e) {
+            int seen[MAXLOC];
+            int ns = 0;
+            for (int i = 0; i < nbv; ++i) {
+                const int o = owner[g.row(i, e)];
+                if (o == INF) continue;
+                bool dup = false;
+                for (int k = 0; k < ns; ++k) dup = dup || seen[k] == o;
+                if (!dup) seen[ns++] = o;
+            }
+            cnt[e] = ns;
+        });
+        i64 *poff = scratch<i64>(c, n + 1, "poff");
+        exscan(c, cnt, poff, n);
+        P = get(c, poff + n);
+        if (P == 0) throw Err{1, "tile plan: no owned rows"};
+        u64 *pk = scratch<u64>(c, P, "pairs"), *pk2 = scratch<u64>(c, P, "pairs2");
+        par_for(c, n, [=] __host__ __device__(i64 e) {
+            int seen[MAXLOC];
+            int ns = 0;
+            i64 pos = poff[e];
+            for (int i = 0; i < nbv; ++i) {
+                const int o = owner[g.row(i, e)];
+                if (o == INF) continue;
+                bool dup = false;
+                for (int k = 0; k < ns; ++k) dup = dup || seen[k] == o;
+                if (!dup) { seen[ns++] = o; pk[pos++] = (u64)o * (u64)n + (u64)e; }
+            }
+        });
+        drop(c, cnt); drop(c, poff);
+        sort_keys(c, pk, pk2, P, bits_for((u64)ntiles * (u64)n));
+        drop(c, pk2);
+        pe = scratch<int>(c, P, "pe");
+        pt = scratch<int>(c, P, "pt");
+        {
+            const u64 *k = pk;
+            int *pe_ = pe, *pt_ = pt;
+            par_for(c, P, [=] __host__ __device__(i64 q) {
+                const u64 T = k[q] / (u64)n;
+                pt_[q] = (int)T;
+                pe_[q] = (int)(k[q] - T * (u64)n);
+            });
+        }
+        drop(c, pk);
+        te_ptr = scratch<i64>(c, ntiles + 1, "te_ptr");
+        {
+            const int *pt_ = pt;
+            boundaries(c, P, ntiles, te_ptr, [=] __host__ __device__(i64 q) { return (i64)pt_[q]; });
+        }
+        if (in.split_factor <= 0.0 || pass >= 2) break;
+        std::vector<i64> h_te;
+        to_host(c, te_ptr, (size_t)ntiles + 1, h_te);
+        std::vector<i64> ne_sorted(ntiles);
+        i64 ne_hi = 0;
+        for (i64 T = 0; T < ntiles; ++T) {
+            ne_sorted[T] = h_te[T + 1] - h_te[T];
+            ne_hi = std::max(ne_hi, ne_sorted[T]);
+        }
+        std::nth_element(ne_sorted.begin(), ne_sorted.begin() + ntiles / 2, ne_sorted.end());
+        const i64 median = ne_sorted[ntiles / 2];
+        const i64 budget = std::max<i64>((i64)(in.split_factor * (double)median + 0.999), 8);
+        if (ne_hi <= budget) break;
+        std::vector<i64> nt2;
+        for (i64 T = 0; T < ntiles; ++T) {
+            const i64 m = h_tstart[T + 1] - h_tstart[T];
+            const i64 ne = h_te[T + 1] - h_te[T];
+            i64 parts = 1;
+            if (ne > budget) parts = std::min<i64>(m, (ne * 5 + budget * 4 - 1) / (budget * 4));
+            for (i64 k = 0; k < parts; ++k) nt2.push_back(h_tstart[T] + (m * k) / parts);
+        }
+        nt2.push_back(n);
+        if (nt2.size() == h_tstart.size()) break;
+        h_tstart.swap(nt2);
+        drop(c, pe); drop(c, pt); drop(c, te_ptr);
     }
-    drop(c, pk);
-    i64 *te_ptr = scratch<i64>(c, ntiles + 1, "te_ptr");
-    boundaries(c, P, ntiles, te_ptr, [=] __host__ __device__(i64 q) { return (i64)pt[q]; });
+    drop(c, etile);
     int *mx = scratch<int>(c, 8, "mx");       // running maxima: ne, nr, nc, ns, nvt, store, bytes_a, bytes_b
     fill<int>(c, mx, 8, 0);
     par_for(c, ntiles, [=] __host__ __device__(i64 T) { amax(&mx[0], (int)(te_ptr[T + 1] - te_ptr[T])); });

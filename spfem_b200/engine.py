@@ -668,7 +668,8 @@ class Engine(object):
         env = os.environ.get
         ckey = (plan.bilinear, spec.n_unique, tuple(spec.alias), spec.nw > 0,
                 env("SPFEM_TILE_MODE", "auto"), env("SPFEM_TILE_E", "0"),
-                env("SPFEM_TILE_SORT", "auto"), env("SPFEM_TILE_BLOCKS", "1"))
+                env("SPFEM_TILE_SORT", "auto"), env("SPFEM_TILE_BLOCKS", "1"),
+                env("SPFEM_TILE_SPLIT", "1.25"))
         if ckey in self._tile_cache:
             return self._tile_cache[ckey]
         force = env("SPFEM_FUSED", "1") == "force"
@@ -729,7 +730,8 @@ class Engine(object):
                                      bsv=bsv if nb > 1 else 1, bsu=bsu if nb > 1 else 1,
                                      with_el=spec.nw > 0, sort_slots=sort_slots, compact=compact,
                                      index_bytes=8 if idt == np.int64 else 4,
-                                     batch_cap=int(env("SPFEM_TILE_BATCH", "0")))
+                                     batch_cap=int(env("SPFEM_TILE_BATCH", "0")),
+                                     split_factor=float(env("SPFEM_TILE_SPLIT", "1.25")))
             except TileTooLarge:
                 tp = None
                 continue

@@ -66,14 +66,31 @@ def _facet_to_element(t2f, nf):
 # ---------------------------------------------------------------------------
 def _entity_table_torch(torch, t, local_tuples, nv):
     k = len(local_tuples[0])
-    if float(nv) ** k >= 2.0 ** 62:
-        raise ValueError("vertex tuples do not fit a 64-bit key")
     blocks = [torch.sort(t[list(loc), :], dim=0).values for loc in local_tuples]
     allc = torch.cat(blocks, 1)
+    del blocks
+    if float(nv) ** k >= 2.0 ** 62:
+        # vertex triples of a large mesh (nv^3 > 2^62): two-level key -- the rank of
+        # the leading pair among the distinct leading pairs is monotone in the
+        # lexicographic order, so (rank, third vertex) sorts like the triple
+        if k != 3 or float(nv) ** 2 >= 2.0 ** 62:
+            raise ValueError("vertex tuples do not fit a 64-bit key")
+        u01, r01 = torch.unique(allc[0] * nv + allc[1], return_inverse=True)
+        if float(u01.numel()) * nv >= 2.0 ** 62:
+            raise ValueError("vertex tuples do not fit a 64-bit key")
+        key = r01 * nv + allc[2]
+        del r01, allc
+        ukey, inverse = torch.unique(key, return_inverse=True)
+        del key
+        pair = u01[ukey // nv]
+        rows = [pair // nv, pair % nv, ukey % nv]
+        return torch.stack(rows, 0), inverse.reshape(len(local_tuples), t.shape[1])
     key = allc[0].clone()
     for r in range(1, k):
         key = key * nv + allc[r]
+    del allc
     ukey, inverse = torch.unique(key, return_inverse=True)
+    del key
     rows = []
     for r in range(k):
         rows.append((ukey // (nv ** (k - 1 - r))) % nv)

@@ -70,7 +70,8 @@ def _build(asm, plan, tv, tu, vt, E, **kw):
 
 VARIANTS = [dict(), dict(sort_slots=1), dict(sort_slots=2), dict(compact=True),
             dict(compact=True, sort_slots=1), dict(batch_cap=3000),
-            dict(batch_cap=1500, sort_slots=1)]
+            dict(batch_cap=1500, sort_slots=1), dict(split_factor=1.05),
+            dict(split_factor=1.1, compact=True, sort_slots=1)]
 
 
 @pytest.mark.parametrize("name,E", [("trip1_lap", 64), ("trip1_lap_r6", 1024),
