@@ -73,6 +73,8 @@ typedef struct SpfemFanArgs {
     const unsigned char *blob;
     double *values;
     int max_a, max_b, max_ns, prefetch;
+    int ntiles, tiles_per_cta;   /* CTA b walks tiles [b*tiles_per_cta, ...) with two
+                                    blob buffers (TMA of the next tile in flight)      */
 } SpfemFanArgs;
 
 int         spfem_abi_version(void);

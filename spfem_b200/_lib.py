@@ -94,6 +94,7 @@ class SpfemFanArgs(C.Structure):
         ("base", SpfemArgs),
         ("desc", C.c_void_p), ("blob", C.c_void_p), ("values", C.c_void_p),
         ("max_a", C.c_int), ("max_b", C.c_int), ("max_ns", C.c_int), ("prefetch", C.c_int),
+        ("ntiles", C.c_int), ("tiles_per_cta", C.c_int),
     ]
 
 

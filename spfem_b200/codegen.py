@@ -84,7 +84,7 @@ struct SpfemArgs {
 # no partial sums in HBM.  For vector elements (SPFEM_NB = bsv*bsu > 1) a slot
 # is the bsv x bsu block of values of one scalar entry: one index decode serves
 # NB values and the plan is NB times smaller.
-TILE_THREADS = int(os.environ.get("SPFEM_TILE_T", "512"))
+TILE_THREADS = int(os.environ.get("SPFEM_TILE_T", "256"))
 DEVICE_HELPERS = r"""
 #ifndef SPFEM_HOST
 static __device__ __forceinline__ unsigned spfem_smem(const void *p)
@@ -155,6 +155,18 @@ struct SpfemPacked {
 #if SPFEM_NB > 1
 /* distinct-value id of component (a, b) of scalar entry j*nbv + i (block plans) */
 __device__ const unsigned short SPFEM_UT[SPFEM_NSIDX * SPFEM_NB] = {@UT@};
+/* one row of the (id * ldl) table in shared memory -> registers, as one vector
+   load where the row is 8 or 16 bytes (the table starts 16-byte aligned)     */
+#if SPFEM_NB == 4
+#define SPFEM_UT_LOAD(u, tab, r) do { const int4 q_ = reinterpret_cast<const int4 *>(tab)[r]; \
+    u[0] = q_.x; u[1] = q_.y; u[2] = q_.z; u[3] = q_.w; } while (0)
+#elif SPFEM_NB == 2
+#define SPFEM_UT_LOAD(u, tab, r) do { const int2 q_ = reinterpret_cast<const int2 *>(tab)[r]; \
+    u[0] = q_.x; u[1] = q_.y; } while (0)
+#else
+#define SPFEM_UT_LOAD(u, tab, r) do { _Pragma("unroll") \
+    for (int z_ = 0; z_ < SPFEM_NB; ++z_) u[z_] = (tab)[(r) * SPFEM_NB + z_]; } while (0)
+#endif
 #endif
 extern "C" __global__ void __launch_bounds__(@THREADS@, @MINB@) @NAME@_tile(const SpfemTileArgs T)
 {
@@ -268,14 +280,17 @@ extern "C" __global__ void __launch_bounds__(@THREADS@, @MINB@) @NAME@_tile(cons
         double acc[SPFEM_NB];
         {
             const unsigned c = cb[k0];
-            const int *ut = sUT + (c >> T.els) * SPFEM_NB;
+            int ut[SPFEM_NB];
+            SPFEM_UT_LOAD(ut, sUT, c >> T.els);
             const double *col = sL + (c & elm);
 #pragma unroll
             for (int ab = 0; ab < SPFEM_NB; ++ab) acc[ab] = col[ut[ab]];
         }
+#pragma unroll 2
         for (unsigned kk = k0 + 1; kk < k1; ++kk) {
             const unsigned c = cb[kk];
-            const int *ut = sUT + (c >> T.els) * SPFEM_NB;
+            int ut[SPFEM_NB];
+            SPFEM_UT_LOAD(ut, sUT, c >> T.els);
             const double *col = sL + (c & elm);
 #pragma unroll
             for (int ab = 0; ab < SPFEM_NB; ++ab) acc[ab] += col[ut[ab]];
@@ -315,6 +330,7 @@ struct SpfemFanArgs {
     const unsigned char *blob;
     double *values;
     int max_a, max_b, max_ns, prefetch;
+    int ntiles, tiles_per_cta;    /* CTA b handles tiles [b*tiles_per_cta, ...)   */
 };
 template <int MAXN, bool TINY>
 SPFEM_DEVICE void @NAME@_fan_row(const SpfemArgs &P, const double2 *__restrict__ pc2,
@@ -354,10 +370,11 @@ SPFEM_DEVICE void @NAME@_fan_row(const SpfemArgs &P, const double2 *__restrict__
     const int posdiag = (int)((w[1] >> 24) & 0xffu);
     const double2 cr = pc2[row];                 /* rows are the first vertices of a tile */
     const int nn = nfan + (closed ? 0 : 1);      /* ring neighbours */
-    double acc[MAXN + 1];
-#pragma unroll
-    for (int q = 0; q < MAXN + 1; ++q) acc[q] = 0.0;
-    double diag = 0.0;
+    /* Slot (r, n_f) receives exactly two triangles: f-1 (where n_f is the far
+       neighbour) and f.  `carry` hands the first over to the next step, so the
+       sum is carry + L[r, n_f] in ring order -- no accumulator array.  Slot 0 of a
+       closed ring gets its second contribution from the last triangle.          */
+    double diag = 0.0, carry = 0.0, a0 = 0.0;
     const double2 c0 = pc2[SPFEM_NBR(0)];
     double2 ca = c0;
 #pragma unroll
@@ -368,69 +385,92 @@ SPFEM_DEVICE void @NAME@_fan_row(const SpfemArgs &P, const double2 *__restrict__
         double L[SPFEM_NUNIQUE];
         @NAME@_core(P, cr.x, cr.y, ca.x, ca.y, cb.x, cb.y, L);
         diag += L[@A00@];                        /* (test r, trial r)       */
-        acc[f] += L[@A10@];                      /* (test r, trial n_f)     */
-        acc[f + 1] += L[@A20@];                  /* (test r, trial n_{f+1}) */
+        if (f == 0) {
+            a0 = L[@A10@];                       /* (test r, trial n_0), first half */
+        } else {
+            /* staged in RING order (slot s0 = diagonal, s0 + 1 + q = neighbour q):
+               the lanes of a warp write with a fixed stride, free of bank conflicts;
+               next to every value goes its CSR position                          */
+            sV[s0 + 1 + f] = carry + L[@A10@];   /* (test r, trial n_f)     */
+            sG[s0 + 1 + f] = g0 + (int)SPFEM_POS(f);
+        }
+        carry = L[@A20@];                        /* (test r, trial n_{f+1}) */
         ca = cb;
     }
-    if (closed) {                                /* the last triangle's n_{f+1} is n_0 */
-        double wrap = 0.0;
+    if (closed) {
+        a0 += carry;                             /* the last triangle's n_{f+1} is n_0 */
+    } else {
 #pragma unroll
-        for (int q = 1; q < MAXN + 1; ++q) if (q == nfan) wrap = acc[q];
-        acc[0] += wrap;
+        for (int q = 1; q < MAXN + 1; ++q)
+            if (q == nfan) { sV[s0 + 1 + q] = carry; sG[s0 + 1 + q] = g0 + (int)SPFEM_POS(q < MAXN ? q : MAXN - 1); }
     }
-    /* staged in RING order (slot s0 = diagonal, s0 + 1 + q = neighbour q): the
-       lanes of a warp write with a fixed stride, free of bank conflicts; next to
-       every value goes its CSR position, so the store phase is two conflict-free
-       shared loads and one global store per slot                               */
     sV[s0] = diag;
     sG[s0] = g0 + posdiag;
-#pragma unroll
-    for (int q = 0; q < MAXN; ++q) {
-        if (q >= nn) break;
-        sV[s0 + 1 + q] = acc[q];
-        sG[s0 + 1 + q] = g0 + (int)SPFEM_POS(q);
-    }
+    sV[s0 + 1] = a0;
+    sG[s0 + 1] = g0 + (int)SPFEM_POS(0);
 #undef SPFEM_POS
 #undef SPFEM_NBR
 }
 #ifndef SPFEM_HOST
+#define SPFEM_FAN_MAXK 64
 template <int MAXN, bool TINY>
 static __device__ __forceinline__ void @NAME@_fan_tile(const SpfemFanArgs &T)
 {
+    /* One CTA walks `tiles_per_cta` consecutive tiles with two blob buffers: the
+       TMA bulk copy of tile i+1 (and i+2, as soon as buffer i is free) is in
+       flight while tile i is computed, so only the first tile of a CTA pays the
+       descriptor -> TMA -> wait latency.                                        */
     extern __shared__ __align__(128) unsigned char spfem_smem_raw[];
-    unsigned char *sA = spfem_smem_raw;                       /* the tile's blob */
-    double *sV = (double *)(sA + T.max_a);
+    unsigned char *buf0 = spfem_smem_raw;
+    unsigned char *buf1 = buf0 + T.max_a;
+    double *sV = (double *)(buf1 + T.max_a);
     unsigned long long *bars = (unsigned long long *)(sV + T.max_ns);
     int *sG = (int *)(bars + 2);
-    const int *d = T.desc + 8 * (size_t)blockIdx.x;
-    const int bytes_a = d[1], bytes_b = d[2], nr = d[3], ns = d[4];
-    if (nr == 0) return;
+    int *sD = sG + T.max_ns;                                   /* descriptors of my tiles */
+    const int K = T.tiles_per_cta;
+    const int t0 = (int)blockIdx.x * K;
+    const int nk = min(K, T.ntiles - t0);
+    for (int i = threadIdx.x; i < 8 * nk; i += blockDim.x) sD[i] = T.desc[8 * (size_t)t0 + i];
     if (threadIdx.x == 0) {
         spfem_mbar_init(&bars[0], 1);
+        spfem_mbar_init(&bars[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        spfem_bulk_load(sA, T.blob + (size_t)(unsigned)d[0] * 16,
-                        (unsigned)(bytes_a + bytes_b), &bars[0]);
     }
     __syncthreads();
     if (threadIdx.x == 0) {
-        /* pull the blob of a tile that will start a few waves later into L2, so
-           its own TMA load does not pay the DRAM latency (issued after the
-           barrier: the descriptor load of that tile must not hold up this CTA)  */
-        const long long tp = (long long)blockIdx.x + T.prefetch;
-        if (T.prefetch > 0 && tp < (long long)gridDim.x) {
-            const int *dp = T.desc + 8 * (size_t)tp;
+        spfem_bulk_load(buf0, T.blob + (size_t)(unsigned)sD[0] * 16,
+                        (unsigned)(sD[1] + sD[2]), &bars[0]);
+        if (nk > 1)
+            spfem_bulk_load(buf1, T.blob + (size_t)(unsigned)sD[8] * 16,
+                            (unsigned)(sD[9] + sD[10]), &bars[1]);
+        /* pull the blobs of a CTA that will start a few waves later into L2, so its
+           first TMA load does not pay the DRAM latency (one contiguous span)      */
+        const long long tp = (long long)t0 + (long long)T.prefetch * K;
+        if (T.prefetch > 0 && tp < (long long)T.ntiles) {
+            const long long tq = min(tp + K, (long long)T.ntiles) - 1;
+            const int *dp = T.desc + 8 * (size_t)tp, *dq = T.desc + 8 * (size_t)tq;
+            const size_t lo = (size_t)(unsigned)dp[0] * 16;
+            const size_t hi = (size_t)(unsigned)dq[0] * 16 + (size_t)(dq[1] + dq[2]);
             asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;"
-                         ::"l"(T.blob + (size_t)(unsigned)dp[0] * 16),
-                           "r"((unsigned)(dp[1] + dp[2])) : "memory");
+                         ::"l"(T.blob + lo), "r"((unsigned)(hi - lo)) : "memory");
         }
     }
-    spfem_mbar_wait(&bars[0], 0);
-    for (int row = threadIdx.x; row < nr; row += blockDim.x)
-        @NAME@_fan_row<MAXN, TINY>(T.base, (const double2 *)sA, sA + bytes_a, nr, row, sV, sG);
-    __syncthreads();
-    /* every slot of the tile exactly once; a warp covers the CSR rows of its
-       threads, so its stores fill whole 32-byte sectors                        */
-    for (int s = threadIdx.x; s < ns; s += blockDim.x) T.values[sG[s]] = sV[s];
+    for (int i = 0; i < nk; ++i) {
+        const int *d = sD + 8 * i;
+        const int bytes_a = d[1], nr = d[3], ns = d[4];
+        unsigned char *sA = (i & 1) ? buf1 : buf0;
+        spfem_mbar_wait(&bars[i & 1], (unsigned)((i >> 1) & 1));
+        for (int row = threadIdx.x; row < nr; row += blockDim.x)
+            @NAME@_fan_row<MAXN, TINY>(T.base, (const double2 *)sA, sA + bytes_a, nr, row, sV, sG);
+        __syncthreads();
+        if (threadIdx.x == 0 && i + 2 < nk)     /* buffer (i & 1) is free again */
+            spfem_bulk_load(sA, T.blob + (size_t)(unsigned)d[16] * 16,
+                            (unsigned)(d[17] + d[18]), &bars[i & 1]);
+        /* every slot of the tile exactly once; a warp covers the CSR rows of its
+           threads, so its stores fill whole 32-byte sectors                      */
+        for (int s = threadIdx.x; s < ns; s += blockDim.x) T.values[sG[s]] = sV[s];
+        if (i + 1 < nk) __syncthreads();
+    }
 }
 /* two instantiations: meshes whose vertices have at most 8 ring neighbours
    (fewer registers, higher occupancy) and the general case (<= 12)         */
@@ -1007,7 +1047,9 @@ def generate_interior(spec, name="spfem_elem"):
                    .replace("@BUNROLL@", os.environ.get("SPFEM_TILE_BUNROLL", "2"))
                    .replace("@TUNROLL@", os.environ.get("SPFEM_TILE_TUNROLL", "4"))
                    .replace("@THREADS@", str(TILE_THREADS))
-                   .replace("@MINB@", os.environ.get("SPFEM_TILE_MINB", "1")))
+                   # registers: three CTAs of 256 threads per SM on 2-D meshes (<= 85
+                   # registers; measured +19 % for vector-P2), two on 3-D meshes
+                   .replace("@MINB@", os.environ.get("SPFEM_TILE_MINB", "3" if dim == 2 else "2")))
     src.append("#else")
     src.append('extern "C" void %s_host(const SpfemArgs *P)\n{' % name)
     src.append("    for (long long k = 0; k < P->n; ++k) {")

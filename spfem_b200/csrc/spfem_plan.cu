@@ -440,7 +440,7 @@ int build(const SpfemPlanIn &in, SpfemPlanOut &out, Ctx &c)
             const int *pt_ = pt;
             boundaries(c, P, ntiles, te_ptr, [=] __host__ __device__(i64 q) { return (i64)pt_[q]; });
         }
-        if (in.split_factor <= 0.0 || pass >= 2) break;
+        if (in.split_factor <= 0.0 || pass >= 4) break;
         std::vector<i64> h_te;
         to_host(c, te_ptr, (size_t)ntiles + 1, h_te);
         std::vector<i64> ne_sorted(ntiles);
@@ -451,7 +451,10 @@ int build(const SpfemPlanIn &in, SpfemPlanOut &out, Ctx &c)
         }
         std::nth_element(ne_sorted.begin(), ne_sorted.begin() + ntiles / 2, ne_sorted.end());
         const i64 median = ne_sorted[ntiles / 2];
-        const i64 budget = std::max<i64>((i64)(in.split_factor * (double)median + 0.999), 8);
+        // the shared-memory image has one column per tile element, padded to a
+        // multiple of 32: the budget is the padded size of a typical tile
+        i64 budget = std::max<i64>((i64)(in.split_factor * (double)median + 0.999), 8);
+        budget = (budget + 31) / 32 * 32;
         if (ne_hi <= budget) break;
         std::vector<i64> nt2;
         for (i64 T = 0; T < ntiles; ++T) {

@@ -328,11 +328,10 @@ class TiledPrepared(Prepared):
             ta.els = tp["els"]
             ta.prefetch = int(os.environ.get("SPFEM_TILE_PREFETCH", "300"))   # about one wave ahead
             self.targs.append((ta, B["ntiles"]))
-        # 256 threads measured best while two or more CTAs share an SM; a tile
-        # that fills the SM alone takes the maximum
-        self.threads = 256 if self.smem <= 113 * 1024 else codegen_tile_threads()
+        # 256 threads measured best (128 and 512 are 0-40 % slower)
+        self.threads = min(256, codegen_tile_threads())
         if os.environ.get("SPFEM_TILE_THREADS"):
-            self.threads = int(os.environ["SPFEM_TILE_THREADS"])
+            self.threads = min(int(os.environ["SPFEM_TILE_THREADS"]), codegen_tile_threads())
         self.n_launches = len(self.targs)
 
     def launch(self):
@@ -361,21 +360,27 @@ class FanPrepared(Prepared):
         fa.blob = fp["blob"].data_ptr()
         fa.values = self.values.data_ptr()
         fa.max_a, fa.max_b, fa.max_ns = fp["max_a"], fp["max_b"], fp["max_ns"]
-        # L2 prefetch distance in tiles (about two waves of resident CTAs ahead)
-        fa.prefetch = int(os.environ.get("SPFEM_FAN_PREFETCH", "2400"))
+        # tiles per CTA (double-buffered TMA: only a CTA's first tile pays the
+        # descriptor -> bulk copy -> wait latency) and the L2 prefetch distance in
+        # CTAs (about two waves of resident CTAs ahead)
+        K = max(1, min(64, int(os.environ.get("SPFEM_FAN_K", "4"))))
+        fa.ntiles, fa.tiles_per_cta = fp["ntiles"], K
+        fa.prefetch = int(os.environ.get("SPFEM_FAN_PREFETCH", str(max(1, 2400 // K))))
         self.fargs = fa
-        self.smem = fp["max_a"] + 12 * fp["max_ns"] + 64
+        self.grid = (fp["ntiles"] + K - 1) // K
+        self.smem = 2 * fp["max_a"] + 12 * fp["max_ns"] + 32 * K + 64
         from . import codegen
         self.threads = codegen.FAN_THREADS
         self.n_launches = 1
         self.tp = {"E": fp["rows_per_tile"], "ldl": 0, "ntiles": fp["ntiles"],
-                   "halo_factor": fp["halo_factor"], "kind": "vertex-fan"}
+                   "halo_factor": fp["halo_factor"], "kind": "vertex-fan",
+                   "tiles_per_cta": K}
 
     def launch(self):
         e = self.engine
         self.fargs.base = self.args
         _lib.check(e.lib.spfem_launch_tiled(self.fan_kernel, C.byref(self.fargs),
-                                            self.fp["ntiles"], self.threads,
+                                            self.grid, self.threads,
                                             self.smem, e._stream()))
         return self.values
 
@@ -669,7 +674,7 @@ class Engine(object):
         ckey = (plan.bilinear, spec.n_unique, tuple(spec.alias), spec.nw > 0,
                 env("SPFEM_TILE_MODE", "auto"), env("SPFEM_TILE_E", "0"),
                 env("SPFEM_TILE_SORT", "auto"), env("SPFEM_TILE_BLOCKS", "1"),
-                env("SPFEM_TILE_SPLIT", "1.25"))
+                env("SPFEM_TILE_SPLIT", "1.02"))
         if ckey in self._tile_cache:
             return self._tile_cache[ckey]
         force = env("SPFEM_FUSED", "1") == "force"
@@ -697,7 +702,8 @@ class Engine(object):
         if srt == "auto":
             # 3-D: a row's slots have 1 ... ~24 contributions; ordering a tile's
             # slots by that count keeps warps converged (TetP2 +25 %, TetP1 +14 %)
-            sort_slots = 1 if dim == 3 else 0
+            # 2-D vector elements: coarse count classes in CSR order (+6 %)
+            sort_slots = 1 if dim == 3 else (2 if nb > 1 else 0)
         else:
             sort_slots = {"bucket": 2, "1": 1}.get(srt, 0)
         nuniq = spec.n_unique
@@ -731,7 +737,7 @@ class Engine(object):
                                      with_el=spec.nw > 0, sort_slots=sort_slots, compact=compact,
                                      index_bytes=8 if idt == np.int64 else 4,
                                      batch_cap=int(env("SPFEM_TILE_BATCH", "0")),
-                                     split_factor=float(env("SPFEM_TILE_SPLIT", "1.25")))
+                                     split_factor=float(env("SPFEM_TILE_SPLIT", "1.02")))
             except TileTooLarge:
                 tp = None
                 continue

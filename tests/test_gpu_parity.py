@@ -142,7 +142,7 @@ def test_both_assembly_paths(name, mode, monkeypatch):
         elif mode == "scalar_slots":                # vector elements without block slots
             monkeypatch.setenv("SPFEM_TILE_BLOCKS", "0")
         elif mode == "batched":
-            monkeypatch.setenv("SPFEM_TILE_BATCH", "20000")
+            monkeypatch.setenv("SPFEM_TILE_BATCH", "2000")
         monkeypatch.setenv("SPFEM_FUSED", "force")   # bypass the "is it worth it" heuristic
         monkeypatch.setenv("SPFEM_FAN", "0")         # (the tile kernel, not the vertex-fan kernel)
     case = cases.BY_NAME[name]
@@ -153,7 +153,9 @@ def test_both_assembly_paths(name, mode, monkeypatch):
         assert prep.n_launches == 2
     else:
         assert type(prep).__name__ == "TiledPrepared"
-        assert (prep.n_launches > 1) == (mode == "batched")
+        assert prep.n_launches == len(prep.tp["batches"])
+        if mode == "batched" and prep.tp["n_contrib"] > 4000:
+            assert prep.n_launches > 1
     prep.launch()
     util.check(prep.result(), util.golden(case))
     prep.launch()                                   # bitwise reproducible
