@@ -10,5 +10,6 @@ from .element import (Element, ElementH1, ElementH1Vec, ElementTriP1,
                       ElementTriMini, ElementTriDG, ElementTetDG, ElementTriPp,
                       ElementHdiv, ElementTriRT0)
 from .utils import direct, stack, const_cell, cell_shape
+from .assembly import Assembler, AssemblerElement, Dofnum
 
 __version__ = "0.1.0"

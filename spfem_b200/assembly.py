@@ -126,6 +126,7 @@ class AssemblerElement(Assembler):
             self.elem_v = elem_v
             self.dofnum_v = Dofnum(mesh, elem_v)
         self._engine = None        # device state, created on first assembly
+        self.row_mask = None       # optional bool [dofnum_v.N]: rows assembled here (multi-GPU)
         self._pou = None
         self.last_stats = {}
 

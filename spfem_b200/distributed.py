@@ -246,6 +246,202 @@ def strip_part(rank, world, refine, unit=None, halo=True):
     return part
 
 
+class SlabPart(LocalPart):
+    """Rank ``rank``'s piece of a structured grid cut into ``world`` slabs along
+    the last axis (:func:`slab_part`).  The maps to global DOF numbers are built
+    on first use: analytically for vertex DOFs and for the edges of the 2-D grid,
+    otherwise by matching vertex tuples against the global mesh (small meshes:
+    tests and the benchmark's parity check)."""
+
+    def __init__(self, mesh, elem_u, elem_v, owned_v, owner_v, n_own_elements, info):
+        self.mesh, self.owned_v, self.owner_v = mesh, owned_v, owner_v
+        self.n_own_elements = n_own_elements
+        self.elem_u, self.elem_v, self.info = elem_u, elem_v, info
+        self.on_global_boundary = None
+        self._maps = None
+
+    def _global_mesh(self):
+        from . import meshgen
+        i = self.info
+        if i["n_total"] > 4000000:
+            raise NotImplementedError("global DOF ids of this element on a slab "
+                                      "partition need the global mesh (small meshes only)")
+        if i["kind"] == "tri":
+            p, t = meshgen.grid_tri(i["size"], ny=i["size"] * i["world"])
+            return _mesh.MeshTri(p, t, validate=False)
+        p, t = meshgen.grid_tet(i["size"], mz=i["size"] * i["world"])
+        return _mesh.MeshTet(p, t, validate=False)
+
+    @staticmethod
+    def _tri_facet_index(v0, v1, nx, ny):
+        """Index of the edge (v0 < v1) of the nx x ny triangle grid in the
+        lexicographic list of its sorted vertex pairs (= ``mesh.facets``)."""
+        s = nx + 1
+        I, J = v0 % s, v0 // s
+        full_rows = J * (3 * nx + 1)
+        prefix = np.where(J < ny, np.where(I == 0, 0, 3 * I - 1), I)
+        d = v1 - v0
+        pos = np.where(d == 1, 0, np.where(d == nx, (I < nx).astype(np.int64),
+                                           (I < nx).astype(np.int64) + (I >= 1)))
+        return full_rows + prefix + pos
+
+    def _dof_maps(self):
+        if self._maps is not None:
+            return self._maps
+        i = self.info
+        lm = self.mesh
+        voff = i["vertex_offset"]
+        maps = []
+        gm = None
+        for elem in (self.elem_u, self.elem_v):
+            if elem is None or (maps and elem is self.elem_u):
+                maps.append(maps[0])
+                continue
+            ldn = Dofnum(lm, elem)
+            l2g = np.empty(ldn.N, dtype=np.int64)
+            nvg = i["nv_global"]
+            offset = elem.n_dofs * nvg
+            if elem.n_dofs:
+                k = np.arange(elem.n_dofs)[:, None]
+                l2g[ldn.n_dof] = (np.arange(lm.p.shape[1])[None, :] + voff) * elem.n_dofs + k
+            N = offset
+            analytic = i["kind"] == "tri"
+            if not analytic and (elem.e_dofs or elem.f_dofs or elem.i_dofs):
+                gm = gm or self._global_mesh()
+            if hasattr(lm, "edges"):
+                ne_g = gm.edges.shape[1] if gm is not None else 0
+                if elem.e_dofs:
+                    gi = _match_tuples(lm.edges + voff, gm.edges, nvg)
+                    l2g[ldn.e_dof] = offset + gi[None, :] * elem.e_dofs + np.arange(elem.e_dofs)[:, None]
+                offset += elem.e_dofs * ne_g
+            if analytic:
+                nx, ny = i["size"], i["size"] * i["world"]
+                nf_g = nx * (ny + 1) + (nx + 1) * ny + nx * ny
+                gi = (self._tri_facet_index(lm.facets[0] + voff, lm.facets[1] + voff, nx, ny)
+                      if elem.f_dofs else None)
+            else:
+                nf_g = gm.facets.shape[1] if gm is not None else 0
+                gi = _match_tuples(lm.facets + voff, gm.facets, nvg) if elem.f_dofs else None
+            if elem.f_dofs:
+                l2g[ldn.f_dof] = offset + gi[None, :] * elem.f_dofs + np.arange(elem.f_dofs)[:, None]
+            offset += elem.f_dofs * nf_g
+            if elem.i_dofs:
+                eg = i["element_offset"] + np.arange(lm.t.shape[1])
+                l2g[ldn.i_dof] = offset + eg[None, :] * elem.i_dofs + np.arange(elem.i_dofs)[:, None]
+            offset += elem.i_dofs * i["n_total"]
+            maps.append((l2g, offset))
+        self._maps = maps
+        return maps
+
+    l2g_u = property(lambda self: self._dof_maps()[0][0])
+    l2g_v = property(lambda self: self._dof_maps()[1][0])
+    N_u = property(lambda self: self._dof_maps()[0][1])
+    N_v = property(lambda self: self._dof_maps()[1][1])
+
+
+def _match_tuples(local, glob, nv):
+    """Index in ``glob`` (k x ng, lexicographically sorted unique columns) of
+    every column of ``local`` (k x nl)."""
+    k = local.shape[0]
+    if float(nv) ** k >= 2.0 ** 62:
+        raise NotImplementedError("vertex tuples do not fit a 64-bit key")
+    kg = glob[0].astype(np.int64)
+    kl = local[0].astype(np.int64)
+    for r in range(1, k):
+        kg = kg * nv + glob[r]
+        kl = kl * nv + local[r]
+    pos = np.searchsorted(kg, kl)
+    if not np.array_equal(kg[np.minimum(pos, len(kg) - 1)], kl):
+        raise ValueError("local entity missing from the global mesh")
+    return pos
+
+
+def slab_part(kind, size, rank, world, elem_u, elem_v=None, halo=True):
+    """Rank ``rank``'s part of the weak-scaling meshes of BASELINE configs 3-5:
+    ``kind="tri"``: the ``size x (size*world)`` triangle grid of the rectangle
+    ``[0,1] x [0,world]`` (``meshgen.grid_tri``), ``kind="tet"``: the Kuhn grid of
+    ``[0,1]^2 x [0,world]`` (``meshgen.grid_tet``), cut into ``world`` slabs of
+    ``size`` cell layers along the last axis.  Every rank builds only its own
+    slab plus (``halo=True``) the layer of cells above it, whose elements touch
+    the rows on the slab's top plane -- the global mesh never exists.
+
+    Ownership is the general rule (lowest rank touching the row): a rank owns
+    the DOFs of its own cells except those on its bottom plane (rank - 1 owns
+    them); DOFs that only the halo layer touches belong to rank + 1.  Works for
+    any element (the masks come from the local ``Dofnum``)."""
+    from . import meshgen
+    k0, k1 = rank * size, (rank + 1) * size
+    top = k1 + (1 if (halo and rank < world - 1) else 0)
+    if kind == "tri":
+        p, t = meshgen.grid_tri(size, ny=size * world, j0=k0, j1=top)
+        mesh = _mesh.MeshTri(p, t, validate=False)
+        plane = size + 1
+        per_layer, axis = 2 * size, 1
+        nv_global = (size + 1) * (size * world + 1)
+    elif kind == "tet":
+        p, t = meshgen.grid_tet(size, mz=size * world, k0=k0, k1=top)
+        mesh = _mesh.MeshTet(p, t, validate=False)
+        plane = (size + 1) * (size + 1)
+        per_layer, axis = 6 * size * size, 2
+        nv_global = plane * (size * world + 1)
+    else:
+        raise ValueError("kind must be 'tri' or 'tet'")
+    n_own = per_layer * size
+    nv_loc = mesh.p.shape[1]
+    v_bottom = np.zeros(nv_loc, dtype=bool)
+    if rank > 0:
+        v_bottom[:plane] = True                      # first vertex plane of the slab
+    parts = []
+    for elem in (elem_u, elem_v if (elem_v is not None and elem_v is not elem_u) else None):
+        if elem is None:
+            parts.append(None)
+            continue
+        dn = Dofnum(mesh, elem)
+        touched = np.zeros(dn.N, dtype=bool)
+        touched[dn.t_dof[:, :n_own]] = True          # DOFs of my own cells
+        bottom = np.zeros(dn.N, dtype=bool)
+        if rank > 0:
+            if elem.n_dofs:
+                bottom[dn.n_dof[:, v_bottom]] = True
+            if hasattr(mesh, "edges") and elem.e_dofs:
+                bottom[dn.e_dof[:, v_bottom[mesh.edges].all(axis=0)]] = True
+            if elem.f_dofs:
+                bottom[dn.f_dof[:, v_bottom[mesh.facets].all(axis=0)]] = True
+        owned = touched & ~bottom
+        owner = np.where(owned, rank, np.where(bottom, rank - 1, rank + 1)).astype(np.int64)
+        parts.append((owned, owner))
+    owned_v, owner_v = parts[1] if parts[1] is not None else parts[0]
+    info = {"kind": kind, "size": size, "world": world, "rank": rank,
+            "vertex_offset": k0 * plane, "nv_global": nv_global,
+            "element_offset": k0 * per_layer, "n_total": per_layer * size * world}
+    part = SlabPart(mesh, elem_u, elem_v if elem_v is not None else elem_u, owned_v, owner_v,
+                    n_own, info)
+    hi = float(world)
+
+    def on_global_boundary(lmesh, lf):
+        """A local boundary facet is on the global boundary iff its midpoint lies
+        on a face of the box [0,1]^(d-1) x [0,world] (the rest are cuts)."""
+        mid = lmesh.p[:, lmesh.facets[:, lf]].mean(axis=1)
+        on = np.zeros(mid.shape[1], dtype=bool)
+        for d in range(mid.shape[0]):
+            top_d = hi if d == axis else 1.0
+            on |= (mid[d] == 0.0) | (mid[d] == top_d)
+        return on
+
+    part.on_global_boundary = on_global_boundary
+    return part
+
+
+def slab_global(kind, size, world):
+    """The whole slab mesh (tests and the benchmark's parity check; small sizes)."""
+    from . import meshgen
+    if kind == "tri":
+        p, t = meshgen.grid_tri(size, ny=size * world)
+        return _mesh.MeshTri(p, t, validate=False)
+    p, t = meshgen.grid_tet(size, mz=size * world)
+    return _mesh.MeshTet(p, t, validate=False)
+
+
 def strip_global(world, refine):
     """The whole strip mesh with the global numbering of :func:`strip_part`
     (tests only; small sizes)."""
@@ -487,6 +683,10 @@ class DistributedAssembler(object):
             raise ValueError("mode='exchange' needs a partition with owner_v "
                              "(partition_global(..., halo=False))")
         self.local = AssemblerElement(self.part.mesh, elem_u, elem_v)
+        if mode == "halo":
+            # rows another rank owns are not assembled here at all (the native tile
+            # plan gives them no slots; the other routes compute and ignore them)
+            self.local.row_mask = np.ascontiguousarray(self.part.owned_v, dtype=bool)
         self._assemble = assemble
         self._assemble_facet = assemble_facet
 

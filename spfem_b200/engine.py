@@ -664,6 +664,14 @@ class Engine(object):
         pat._fan_plan = fp
         return fp
 
+    def _row_mask(self):
+        rm = getattr(self.asm, "row_mask", None)
+        if rm is None:
+            return None
+        if getattr(self, "_row_mask_t", None) is None:
+            self._row_mask_t = self._dev(np.asarray(rm), np.uint8)
+        return self._row_mask_t
+
     def tile_plan(self, plan):
         """``(pattern, tile plan)`` of the fused kernel for the whole mesh (built
         natively, ``tileplan.build_tile_plan``; cached per distinct-value layout),
@@ -735,6 +743,7 @@ class Engine(object):
                                      E, spec.alias, nuniq, dim,
                                      bsv=bsv if nb > 1 else 1, bsu=bsu if nb > 1 else 1,
                                      with_el=spec.nw > 0, sort_slots=sort_slots, compact=compact,
+                                     row_mask=self._row_mask(),
                                      index_bytes=8 if idt == np.int64 else 4,
                                      batch_cap=int(env("SPFEM_TILE_BATCH", "0")),
                                      split_factor=float(env("SPFEM_TILE_SPLIT", "1.02")))
@@ -754,7 +763,7 @@ class Engine(object):
         if tp is not None and not force and n_terms * tp["halo_factor"] > 1500:
             tp = None
         if tp is not None and not bilinear and tp["nnz"] != asm.dofnum_v.N:
-            tp = None                   # untouched DOFs: the dense vector needs zeros there
+            tp = None                   # untouched / masked DOFs: the dense vector needs zeros there
         hit = None
         if tp is not None:
             fill_coordinates(tp, self.p)

@@ -31,6 +31,6 @@ def test_partitioned_assembly_matches_reference(world):
         if out.returncode == 0:
             break
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
-    for label, count in (("dist ok", 7), ("xchg ok", 7), ("strip ok", 3), ("facet ok", 19), ("interior facet ok", 3), ("strip facet ok", 4),
-                         ("strip exchange ok", 3)):
+    for label, count in (("dist ok", 7), ("xchg ok", 7), ("strip ok", 3), ("facet ok", 21), ("interior facet ok", 3), ("strip facet ok", 4),
+                         ("strip exchange ok", 3), ("slab ok", 8), ("slab facet ok", 2)):
         assert out.stdout.count(label) == count, out.stdout

@@ -4,6 +4,7 @@ tracer rules, NVRTC compilation for sm_100a, and the C-ABI exports."""
 import os
 import re
 import subprocess
+import sys
 
 import numpy as np
 import pytest
@@ -154,3 +155,19 @@ def test_chunked_assembly_matches_single_call(name, monkeypatch):
     util.check(out, util.golden(case))
     monkeypatch.setenv("SPFEM_MAX_ENTRIES", str(2 ** 31 - 1))
     assert asm._chunks_needed(plan, None) == 1
+
+
+def test_spfem_alias_package():
+    """``compat/spfem``: reference-style imports resolve to spfem_b200
+    (spfem/__init__.py:1-6, spfem/asm.py:7)."""
+    code = ("import spfem, spfem.mesh, spfem.asm, spfem.element\n"
+            "from spfem.asm import AssemblerElement\n"
+            "from spfem.mesh import MeshTri\n"
+            "import spfem_b200.assembly as a\n"
+            "assert AssemblerElement is a.AssemblerElement and spfem.asm is a\n"
+            "m = MeshTri(); m.refine(2)\n"
+            "assert spfem.AssemblerElement(m, spfem.ElementTriP1()).dofnum_u.N == 25\n"
+            "print('alias ok')\n")
+    env = dict(os.environ, PYTHONPATH=os.path.join(ROOT, "compat") + os.pathsep + ROOT)
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env)
+    assert out.returncode == 0 and "alias ok" in out.stdout, out.stderr[-2000:]
