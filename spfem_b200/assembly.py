@@ -453,6 +453,16 @@ class AssemblerElement(Assembler):
         plan = self.plan_iasm(form, intorder=intorder, interp=interp)
         return self._get_engine().prepare_interior(plan, tind, interp)
 
+    def prepare_fasm(self, form, find=None, interior=False, intorder=None,
+                     normals=True, interp=None):
+        """Staged facet assembly (see :meth:`prepare_iasm`)."""
+        if find is None:
+            find = (self.mesh.interior_facets() if interior
+                    else self.mesh.boundary_facets())
+        plan = self.plan_fasm(form, interior=interior, intorder=intorder,
+                              normals=normals, interp=interp)
+        return self._get_engine().prepare_facet(plan, np.asarray(find), interior, interp)
+
     # ------------------------------------------------------------------
     # error norms (spfem/assembly.py:1353-1485) on top of the device path
     # ------------------------------------------------------------------

@@ -712,6 +712,8 @@ class DistributedAssembler(object):
         pkey = (kind, bilinear, id(getattr(loc, "pattern", None)), int(values.numel()))
         hit = self._xchg.get(pkey)
         if hit is None:                # (the pattern is kept alive with its plan)
+            while len(self._xchg) >= 8:            # bounded: oldest plan out
+                self._xchg.pop(next(iter(self._xchg)))
             hit = self._xchg[pkey] = (InterfaceExchange(
                 self.part, rows, cols, self.group, self.rank, self.world),
                 getattr(loc, "pattern", None))

@@ -396,6 +396,7 @@ class Engine(object):
         self.stats = {}
         self._tile_plans = []
         self._tile_cache = {}
+        self._facet_cache = {}        # facet set -> (pattern, index tables)
         self.p_version = 0
         self.fused = os.environ.get("SPFEM_FUSED", "1") != "0"
         mesh = asm.mesh
@@ -813,25 +814,37 @@ class Engine(object):
             out = res
         return _to_host(out)
 
-    def run_facet(self, plan, find, interior, interp=None, to_host=True):
-        torch, lib, asm = self.torch, self.lib, self.asm
+    def prepare_facet(self, plan, find, interior, interp=None):
+        """Facet assembly up to the launch.  The index tables and the sparsity
+        pattern of a facet set are cached per (facet set, interior, bilinear,
+        element pair): a time loop that calls ``fasm`` with the same facets again
+        only traces, launches and copies (bounded cache, least recently used out)."""
+        import hashlib
+        torch, asm = self.torch, self.asm
         spec = plan.spec
         kernel = get_kernel(plan.source, plan.name)
         find = np.asarray(find)
         if find.dtype == bool:
             find = np.nonzero(find)[0]
+        find = np.ascontiguousarray(find, dtype=np.int64)
         n = int(find.shape[0])
         nblk = len(spec.blocks)
-        fv, e1, e2, lf1 = asm.facet_tables(find)
-        rows, cols = asm.facet_dofs(find, interior)
-        rowdof = self._dev(rows, np.int32)
-        coldof = self._dev(cols, np.int32) if plan.bilinear else None
-        pat = self.build_pattern(rowdof, coldof, asm.dofnum_v.N,
-                                 asm.dofnum_u.N if plan.bilinear else 1)
-        fv_d = self._dev(fv, np.int32)
-        e1_d = self._elements(e1).to(torch.int32)
-        e2_d = self._elements(e2).to(torch.int32)
-        lf_d = self._dev(lf1, np.int32)
+        key = (bool(interior), bool(plan.bilinear), n,
+               hashlib.sha1(find.tobytes()).hexdigest())
+        hit = self._facet_cache.pop(key, None)
+        if hit is None:
+            fv, e1, e2, lf1 = asm.facet_tables(find)
+            rows, cols = asm.facet_dofs(find, interior)
+            rowdof = self._dev(rows, np.int32)
+            coldof = self._dev(cols, np.int32) if plan.bilinear else None
+            pat = self.build_pattern(rowdof, coldof, asm.dofnum_v.N,
+                                     asm.dofnum_u.N if plan.bilinear else 1)
+            hit = (pat, self._dev(fv, np.int32), self._elements(e1).to(torch.int32),
+                   self._elements(e2).to(torch.int32), self._dev(lf1, np.int32))
+        self._facet_cache[key] = hit                  # (re-)insert as most recent
+        while len(self._facet_cache) > 8:
+            self._facet_cache.pop(next(iter(self._facet_cache)))
+        pat, fv_d, e1_d, e2_d, lf_d = hit
         local = self._empty(max(spec.n_entries * nblk * n, 1), torch.float64)
         wt = self._interp_tensors(plan, interp)
         a = _lib.SpfemArgs()
@@ -842,10 +855,13 @@ class Engine(object):
         a.fv, a.e1, a.e2, a.lf1 = (fv_d.data_ptr(), e1_d.data_ptr(),
                                    e2_d.data_ptr(), lf_d.data_ptr())
         a.out = local.data_ptr()
-        prep = Prepared(self, plan, kernel, a, 64, local, pat,
+        return Prepared(self, plan, kernel, a, 64, local, pat,
                         keep=(fv_d, e1_d, e2_d, lf_d, wt))
+
+    def run_facet(self, plan, find, interior, interp=None, to_host=True):
+        prep = self.prepare_facet(plan, find, interior, interp)
         values = prep.launch()
-        return self._finish(values, pat, plan.bilinear, to_host)
+        return self._finish(values, prep.pattern, plan.bilinear, to_host)
 
     def run_facet_functional(self, plan, find, interp):
         """One value per facet (``fnorm``): the generated facet kernel has a
