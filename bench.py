@@ -243,6 +243,7 @@ def vec_nitsche(u, v, du, dv, h, n):
 # name: (grid kind, default size, C = connectivity ints per element, description)
 CONFIGS = {
     "trip1_refine13": ("refine", 13, 3, "MeshTri.refine(13) ElementTriP1 Laplace (target size: >= 50 M elements per GPU)"),
+    "trip1_grid": ("tri", 5792, 3, "n x n grid (67 M triangles, row-major vertex numbering), ElementTriP1 Laplace"),
     "vecp2_elasticity": ("tri", 3162, 6, "config 3: n x n grid, ElementH1Vec(ElementTriP2) linear elasticity"),
     "stokes_A": ("tri", 3162, 6, "config 5: Taylor-Hood velocity block, vector-P2 sym-grad form"),
     "stokes_B": ("tri", 3162, 6, "config 5: divergence block, rows P1 x columns vector-P2"),
@@ -293,6 +294,7 @@ def run_config(name, args, world, rank, peak, traffic, barrier):
     vecp2 = lambda: sp.ElementH1Vec(sp.ElementTriP2())
     spec = {
         "trip1_refine13": (sp.ElementTriP1, None, lap2, "iasm"),
+        "trip1_grid": (sp.ElementTriP1, None, lap2, "iasm"),
         "vecp2_elasticity": (vecp2, None, elasticity, "iasm"),
         "stokes_A": (vecp2, None, stokes_a, "iasm"),
         "stokes_B": (vecp2, sp.ElementTriP1, stokes_b, "iasm"),

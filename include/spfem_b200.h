@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define SPFEM_ABI_VERSION 2
+#define SPFEM_ABI_VERSION 3
 
 /* Argument block of every generated kernel (see spfem_b200/codegen.py; the
  * generated source declares the identical struct). */
@@ -47,6 +47,9 @@ typedef struct SpfemArgs {
     const int *lf1;          /* facet kernels: local facet index inside e1        */
     double *out;             /* local entries out[entry*ldo + k*ldk]              */
     long long ldk;           /* stride between items inside an entry plane (1)     */
+    double params[32];       /* run-time scalars of the traced form (captured Python
+                                numbers that are not structural constants: a time
+                                step, a penalty, ...), in the order codegen assigned  */
 } SpfemArgs;
 
 /* Argument block of the fused tile kernel `<name>_tile` (codegen.TILE_KERNEL);
@@ -73,8 +76,6 @@ typedef struct SpfemFanArgs {
     const unsigned char *blob;
     double *values;
     int max_a, max_b, max_ns, prefetch;
-    int ntiles, tiles_per_cta;   /* CTA b walks tiles [b*tiles_per_cta, ...) with two
-                                    blob buffers (TMA of the next tile in flight)      */
 } SpfemFanArgs;
 
 int         spfem_abi_version(void);
@@ -203,6 +204,8 @@ typedef struct SpfemPlanIn {
     double split_factor;      /* > 0: tiles whose element list (with halo) exceeds
                                  split_factor x the median are split (the Morton curve
                                  jumps; the largest tile sizes every CTA's shared memory) */
+    int ne_budget;            /* > 0: split tiles with more than ne_budget elements
+                                 (absolute form of the same rule; never below the median) */
 } SpfemPlanIn;
 
 typedef struct SpfemPlanBatch {

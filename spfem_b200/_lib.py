@@ -33,7 +33,13 @@ class SpfemArgs(C.Structure):
         ("lf1", C.c_void_p),
         ("out", C.c_void_p),
         ("ldk", C.c_longlong),
+        ("params", C.c_double * 32),
     ]
+
+    def set_params(self, plan):
+        """Values of the form's run-time scalars (``codegen.Emitter.params``)."""
+        for i, v in enumerate(getattr(plan.spec, "params", ())):
+            self.params[i] = v
 
 
 class SpfemTileArgs(C.Structure):
@@ -64,7 +70,7 @@ class SpfemPlanIn(C.Structure):
         ("alias", C.c_void_p), ("nuniq", C.c_int),
         ("E", C.c_int), ("with_el", C.c_int), ("sort_slots", C.c_int), ("compact", C.c_int),
         ("row_mask", C.c_void_p), ("index_bytes", C.c_int), ("batch_cap", C.c_longlong),
-        ("split_factor", C.c_double),
+        ("split_factor", C.c_double), ("ne_budget", C.c_int),
     ]
 
 
@@ -94,7 +100,6 @@ class SpfemFanArgs(C.Structure):
         ("base", SpfemArgs),
         ("desc", C.c_void_p), ("blob", C.c_void_p), ("values", C.c_void_p),
         ("max_a", C.c_int), ("max_b", C.c_int), ("max_ns", C.c_int), ("prefetch", C.c_int),
-        ("ntiles", C.c_int), ("tiles_per_cta", C.c_int),
     ]
 
 
@@ -179,7 +184,7 @@ def load():
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
-    if lib.spfem_abi_version() != 2:
+    if lib.spfem_abi_version() != 3:
         raise SpfemError("libspfem_b200.so ABI version mismatch; rebuild")
     _lib = lib
     return lib

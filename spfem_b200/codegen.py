@@ -53,6 +53,7 @@ struct uint2 { unsigned x, y; };
 #else
 #define SPFEM_DEVICE static __device__ __forceinline__
 #endif
+#define SPFEM_MAX_PARAMS 32
 struct SpfemArgs {
     long long n;              /* number of elements / facets to process        */
     long long ldo;            /* leading dimension of the entry-major output    */
@@ -70,6 +71,7 @@ struct SpfemArgs {
     const int *lf1;           /* facet kernels: local facet index inside e1     */
     double *out;              /* out[entry*ldo + k*ldk]                         */
     long long ldk;
+    double params[SPFEM_MAX_PARAMS]; /* captured Python scalars (dt, penalties ...) */
 };
 """
 
@@ -330,7 +332,6 @@ struct SpfemFanArgs {
     const unsigned char *blob;
     double *values;
     int max_a, max_b, max_ns, prefetch;
-    int ntiles, tiles_per_cta;    /* CTA b handles tiles [b*tiles_per_cta, ...)   */
 };
 template <int MAXN, bool TINY>
 SPFEM_DEVICE void @NAME@_fan_row(const SpfemArgs &P, const double2 *__restrict__ pc2,
@@ -383,7 +384,12 @@ SPFEM_DEVICE void @NAME@_fan_row(const SpfemArgs &P, const double2 *__restrict__
         double2 cb = c0;                         /* closed ring wraps to neighbour 0 */
         if (f + 1 < nn) cb = pc2[SPFEM_NBR((f + 1) < MAXN ? (f + 1) : MAXN - 1)];
         double L[SPFEM_NUNIQUE];
+#ifdef SPFEM_FAN_NOCOMPUTE     /* experiment: same memory behaviour, no geometry / form */
+#pragma unroll
+        for (int z = 0; z < SPFEM_NUNIQUE; ++z) L[z] = cr.x + ca.y + cb.x;
+#else
         @NAME@_core(P, cr.x, cr.y, ca.x, ca.y, cb.x, cb.y, L);
+#endif
         diag += L[@A00@];                        /* (test r, trial r)       */
         if (f == 0) {
             a0 = L[@A10@];                       /* (test r, trial n_0), first half */
@@ -412,65 +418,43 @@ SPFEM_DEVICE void @NAME@_fan_row(const SpfemArgs &P, const double2 *__restrict__
 #undef SPFEM_NBR
 }
 #ifndef SPFEM_HOST
-#define SPFEM_FAN_MAXK 64
 template <int MAXN, bool TINY>
 static __device__ __forceinline__ void @NAME@_fan_tile(const SpfemFanArgs &T)
 {
-    /* One CTA walks `tiles_per_cta` consecutive tiles with two blob buffers: the
-       TMA bulk copy of tile i+1 (and i+2, as soon as buffer i is free) is in
-       flight while tile i is computed, so only the first tile of a CTA pays the
-       descriptor -> TMA -> wait latency.                                        */
     extern __shared__ __align__(128) unsigned char spfem_smem_raw[];
-    unsigned char *buf0 = spfem_smem_raw;
-    unsigned char *buf1 = buf0 + T.max_a;
-    double *sV = (double *)(buf1 + T.max_a);
+    unsigned char *sA = spfem_smem_raw;                       /* the tile's blob */
+    double *sV = (double *)(sA + T.max_a);
     unsigned long long *bars = (unsigned long long *)(sV + T.max_ns);
     int *sG = (int *)(bars + 2);
-    int *sD = sG + T.max_ns;                                   /* descriptors of my tiles */
-    const int K = T.tiles_per_cta;
-    const int t0 = (int)blockIdx.x * K;
-    const int nk = min(K, T.ntiles - t0);
-    for (int i = threadIdx.x; i < 8 * nk; i += blockDim.x) sD[i] = T.desc[8 * (size_t)t0 + i];
+    const int *d = T.desc + 8 * (size_t)blockIdx.x;
+    const int bytes_a = d[1], bytes_b = d[2], nr = d[3], ns = d[4];
+    if (nr == 0) return;
     if (threadIdx.x == 0) {
         spfem_mbar_init(&bars[0], 1);
-        spfem_mbar_init(&bars[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        spfem_bulk_load(sA, T.blob + (size_t)(unsigned)d[0] * 16,
+                        (unsigned)(bytes_a + bytes_b), &bars[0]);
     }
     __syncthreads();
     if (threadIdx.x == 0) {
-        spfem_bulk_load(buf0, T.blob + (size_t)(unsigned)sD[0] * 16,
-                        (unsigned)(sD[1] + sD[2]), &bars[0]);
-        if (nk > 1)
-            spfem_bulk_load(buf1, T.blob + (size_t)(unsigned)sD[8] * 16,
-                            (unsigned)(sD[9] + sD[10]), &bars[1]);
-        /* pull the blobs of a CTA that will start a few waves later into L2, so its
-           first TMA load does not pay the DRAM latency (one contiguous span)      */
-        const long long tp = (long long)t0 + (long long)T.prefetch * K;
-        if (T.prefetch > 0 && tp < (long long)T.ntiles) {
-            const long long tq = min(tp + K, (long long)T.ntiles) - 1;
-            const int *dp = T.desc + 8 * (size_t)tp, *dq = T.desc + 8 * (size_t)tq;
-            const size_t lo = (size_t)(unsigned)dp[0] * 16;
-            const size_t hi = (size_t)(unsigned)dq[0] * 16 + (size_t)(dq[1] + dq[2]);
+        /* pull the blob of a tile that will start a few waves later into L2, so
+           its own TMA load does not pay the DRAM latency (issued after the
+           barrier: the descriptor load of that tile must not hold up this CTA)  */
+        const long long tp = (long long)blockIdx.x + T.prefetch;
+        if (T.prefetch > 0 && tp < (long long)gridDim.x) {
+            const int *dp = T.desc + 8 * (size_t)tp;
             asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;"
-                         ::"l"(T.blob + lo), "r"((unsigned)(hi - lo)) : "memory");
+                         ::"l"(T.blob + (size_t)(unsigned)dp[0] * 16),
+                           "r"((unsigned)(dp[1] + dp[2])) : "memory");
         }
     }
-    for (int i = 0; i < nk; ++i) {
-        const int *d = sD + 8 * i;
-        const int bytes_a = d[1], nr = d[3], ns = d[4];
-        unsigned char *sA = (i & 1) ? buf1 : buf0;
-        spfem_mbar_wait(&bars[i & 1], (unsigned)((i >> 1) & 1));
-        for (int row = threadIdx.x; row < nr; row += blockDim.x)
-            @NAME@_fan_row<MAXN, TINY>(T.base, (const double2 *)sA, sA + bytes_a, nr, row, sV, sG);
-        __syncthreads();
-        if (threadIdx.x == 0 && i + 2 < nk)     /* buffer (i & 1) is free again */
-            spfem_bulk_load(sA, T.blob + (size_t)(unsigned)d[16] * 16,
-                            (unsigned)(d[17] + d[18]), &bars[i & 1]);
-        /* every slot of the tile exactly once; a warp covers the CSR rows of its
-           threads, so its stores fill whole 32-byte sectors                      */
-        for (int s = threadIdx.x; s < ns; s += blockDim.x) T.values[sG[s]] = sV[s];
-        if (i + 1 < nk) __syncthreads();
-    }
+    spfem_mbar_wait(&bars[0], 0);
+    for (int row = threadIdx.x; row < nr; row += blockDim.x)
+        @NAME@_fan_row<MAXN, TINY>(T.base, (const double2 *)sA, sA + bytes_a, nr, row, sV, sG);
+    __syncthreads();
+    /* every slot of the tile exactly once; a warp covers the CSR rows of its
+       threads, so its stores fill whole 32-byte sectors                        */
+    for (int s = threadIdx.x; s < ns; s += blockDim.x) T.values[sG[s]] = sV[s];
 }
 /* two instantiations: meshes whose vertices have at most 8 ring neighbours
    (fewer registers, higher occupancy) and the general case (<= 12)         */
@@ -528,20 +512,47 @@ _FUN1 = {"abs": "fabs", "sin": "sin", "cos": "cos", "tan": "tan", "exp": "exp",
 _CMP = {"lt": "<", "le": "<=", "gt": ">", "ge": ">=", "eq": "==", "ne": "!="}
 
 
+MAX_PARAMS = 32
+
+
+def structural_constant(v):
+    """Constants that are part of a form's structure (0, +-1, +-2, 1/2, 1/4, ...
+    -- what sym-grad / trace / identity expressions are made of) stay literals;
+    every other captured Python scalar (a time step, a penalty, a material
+    parameter, ``np.pi`` multiples) becomes a run-time parameter, so a time loop
+    or a continuation over such a value re-uses one compiled kernel."""
+    v = float(v)
+    return v == v and abs(v) <= 4.0 and (v * 4.0) == int(v * 4.0)
+
+
 class Emitter(object):
     """Emits the coefficient DAG as straight-line C; ``scope`` separates the
-    copies of point-dependent nodes (one per quadrature point)."""
+    copies of point-dependent nodes (one per quadrature point).  ``params``
+    collects the values of the non-structural constants in the order of their
+    first use: the generated code reads them from ``P.params[i]``."""
 
     def __init__(self):
         self.lines = []
         self.done = {}
+        self.params = []
+        self._pidx = {}
+        self._n = 0
 
     def emit(self, s):
         self.lines.append("    " + s)
 
     def name(self, node, scope, symname):
         if node.kind == "const":
-            return lit(node.value)
+            if (structural_constant(node.value) or os.environ.get("SPFEM_PARAMS", "1") == "0"
+                    or node.value != node.value or abs(node.value) == float("inf")):
+                return lit(node.value)
+            i = self._pidx.get(node.uid)
+            if i is None:
+                if len(self.params) >= MAX_PARAMS:
+                    return lit(node.value)
+                i = self._pidx[node.uid] = len(self.params)
+                self.params.append(float(node.value))
+            return "P.params[%d]" % i
         sc = scope if node.qdep else ""
         key = (node.uid, sc)
         nm = self.done.get(key)
@@ -585,7 +596,10 @@ class Emitter(object):
             e = "((%s > 0.0) ? 1.0 : ((%s < 0.0) ? -1.0 : 0.0))" % (a[0], a[0])
         else:
             raise NotImplementedError("codegen: operator %s" % k)
-        nm = "c%d%s" % (node.uid, ("_" + sc) if sc else "")
+        # numbered in emission order (not by the interned node id): the same form
+        # traced twice gives the same text, hence the same kernel-cache key
+        nm = "c%d%s" % (self._n, ("_" + sc) if sc else "")
+        self._n += 1
         self.emit("const double %s = %s;" % (nm, e))
         self.done[key] = nm
         return nm
@@ -963,6 +977,7 @@ def generate_interior(spec, name="spfem_elem"):
         body.append("  } }")
     spec.alias = alias
     spec.n_unique = len(order_u)
+    spec.params = list(em.params)
     # multiply-adds per element (cost estimate: is recomputing halo elements cheap?)
     spec.n_terms = sum(groups[g][1].count(" * ") for g in order_u) + len(em.lines)
     # Vertex-fan variant (TriP1-like: one DOF per vertex, element-constant
@@ -976,6 +991,8 @@ def generate_interior(spec, name="spfem_elem"):
                 + body[n_geom_lines:])
 
     src = [PRELUDE, DEVICE_HELPERS]
+    if os.environ.get("SPFEM_FAN_NOCOMPUTE", "0") == "1":
+        src.append("#define SPFEM_FAN_NOCOMPUTE 1")
     src.append("#define SPFEM_NENTRIES %d" % spec.n_entries)
     src.append("#define SPFEM_NUNIQUE %d" % spec.n_unique)
     src.append("#define SPFEM_NPART %d" % spec.npart)
@@ -1303,6 +1320,7 @@ def generate_facet(spec, name="spfem_facet"):
     A("    P.out[(long long)z * P.ldo + (long long)b * P.n + k] = acc[b * %d + z];"
       % spec.n_entries)
 
+    spec.params = list(em.params)
     src = [PRELUDE]
     src.append("#define SPFEM_NENTRIES %d" % spec.n_entries)
     src.append("SPFEM_DEVICE void %s_body(const SpfemArgs &P, const long long k)\n{" % name)

@@ -440,7 +440,7 @@ int build(const SpfemPlanIn &in, SpfemPlanOut &out, Ctx &c)
             const int *pt_ = pt;
             boundaries(c, P, ntiles, te_ptr, [=] __host__ __device__(i64 q) { return (i64)pt_[q]; });
         }
-        if (in.split_factor <= 0.0 || pass >= 4) break;
+        if ((in.split_factor <= 0.0 && in.ne_budget <= 0) || pass >= 4) break;
         std::vector<i64> h_te;
         to_host(c, te_ptr, (size_t)ntiles + 1, h_te);
         std::vector<i64> ne_sorted(ntiles);
@@ -455,6 +455,7 @@ int build(const SpfemPlanIn &in, SpfemPlanOut &out, Ctx &c)
         // multiple of 32: the budget is the padded size of a typical tile
         i64 budget = std::max<i64>((i64)(in.split_factor * (double)median + 0.999), 8);
         budget = (budget + 31) / 32 * 32;
+        if (in.ne_budget > 0) budget = std::max<i64>(in.ne_budget, median + 1);
         if (ne_hi <= budget) break;
         std::vector<i64> nt2;
         for (i64 T = 0; T < ntiles; ++T) {
@@ -474,7 +475,7 @@ int build(const SpfemPlanIn &in, SpfemPlanOut &out, Ctx &c)
     fill<int>(c, mx, 8, 0);
     par_for(c, ntiles, [=] __host__ __device__(i64 T) { amax(&mx[0], (int)(te_ptr[T + 1] - te_ptr[T])); });
     const int ne_max = get(c, mx);
-    const int ldl = ((ne_max + 31) / 32) * 32 + 1;
+    const int ldl = ne_max | 1;          // odd: consecutive value rows shift banks
     int els = 0;
     while ((1 << els) < ne_max) ++els;
     const int nsidx = nbv * nbu;

@@ -46,7 +46,10 @@ def codegen_tile_threads():
     return codegen.TILE_THREADS
 
 _KCACHE_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_kcache")
-_MODULES = {}     # source hash -> (module handle, kernel handle, image bytes)
+_ARCH = "sm_100a"
+_MODULES = {}     # cache key -> (module handle, {kernel name: handle}, image buffer); LRU
+_MAX_MODULES = int(os.environ.get("SPFEM_MAX_MODULES", "64"))
+_MAX_KCACHE_FILES = int(os.environ.get("SPFEM_MAX_KCACHE_FILES", "512"))
 
 
 def _torch():
@@ -57,42 +60,99 @@ def _torch():
     return torch
 
 
+def _cache_key(source):
+    """Key of a compiled kernel: the source AND what it was compiled for / with
+    (the same text gives a different cubin on another architecture or NVRTC)."""
+    return source_key("%s|abi%d|%s" % (_ARCH, 3, source))
+
+
+def _trim_kcache():
+    """Keep the on-disk cubin cache bounded (oldest files out)."""
+    try:
+        files = [os.path.join(_KCACHE_DIR, f) for f in os.listdir(_KCACHE_DIR)
+                 if f.endswith(".cubin")]
+        if len(files) <= _MAX_KCACHE_FILES:
+            return
+        files.sort(key=os.path.getmtime)
+        for f in files[:len(files) - _MAX_KCACHE_FILES]:
+            os.remove(f)
+    except OSError:
+        pass
+
+
 def compile_cached(source):
     """cubin image of ``source`` (in-process + on-disk cache)."""
-    key = source_key(source)
+    key = _cache_key(source)
     path = os.path.join(_KCACHE_DIR, key + ".cubin")
     if os.path.exists(path):
         with open(path, "rb") as fh:
-            return key, fh.read()
-    image = _lib.nvrtc_compile(source)
+            image = fh.read()
+        try:
+            os.utime(path)                      # most recently used
+        except OSError:
+            pass
+        return key, image
+    image = _lib.nvrtc_compile(source, _ARCH)
     try:
         os.makedirs(_KCACHE_DIR, exist_ok=True)
         tmp = path + ".%d.tmp" % os.getpid()
         with open(tmp, "wb") as fh:
             fh.write(image)
         os.replace(tmp, path)
+        _trim_kcache()
     except OSError:
         pass
     return key, image
 
 
 def get_kernel(source, name):
-    """Kernel handle ``name`` of the module generated from ``source``."""
-    key = source_key(source)
-    hit = _MODULES.get(key)
+    """Kernel handle ``name`` of the module generated from ``source``.  Loaded
+    modules are kept in a bounded LRU; the evicted ones are unloaded
+    (``spfem_module_unload``), so a long-running process that keeps tracing new
+    forms does not accumulate device code."""
+    key = _cache_key(source)
+    hit = _MODULES.pop(key, None)
     lib = _lib.load()
     if hit is None:
         key, image = compile_cached(source)
         module = C.c_void_p()
         buf = C.create_string_buffer(image, len(image))
         _lib.check(lib.spfem_module_load(buf, len(image), C.byref(module)))
-        hit = _MODULES[key] = (module, {}, buf)
+        hit = (module, {}, buf)
+    _MODULES[key] = hit                         # (re-)insert as most recently used
+    if len(_MODULES) > _MAX_MODULES:
+        # evict the least recently used modules that no staged assembly holds
+        for k in [k for k in _MODULES if _PINS.get(k, 0) == 0][:len(_MODULES) - _MAX_MODULES]:
+            if k == key:
+                continue
+            old = _MODULES.pop(k)
+            try:
+                _torch().cuda.synchronize()     # its kernels may still be queued
+                lib.spfem_module_unload(old[0])
+            except Exception:
+                pass
     kernels = hit[1]
     if name not in kernels:
         kernel = C.c_void_p()
         _lib.check(lib.spfem_module_get_kernel(hit[0], name.encode(), C.byref(kernel)))
         kernels[name] = kernel
     return kernels[name]
+
+
+_PINS = {}        # cache key -> number of live Prepared objects using the module
+
+
+def pin_module(source, owner):
+    """Keep the module of ``source`` loaded while ``owner`` is alive."""
+    import weakref
+    key = _cache_key(source)
+    _PINS[key] = _PINS.get(key, 0) + 1
+
+    def unpin(k=key):
+        _PINS[k] = _PINS.get(k, 1) - 1
+        if _PINS[k] <= 0:
+            _PINS.pop(k, None)
+    weakref.finalize(owner, unpin)
 
 
 def scipy_index_dtype(n_entries, nrows, ncols):
@@ -268,6 +328,7 @@ class Prepared(object):
         self.engine, self.plan, self.kernel = engine, plan, kernel
         self.args, self.block, self.local, self.pattern = args, block, local, pattern
         self._keep = keep
+        pin_module(plan.source, self)
         torch = engine.torch
         n = pattern.nnz if plan.bilinear else pattern.nrows
         self.values = engine._empty(max(n, 1), torch.float64)[:n]
@@ -360,27 +421,24 @@ class FanPrepared(Prepared):
         fa.blob = fp["blob"].data_ptr()
         fa.values = self.values.data_ptr()
         fa.max_a, fa.max_b, fa.max_ns = fp["max_a"], fp["max_b"], fp["max_ns"]
-        # tiles per CTA (double-buffered TMA: only a CTA's first tile pays the
-        # descriptor -> bulk copy -> wait latency) and the L2 prefetch distance in
-        # CTAs (about two waves of resident CTAs ahead)
-        K = max(1, min(64, int(os.environ.get("SPFEM_FAN_K", "4"))))
-        fa.ntiles, fa.tiles_per_cta = fp["ntiles"], K
-        fa.prefetch = int(os.environ.get("SPFEM_FAN_PREFETCH", str(max(1, 2400 // K))))
+        # L2 prefetch distance in tiles (about two waves of resident CTAs ahead).
+        # (Measured and rejected in round 2 as well: several tiles per CTA with
+        # double-buffered TMA copies -- 2 ... 32 tiles per CTA are 6 ... 46 % slower,
+        # profiles/r02_fan_tiles_per_cta.jsonl.)
+        fa.prefetch = int(os.environ.get("SPFEM_FAN_PREFETCH", "2400"))
         self.fargs = fa
-        self.grid = (fp["ntiles"] + K - 1) // K
-        self.smem = 2 * fp["max_a"] + 12 * fp["max_ns"] + 32 * K + 64
+        self.smem = fp["max_a"] + 12 * fp["max_ns"] + 64
         from . import codegen
         self.threads = codegen.FAN_THREADS
         self.n_launches = 1
         self.tp = {"E": fp["rows_per_tile"], "ldl": 0, "ntiles": fp["ntiles"],
-                   "halo_factor": fp["halo_factor"], "kind": "vertex-fan",
-                   "tiles_per_cta": K}
+                   "halo_factor": fp["halo_factor"], "kind": "vertex-fan"}
 
     def launch(self):
         e = self.engine
         self.fargs.base = self.args
         _lib.check(e.lib.spfem_launch_tiled(self.fan_kernel, C.byref(self.fargs),
-                                            self.grid, self.threads,
+                                            self.fp["ntiles"], self.threads,
                                             self.smem, e._stream()))
         return self.values
 
@@ -592,6 +650,7 @@ class Engine(object):
         kernel = get_kernel(plan.source, plan.name)
         wt = self._interp_tensors(plan, interp)
         a = _lib.SpfemArgs()
+        a.set_params(plan)
         a.tdof_u, a.ldd = self.tdof_u.data_ptr(), self.tdof_u.shape[1]
         for s, w in enumerate(wt):
             a.interp[s] = w.data_ptr()
@@ -683,7 +742,7 @@ class Engine(object):
         ckey = (plan.bilinear, spec.n_unique, tuple(spec.alias), spec.nw > 0,
                 env("SPFEM_TILE_MODE", "auto"), env("SPFEM_TILE_E", "0"),
                 env("SPFEM_TILE_SORT", "auto"), env("SPFEM_TILE_BLOCKS", "1"),
-                env("SPFEM_TILE_SPLIT", "1.02"))
+                env("SPFEM_TILE_SPLIT", "0"), env("SPFEM_TILE_BUDGET", "1"))
         if ckey in self._tile_cache:
             return self._tile_cache[ckey]
         force = env("SPFEM_FUSED", "1") == "force"
@@ -732,6 +791,18 @@ class Engine(object):
         n_entries = spec.n_entries * self.nt
         idt = scipy_index_dtype(n_entries, asm.dofnum_v.N, asm.dofnum_u.N if bilinear else 1)
         t0 = time.perf_counter()
+
+        def build(E, ne_budget=0):
+            return build_tile_plan(torch, self.tdof_v, self.tdof_u if bilinear else None,
+                                   self.t, asm.dofnum_v.N, asm.dofnum_u.N if bilinear else 1,
+                                   E, spec.alias, nuniq, dim,
+                                   bsv=bsv if nb > 1 else 1, bsu=bsu if nb > 1 else 1,
+                                   with_el=spec.nw > 0, sort_slots=sort_slots, compact=compact,
+                                   row_mask=self._row_mask(),
+                                   index_bytes=8 if idt == np.int64 else 4,
+                                   batch_cap=int(env("SPFEM_TILE_BATCH", "0")),
+                                   split_factor=float(env("SPFEM_TILE_SPLIT", "0")),
+                                   ne_budget=ne_budget)
         tp = None
         for E in cands:
             if E_env <= 0 and not compact and E > 64 and 8 * nuniq * (1.3 * E + 32) > prefer:
@@ -739,15 +810,7 @@ class Engine(object):
             if E_env <= 0 and compact and E > 64:
                 continue
             try:
-                tp = build_tile_plan(torch, self.tdof_v, self.tdof_u if bilinear else None,
-                                     self.t, asm.dofnum_v.N, asm.dofnum_u.N if bilinear else 1,
-                                     E, spec.alias, nuniq, dim,
-                                     bsv=bsv if nb > 1 else 1, bsu=bsu if nb > 1 else 1,
-                                     with_el=spec.nw > 0, sort_slots=sort_slots, compact=compact,
-                                     row_mask=self._row_mask(),
-                                     index_bytes=8 if idt == np.int64 else 4,
-                                     batch_cap=int(env("SPFEM_TILE_BATCH", "0")),
-                                     split_factor=float(env("SPFEM_TILE_SPLIT", "1.02")))
+                tp = build(E)
             except TileTooLarge:
                 tp = None
                 continue
@@ -761,6 +824,31 @@ class Engine(object):
             if E_env > 0 or smem <= prefer or E <= 64:
                 break
             tp = None
+        # The largest tile sizes the shared memory of every CTA.  The Morton curve
+        # does not follow the cells of a grid whose size is not a power of two, so a
+        # tail of tiles has far more halo elements than the typical one: if splitting
+        # that tail lets one more CTA share an SM, rebuild with an element budget.
+        if tp is not None and env("SPFEM_TILE_BUDGET", "1") != "0":
+            smem = tile_smem_bytes(nuniq, tp, nsidx, nb)
+            per_sm = 227 * 1024
+            cmax = 3 if dim == 2 else 2           # CTAs per SM the registers allow
+            c_now = min(cmax, per_sm // (smem + 1024))
+            mean_ne = tp["halo_factor"] * self.nt / max(tp["ntiles"], 1)
+            fixed = tp["max_bytes_b"] + 64 + (4 * nsidx * nb if nb > 1 else 0)
+            per_ne = ((8.0 * (tp["max_store"] + 2) if compact else 8.0 * nuniq * tp["ldl"])
+                      + tp["max_bytes_a"]) / max(tp["max_ne"], 1)
+            for c in range(cmax, c_now, -1):
+                budget = int((per_sm // c - 1024 - fixed) / per_ne) - 2
+                if budget < 1.04 * mean_ne or budget >= tp["max_ne"]:
+                    continue
+                try:
+                    tp2 = build(tp["E"], ne_budget=budget)
+                except TileTooLarge:
+                    break
+                smem2 = tile_smem_bytes(nuniq, tp2, nsidx, nb)
+                if min(cmax, per_sm // (smem2 + 1024)) > c_now:
+                    tp = tp2
+                break
         if tp is not None and not force and n_terms * tp["halo_factor"] > 1500:
             tp = None
         if tp is not None and not bilinear and tp["nnz"] != asm.dofnum_v.N:
@@ -800,6 +888,7 @@ class Engine(object):
         out = self._empty(max(n, 1), torch.float64)
         wt = self._interp_tensors(plan, interp)
         a = _lib.SpfemArgs()
+        a.set_params(plan)
         a.n, a.ldo, a.ldk = n, n, 1
         a.t, a.ldt = self.t.data_ptr(), self.t.shape[1]
         a.p, a.ldp = self.p.data_ptr(), self.p.shape[1]
@@ -848,6 +937,7 @@ class Engine(object):
         local = self._empty(max(spec.n_entries * nblk * n, 1), torch.float64)
         wt = self._interp_tensors(plan, interp)
         a = _lib.SpfemArgs()
+        a.set_params(plan)
         a.n, a.ldo, a.ldk = n, nblk * n, 1
         a.tdof_u, a.ldd = self.tdof_u.data_ptr(), self.tdof_u.shape[1]
         for s, w in enumerate(wt):
@@ -877,6 +967,7 @@ class Engine(object):
         out = self._empty(max(n, 1), torch.float64)
         wt = self._interp_tensors(plan, interp)
         a = _lib.SpfemArgs()
+        a.set_params(plan)
         a.n, a.ldo, a.ldk = n, n, 1
         a.t, a.ldt = self.t.data_ptr(), self.t.shape[1]
         a.p, a.ldp = self.p.data_ptr(), self.p.shape[1]

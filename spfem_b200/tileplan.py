@@ -102,7 +102,7 @@ class _Arena(object):
 def build_tile_plan(torch, rowdof, coldof, vt, nrows, ncols, E, alias, nuniq,
                     dim, bsv=1, bsu=1, with_el=False, sort_slots=0, compact=False,
                     row_mask=None, index_bytes=4, batch_cap=0, split_factor=0.0,
-                    stream=None):
+                    ne_budget=0, stream=None):
     """Pattern + tile plan for the DOF tables ``rowdof`` (nloc_v, n) /
     ``coldof`` (nloc_u, n) or ``None`` (int32, one device, element order of the
     kernel) and the vertex table ``vt`` (nve, n).  Returns a dict; raises
@@ -135,6 +135,7 @@ def build_tile_plan(torch, rowdof, coldof, vt, nrows, ncols, E, alias, nuniq,
     pin.index_bytes = int(index_bytes)
     pin.batch_cap = int(batch_cap)
     pin.split_factor = float(split_factor)
+    pin.ne_budget = int(ne_budget)
     pout = _lib.SpfemPlanOut()
     arena = _Arena(torch, dev)
     if stream is None and on_dev:

@@ -63,6 +63,7 @@ def run_interior(asm, plan, tind=None, interp=None):
     n = t.shape[1] if sel is None else sel.shape[0]
     out = np.zeros((plan.spec.n_entries, n))
     a = SpfemArgs()
+    a.set_params(plan)
     a.n, a.ldo, a.ldk = n, n, 1
     a.sel = _ptr(sel) if sel is not None else None
     a.t, a.ldt = _ptr(t), t.shape[1]
@@ -116,6 +117,7 @@ def fasm(asm, form, find=None, interior=False, intorder=None, normals=True,
     lf1 = np.ascontiguousarray(lf1, dtype=np.int32)
     out = np.zeros((plan.spec.n_entries, nblk * n))
     a = SpfemArgs()
+    a.set_params(plan)
     a.n, a.ldo, a.ldk = n, nblk * n, 1
     a.t, a.ldt = _ptr(t), t.shape[1]
     a.p, a.ldp = _ptr(p), p.shape[1]
@@ -159,6 +161,7 @@ def fan_iasm(asm, form, rows_per_tile=64, tiny=True):
     sV = np.zeros(fp["max_ns"] + 16)
     sG = np.zeros(fp["max_ns"] + 16, dtype=np.int32)
     a = SpfemFanArgs()
+    a.base.set_params(plan)
     a.desc, a.blob, a.values = _ptr(fp["desc"]), _ptr(fp["blob"]), _ptr(values)
     a.max_a, a.max_b, a.max_ns = fp["max_a"], fp["max_b"], fp["max_ns"]
     fn(C.byref(a), fp["ntiles"], _ptr(sV), _ptr(sG),
@@ -212,6 +215,7 @@ def fnorm(asm, form, interp, intorder=None, interior=False, normals=True):
     lf1 = np.ascontiguousarray(lf1, dtype=np.int32)
     out = np.zeros(n)
     a = SpfemArgs()
+    a.set_params(plan)
     a.n, a.ldo, a.ldk = n, n, 1
     a.t, a.ldt = _ptr(t), t.shape[1]
     a.p, a.ldp = _ptr(p), p.shape[1]

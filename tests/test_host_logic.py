@@ -34,7 +34,7 @@ def test_c_abi_exports_every_declared_symbol(lib):
     exported = set(re.findall(r"\bT (spfem_[a-z_0-9]+)", out))
     assert declared <= exported, declared - exported
     assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
-    assert lib.spfem_abi_version() == 2
+    assert lib.spfem_abi_version() == 3
     assert lib.spfem_device_count() >= 0
 
 
@@ -171,3 +171,32 @@ def test_spfem_alias_package():
     env = dict(os.environ, PYTHONPATH=os.path.join(ROOT, "compat") + os.pathsep + ROOT)
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env)
     assert out.returncode == 0 and "alias ok" in out.stdout, out.stderr[-2000:]
+
+
+def test_captured_scalars_are_runtime_parameters():
+    """A Python scalar captured by the form (time step, penalty ...) must not be
+    baked into the kernel source: two values -> the same source (one NVRTC
+    compile), different ``params``; structural constants stay literals."""
+    import hostemu
+    m = sp.MeshTri()
+    m.refine(2)
+    a = AssemblerElement(m, sp.ElementTriP1())
+
+    def make(dt, kappa):
+        return lambda u, v, du, dv: u * v + dt * kappa * (du[0] * dv[0] + du[1] * dv[1]) + 0.5 * u * v
+
+    p1 = a.plan_iasm(make(0.013, 3.7))
+    p2 = a.plan_iasm(make(0.029, 1.1))
+    assert p1.source == p2.source
+    assert p1.spec.params != p2.spec.params and len(p1.spec.params) == 1
+    assert "0x1.0000000000000p-1" in p1.source or "0.5" in p1.source or "p-1" in p1.source
+    M = hostemu.iasm(a, lambda u, v: u * v)
+    K = hostemu.iasm(a, lambda du, dv: du[0] * dv[0] + du[1] * dv[1])
+    for dt, kappa in ((0.013, 3.7), (0.029, 1.1)):
+        A = hostemu.iasm(a, make(dt, kappa))
+        ref = 1.5 * M + dt * kappa * K
+        assert abs(A - ref).max() < 1e-13
+    # facet forms as well
+    f1 = a.plan_fasm(lambda u, v, h: 17.3 / h * u * v)
+    f2 = a.plan_fasm(lambda u, v, h: 41.9 / h * u * v)
+    assert f1.source == f2.source and f1.spec.params == [17.3] and f2.spec.params == [41.9]
