@@ -53,6 +53,22 @@ struct uint2 { unsigned x, y; };
 #else
 #define SPFEM_DEVICE static __device__ __forceinline__
 #endif
+#if defined(SPFEM_HOST) || defined(SPFEM_IEEE_RCP)
+#define spfem_rcp(x) (1.0 / (x))
+#else
+/* 1/x for the Jacobian determinant: MUFU.RCP64H seed (20 bits) + two Newton steps
+   (5 instructions, <= 1 ulp from the IEEE quotient for normal x; the compiler's
+   1.0/x adds a correction step and a range check with a slow-path call).      */
+static __device__ __forceinline__ double spfem_rcp(const double x)
+{
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-x, r, 1.0);
+    return fma(r, e, r);
+}
+#endif
 #define SPFEM_MAX_PARAMS 32
 struct SpfemArgs {
     long long n;              /* number of elements / facets to process        */
@@ -324,7 +340,7 @@ extern "C" __global__ void __launch_bounds__(@THREADS@, @MINB@) @NAME@_tile(cons
 #   plane 0 {g0 - s0, s0 | nfan << 16 | closed << 24, neighbours 0..3}, plane 1
 #   further ring neighbours (16-bit tile-local vertex ids); plus one byte per
 #   slot mapping CSR order to the ring order of the staging buffer
-FAN_THREADS = int(os.environ.get("SPFEM_FAN_T", "128"))
+FAN_THREADS = int(os.environ.get("SPFEM_FAN_T", "128")) // 32 * 32
 FAN_KERNEL = r"""
 struct SpfemFanArgs {
     SpfemArgs base;
@@ -405,6 +421,9 @@ SPFEM_DEVICE void @NAME@_fan_row(const SpfemArgs &P, const double2 *__restrict__
     }
     if (closed) {
         a0 += carry;                             /* the last triangle's n_{f+1} is n_0 */
+    } else if (TINY) {                           /* open ring: the last neighbour's slot */
+        sV[s0 + 1 + nfan] = carry;
+        sG[s0 + 1 + nfan] = g0 + (int)((pw[0] >> (4 * (nfan & 7))) & 0xfu);
     } else {
 #pragma unroll
         for (int q = 1; q < MAXN + 1; ++q)
@@ -418,6 +437,15 @@ SPFEM_DEVICE void @NAME@_fan_row(const SpfemArgs &P, const double2 *__restrict__
 #undef SPFEM_NBR
 }
 #ifndef SPFEM_HOST
+#if defined(SPFEM_FAN_STCS)
+#define SPFEM_FAN_ST(p, v) __stcs((p), (v))
+#elif defined(SPFEM_FAN_STCG)
+#define SPFEM_FAN_ST(p, v) __stcg((p), (v))
+#elif defined(SPFEM_FAN_STWT)
+#define SPFEM_FAN_ST(p, v) __stwt((p), (v))
+#else
+#define SPFEM_FAN_ST(p, v) (*(p) = (v))
+#endif
 template <int MAXN, bool TINY>
 static __device__ __forceinline__ void @NAME@_fan_tile(const SpfemFanArgs &T)
 {
@@ -426,7 +454,11 @@ static __device__ __forceinline__ void @NAME@_fan_tile(const SpfemFanArgs &T)
     double *sV = (double *)(sA + T.max_a);
     unsigned long long *bars = (unsigned long long *)(sV + T.max_ns);
     int *sG = (int *)(bars + 2);
+#ifdef SPFEM_FAN_X_SAMEBLOB   /* experiment: every CTA works on one of 64 L2-resident tiles */
+    const int *d = T.desc + 8 * (size_t)(blockIdx.x & 63);
+#else
     const int *d = T.desc + 8 * (size_t)blockIdx.x;
+#endif
     const int bytes_a = d[1], bytes_b = d[2], nr = d[3], ns = d[4];
     if (nr == 0) return;
     if (threadIdx.x == 0) {
@@ -451,10 +483,32 @@ static __device__ __forceinline__ void @NAME@_fan_tile(const SpfemFanArgs &T)
     spfem_mbar_wait(&bars[0], 0);
     for (int row = threadIdx.x; row < nr; row += blockDim.x)
         @NAME@_fan_row<MAXN, TINY>(T.base, (const double2 *)sA, sA + bytes_a, nr, row, sV, sG);
+#if defined(SPFEM_FAN_X_NOSTORE)          /* experiment: load + compute only */
+    __syncthreads();
+    for (int s = threadIdx.x; s < ns; s += blockDim.x) { const double v = sV[s]; if (v == 1.2345e-300) T.values[sG[s]] = v; }
+#elif defined(SPFEM_FAN_X_LINEAR)         /* experiment: contiguous (wrong) store positions */
+    __syncthreads();
+    for (int s = threadIdx.x; s < ns; s += blockDim.x) T.values[d[6] + s] = sV[s];
+#elif !defined(SPFEM_FAN_CTASTORE)
+    /* the slots of a warp's 32 rows are one contiguous range of the staging
+       buffer: no CTA-wide barrier, every warp stores as soon as it is done
+       (blockDim.x is a multiple of 32)                                          */
+    {
+        const int wrow = (int)(threadIdx.x & ~31u);
+        const uint4 *rec4 = reinterpret_cast<const uint4 *>(sA + bytes_a);
+        for (int r0 = wrow; r0 < nr; r0 += blockDim.x) {
+            const int sb = (int)(rec4[r0].y & 0xffffu);
+            const int se = (r0 + 32 < nr) ? (int)(rec4[r0 + 32].y & 0xffffu) : ns;
+            __syncwarp();
+            for (int s = sb + (int)(threadIdx.x & 31u); s < se; s += 32) SPFEM_FAN_ST(T.values + sG[s], sV[s]);
+        }
+    }
+#else
     __syncthreads();
     /* every slot of the tile exactly once; a warp covers the CSR rows of its
        threads, so its stores fill whole 32-byte sectors                        */
-    for (int s = threadIdx.x; s < ns; s += blockDim.x) T.values[sG[s]] = sV[s];
+    for (int s = threadIdx.x; s < ns; s += blockDim.x) SPFEM_FAN_ST(T.values + sG[s], sV[s]);
+#endif
 }
 /* two instantiations: meshes whose vertices have at most 8 ring neighbours
    (fewer registers, higher occupancy) and the general case (<= 12)         */
@@ -531,12 +585,54 @@ class Emitter(object):
     collects the values of the non-structural constants in the order of their
     first use: the generated code reads them from ``P.params[i]``."""
 
-    def __init__(self):
+    def __init__(self, adjugate=False):
         self.lines = []
         self.done = {}
         self.params = []
         self._pidx = {}
         self._n = 0
+        # affine interior kernels: |detA| * (sum of products of two entries of
+        # A^{-1}) is emitted as (the same sum over the adjugate) / |detA| -- the
+        # stiffness-type coefficients G = |detA| A^{-1} A^{-T} without forming A^{-1}
+        self.adjugate = adjugate
+        self._quad = {}
+        self._done_adj = {}
+
+    def _is_quad(self, node):
+        """``node`` is homogeneous of degree two in the ``iA`` symbols."""
+        r = self._quad.get(node.uid)
+        if r is None:
+            k, a = node.kind, node.args
+            if k == "mul":
+                iA = lambda x: x.kind == "sym" and x.value.startswith("iA") and not x.qdep
+                cst = lambda x: x.kind == "const" and structural_constant(x.value)
+                r = ((iA(a[0]) and iA(a[1])) or (cst(a[0]) and self._is_quad(a[1]))
+                     or (cst(a[1]) and self._is_quad(a[0])))
+            elif k in ("add", "sub"):
+                r = self._is_quad(a[0]) and self._is_quad(a[1])
+            elif k == "neg":
+                r = self._is_quad(a[0])
+            else:
+                r = False
+            self._quad[node.uid] = r
+        return r
+
+    def _name_adj(self, node, symname):
+        """Emit a quadratic ``iA`` expression over the adjugate symbols ``jA``."""
+        nm = self._done_adj.get(node.uid)
+        if nm is not None:
+            return nm
+        if node.kind == "sym":
+            return "jA_" + node.value[2:]
+        if node.kind == "const":
+            return lit(node.value)
+        a = [self._name_adj(x, symname) for x in node.args]
+        e = {"mul": "%s * %s", "add": "%s + %s", "sub": "%s - %s", "neg": "-%s"}[node.kind] % tuple(a)
+        nm = "c%d" % self._n
+        self._n += 1
+        self.emit("const double %s = %s;" % (nm, e))
+        self._done_adj[node.uid] = nm
+        return nm
 
     def emit(self, s):
         self.lines.append("    " + s)
@@ -562,8 +658,17 @@ class Emitter(object):
             nm = symname(node.value, sc)
             self.done[key] = nm
             return nm
-        a = [self.name(x, scope, symname) for x in node.args]
         k = node.kind
+        if k == "mul" and self.adjugate:
+            for i in (0, 1):
+                sy, q = node.args[i], node.args[1 - i]
+                if sy.kind == "sym" and sy.value == "absdet" and self._is_quad(q):
+                    nm = "c%d" % self._n
+                    self._n += 1
+                    self.emit("const double %s = %s * rabsdet;" % (nm, self._name_adj(q, symname)))
+                    self.done[key] = nm
+                    return nm
+        a = [self.name(x, scope, symname) for x in node.args]
         if k == "add":
             e = "%s + %s" % (a[0], a[1])
         elif k == "sub":
@@ -705,9 +810,11 @@ def affine_geometry(dim, sfx="", elem="e", vt="P.t", ldv="P.ldt",
         }
     if fast_inverse:
         # one division: adj * (1/det) instead of adj / det (<= 1 ulp apart)
-        L.append("const double rdetA%s = 1.0 / detA%s;" % (sfx, sfx))
+        L.append("const double rdetA%s = spfem_rcp(detA%s);" % (sfx, sfx))
+        L.append("const double rabsdet%s = fabs(rdetA%s);" % (sfx, sfx))
         for (i, j), e in sorted(inv.items()):
-            L.append("const double iA%s_%d%d = %s * rdetA%s;" % (sfx, i, j, e, sfx))
+            L.append("const double jA%s_%d%d = %s;" % (sfx, i, j, e))
+            L.append("const double iA%s_%d%d = jA%s_%d%d * rdetA%s;" % (sfx, i, j, sfx, i, j, sfx))
     else:
         for (i, j), e in sorted(inv.items()):
             L.append("const double iA%s_%d%d = %s;" % (sfx, i, j,
@@ -852,8 +959,8 @@ def generate_interior(spec, name="spfem_elem"):
     dim, nq = spec.dim, len(spec.W)
     entries, uses = interior_terms(spec)
     syms = collect_syms(list(spec.blocks.values()))
-    em = Emitter()
     quad = spec.refdom == "quad"
+    em = Emitter(adjugate=not quad and os.environ.get("SPFEM_ADJUGATE", "1") != "0")
 
     body = []
     if quad:
@@ -991,8 +1098,13 @@ def generate_interior(spec, name="spfem_elem"):
                 + body[n_geom_lines:])
 
     src = [PRELUDE, DEVICE_HELPERS]
+    if os.environ.get("SPFEM_RCP", "0") == "0":      # measured: the Newton reciprocal is not faster
+        src.insert(0, "#define SPFEM_IEEE_RCP 1")
     if os.environ.get("SPFEM_FAN_NOCOMPUTE", "0") == "1":
         src.append("#define SPFEM_FAN_NOCOMPUTE 1")
+    for flag in os.environ.get("SPFEM_FAN_X", "").split(","):    # kernel experiments (tools/fan_variants.py)
+        if flag:
+            src.append("#define SPFEM_FAN_%s 1" % flag)
     src.append("#define SPFEM_NENTRIES %d" % spec.n_entries)
     src.append("#define SPFEM_NUNIQUE %d" % spec.n_unique)
     src.append("#define SPFEM_NPART %d" % spec.npart)

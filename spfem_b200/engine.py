@@ -713,7 +713,8 @@ class Engine(object):
             fp = build_fan_plan(torch, self.p, dev64(mesh.t), dev64(mesh.t2f), dev64(mesh.f2t),
                                 pat.indptr, pat.indices,
                                 int(os.environ.get("SPFEM_FAN_ROWS", "128")),
-                                tiny=os.environ.get("SPFEM_FAN_TINY", "1") != "0")
+                                tiny=os.environ.get("SPFEM_FAN_TINY", "1") != "0",
+                                row_order=os.environ.get("SPFEM_FAN_ROWORDER", "id"))
         except FanPlanError:
             return None
         fill_fan_coordinates(fp, self.p)

@@ -121,7 +121,8 @@ def _wrap32(torch, x):
     return torch.where(x >= 2 ** 31, x - 2 ** 32, x).to(torch.int32)
 
 
-def build_fan_plan(torch, p, t, t2f, f2t, indptr, indices, rows_per_tile=128, tiny=True):
+def build_fan_plan(torch, p, t, t2f, f2t, indptr, indices, rows_per_tile=128, tiny=True,
+                   row_order="id"):
     """Torch version of :func:`fanplan.build_fan_plan`; all tensor arguments on
     one device (int64 topology, float64 coordinates).  Returns the same dict with
     tensors instead of arrays."""
@@ -162,7 +163,12 @@ def build_fan_plan(torch, p, t, t2f, f2t, indptr, indices, rows_per_tile=128, ti
     ntiles = (nv + R - 1) // R
     vperm = _morton_vertices(torch, p)
     tile_of_row = arv // R
-    order = _lexsort(torch, [p[0][vperm], p[1][vperm], tile_of_row])
+    if row_order == "id":
+        # rows of a tile in CSR order: rows with consecutive ids are neighbours in a
+        # warp, so the sectors two of them share are written by one store request
+        order = _lexsort(torch, [vperm, tile_of_row])
+    else:
+        order = _lexsort(torch, [p[0][vperm], p[1][vperm], tile_of_row])
     rows = vperm[order]
     nr = torch.bincount(tile_of_row, minlength=ntiles)
     r0 = torch.cumsum(nr, 0) - nr

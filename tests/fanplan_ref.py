@@ -136,7 +136,7 @@ def vertex_rings(mesh):
     return nb, nfan, closed
 
 
-def build_fan_plan(mesh, indptr, indices, rows_per_tile=256, tiny=True):
+def build_fan_plan(mesh, indptr, indices, rows_per_tile=256, tiny=True, row_order="id"):
     """Host arrays of the vertex-fan plan for the CSR pattern ``indptr/indices``
     (rows = columns = vertices).  Raises :class:`FanPlanError` if it does not
     apply."""
@@ -178,7 +178,10 @@ def build_fan_plan(mesh, indptr, indices, rows_per_tile=256, tiny=True):
     ntiles = (nv + R - 1) // R
     vperm = _morton_vertices(p)
     tile_of_pos = np.arange(nv) // R
-    order = np.lexsort((p[0][vperm], p[1][vperm], tile_of_pos))
+    if row_order == "id":
+        order = np.lexsort((vperm, tile_of_pos))
+    else:
+        order = np.lexsort((p[0][vperm], p[1][vperm], tile_of_pos))
     rows = vperm[order]                                   # all rows, tile after tile
     tile_of_row = tile_of_pos                             # (positions are tile-major)
     nr = np.bincount(tile_of_row, minlength=ntiles)
