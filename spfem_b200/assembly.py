@@ -331,6 +331,14 @@ class AssemblerElement(Assembler):
         plan = self.plan_iasm(form, intorder=intorder, interp=interp)
         chunks = self._chunks_needed(plan, tind)
         if chunks > 1:
+            if tind is None and "SPFEM_MAX_ENTRIES" not in os.environ:
+                # the native tile plan is built batch by batch and has no 2^31 limit:
+                # one fused launch per batch; only forms that need the two-kernel
+                # route fall back to the element-chunk loop
+                try:
+                    return self._get_engine().run_interior(plan, None, interp)
+                except NotImplementedError:
+                    pass
             return self._iasm_chunked(form, plan, intorder, interp, chunks)
         return self._get_engine().run_interior(plan, tind, interp)
 
