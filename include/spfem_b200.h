@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define SPFEM_ABI_VERSION 3
+#define SPFEM_ABI_VERSION 4
 
 /* Argument block of every generated kernel (see spfem_b200/codegen.py; the
  * generated source declares the identical struct). */
@@ -50,6 +50,10 @@ typedef struct SpfemArgs {
     double params[32];       /* run-time scalars of the traced form (captured Python
                                 numbers that are not structural constants: a time
                                 step, a penalty, ...), in the order codegen assigned  */
+    const double *fields[8]; /* host-evaluated coefficient fields (opaque callables of
+                                x / h / w, spfem/mesh.py:885-901): fields[i][q*ldf + e],
+                                q = quadrature point, e = element in device order      */
+    long long ldf;
 } SpfemArgs;
 
 /* Argument block of the fused tile kernel `<name>_tile` (codegen.TILE_KERNEL);

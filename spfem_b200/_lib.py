@@ -34,6 +34,8 @@ class SpfemArgs(C.Structure):
         ("out", C.c_void_p),
         ("ldk", C.c_longlong),
         ("params", C.c_double * 32),
+        ("fields", C.c_void_p * 8),
+        ("ldf", C.c_longlong),
     ]
 
     def set_params(self, plan):
@@ -184,7 +186,7 @@ def load():
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
-    if lib.spfem_abi_version() != 3:
+    if lib.spfem_abi_version() != 4:
         raise SpfemError("libspfem_b200.so ABI version mismatch; rebuild")
     _lib = lib
     return lib

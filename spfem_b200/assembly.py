@@ -30,6 +30,7 @@ from .quadrature import get_quadrature
 from .tracer import (Coef, Form, TraceError, basis_args, hdiv_args, zero_like,  # noqa: F401
                      call_form)
 from . import codegen
+from . import tracer as _tracer
 
 __all__ = ["Assembler", "AssemblerElement", "Dofnum", "TraceError"]
 
@@ -150,7 +151,50 @@ class AssemblerElement(Assembler):
         return keys
 
     def plan_iasm(self, form, intorder=None, interp=None):
-        """Trace ``form`` and generate the interior kernel (no device work)."""
+        """Trace ``form`` and generate the interior kernel (no device work).
+
+        A form the tracer cannot follow symbolically (it applies an opaque
+        callable -- ``np.interp``, a SymPy ``lambdify`` with ``Piecewise``, a
+        matplotlib interpolator, spfem/mesh.py:885-901 -- to ``x``, ``h`` or
+        ``w``) is traced a second time in *field mode*: those arguments are the
+        reference's own ``(elements, quadrature points)`` NumPy arrays
+        (spfem/assembly.py:947-959), whatever the form computes from them is
+        evaluated on the host exactly as the reference does and streamed to the
+        kernel as coefficient fields; ``u, v, du, dv`` stay symbolic.  Forms that
+        are not multilinear in the basis functions still raise ``TraceError``."""
+        try:
+            return self._plan_iasm(form, intorder, interp, False)
+        except TraceError as exc:
+            if os.environ.get("SPFEM_FIELDS", "1") == "0":
+                raise
+            try:
+                return self._plan_iasm(form, intorder, interp, True)
+            except Exception as exc2:
+                # neither symbolically nor on the reference's arrays: report the
+                # tracer's diagnosis, chained to what the array evaluation said
+                raise exc from exc2
+
+    def _host_point_data(self, X, interp, wkeys, bu):
+        """``x``, ``h``, ``w`` as the reference evaluates them on the host
+        (spfem/assembly.py:947-959, 974): arrays of shape (nt, nq)."""
+        mp = self.mapping
+        x = mp.F(X)
+        det = mp.detDF(X)
+        dim = self.mesh.p.shape[0]
+        h = np.abs(det) ** (1.0 / dim)
+        w = {}
+        if wkeys:
+            phi, _ = _element.tabulate(bu, X)           # (nbfun, nq) of the scalar parent
+            td = self.dofnum_u.t_dof
+            for key in wkeys:
+                vec = np.asarray(interp[key], dtype=np.float64)
+                acc = 0.0 * x[0]
+                for j in range(td.shape[0]):
+                    acc = acc + np.outer(vec[td[j, :]], phi[j])
+                w[key] = acc
+        return x, h, w
+
+    def _plan_iasm(self, form, intorder, interp, field_mode):
         mesh = self.mesh
         if intorder is None:
             intorder = self.elem_u.maxdeg + self.elem_v.maxdeg
@@ -181,6 +225,12 @@ class AssemblerElement(Assembler):
         x = {k: Form.coef(Coef.sym("x%d" % k, True)) for k in range(dim)}
         w = {key: Form.coef(Coef.sym("w%d" % s, True))
              for s, key in enumerate(wkeys)}
+        fctx = None
+        if field_mode:
+            if ncu > 1 and wkeys:
+                raise TraceError("field mode: interpolated fields of vector elements")
+            x, h, w = self._host_point_data(X, interp, wkeys, bu)
+            fctx = _tracer.FieldContext((mesh.t.shape[1], X.shape[1]))
         hdiv_u, hdiv_v = getattr(bu, "hdiv", False), getattr(bv, "hdiv", False)
         if hdiv_u or hdiv_v:
             if quad or dim != 2:
@@ -188,26 +238,44 @@ class AssemblerElement(Assembler):
             df = {k: {l: Coef.sym("A_%d%d" % (k, l)) for l in range(dim)} for k in range(dim)}
             rdet = Coef.op("div", Coef.const(1.0), Coef.sym("detA"))
         blocks = {}
-        for cu in range(ncu if bilinear else 1):
-            for cv in range(ncv):
-                v, dv = (hdiv_args(1, dim, df, rdet) if hdiv_v
-                         else basis_args(ncv, cv, 1, dim, invdf))
-                avail = {'v': v, 'dv': dv, 'x': x, 'w': w, 'h': h}
-                if bilinear:
-                    u, du = (hdiv_args(0, dim, df, rdet) if hdiv_u
-                             else basis_args(ncu, cu, 0, dim, invdf))
-                    avail['u'] = u
-                    avail['du'] = du
-                f = call_form(form, names, avail)
-                # the Jacobian factor |detDF| of spfem/assembly.py:980-981
-                blocks[(cu, cv)] = f * Form.coef(absdet)
+        _tracer._FIELDS = fctx
+        try:
+            for cu in range(ncu if bilinear else 1):
+                for cv in range(ncv):
+                    v, dv = (hdiv_args(1, dim, df, rdet) if hdiv_v
+                             else basis_args(ncv, cv, 1, dim, invdf))
+                    avail = {'v': v, 'dv': dv, 'x': x, 'w': w, 'h': h}
+                    if bilinear:
+                        u, du = (hdiv_args(0, dim, df, rdet) if hdiv_u
+                                 else basis_args(ncu, cu, 0, dim, invdf))
+                        avail['u'] = u
+                        avail['du'] = du
+                    try:
+                        f = call_form(form, names, avail)
+                    except TraceError:
+                        raise
+                    except (TypeError, ValueError, AttributeError, NotImplementedError) as exc:
+                        if field_mode:
+                            raise
+                        # an opaque callable choked on the symbolic proxies
+                        raise TraceError("the form could not be traced symbolically (%s: %s)"
+                                         % (type(exc).__name__, exc))
+                    # the Jacobian factor |detDF| of spfem/assembly.py:980-981
+                    blocks[(cu, cv)] = f * Form.coef(absdet)
+        finally:
+            _tracer._FIELDS = None
         tab_u = self._tables(bu, X)
         tab_v = self._tables(bv, X)
+        nfld = len(fctx.arrays) if fctx is not None else 0
         spec = codegen.InteriorSpec(mesh.refdom, dim, bilinear,
                                     bu.nbfun_ref(), bv.nbfun_ref(), ncu, ncv,
-                                    blocks, X, W, tab_u, tab_v, nw=len(wkeys))
+                                    blocks, X, W, tab_u, tab_v,
+                                    nw=0 if field_mode else len(wkeys), nfld=nfld)
         src = codegen.generate_interior(spec, "spfem_elem")
-        return _Plan("interior", spec, src, "spfem_elem", bilinear, wkeys)
+        plan = _Plan("interior", spec, src, "spfem_elem", bilinear,
+                     [] if field_mode else wkeys)
+        plan.fields = fctx.arrays if fctx is not None else []
+        return plan
 
     @staticmethod
     def _tables(base, X):

@@ -88,6 +88,8 @@ struct SpfemArgs {
     double *out;              /* out[entry*ldo + k*ldk]                         */
     long long ldk;
     double params[SPFEM_MAX_PARAMS]; /* captured Python scalars (dt, penalties ...) */
+    const double *fields[8];  /* host-evaluated coefficient fields, fields[i][q*ldf + e] */
+    long long ldf;
 };
 """
 
@@ -869,11 +871,17 @@ class InteriorSpec(object):
     derivative of the *scalar* parent element."""
 
     def __init__(self, refdom, dim, bilinear, nbu, nbv, ncu, ncv, blocks,
-                 X, W, tab_u, tab_v, nw=0):
+                 X, W, tab_u, tab_v, nw=0, nfld=0):
         self.refdom, self.dim, self.bilinear = refdom, dim, bilinear
         self.nbu, self.nbv, self.ncu, self.ncv = nbu, nbv, ncu, ncv
         self.blocks, self.X, self.W = blocks, X, W
         self.tab_u, self.tab_v, self.nw = tab_u, tab_v, nw
+        self.nfld = nfld            # host-evaluated coefficient fields (tracer.FieldContext)
+
+    @property
+    def needs_el(self):
+        """The kernel indexes per-element data (``interp`` gathers, fields)."""
+        return self.nw > 0 or self.nfld > 0
 
     @property
     def n_rows(self):
@@ -1028,6 +1036,12 @@ def generate_interior(spec, name="spfem_elem"):
                     body.append("const double dw%d_%d_%d = %s;" % (
                         s, a, q, " + ".join("%s * gw%d_%d_%d" % (inv(l), s, l, q) for l in range(dim))))
 
+    # host-evaluated coefficient fields: one value per element and quadrature point
+    for i in range(spec.nfld):
+        if ("fld%d" % i) in syms:
+            for q in range(nq):
+                body.append("const double fld%d_%d = P.fields[%d][%dLL * P.ldf + e];" % (i, q, i, q))
+
     def symname(nm, scope):
         if nm.startswith("iA"):
             return "iA_" + nm[2:]
@@ -1091,7 +1105,7 @@ def generate_interior(spec, name="spfem_elem"):
     # coefficients): the same computation with the vertex coordinates passed in
     spec.fan_ok = (spec.refdom == "tri" and spec.bilinear and spec.ncu == 1 and spec.ncv == 1
                    and spec.nbu == 3 and spec.nbv == 3
-                   and not any(nm[0] in "xwd" for nm in syms))
+                   and not any(nm[0] in "xwdf" for nm in syms))
     core = []
     if spec.fan_ok:
         core = (affine_geometry(dim, fast_inverse=True, coords_given=True)
@@ -1161,7 +1175,7 @@ def generate_interior(spec, name="spfem_elem"):
     if True:    # bilinear forms and load vectors alike (a vector = one CSR slot per row)
         nve = 4 if quad else dim + 1
         # element id (only needed for the interp gathers through P.tdof_u)
-        elem = "(long long)((const int *)(sA + d[13]))[el]" if spec.nw > 0 else "0LL"
+        elem = "(long long)((const int *)(sA + d[13]))[el]" if spec.needs_el else "0LL"
         cases = "\n".join(
             "        case %d: %s_body<true, %d>(T.base, %s, vt, (long long)ne_pad, (long long)el, "
             "pc, ldpc, sL, (long long)ldl, (long long)el); break;" % (c, name, c, elem)

@@ -63,7 +63,7 @@ def _torch():
 def _cache_key(source):
     """Key of a compiled kernel: the source AND what it was compiled for / with
     (the same text gives a different cubin on another architecture or NVRTC)."""
-    return source_key("%s|abi%d|%s" % (_ARCH, 3, source))
+    return source_key("%s|abi%d|%s" % (_ARCH, 4, source))
 
 
 def _trim_kcache():
@@ -626,6 +626,24 @@ class Engine(object):
             out.append(self._dev(np.asarray(interp[key]), np.float64))
         return out
 
+    def _field_tensors(self, plan):
+        """Device copies ``(nq, nt)`` (device element order) of the plan's
+        host-evaluated coefficient fields, and their leading dimension."""
+        torch = self.torch
+        out = []
+        for f in getattr(plan, "fields", ()) or ():
+            t = torch.from_numpy(np.ascontiguousarray(f.T)).to(self.device)
+            if self.perm is not None:
+                t = t.index_select(1, self.perm_l).contiguous()
+            out.append(t)
+        return out
+
+    @staticmethod
+    def _set_fields(a, ft):
+        for i, t in enumerate(ft):
+            a.fields[i] = t.data_ptr()
+        a.ldf = ft[0].shape[1] if ft else 0
+
     def _sorted_pattern(self, bilinear):
         """Whole-mesh pattern with contribution lists (global radix sort): what
         the two-kernel route and the vertex-fan plan need."""
@@ -649,11 +667,14 @@ class Engine(object):
         spec = plan.spec
         kernel = get_kernel(plan.source, plan.name)
         wt = self._interp_tensors(plan, interp)
+        ft = self._field_tensors(plan)
+        wt = (wt, ft)                      # kept alive by the Prepared object
         a = _lib.SpfemArgs()
         a.set_params(plan)
         a.tdof_u, a.ldd = self.tdof_u.data_ptr(), self.tdof_u.shape[1]
-        for s, w in enumerate(wt):
+        for s, w in enumerate(wt[0]):
             a.interp[s] = w.data_ptr()
+        self._set_fields(a, ft)
         if tind is None:
             n, sel = self.nt, None
             a.n, a.ldo, a.ldk = n, n, 1
@@ -740,7 +761,7 @@ class Engine(object):
         from .tileplan import build_tile_plan, fill_coordinates, TileTooLarge
         torch, asm, spec = self.torch, self.asm, plan.spec
         env = os.environ.get
-        ckey = (plan.bilinear, spec.n_unique, tuple(spec.alias), spec.nw > 0,
+        ckey = (plan.bilinear, spec.n_unique, tuple(spec.alias), spec.needs_el,
                 env("SPFEM_TILE_MODE", "auto"), env("SPFEM_TILE_E", "0"),
                 env("SPFEM_TILE_SORT", "auto"), env("SPFEM_TILE_BLOCKS", "1"),
                 env("SPFEM_TILE_SPLIT", "0"), env("SPFEM_TILE_BUDGET", "1"))
@@ -798,7 +819,7 @@ class Engine(object):
                                    self.t, asm.dofnum_v.N, asm.dofnum_u.N if bilinear else 1,
                                    E, spec.alias, nuniq, dim,
                                    bsv=bsv if nb > 1 else 1, bsu=bsu if nb > 1 else 1,
-                                   with_el=spec.nw > 0, sort_slots=sort_slots, compact=compact,
+                                   with_el=spec.needs_el, sort_slots=sort_slots, compact=compact,
                                    row_mask=self._row_mask(),
                                    index_bytes=8 if idt == np.int64 else 4,
                                    batch_cap=int(env("SPFEM_TILE_BATCH", "0")),

@@ -176,9 +176,56 @@ class Coef(object):
         return "%s(%s)" % (self.kind, ", ".join(map(repr, self.args)))
 
 
+class FieldContext(object):
+    """Host-evaluated coefficient fields (the H3 fallback of SURVEY.md 7 /
+    Appendix B).  When a form applies something the tracer cannot follow to
+    ``x``, ``h`` or ``w`` -- ``np.interp``, a SymPy ``lambdify`` with
+    ``Piecewise``, a matplotlib interpolator (spfem/mesh.py:885-901,
+    spfem/test_module.py:759-765) -- it is traced again with those arguments as
+    the reference's own ``(elements, quadrature points)`` NumPy arrays
+    (spfem/assembly.py:947-959).  Whatever the opaque code computes from them is
+    an ordinary array; the moment such an array meets a basis-function proxy it
+    becomes a *field*: a point-dependent symbol ``fld<i>`` whose values the
+    kernel streams from HBM."""
+
+    MAX_FIELDS = 8
+
+    def __init__(self, shape):
+        self.shape = tuple(shape)
+        self.arrays = []
+        self._index = {}
+
+    def register(self, arr):
+        import zlib
+        a = np.asarray(arr)
+        if a.dtype == object:
+            raise TraceError("an object array met a basis function inside a form")
+        try:
+            b = np.broadcast_to(a.astype(np.float64, copy=False), self.shape)
+        except ValueError:
+            raise TraceError("an array of shape %s does not broadcast to (elements, "
+                             "quadrature points) = %s" % (a.shape, self.shape))
+        b = np.ascontiguousarray(b)
+        key = (zlib.adler32(memoryview(b).cast("B")), b.shape)
+        for idx in self._index.get(key, ()):          # the same field, computed again
+            if np.array_equal(self.arrays[idx], b, equal_nan=True):   # (vector elements: one
+                return idx                                            # call per component pair)
+        if len(self.arrays) >= self.MAX_FIELDS:
+            raise TraceError("more than %d distinct host-evaluated coefficient fields in "
+                             "one form" % self.MAX_FIELDS)
+        self.arrays.append(b)
+        self._index.setdefault(key, []).append(len(self.arrays) - 1)
+        return len(self.arrays) - 1
+
+
+_FIELDS = None        # the FieldContext of the trace in progress (field mode only)
+
+
 def as_coef(x):
     if isinstance(x, Coef):
         return x
+    if _FIELDS is not None and isinstance(x, np.ndarray) and x.ndim >= 1 and x.dtype != object:
+        return Coef.sym("fld%d" % _FIELDS.register(x), True)
     if isinstance(x, (bool, np.bool_)):
         return Coef.const(1.0 if x else 0.0)
     if isinstance(x, (int, float, np.integer, np.floating)):
@@ -439,6 +486,8 @@ def finalize(result):
     if isinstance(result, np.ndarray):
         if result.dtype == object and result.size == 1:
             return finalize(result.reshape(-1)[0])
+        if _FIELDS is not None and result.dtype != object and result.ndim >= 1:
+            return Form.coef(result)          # a form without basis functions (norms)
         if result.size == 1:
             return Form.coef(float(result.reshape(-1)[0]))
         raise TraceError("the form returned an array of shape %s; a scalar "

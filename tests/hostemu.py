@@ -74,6 +74,11 @@ def run_interior(asm, plan, tind=None, interp=None):
         arr = np.ascontiguousarray(interp[key], dtype=np.float64)
         keep.append(arr)
         a.interp[s] = arr.ctypes.data
+    for i, f in enumerate(getattr(plan, "fields", ()) or ()):
+        arr = np.ascontiguousarray(f.T, dtype=np.float64)      # (nq, nt), mesh element order
+        keep.append(arr)
+        a.fields[i] = arr.ctypes.data
+        a.ldf = arr.shape[1]
     a.out = _ptr(out)
     compile_host(plan)(C.byref(a))
     return out

@@ -34,7 +34,7 @@ def test_c_abi_exports_every_declared_symbol(lib):
     exported = set(re.findall(r"\bT (spfem_[a-z_0-9]+)", out))
     assert declared <= exported, declared - exported
     assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
-    assert lib.spfem_abi_version() == 3
+    assert lib.spfem_abi_version() == 4
     assert lib.spfem_device_count() >= 0
 
 
