@@ -33,7 +33,8 @@ sameblob SPFEM_FAN_X=X_SAMEBLOB
 warpstore SPFEM_FAN_X=WARPSTORE
 """
 KEYS = ("SPFEM_FAN_NOCOMPUTE", "SPFEM_FAN_X", "SPFEM_FAN_T", "SPFEM_FAN_ROWS", "SPFEM_FAN_MINB8",
-        "SPFEM_FAN_PREFETCH", "SPFEM_FAN_TINY", "SPFEM_FAN_ROWORDER", "SPFEM_RCP", "SPFEM_ADJUGATE")
+        "SPFEM_FAN_PREFETCH", "SPFEM_FAN_TINY", "SPFEM_FAN_ROWORDER", "SPFEM_RCP", "SPFEM_ADJUGATE",
+        "SPFEM_FAN_NCOPY")
 
 
 def sample(prep, steps=30):

@@ -1,0 +1,5 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 900 python tools/fan_variants.py 11 tools/fan_variants_e.txt 7 > gpurun_out/r02_c14_fan_variants.jsonl 2> gpurun_out/r02_c14_fan_variants.err
+tail -n 5 gpurun_out/r02_c14_fan_variants.err
+cut -c1-420 gpurun_out/r02_c14_fan_variants.jsonl

@@ -53,6 +53,10 @@ def run(kind, size):
         p, t = meshgen.grid_tet(size)
         m = sp.MeshTet(p, t, validate=False)
         elem, form, C = sp.ElementTetP2(), cases.lap3, 10
+    elif kind in ("q1", "q2"):
+        m = sp.MeshQuad()
+        m.refine(size)
+        elem, form, C = (sp.ElementQ1() if kind == "q1" else sp.ElementQ2()), cases.lap2, 4
     elif kind == "trip1":
         m = sp.MeshTri()
         m.refine(size)
