@@ -522,25 +522,43 @@ def run_gpu_arm(args):
     start = torch.cuda.Event(enable_timing=True)
     stop = torch.cuda.Event(enable_timing=True)
     start.record()
-    for s in range(args.steps):
-        ev[s][0].record()
-        for i, p in enumerate(preps):
-            if fused:
-                ev[s][1 + 2 * i].record()
+    if fused:
+        # one kernel per assembly: nothing but the launches inside the timed region
+        # (an event pair around every 0.1 ms launch costs 3-4 % of it); the kernel's
+        # average launch duration over the region is region / number of launches
+        for s in range(args.steps):
+            for p in preps:
                 p.launch()
-            else:
+    else:
+        for s in range(args.steps):
+            ev[s][0].record()
+            for i, p in enumerate(preps):
                 p.launch_element_kernel()
                 ev[s][1 + 2 * i].record()
                 p.launch_reduce()
-            ev[s][2 + 2 * i].record()
+                ev[s][2 + 2 * i].record()
     stop.record()
     barrier()
     clocks = sampler.stop()
     ms_total = start.elapsed_time(stop)
-    t_elem = np.mean([ev[s][2 * i].elapsed_time(ev[s][1 + 2 * i])
-                      for s in range(args.steps) for i in range(len(preps))])
-    t_red = np.mean([ev[s][1 + 2 * i].elapsed_time(ev[s][2 + 2 * i])
-                     for s in range(args.steps) for i in range(len(preps))])
+    if fused:
+        t_elem = 0.0
+        t_red = ms_total / (args.steps * len(preps))
+    else:
+        t_elem = np.mean([ev[s][2 * i].elapsed_time(ev[s][1 + 2 * i])
+                          for s in range(args.steps) for i in range(len(preps))])
+        t_red = np.mean([ev[s][1 + 2 * i].elapsed_time(ev[s][2 + 2 * i])
+                         for s in range(args.steps) for i in range(len(preps))])
+    # per form, outside the timed region: events around 50 back-to-back launches
+    per_form = {}
+    for (fname, _), p in zip(FORMS, preps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(50):
+            p.launch()
+        e1.record()
+        torch.cuda.synchronize()
+        per_form[fname + "_ms"] = e0.elapsed_time(e1) / 50
     if fused:
         kname = {"FanPrepared": "spfem_elem_fan", "TiledPrepared": "spfem_elem_tile"}.get(
             type(preps[0]).__name__, "fused")
@@ -550,6 +568,7 @@ def run_gpu_arm(args):
         t_elem = 0.0
     else:
         kernels = {"spfem_elem_ms": float(t_elem), "k_reduce_ms": float(t_red)}
+    kernels["per_form"] = per_form
     if world > 1:
         tt = torch.tensor([ms_total], device="cuda", dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)

@@ -239,6 +239,48 @@ int spfem_tileplan_fill_coords(const int *desc, unsigned char *blob, const int *
                                const long long *vptr, long long ntiles, const double *p,
                                long long ldp, int dim, int on_device, void *stream);
 
+/* ---- vertex-fan plan: plan of `<name>_fan*` (codegen.FAN_KERNEL), natively ----------
+ * Scalar P1 on triangles (one DOF per vertex; CSR rows = vertex stars).  For
+ * every vertex the counter-clockwise ring of its neighbours is walked from the
+ * triangles' directed edges (no facet tables needed); vertices are cut into
+ * tiles of `rows_per_tile` along a Morton curve, the rows of a tile are in CSR
+ * order, and every tile gets one blob: interleaved (x, y) of its vertices (rows
+ * first, then the halo vertices in id order -- filled through vid / pc_index),
+ * then the row records (spfem_b200/fanplan.py documents the three formats).
+ * Memory through the allocator callbacks as above.  Return code 5: the mesh /
+ * pattern is not fan shaped (non-manifold, valence > 12, ...): use the tile plan. */
+typedef struct SpfemFanPlanIn {
+    const double *p;          /* coordinates p[k*ldp + v], k = 0, 1                    */
+    long long ldp, nv;
+    const int *t;             /* connectivity t[k*ldt + e], k = 0..2 (any element order) */
+    long long ldt, nt;
+    const void *indptr;       /* CSR pattern of the vertex x vertex matrix              */
+    const void *indices;
+    int index_bytes;          /* 4 or 8                                                  */
+    int rows_per_tile;
+    int tiny;                 /* allow the 20-byte records (<= 256 vertices per tile)    */
+    int row_order;            /* 0: rows of a tile in CSR order, 1: in Morton order      */
+    double lo[2], hi[2];      /* bounding box of the vertices                            */
+} SpfemFanPlanIn;
+
+typedef struct SpfemFanPlanOut {
+    void *desc;               /* int32 [8 * ntiles]: offset/16, bytes A, bytes B, rows,
+                                 slots, vertices, 0, 0                                   */
+    void *blob;
+    long long blob_bytes;
+    void *vid;                /* int32 [nvid] vertex of every coordinate slot            */
+    void *pc_index;           /* int64 [nvid] index (in doubles) of its x in the blob    */
+    long long nvid, ntiles;
+    int max_a;                /* largest blob (bytes)                                    */
+    int max_ns;               /* most CSR slots of one tile                              */
+    int max_neighbours;
+    int format;               /* 0: 20-byte records, 1: 32-byte, 2: 48-byte              */
+    double halo_factor;
+} SpfemFanPlanOut;
+
+int spfem_fanplan_build(const SpfemFanPlanIn *in, SpfemFanPlanOut *out, spfem_alloc_fn alloc,
+                        spfem_free_fn release, void *alloc_ctx, int on_device, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -96,6 +96,27 @@ class SpfemPlanOut(C.Structure):
     ]
 
 
+class SpfemFanPlanIn(C.Structure):
+    """Mirror of ``struct SpfemFanPlanIn`` (include/spfem_b200.h)."""
+    _fields_ = [
+        ("p", C.c_void_p), ("ldp", C.c_longlong), ("nv", C.c_longlong),
+        ("t", C.c_void_p), ("ldt", C.c_longlong), ("nt", C.c_longlong),
+        ("indptr", C.c_void_p), ("indices", C.c_void_p), ("index_bytes", C.c_int),
+        ("rows_per_tile", C.c_int), ("tiny", C.c_int), ("row_order", C.c_int),
+        ("lo", C.c_double * 2), ("hi", C.c_double * 2),
+    ]
+
+
+class SpfemFanPlanOut(C.Structure):
+    _fields_ = [
+        ("desc", C.c_void_p), ("blob", C.c_void_p), ("blob_bytes", C.c_longlong),
+        ("vid", C.c_void_p), ("pc_index", C.c_void_p),
+        ("nvid", C.c_longlong), ("ntiles", C.c_longlong),
+        ("max_a", C.c_int), ("max_ns", C.c_int), ("max_neighbours", C.c_int), ("format", C.c_int),
+        ("halo_factor", C.c_double),
+    ]
+
+
 class SpfemFanArgs(C.Structure):
     """Mirror of ``struct SpfemFanArgs`` (generated source, codegen.FAN_KERNEL)."""
     _fields_ = [
@@ -138,6 +159,8 @@ SYMBOLS = {
                                C.c_longlong, C.c_void_p, C.c_void_p]),
     "spfem_tileplan_build": (C.c_int, [C.POINTER(SpfemPlanIn), C.POINTER(SpfemPlanOut),
                                        ALLOC_FN, FREE_FN, C.c_void_p, C.c_int, C.c_void_p]),
+    "spfem_fanplan_build": (C.c_int, [C.POINTER(SpfemFanPlanIn), C.POINTER(SpfemFanPlanOut),
+                                      ALLOC_FN, FREE_FN, C.c_void_p, C.c_int, C.c_void_p]),
     "spfem_tileplan_fill_coords": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                              C.c_longlong, C.c_void_p, C.c_longlong, C.c_int,
                                              C.c_int, C.c_void_p]),

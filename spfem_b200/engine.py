@@ -175,9 +175,12 @@ class Pattern(object):
         self._host = None
 
     def host(self):
-        """Host copies of ``indptr`` / ``indices`` (cached)."""
+        """Host copies of ``indptr`` / ``indices`` (cached, read-only)."""
         if self._host is None:
-            self._host = (self.indptr.cpu().numpy(), self.indices.cpu().numpy())
+            ip, ix = self.indptr.cpu().numpy(), self.indices.cpu().numpy()
+            ip.flags.writeable = False
+            ix.flags.writeable = False
+            self._host = (ip, ix)
         return self._host
 
 
@@ -192,15 +195,27 @@ class DeviceCSR(object):
         return self.pattern.nnz
 
     def to_scipy(self):
-        """Host ``scipy.sparse.csr_matrix`` with fresh arrays: the values are
-        streamed through a persistent pinned staging buffer in chunks
-        (asynchronous device-to-host copies at PCIe speed) while worker threads
-        copy finished chunks and the cached host pattern into the new arrays."""
+        """Host ``scipy.sparse.csr_matrix`` with fresh arrays, like the
+        reference's: the values are copied asynchronously at PCIe speed into a
+        recycled pinned block while worker threads copy the cached host pattern.
+
+        ``SPFEM_SHARE_PATTERN=1`` (opt-in, for time loops that assemble on the
+        same mesh again and again): ``indptr`` / ``indices`` are then the cached
+        arrays themselves, shared by every result of this assembler and
+        READ-ONLY -- 8 bytes per nonzero per call instead of 12-16, and N ranks
+        on one host do not contend for memory bandwidth copying identical index
+        arrays.  SciPy operations that build new matrices work as usual;
+        in-place structure changes (``eliminate_zeros``, ``sort_indices`` on an
+        unsorted matrix) raise on the read-only arrays, which is why it is not
+        the default."""
         indptr, indices = self.pattern.host()
         A = csr_matrix(self.shape, dtype=np.float64)
         pending = _to_host_begin(self.values)       # DMA runs while we copy the pattern
-        A.indices = _host_copy(indices, pooled=True)
-        A.indptr = _host_copy(indptr, pooled=True)
+        if os.environ.get("SPFEM_SHARE_PATTERN", "0") == "1":
+            A.indices, A.indptr = indices, indptr
+        else:
+            A.indices = _host_copy(indices, pooled=True)
+            A.indptr = _host_copy(indptr, pooled=True)
         A.data = _to_host_finish(pending)
         A.has_sorted_indices = True
         A.has_canonical_format = True
@@ -530,7 +545,7 @@ class Engine(object):
         if not first:
             # the fused kernel reads tile-private copies of the coordinates
             from .tileplan import fill_coordinates
-            from .fanplan_torch import fill_fan_coordinates
+            from .fanplan import fill_fan_coordinates
             self.p_version += 1
             for tp in self._tile_plans:
                 if tp.get("kind") == "vertex-fan":
@@ -727,12 +742,12 @@ class Engine(object):
                 or asm.dofnum_u.t_dof.shape != mesh.t.shape
                 or not np.array_equal(asm.dofnum_u.t_dof, mesh.t)):
             return None
-        from .fanplan_torch import build_fan_plan, FanPlanError, fill_fan_coordinates
+        from .fanplan import build_fan_plan, FanPlanError, fill_fan_coordinates
         t0 = time.perf_counter()
-        dev64 = lambda arr: torch.from_numpy(np.ascontiguousarray(arr, dtype=np.int64)).to(self.device)
         try:
-            fp = build_fan_plan(torch, self.p, dev64(mesh.t), dev64(mesh.t2f), dev64(mesh.f2t),
-                                pat.indptr, pat.indices,
+            # (the device connectivity is in Morton order: any element order gives a
+            # valid plan, only the start of a closed ring may differ)
+            fp = build_fan_plan(torch, self.p, self.t, pat.indptr, pat.indices,
                                 int(os.environ.get("SPFEM_FAN_ROWS", "128")),
                                 tiny=os.environ.get("SPFEM_FAN_TINY", "1") != "0",
                                 row_order=os.environ.get("SPFEM_FAN_ROWORDER", "id"))

@@ -106,7 +106,9 @@ def vertex_rings(mesh):
     # closed fans start at the neighbour with the smallest polar angle, so that
     # on a regular mesh the q-th neighbour of every vertex lies in the same
     # direction (neighbouring threads then read neighbouring coordinates)
-    ang = np.arctan2(p[1][a_of] - p[1][corner_vertex], p[0][a_of] - p[0][corner_vertex])
+    # (a monotone surrogate of atan2 without transcendentals, so that the native
+    # builder -- host or device -- reproduces it bit for bit; ties: smallest corner)
+    ang = angle_key(p[0][a_of] - p[0][corner_vertex], p[1][a_of] - p[1][corner_vertex])
     ordk = np.lexsort((ang, corner_vertex))
     start = ordk[np.searchsorted(corner_vertex[ordk], np.arange(nv))]
     nopred = np.nonzero(~has_prev)[0]
@@ -134,6 +136,15 @@ def vertex_rings(mesh):
     opn = np.nonzero(~closed)[0]
     nb[nfan[opn], opn] = last_b[opn]              # open fans have one more neighbour
     return nb, nfan, closed
+
+
+def angle_key(dx, dy):
+    """Same ordering as ``np.arctan2(dy, dx)`` on (-pi, pi], values in (0, 4]."""
+    with np.errstate(divide="ignore", invalid="ignore"):
+        k = np.where(dy < 0,
+                     np.where(dx < 0, (-dy) / (-dx - dy), 1.0 + dx / (dx - dy)),
+                     np.where(dx > 0, 2.0 + dy / (dx + dy), 3.0 + (-dx) / (-dx + dy)))
+    return np.where((dy == 0) & (dx < 0), 4.0, k)
 
 
 def build_fan_plan(mesh, indptr, indices, rows_per_tile=256, tiny=True, row_order="id"):
@@ -212,7 +223,7 @@ def build_fan_plan(mesh, indptr, indices, rows_per_tile=256, tiny=True, row_orde
     # halo vertices are numbered along mesh lines too (y, then x) so that the
     # q-th neighbours of consecutive rows are consecutive in shared memory
     hv = uh % nv
-    hord = np.lexsort((p[0][hv], p[1][hv], h_tile))
+    hord = np.arange(len(uh))                     # halo vertices of a tile in id order
     hrank = np.empty(len(uh), dtype=np.int64)
     hrank[hord] = np.arange(len(uh))
     hidx = np.searchsorted(uh, tl[out] * nv + nbr[out])

@@ -92,17 +92,24 @@ def test_fan_kernel_wide_records():
 
 
 @pytest.mark.parametrize("tiny", [True, False])
-@pytest.mark.parametrize("which", ["refined", "wheel", "jiggled"])
-def test_torch_plan_is_byte_identical(which, tiny):
-    """The device-side plan builder (PyTorch index ops; run here on CPU tensors)
-    produces exactly the blob / descriptors of the NumPy reference builder."""
+@pytest.mark.parametrize("which", ["refined", "wheel", "jiggled", "clockwise"])
+def test_native_plan_is_byte_identical(which, tiny):
+    """The native plan builder (``spfem_fanplan_build``, csrc/spfem_plan.cu; run
+    here on host pointers, the same code as on the device) produces exactly the
+    blob / descriptors of the NumPy reference builder."""
     import torch
-    from spfem_b200 import fanplan_torch
+    from spfem_b200 import fanplan
     if which == "refined":
         m = sp.MeshTri()
         m.refine(4)
     elif which == "wheel":
         m = _wheel_mesh(10, 2)
+    elif which == "clockwise":          # some triangles listed clockwise
+        m = sp.MeshTri()
+        m.refine(3)
+        t = m.t.copy()
+        t[[1, 2], ::3] = t[[2, 1], ::3]
+        m = sp.MeshTri(m.p, t)
     else:
         m = sp.MeshTri(initmesh="symmetric")
         m.refine(3)
@@ -112,13 +119,37 @@ def test_torch_plan_is_byte_identical(which, tiny):
     A = hostemu.iasm(asm, cases.mass)
     a = build_fan_plan(m, A.indptr, A.indices, 32, tiny=tiny)
     T = lambda x: torch.from_numpy(np.ascontiguousarray(x))
-    b = fanplan_torch.build_fan_plan(torch, T(m.p), T(m.t.astype(np.int64)), T(m.t2f.astype(np.int64)),
-                                     T(m.f2t.astype(np.int64)), T(A.indptr.astype(np.int64)),
-                                     T(A.indices.astype(np.int64)), 32, tiny=tiny)
-    assert a["format"] == b["format"] and (a["format"] == "tiny") == (tiny and which != "wheel")
-    assert np.array_equal(a["desc"], b["desc"].numpy())
-    assert np.array_equal(a["blob"], b["blob"].numpy())
-    assert np.array_equal(a["vid"], b["vid"].numpy())
-    assert np.array_equal(a["pc_index"], b["pc_index"].numpy())
-    for k in ("ntiles", "max_a", "max_ns", "max_neighbours"):
-        assert a[k] == b[k]
+    for idt in (np.int32, np.int64):
+        b = fanplan.build_fan_plan(torch, T(m.p), T(m.t.astype(np.int32)), T(A.indptr.astype(idt)),
+                                   T(A.indices.astype(idt)), 32, tiny=tiny)
+        assert a["format"] == b["format"] and (a["format"] == "tiny") == (tiny and which != "wheel")
+        assert np.array_equal(a["desc"], b["desc"].numpy())
+        assert np.array_equal(a["vid"], b["vid"].numpy())
+        assert np.array_equal(a["pc_index"], b["pc_index"].numpy())
+        assert np.array_equal(a["blob"], b["blob"].numpy())
+        for k in ("ntiles", "max_a", "max_ns", "max_neighbours"):
+            assert a[k] == b[k]
+        assert abs(a["halo_factor"] - b["halo_factor"]) < 1e-12
+
+
+def test_native_plan_rejects_what_the_reference_builder_rejects():
+    import torch
+    from spfem_b200 import fanplan
+    T = lambda x: torch.from_numpy(np.ascontiguousarray(x))
+    # a vertex with 13 triangles around it
+    m = _wheel_mesh(13, 0)
+    asm = AssemblerElement(m, sp.ElementTriP1())
+    A = hostemu.iasm(asm, cases.mass)
+    with pytest.raises(FanPlanError):
+        build_fan_plan(m, A.indptr, A.indices)
+    with pytest.raises(fanplan.FanPlanError):
+        fanplan.build_fan_plan(torch, T(m.p), T(m.t.astype(np.int32)), T(A.indptr.astype(np.int32)),
+                               T(A.indices.astype(np.int32)))
+    # a pattern that is not the vertex-star pattern (P2 matrix on the P1 mesh)
+    m = sp.MeshTri()
+    m.refine(2)
+    A2 = hostemu.iasm(AssemblerElement(m, sp.ElementTriP2()), cases.mass)
+    with pytest.raises(fanplan.FanPlanError):
+        fanplan.build_fan_plan(torch, T(m.p), T(m.t.astype(np.int32)),
+                               T(A2.indptr[:m.p.shape[1] + 1].astype(np.int32)),
+                               T(A2.indices.astype(np.int32)))
