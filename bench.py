@@ -250,6 +250,7 @@ CONFIGS = {
     "stokes_C": ("tri", 3162, 3, "config 5: pressure mass block, ElementTriP1"),
     "nitsche_fasm": ("tri", 3162, 0, "config 5: boundary fasm, Nitsche terms on vector-P2 (4 n facets)"),
     "tetp2_laplace": ("tet", 203, 10, "config 4: Kuhn m^3 grid, ElementTetP2 Laplace"),
+    "q2_laplace": ("quadrefine", 11, 4, "MeshQuad.refine(11) ElementQ2 Laplace (MappingQ1: quadrature-point loop)"),
 }
 
 
@@ -301,15 +302,16 @@ def run_config(name, args, world, rank, peak, traffic, barrier):
         "stokes_C": (sp.ElementTriP1, None, mass, "iasm"),
         "nitsche_fasm": (vecp2, None, vec_nitsche, "fasm"),
         "tetp2_laplace": (sp.ElementTetP2, None, lap3, "iasm"),
+        "q2_laplace": (sp.ElementQ2, None, lap2, "iasm"),
     }[name]
     eu = spec[0]()
     ev = spec[1]() if spec[1] is not None else None
     form, how = spec[2], spec[3]
     part = None
-    if kind == "refine":
+    if kind in ("refine", "quadrefine"):
         if world > 1:
             return dict(out, skipped="single-GPU configuration")
-        m = sp.MeshTri()
+        m = sp.MeshTri() if kind == "refine" else sp.MeshQuad()
         m.refine(size)
         nt_own = m.t.shape[1]
     elif world == 1:

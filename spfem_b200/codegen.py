@@ -962,8 +962,212 @@ def interior_terms(spec, drop_tol=1e-15):
     return entries, uses
 
 
+def _ctable(name, arr):
+    """A constant table: ``__constant__`` memory on the device (uniform reads:
+    every thread of a warp is at the same quadrature point), a static array in
+    the host emulation."""
+    arr = np.asarray(arr, dtype=np.float64)
+    dims = "".join("[%d]" % n for n in arr.shape)
+
+    def braces(a):
+        if a.ndim == 1:
+            return "{" + ", ".join(lit(v) for v in a) + "}"
+        return "{" + ", ".join(braces(x) for x in a) + "}"
+    return "SPFEM_CONST double %s%s = %s;" % (name, dims, braces(arr))
+
+
+def looped_quad_body(spec, syms, em):
+    """Element body for ``MappingQ1`` meshes as a LOOP over the quadrature points
+    (spfem/mapping.py:47-191, spfem/assembly.py:961-984).
+
+    The straight-line generator folds ``W_q psi_j(X_q) psi_i(X_q)`` into one
+    constant per (entry, point, coefficient): 45 x 16 x 3 terms for Q2 Laplace,
+    about 100 KB of code that no instruction cache holds.  Here the reference
+    tables live in constant memory; per point the bilinear Jacobian and the
+    coefficient DAG are evaluated once, then
+
+        H^b_j = sum_a G^{ab} (W_q psi^a_j)        (per trial function and b)
+        A[j, i] += sum_b H^b_j psi^b_i            (distinct entries only)
+
+    Returns ``(tables, body, alias, n_unique, n_terms)``."""
+    dim, nq = spec.dim, len(spec.W)
+    nbu = spec.nbu if spec.bilinear else 1
+    X = spec.X
+    tables = [_ctable("SPFEM_QT", [1.0 - X[1], 1.0 + X[1], 1.0 - X[0], 1.0 + X[0]]),
+              _ctable("SPFEM_QN", [[_q1_basis(X[0, q], X[1, q], c) for q in range(nq)]
+                                   for c in range(4)]),
+              _ctable("SPFEM_QW", spec.W),
+              _ctable("SPFEM_TV", np.asarray(spec.tab_v, dtype=np.float64))]
+    if spec.bilinear:
+        tables.append(_ctable("SPFEM_TUW", np.asarray(spec.tab_u, dtype=np.float64)
+                              * np.asarray(spec.W)[None, None, :]))
+    if spec.nw:
+        tables.append(_ctable("SPFEM_TU0", np.asarray(spec.tab_u[0], dtype=np.float64)))
+    body = []
+    for k in range(4):
+        body.append("const int vtx_%d = vt[%d * ldv + ev];" % (k, k))
+    for k in range(4):
+        body.append("double Q0_%d, Q1_%d;" % (k, k))
+        body.append("if (TILED) { const double2 cxy = reinterpret_cast<const double2 *>(pc)[vtx_%d]; "
+                    "Q0_%d = cxy.x; Q1_%d = cxy.y; } else { Q0_%d = pc[vtx_%d]; "
+                    "Q1_%d = pc[ldpc + vtx_%d]; }" % (k, k, k, k, k, k, k))
+    for sw in range(spec.nw):
+        if ("w%d" % sw) in syms:
+            for j in range(spec.nbu):
+                body.append("const double wc%d_%d = P.interp[%d][P.tdof_u[%d * P.ldd + e]];"
+                            % (sw, j, sw, j))
+    if any(nm.startswith("dw") for nm in syms):
+        raise NotImplementedError("gradients of interpolated fields on quadrilaterals")
+
+    # ---- entries -> term lists (a, b, coefficient), distinct entries -------------
+    same_tab = spec.bilinear and spec.tab_u is spec.tab_v or (
+        spec.bilinear and np.array_equal(np.asarray(spec.tab_u), np.asarray(spec.tab_v)))
+    tu = np.asarray(spec.tab_u, dtype=np.float64) if spec.bilinear else None
+    tv = np.asarray(spec.tab_v, dtype=np.float64)
+    eterms = [[] for _ in range(spec.n_entries)]
+    for (cu, cv), form in sorted(spec.blocks.items()):
+        for (a, b), coef in sorted(form.terms.items(), key=lambda kv: kv[0]):
+            if a != NONE and not spec.bilinear:
+                raise ValueError("trial function in a linear form")
+            for j in range(nbu):
+                if a != NONE and not np.any(tu[a][j]):
+                    continue
+                for i in range(spec.nbv):
+                    if b != NONE and not np.any(tv[b][i]):
+                        continue
+                    idx = (j * spec.ncu + cu) * spec.n_rows + (i * spec.ncv + cv)
+                    eterms[idx].append((a, j, b, i, coef, cu, cv))
+    groups, order_u, alias = {}, [], [0] * spec.n_entries
+    for idx, terms in enumerate(eterms):
+        key = []
+        for a, j, b, i, coef, cu, cv in terms:
+            f1, f2 = ("u", a, j), ("v", b, i)
+            if same_tab:                   # psi^a_j psi^b_i is symmetric in the two factors
+                f1, f2 = sorted([(a, j), (b, i)])
+            key.append((coef.uid, f1, f2))
+        gkey = tuple(sorted(key))
+        if gkey not in groups:
+            groups[gkey] = (len(order_u), idx, [])
+            order_u.append(gkey)
+        groups[gkey][2].append(idx)
+        alias[idx] = groups[gkey][0]
+    n_unique = len(order_u)
+    npart = int(os.environ.get("SPFEM_TILE_NPART", "0"))
+    if npart <= 0:
+        npart = 1 if n_unique <= 24 else 2
+    spec.npart = npart
+    for gkey in order_u:
+        u = groups[gkey][0]
+        body.append("double acc_%d = 0.0;" % u)
+
+    # ---- the loop over the quadrature points --------------------------------------
+    L = ["for (int q = 0; q < %d; ++q) {" % nq]
+    L.append("const double omy = SPFEM_QT[0][q], opy = SPFEM_QT[1][q], omx = SPFEM_QT[2][q], "
+             "opx = SPFEM_QT[3][q];")
+    for i in range(2):
+        P = ["Q%d_%d" % (i, k) for k in range(4)]
+        e0 = _sub(_add(_add(_mul(_neg(P[0]), "omy"), _mul(P[1], "omy")), _mul(P[2], "opy")),
+                  _mul(P[3], "opy"))
+        e1 = _add(_add(_sub(_mul(_neg(P[0]), "omx"), _mul(P[1], "opx")), _mul(P[2], "opx")),
+                  _mul(P[3], "omx"))
+        L.append("const double J%d0_L = %s;" % (i, _mul("0.25", e0)))
+        L.append("const double J%d1_L = %s;" % (i, _mul("0.25", e1)))
+    L.append("const double detJ_L = %s;" % _sub(_mul("J00_L", "J11_L"), _mul("J01_L", "J10_L")))
+    # one division per point: adj * (1 / det) instead of adj / det (<= 1 ulp apart,
+    # like the affine path; on axis-aligned meshes J01 = J10 = 0 exactly and a
+    # zero numerator would send every one of those divisions down the slow path)
+    L.append("const double rdetJ_L = 1.0 / detJ_L;")
+    L.append("const double iJ_00_L = J11_L * rdetJ_L;")
+    L.append("const double iJ_01_L = (-J01_L) * rdetJ_L;")
+    L.append("const double iJ_10_L = (-J10_L) * rdetJ_L;")
+    L.append("const double iJ_11_L = J00_L * rdetJ_L;")
+    L.append("const double absdetq_L = fabs(detJ_L);")
+    if "hq" in syms:
+        L.append("const double hq_L = pow(absdetq_L, %s);" % lit(1.0 / dim))
+    for k in range(dim):
+        if ("x%d" % k) in syms:
+            acc = _mul("Q%d_0" % k, "SPFEM_QN[0][q]")
+            for c in range(1, 4):
+                acc = _add(acc, _mul("Q%d_%d" % (k, c), "SPFEM_QN[%d][q]" % c))
+            L.append("const double x%d_L = %s;" % (k, acc))
+    for sw in range(spec.nw):
+        if ("w%d" % sw) in syms:
+            L.append("const double w%d_L = 0.0 + %s;" % (sw, " + ".join(
+                "wc%d_%d * SPFEM_TU0[%d][q]" % (sw, j, j) for j in range(spec.nbu))))
+    for i in range(spec.nfld):
+        if ("fld%d" % i) in syms:
+            L.append("const double fld%d_L = P.fields[%d][(long long)q * P.ldf + e];" % (i, i))
+
+    def symname(nm, scope):
+        if nm.startswith("iJ"):
+            return "iJ_%s_L" % nm[2:]
+        return "%s_L" % nm if scope else nm
+
+    # coefficient DAG, once (element-constant sub-expressions are hoisted by the compiler)
+    cname = {}
+    for terms in eterms:
+        for a, j, b, i, coef, cu, cv in terms:
+            if coef.uid not in cname:
+                cname[coef.uid] = em.name(coef, "L", symname)
+    L += [ln.strip() for ln in em.lines]
+    # H^b_j per (block, trial function, b) that some distinct entry needs
+    reps = [groups[g][1] for g in order_u]
+    need_h, hterms = [], {}
+    for idx in reps:
+        for a, j, b, i, coef, cu, cv in eterms[idx]:
+            hk = (cu, cv, j, b)
+            if hk not in hterms:
+                hterms[hk] = []
+                need_h.append(hk)
+    for (cu, cv), form in sorted(spec.blocks.items()):
+        for (a, b), coef in sorted(form.terms.items(), key=lambda kv: kv[0]):
+            for j in range(nbu):
+                hk = (cu, cv, j, b)
+                if hk in hterms and not (a != NONE and not np.any(tu[a][j])):
+                    fac = "SPFEM_QW[q]" if a == NONE else "SPFEM_TUW[%d][%d][q]" % (a, j)
+                    hterms[hk].append("%s * %s" % (cname[coef.uid], fac))
+    n_terms = 0
+    hname = {}
+    for hk in need_h:
+        cu, cv, j, b = hk
+        hname[hk] = "H_%d_%d_%d_%s" % (cu, cv, j, "n" if b == NONE else str(b))
+        L.append("const double %s = %s;" % (hname[hk], " + ".join(hterms[hk]) or "0.0"))
+        n_terms += len(hterms[hk])
+    for gkey in order_u:
+        u, idx, idxs = groups[gkey]
+        by_b = {}
+        for a, j, b, i, coef, cu, cv in eterms[idx]:
+            by_b.setdefault((cu, cv, j, b), i)
+        parts = []
+        for (cu, cv, j, b), i in by_b.items():
+            parts.append(hname[(cu, cv, j, b)] if b == NONE
+                         else "%s * SPFEM_TV[%d][%d][q]" % (hname[(cu, cv, j, b)], b, i))
+        n_terms += len(parts)
+        if parts:
+            L.append("if (PART < 0 || PART == %d) acc_%d += %s;" % (u % npart, u, " + ".join(parts)))
+    L.append("}")
+    body += L
+    for gkey in order_u:
+        u, idx, idxs = groups[gkey]
+        body.append("if (PART < 0 || PART == %d) { const double val = acc_%d;" % (u % npart, u))
+        body.append("  if (TILED) { out[(long long)%d * ldo + k] = val; } else {" % u)
+        for ii in idxs:
+            body.append("    SPFEM_PUT(%d, val);" % ii)
+        body.append("  } }")
+    return tables, body, alias, n_unique, n_terms * nq // 4 + 40
+
+
 def generate_interior(spec, name="spfem_elem"):
     """Source text of the interior element kernel for ``spec``."""
+    dim, nq = spec.dim, len(spec.W)
+    if spec.refdom == "quad" and os.environ.get("SPFEM_QLOOP", "1") != "0":
+        syms = collect_syms(list(spec.blocks.values()))
+        if not any(nm.startswith("dw") for nm in syms):   # (inorm's gradients: straight-line path)
+            return _generate_interior_source(spec, name, looped=True)
+    return _generate_interior_source(spec, name, looped=False)
+
+
+def _generate_interior_source(spec, name, looped):
     dim, nq = spec.dim, len(spec.W)
     entries, uses = interior_terms(spec)
     syms = collect_syms(list(spec.blocks.values()))
@@ -971,7 +1175,12 @@ def generate_interior(spec, name="spfem_elem"):
     em = Emitter(adjugate=not quad and os.environ.get("SPFEM_ADJUGATE", "1") != "0")
 
     body = []
-    if quad:
+    tables = []
+    if looped:
+        tables, body, l_alias, l_nuniq, l_nterms = looped_quad_body(spec, syms, em)
+    if looped:
+        pass
+    elif quad:
         for k in range(4):
             body.append("const int vtx_%d = vt[%d * ldv + ev];" % (k, k))
         for k in range(4):
@@ -990,127 +1199,138 @@ def generate_interior(spec, name="spfem_elem"):
         n_geom_lines = len(body)
         if "h" in syms:
             body.append("const double h = pow(absdet, %s);" % lit(1.0 / dim))
-    # global coordinates of the quadrature points (only if the form uses x)
-    for k in range(dim):
-        if ("x%d" % k) not in syms:
-            continue
-        for q in range(nq):
-            if quad:
-                # sum_k P_k * N_k(X_q)                (spfem/mapping.py:104-110)
-                acc = _mul("Q%d_0" % k, lit(_q1_basis(spec.X[0, q], spec.X[1, q], 0)))
-                for c in range(1, 4):
-                    acc = _add(acc, _mul("Q%d_%d" % (k, c), lit(
-                        _q1_basis(spec.X[0, q], spec.X[1, q], c))))
-                body.append("const double x%d_%d = %s;" % (k, q, acc))
-            else:
-                # outer(A_k0, X0) + outer(A_k1, X1) (+ ...) + b_k
-                #                                    (spfem/mapping.py:318-319)
-                acc = _mul("A_%d0" % k, lit(spec.X[0, q]))
-                for l in range(1, dim):
-                    acc = _add(acc, _mul("A_%d%d" % (k, l), lit(spec.X[l, q])))
-                body.append("const double x%d_%d = %s;" % (k, q, _add(acc, "b_%d" % k)))
-    # interpolated fields w[k] = sum_j interp[k][t_dof_u[j, e]] phi_j(X_q)
-    #                                          (spfem/assembly.py:955-959)
-    for s in range(spec.nw):
-        use_w = ("w%d" % s) in syms
-        use_dw = any(("dw%d_%d" % (s, a)) in syms for a in range(dim))
-        if not (use_w or use_dw):
-            continue
-        for j in range(spec.nbu):
-            body.append("const double wc%d_%d = P.interp[%d][P.tdof_u[%d * P.ldd + e]];"
-                        % (s, j, s, j))
-        for q in range(nq):
-            if use_w:
-                terms = ["wc%d_%d * %s" % (s, j, lit(spec.tab_u[0][j][q]))
-                         for j in range(spec.nbu)]
-                body.append("const double w%d_%d = 0.0 + %s;" % (s, q, " + ".join(terms)))
-            if use_dw:
-                # gradient of the interpolated field: DF^{-T} applied to the
-                # reference gradient sum_j c_j dphi_j(X_q)  (inorm, assembly.py:1340-1346)
-                for l in range(dim):
-                    terms = ["wc%d_%d * %s" % (s, j, lit(spec.tab_u[1 + l][j][q]))
-                             for j in range(spec.nbu)]
-                    body.append("const double gw%d_%d_%d = 0.0 + %s;" % (s, l, q, " + ".join(terms)))
-                for a in range(dim):
-                    inv = (lambda l: "iJ_%d%d_%d" % (l, a, q)) if quad else (lambda l: "iA_%d%d" % (l, a))
-                    body.append("const double dw%d_%d_%d = %s;" % (
-                        s, a, q, " + ".join("%s * gw%d_%d_%d" % (inv(l), s, l, q) for l in range(dim))))
-
-    # host-evaluated coefficient fields: one value per element and quadrature point
-    for i in range(spec.nfld):
-        if ("fld%d" % i) in syms:
+    if looped:
+        spec.alias, spec.n_unique, spec.n_terms = l_alias, l_nuniq, l_nterms
+        alias = l_alias
+        spec.params = list(em.params)
+        spec.fan_ok = False
+        core = []
+    else:
+        # global coordinates of the quadrature points (only if the form uses x)
+        for k in range(dim):
+            if ("x%d" % k) not in syms:
+                continue
             for q in range(nq):
-                body.append("const double fld%d_%d = P.fields[%d][%dLL * P.ldf + e];" % (i, q, i, q))
+                if quad:
+                    # sum_k P_k * N_k(X_q)                (spfem/mapping.py:104-110)
+                    acc = _mul("Q%d_0" % k, lit(_q1_basis(spec.X[0, q], spec.X[1, q], 0)))
+                    for c in range(1, 4):
+                        acc = _add(acc, _mul("Q%d_%d" % (k, c), lit(
+                            _q1_basis(spec.X[0, q], spec.X[1, q], c))))
+                    body.append("const double x%d_%d = %s;" % (k, q, acc))
+                else:
+                    # outer(A_k0, X0) + outer(A_k1, X1) (+ ...) + b_k
+                    #                                    (spfem/mapping.py:318-319)
+                    acc = _mul("A_%d0" % k, lit(spec.X[0, q]))
+                    for l in range(1, dim):
+                        acc = _add(acc, _mul("A_%d%d" % (k, l), lit(spec.X[l, q])))
+                    body.append("const double x%d_%d = %s;" % (k, q, _add(acc, "b_%d" % k)))
+        # interpolated fields w[k] = sum_j interp[k][t_dof_u[j, e]] phi_j(X_q)
+        #                                          (spfem/assembly.py:955-959)
+        for s in range(spec.nw):
+            use_w = ("w%d" % s) in syms
+            use_dw = any(("dw%d_%d" % (s, a)) in syms for a in range(dim))
+            if not (use_w or use_dw):
+                continue
+            for j in range(spec.nbu):
+                body.append("const double wc%d_%d = P.interp[%d][P.tdof_u[%d * P.ldd + e]];"
+                            % (s, j, s, j))
+            for q in range(nq):
+                if use_w:
+                    terms = ["wc%d_%d * %s" % (s, j, lit(spec.tab_u[0][j][q]))
+                             for j in range(spec.nbu)]
+                    body.append("const double w%d_%d = 0.0 + %s;" % (s, q, " + ".join(terms)))
+                if use_dw:
+                    # gradient of the interpolated field: DF^{-T} applied to the
+                    # reference gradient sum_j c_j dphi_j(X_q)  (inorm, assembly.py:1340-1346)
+                    for l in range(dim):
+                        terms = ["wc%d_%d * %s" % (s, j, lit(spec.tab_u[1 + l][j][q]))
+                                 for j in range(spec.nbu)]
+                        body.append("const double gw%d_%d_%d = 0.0 + %s;" % (s, l, q, " + ".join(terms)))
+                    for a in range(dim):
+                        inv = (lambda l: "iJ_%d%d_%d" % (l, a, q)) if quad else (lambda l: "iA_%d%d" % (l, a))
+                        body.append("const double dw%d_%d_%d = %s;" % (
+                            s, a, q, " + ".join("%s * gw%d_%d_%d" % (inv(l), s, l, q) for l in range(dim))))
 
-    def symname(nm, scope):
-        if nm.startswith("iA"):
-            return "iA_" + nm[2:]
-        if nm.startswith("iJ"):
-            return "iJ_%s_%s" % (nm[2:], scope)
-        if scope:
-            return "%s_%s" % (nm, scope)
-        return nm
+        # host-evaluated coefficient fields: one value per element and quadrature point
+        for i in range(spec.nfld):
+            if ("fld%d" % i) in syms:
+                for q in range(nq):
+                    body.append("const double fld%d_%d = P.fields[%d][%dLL * P.ldf + e];" % (i, q, i, q))
 
-    names = {}
-    for node, scope in uses:
-        names[(node.uid, scope)] = em.name(node, scope, symname)
-    body += [ln.strip() for ln in em.lines]
+        def symname(nm, scope):
+            if nm.startswith("iA"):
+                return "iA_" + nm[2:]
+            if nm.startswith("iJ"):
+                return "iJ_%s_%s" % (nm[2:], scope)
+            if scope:
+                return "%s_%s" % (nm, scope)
+            return nm
 
-    # Entries with identical term lists (symmetric forms: A_loc[j,i] == A_loc[i,j];
-    # P1 mass: all off-diagonal entries) are *aliases*: the fused tile kernel
-    # computes and stores each distinct value once (``alias[idx]`` = its slot in
-    # shared memory); the two-kernel route stores every entry.
-    groups, order_u, alias = {}, [], [0] * len(entries)
-    for idx, terms in enumerate(entries):
-        # merge terms that multiply the same coefficient (e.g. G^{12} == G^{21})
-        merged, order = {}, []
-        for K, node, scope in terms:
-            key = (node.uid, scope)
-            if key in merged:
-                merged[key] = (merged[key][0] + K, node, scope)
-            else:
-                merged[key] = (K, node, scope)
-                order.append(key)
-        terms = [merged[k] for k in order if merged[k][0] != 0.0]
-        gkey = tuple(sorted((node.uid, scope, float(K).hex()) for K, node, scope in terms))
-        if gkey not in groups:
-            if terms:
-                expr = " + ".join("%s * %s" % (lit(K), names[(node.uid, scope)])
-                                  for K, node, scope in terms)
-            else:
-                expr = "0.0"
-            groups[gkey] = (len(order_u), expr, [])
-            order_u.append(gkey)
-        groups[gkey][2].append(idx)
-        alias[idx] = groups[gkey][0]
-    # threads per element in the tile kernel's phase A (distinct values dealt
-    # round-robin to the parts)
-    npart = int(os.environ.get("SPFEM_TILE_NPART", "0"))
-    if npart <= 0:
-        npart = 1 if len(order_u) <= 24 else 2
-    spec.npart = npart
-    for gkey in order_u:
-        u, expr, idxs = groups[gkey]
-        body.append("if (PART < 0 || PART == %d) { const double val = %s;" % (u % npart, expr))
-        body.append("  if (TILED) { out[(long long)%d * ldo + k] = val; } else {" % u)
-        for idx in idxs:
-            body.append("    SPFEM_PUT(%d, val);" % idx)
-        body.append("  } }")
-    spec.alias = alias
-    spec.n_unique = len(order_u)
-    spec.params = list(em.params)
-    # multiply-adds per element (cost estimate: is recomputing halo elements cheap?)
-    spec.n_terms = sum(groups[g][1].count(" * ") for g in order_u) + len(em.lines)
-    # Vertex-fan variant (TriP1-like: one DOF per vertex, element-constant
-    # coefficients): the same computation with the vertex coordinates passed in
-    spec.fan_ok = (spec.refdom == "tri" and spec.bilinear and spec.ncu == 1 and spec.ncv == 1
-                   and spec.nbu == 3 and spec.nbv == 3
-                   and not any(nm[0] in "xwdf" for nm in syms))
-    core = []
-    if spec.fan_ok:
-        core = (affine_geometry(dim, fast_inverse=True, coords_given=True)
-                + body[n_geom_lines:])
+        names = {}
+        for node, scope in uses:
+            names[(node.uid, scope)] = em.name(node, scope, symname)
+        body += [ln.strip() for ln in em.lines]
 
+        # Entries with identical term lists (symmetric forms: A_loc[j,i] == A_loc[i,j];
+        # P1 mass: all off-diagonal entries) are *aliases*: the fused tile kernel
+        # computes and stores each distinct value once (``alias[idx]`` = its slot in
+        # shared memory); the two-kernel route stores every entry.
+        groups, order_u, alias = {}, [], [0] * len(entries)
+        for idx, terms in enumerate(entries):
+            # merge terms that multiply the same coefficient (e.g. G^{12} == G^{21})
+            merged, order = {}, []
+            for K, node, scope in terms:
+                key = (node.uid, scope)
+                if key in merged:
+                    merged[key] = (merged[key][0] + K, node, scope)
+                else:
+                    merged[key] = (K, node, scope)
+                    order.append(key)
+            terms = [merged[k] for k in order if merged[k][0] != 0.0]
+            gkey = tuple(sorted((node.uid, scope, float(K).hex()) for K, node, scope in terms))
+            if gkey not in groups:
+                if terms:
+                    expr = " + ".join("%s * %s" % (lit(K), names[(node.uid, scope)])
+                                      for K, node, scope in terms)
+                else:
+                    expr = "0.0"
+                groups[gkey] = (len(order_u), expr, [])
+                order_u.append(gkey)
+            groups[gkey][2].append(idx)
+            alias[idx] = groups[gkey][0]
+        # threads per element in the tile kernel's phase A (distinct values dealt
+        # round-robin to the parts)
+        npart = int(os.environ.get("SPFEM_TILE_NPART", "0"))
+        if npart <= 0:
+            npart = 1 if len(order_u) <= 24 else 2
+        spec.npart = npart
+        for gkey in order_u:
+            u, expr, idxs = groups[gkey]
+            body.append("if (PART < 0 || PART == %d) { const double val = %s;" % (u % npart, expr))
+            body.append("  if (TILED) { out[(long long)%d * ldo + k] = val; } else {" % u)
+            for idx in idxs:
+                body.append("    SPFEM_PUT(%d, val);" % idx)
+            body.append("  } }")
+        spec.alias = alias
+        spec.n_unique = len(order_u)
+        spec.params = list(em.params)
+        # multiply-adds per element (cost estimate: is recomputing halo elements cheap?)
+        spec.n_terms = sum(groups[g][1].count(" * ") for g in order_u) + len(em.lines)
+        # Vertex-fan variant (TriP1-like: one DOF per vertex, element-constant
+        # coefficients): the same computation with the vertex coordinates passed in
+        spec.fan_ok = (spec.refdom == "tri" and spec.bilinear and spec.ncu == 1 and spec.ncv == 1
+                       and spec.nbu == 3 and spec.nbv == 3
+                       and not any(nm[0] in "xwdf" for nm in syms))
+        core = []
+        if spec.fan_ok:
+            core = (affine_geometry(dim, fast_inverse=True, coords_given=True)
+                    + body[n_geom_lines:])
+
+    spec.looped = bool(looped)
+    spec.minb = 3 if dim == 2 else 2          # CTAs of the tile kernel per SM (register cap)
+    if looped and spec.n_unique > 24:
+        spec.minb = 2
     src = [PRELUDE, DEVICE_HELPERS]
     if os.environ.get("SPFEM_RCP", "0") == "0":      # measured: the Newton reciprocal is not faster
         src.insert(0, "#define SPFEM_IEEE_RCP 1")
@@ -1119,6 +1339,14 @@ def generate_interior(spec, name="spfem_elem"):
     for flag in os.environ.get("SPFEM_FAN_X", "").split(","):    # kernel experiments (tools/fan_variants.py)
         if flag:
             src.append("#define SPFEM_FAN_%s 1" % flag)
+    # small tables (Q1: 4 points) sit in constant memory; larger ones (Q2: 7.6 KB) would
+    # thrash the constant cache -- global memory through L1 instead (measured, Q2: 2 x)
+    tbytes = 8 * sum(t.count(",") + 1 for t in tables)
+    space = os.environ.get("SPFEM_TABLE_SPACE", "constant" if tbytes <= 2048 else "global")
+    space = "__constant__" if space == "constant" else "__device__ const"
+    src.append("#ifdef SPFEM_HOST\n#define SPFEM_CONST static const\n#else\n"
+               "#define SPFEM_CONST %s\n#endif" % space)
+    src += tables
     src.append("#define SPFEM_NENTRIES %d" % spec.n_entries)
     src.append("#define SPFEM_NUNIQUE %d" % spec.n_unique)
     src.append("#define SPFEM_NPART %d" % spec.npart)
@@ -1192,7 +1420,9 @@ def generate_interior(spec, name="spfem_elem"):
                    .replace("@THREADS@", str(TILE_THREADS))
                    # registers: three CTAs of 256 threads per SM on 2-D meshes (<= 85
                    # registers; measured +19 % for vector-P2), two on 3-D meshes
-                   .replace("@MINB@", os.environ.get("SPFEM_TILE_MINB", "3" if dim == 2 else "2")))
+                   # (the quadrature loop of the larger quadrilateral elements keeps ~25
+                   # accumulators + the H vectors live: 128 registers, two CTAs)
+                   .replace("@MINB@", os.environ.get("SPFEM_TILE_MINB", str(spec.minb))))
     src.append("#else")
     src.append('extern "C" void %s_host(const SpfemArgs *P)\n{' % name)
     src.append("    for (long long k = 0; k < P->n; ++k) {")

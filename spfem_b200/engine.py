@@ -813,7 +813,8 @@ class Engine(object):
             sort_slots = {"bucket": 2, "1": 1}.get(srt, 0)
         nuniq = spec.n_unique
         nsidx = (spec.n_rows // spec.bsv) * (spec.n_cols // spec.bsu)
-        prefer = (96 if compact else 56) * 1024
+        minb = int(env("SPFEM_TILE_MINB", str(getattr(spec, "minb", 3 if dim == 2 else 2))))
+        prefer = (110 if minb <= 2 and not compact else 96 if compact else 56) * 1024
         limit = 220 * 1024
         E_env = int(env("SPFEM_TILE_E", "0"))
         if E_env > 0:
@@ -846,6 +847,11 @@ class Engine(object):
                 continue                # cannot fit the preferred footprint
             if E_env <= 0 and compact and E > 64:
                 continue
+            # quadrature-loop bodies are long: one pass of phase A over the CTA's threads
+            # (NPART threads per tile element) beats a second, half-empty pass
+            if (E_env <= 0 and getattr(spec, "looped", False) and spec.n_unique > 24 and E > 64
+                    and 1.25 * E * spec.npart > codegen_tile_threads()):
+                continue
             try:
                 tp = build(E)
             except TileTooLarge:
@@ -868,7 +874,7 @@ class Engine(object):
         if tp is not None and env("SPFEM_TILE_BUDGET", "1") != "0":
             smem = tile_smem_bytes(nuniq, tp, nsidx, nb)
             per_sm = 227 * 1024
-            cmax = 3 if dim == 2 else 2           # CTAs per SM the registers allow
+            cmax = min(minb, 3 if dim == 2 else 2)        # CTAs per SM the registers allow
             c_now = min(cmax, per_sm // (smem + 1024))
             mean_ne = tp["halo_factor"] * self.nt / max(tp["ntiles"], 1)
             fixed = tp["max_bytes_b"] + 64 + (4 * nsidx * nb if nb > 1 else 0)

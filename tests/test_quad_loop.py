@@ -1,0 +1,94 @@
+# -*- coding: utf-8 -*-
+"""Quadrilateral elements (``MappingQ1``, spfem/mapping.py:47-191): the interior
+kernel is a loop over the quadrature points with the reference tables in
+constant / global memory (``codegen.looped_quad_body``).  Forms with every kind
+of point data against the oracle, on the host emulation and on the GPU, and the
+straight-line generator (``SPFEM_QLOOP=0``) as a second opinion."""
+import numpy as np
+import pytest
+
+import cases
+import hostemu
+import util
+import asm_oracle
+import spfem_b200 as sp
+from spfem_b200.assembly import AssemblerElement
+
+
+def f_x(u, v, du, dv, x, h):
+    return (1.0 + x[0] * x[1]) * (du[0] * dv[0] + du[1] * dv[1]) + np.sin(x[0]) * h * u * v
+
+
+def f_w(u, v, w):
+    return (1.0 + w[0] * w[0]) * u * v
+
+
+def f_load(v, dv, x):
+    return np.cos(x[0] + x[1]) * v + x[0] * dv[1]
+
+
+def f_vec(du, dv):
+    e = lambda d: [[d[0][0], 0.5 * (d[0][1] + d[1][0])], [0.5 * (d[0][1] + d[1][0]), d[1][1]]]
+    eu, ev = e(du), e(dv)
+    return 2.0 * sum(eu[i][j] * ev[i][j] for i in range(2) for j in range(2)) + \
+        (eu[0][0] + eu[1][1]) * (ev[0][0] + ev[1][1])
+
+
+def f_nonsym(u, dv, x):
+    return x[1] * u * dv[0]
+
+
+def f_opaque(u, v, x):
+    return np.interp(x[0], [0.0, 0.5, 1.0], [1.0, 3.0, 2.0]) * u * v
+
+
+CASES = {
+    "q1_x": (f_x, "Q1", 1, False), "q2_x": (f_x, "Q2", 1, False),
+    "q1_w": (f_w, "Q1", 1, True), "q2_w": (f_w, "Q2", 1, True),
+    "q2_load": (f_load, "Q2", 1, False),
+    "vecq1_elasticity": (f_vec, "Q1", 2, False),
+    "q2_nonsym": (f_nonsym, "Q2", 1, False),
+    "q1_opaque": (f_opaque, "Q1", 1, False),
+}
+
+
+def _setup(name, jiggle=True):
+    form, ename, ncomp, use_w = CASES[name]
+    m = sp.MeshQuad()
+    m.refine(2)
+    if jiggle:      # genuinely bilinear maps: the Jacobian varies from point to point
+        I = m.interior_nodes()
+        m.p[:, I] += 0.03 * np.random.default_rng(2).standard_normal((2, len(I)))
+    a = AssemblerElement(m, util.element(ename, ncomp))
+    interp = {0: np.random.default_rng(3).random(a.dofnum_u.N)} if use_w else None
+    ref = asm_oracle.iasm(m, ename, form, ncomp_u=ncomp, ncomp_v=ncomp, interp=interp)
+    return a, form, interp, ref
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_quadrature_loop_host(name, monkeypatch):
+    a, form, interp, ref = _setup(name)
+    plan = a.plan_iasm(form, interp=interp)
+    assert plan.spec.looped and "for (int q = 0;" in plan.source
+    util.check(hostemu.iasm(a, form, interp=interp), ref)
+    monkeypatch.setenv("SPFEM_QLOOP", "0")
+    plan0 = a.plan_iasm(form, interp=interp)
+    assert not plan0.spec.looped
+    util.check(hostemu.iasm(a, form, interp=interp), ref)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_quadrature_loop_cuda(name):
+    a, form, interp, ref = _setup(name)
+    util.check(a.iasm(form, interp=interp), ref)                      # tile kernel
+    tind = np.arange(a.mesh.t.shape[1])
+    util.check(a.iasm(form, interp=interp, tind=tind), ref)           # two-kernel route
+
+
+def test_symmetric_entries_are_aliased_in_the_loop():
+    a, form, interp, ref = _setup("q2_x")
+    spec = a.plan_iasm(form).spec
+    assert spec.n_unique == 45 and len(set(spec.alias)) == 45          # 81 entries, 45 distinct
+    spec = a.plan_iasm(f_nonsym).spec
+    assert spec.n_unique == 81
