@@ -374,8 +374,15 @@ def run_config(name, args, world, rank, peak, traffic, barrier):
                     if tp.get(k) is not None}
             tile["smem_bytes"] = prep.smem
             tile["threads"] = prep.threads
+        # DRAM bytes per launch: ncu capture of the same kernel on a smaller grid of the
+        # same family, scaled by the number of elements (profiles/traffic_r02.json)
+        tr = traffic.get(name)
         out["roofline"] = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
-                           "frac": ach / peak, "traffic": traffic.get(name),
+                           "frac": ach / peak,
+                           "traffic": (int(tr["dram_bytes_per_element"] * nt_own) if tr else None),
+                           "traffic_source": (("ncu on %s, %.1f B/element x elements"
+                                               % (tr["measured_on"], tr["dram_bytes_per_element"]))
+                                              if tr else None),
                            "algorithmic_bytes_per_assembly": balg,
                            "algorithmic_bytes_per_element": round(balg / nt_own, 1),
                            "tile": tile}
@@ -632,7 +639,7 @@ def run_gpu_arm(args):
                 break
             except Exception:
                 traffic_all = {}
-    cfg_traffic = traffic_all.get("configs", {})
+    cfg_traffic = traffic_all.get("configs_per_element", {})
 
     # ---- N > 1: results on hardware + cost of the interface exchange -------------
     parity_checked, exchange = None, None
