@@ -45,6 +45,11 @@ def run(kind, size):
         p, t = meshgen.grid_tri(size)
         m = sp.MeshTri(p, t, validate=False)
         elem, form, C = sp.ElementH1Vec(sp.ElementTriP2()), cases.elasticity, 6
+    elif kind == "stokesb":
+        p, t = meshgen.grid_tri(size)
+        m = sp.MeshTri(p, t, validate=False)
+        elem, form, C = sp.ElementH1Vec(sp.ElementTriP2()), cases.stokes_b, 6
+        elem_v = sp.ElementTriP1()
     elif kind == "trip2":
         p, t = meshgen.grid_tri(size)
         m = sp.MeshTri(p, t, validate=False)
@@ -67,7 +72,7 @@ def run(kind, size):
     nt, nv, dim = m.t.shape[1], m.p.shape[1], m.p.shape[0]
     res["nt"] = nt
     t0 = time.perf_counter()
-    a = AssemblerElement(m, elem)
+    a = AssemblerElement(m, elem, locals().get('elem_v'))
     res["dofnum_s"] = round(time.perf_counter() - t0, 2)
     t0 = time.perf_counter()
     prep = a.prepare_iasm(form)
