@@ -116,7 +116,20 @@ class AssemblerElement(Assembler):
         if not isinstance(elem_u, _element.Element):
             raise Exception("Second parameter must be an instance of "
                             "spfem.element.Element!")
-        self.mapping = mesh.mapping() if mapping is None else mapping
+        default = mesh.mapping()
+        def same_mesh(mp):
+            if getattr(mp, "_mesh", None) is mesh:                   # MappingAffine
+                return True
+            return getattr(mp, "p", None) is mesh.p and getattr(mp, "t", None) is mesh.t
+        if mapping is not None and not (type(mapping) is type(default) and same_mesh(mapping)):
+            # the device kernels rebuild the geometry from mesh.p / mesh.t with the
+            # mesh's default map (spfem/assembly.py:829-832 stores any mapping and
+            # uses it for F / invDF / detDF): a different map would be ignored silently
+            raise NotImplementedError(
+                "AssemblerElement: only the mesh's own mapping (mesh.mapping()) is "
+                "supported on the device path; deform mesh.p instead of passing a "
+                "pre-deformed mapping")
+        self.mapping = default if mapping is None else mapping
         self.mesh = mesh
         self.elem_u = elem_u
         self.dofnum_u = Dofnum(mesh, elem_u)

@@ -274,10 +274,17 @@ class _PinnedPool(object):
     block: device-to-host copies run at PCIe speed straight into the memory the
     caller owns, with no staging copy and no repeated page-locking."""
 
-    def __init__(self, max_cached_bytes=2 << 30):
+    def __init__(self, max_cached_bytes=2 << 30, max_held_bytes=None):
         self.free = {}            # (dtype, capacity) -> [tensor, ...]
         self.cached = 0
         self.max_cached = max_cached_bytes
+        # page-locked bytes the callers still hold (results they keep alive): above
+        # the budget new results come in pageable memory (staged copy), so that a
+        # user who keeps many matrices does not exhaust lockable memory
+        self.held = 0
+        if max_held_bytes is None:
+            max_held_bytes = int(os.environ.get("SPFEM_PINNED_BUDGET", str(16 << 30)))
+        self.max_held = max_held_bytes
 
     def take(self, torch_dtype, n):
         import torch
@@ -291,7 +298,10 @@ class _PinnedPool(object):
             buf = lst.pop()
             self.cached -= buf.numel() * buf.element_size()
         else:
-            buf = torch.empty(cap, dtype=torch_dtype, pin_memory=True)
+            nbytes = cap * torch.empty(0, dtype=torch_dtype).element_size()
+            pin = self.held + nbytes <= self.max_held
+            buf = torch.empty(cap, dtype=torch_dtype, pin_memory=pin)
+        self.held += buf.numel() * buf.element_size()
         # the finalizer hangs on the array that wraps the whole buffer: every view
         # the caller (or SciPy) derives keeps that array alive through ``.base``
         full = buf.numpy()
@@ -300,7 +310,8 @@ class _PinnedPool(object):
 
     def _release(self, key, buf):
         nbytes = buf.numel() * buf.element_size()
-        if self.cached + nbytes <= self.max_cached:
+        self.held -= nbytes
+        if buf.is_pinned() and self.cached + nbytes <= self.max_cached:
             self.free.setdefault(key, []).append(buf)
             self.cached += nbytes
 

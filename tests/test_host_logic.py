@@ -200,3 +200,18 @@ def test_captured_scalars_are_runtime_parameters():
     f1 = a.plan_fasm(lambda u, v, h: 17.3 / h * u * v)
     f2 = a.plan_fasm(lambda u, v, h: 41.9 / h * u * v)
     assert f1.source == f2.source and f1.spec.params == [17.3] and f2.spec.params == [41.9]
+
+
+def test_foreign_mapping_is_rejected():
+    """A mapping that is not the mesh's own would be ignored by the device
+    kernels (spfem/assembly.py:829-832 uses whatever mapping it is given)."""
+    m = sp.MeshTri()
+    m.refine(1)
+    AssemblerElement(m, sp.ElementTriP1(), mapping=m.mapping())          # the mesh's own map: fine
+    other = sp.MeshTri()
+    other.refine(1)
+    other.p[0] *= 2.0
+    with pytest.raises(NotImplementedError):
+        AssemblerElement(m, sp.ElementTriP1(), mapping=other.mapping())
+    q = sp.MeshQuad()
+    AssemblerElement(q, sp.ElementQ1(), mapping=q.mapping())
