@@ -1388,9 +1388,19 @@ def _generate_interior_source(spec, name, looped):
         src.append("    const bool TILED = true; const int PART = -1; const long long ldo = 1, k = 0;")
         src += ["    " + ln for ln in core]
         src.append("}")
-        src.append(FAN_KERNEL.replace("@NAME@", name).replace("@FANTHREADS@", str(FAN_THREADS))
-                   .replace("@FANMINB8@", os.environ.get("SPFEM_FAN_MINB8", "7"))
-                   .replace("@FANMINB@", os.environ.get("SPFEM_FAN_MINB", "6"))
+        # rows per tile = threads per CTA.  Forms that are cheap per triangle (mass: |detA|
+        # times constants) are bound by the per-tile fixed cost (descriptor, TMA wait,
+        # barrier): 160 rows per tile; forms with a real local row (Laplace: adjugate,
+        # reciprocal, 62 registers) run best with 128 (measured, interleaved:
+        # profiles/r02_fan_diagnostics.jsonl -- mass 0.1043 -> 0.1007 ms, Laplace
+        # 0.0991 -> 0.102 ms with 160)
+        heavy = spec.n_terms > 12
+        spec.fan_rows = int(os.environ.get("SPFEM_FAN_ROWS", "128" if heavy else "160"))
+        spec.fan_threads = int(os.environ.get("SPFEM_FAN_T", str(spec.fan_rows))) // 32 * 32
+        minb8 = os.environ.get("SPFEM_FAN_MINB8", "7" if spec.fan_threads <= 128 else "5")
+        src.append(FAN_KERNEL.replace("@NAME@", name).replace("@FANTHREADS@", str(spec.fan_threads))
+                   .replace("@FANMINB8@", minb8)
+                   .replace("@FANMINB@", os.environ.get("SPFEM_FAN_MINB", "6" if spec.fan_threads <= 128 else "4"))
                    .replace("@A00@", str(alias[0])).replace("@A10@", str(alias[3]))
                    .replace("@A20@", str(alias[6])))
     src.append("#ifndef SPFEM_HOST")

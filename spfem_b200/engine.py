@@ -455,7 +455,7 @@ class FanPrepared(Prepared):
         self.fargs = fa
         self.smem = fp["max_a"] + 12 * fp["max_ns"] + 64
         from . import codegen
-        self.threads = codegen.FAN_THREADS
+        self.threads = getattr(plan.spec, "fan_threads", codegen.FAN_THREADS)
         self.n_launches = 1
         self.tp = {"E": fp["rows_per_tile"], "ldl": 0, "ntiles": fp["ntiles"],
                    "halo_factor": fp["halo_factor"], "kind": "vertex-fan"}
@@ -709,7 +709,7 @@ class Engine(object):
                         and os.environ.get("SPFEM_FAN", "1") != "0"
                         and spec.n_entries * n <= 2 ** 31 - 1):
                     pat = self._sorted_pattern(True)
-                    fp = self.fan_plan(pat)
+                    fp = self.fan_plan(pat, getattr(spec, "fan_rows", 128))
                     if fp is not None:
                         fk = get_kernel(plan.source, plan.name + {
                             "tiny": "_fan8t", "fan8": "_fan8"}.get(fp["format"], "_fan"))
@@ -741,13 +741,15 @@ class Engine(object):
         a.out = local.data_ptr()
         return Prepared(self, plan, kernel, a, 128, local, pat, keep=(sel, wt))
 
-    def fan_plan(self, pat):
-        """Plan of the vertex-fan kernel for ``pat`` (cached on the pattern), or
-        ``None`` when the assembler is not scalar-P1-on-triangles shaped."""
-        if hasattr(pat, "_fan_plan"):
-            return pat._fan_plan
+    def fan_plan(self, pat, rows=128):
+        """Plan of the vertex-fan kernel for ``pat`` with ``rows`` rows per tile
+        (cached on the pattern), or ``None`` when the assembler is not
+        scalar-P1-on-triangles shaped."""
+        cache = pat.__dict__.setdefault("_fan_plans", {})
+        if rows in cache:
+            return cache[rows]
         asm, torch = self.asm, self.torch
-        pat._fan_plan = None
+        cache[rows] = None
         mesh = asm.mesh
         if (asm.dofnum_u is not asm.dofnum_v or mesh.refdom != "tri"
                 or asm.dofnum_u.t_dof.shape != mesh.t.shape
@@ -758,8 +760,7 @@ class Engine(object):
         try:
             # (the device connectivity is in Morton order: any element order gives a
             # valid plan, only the start of a closed ring may differ)
-            fp = build_fan_plan(torch, self.p, self.t, pat.indptr, pat.indices,
-                                int(os.environ.get("SPFEM_FAN_ROWS", "128")),
+            fp = build_fan_plan(torch, self.p, self.t, pat.indptr, pat.indices, int(rows),
                                 tiny=os.environ.get("SPFEM_FAN_TINY", "1") != "0",
                                 row_order=os.environ.get("SPFEM_FAN_ROWORDER", "id"))
         except FanPlanError:
@@ -769,7 +770,7 @@ class Engine(object):
         self._tile_plans.append(fp)
         self.torch.cuda.synchronize(self.device)
         self.stats["fan_plan_s"] = time.perf_counter() - t0
-        pat._fan_plan = fp
+        cache[rows] = fp
         return fp
 
     def _row_mask(self):

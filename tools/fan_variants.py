@@ -68,8 +68,7 @@ def main():
         codegen.FAN_THREADS = int(os.environ.get("SPFEM_FAN_T", "128"))
         eng = a._get_engine()
         for pat in eng.patterns.values():           # rows per tile / format may differ
-            if hasattr(pat, "_fan_plan"):
-                del pat._fan_plan
+            pat.__dict__.pop("_fan_plans", None)
         eng._tile_plans = [tp for tp in eng._tile_plans if tp.get("kind") != "vertex-fan"]
         res = {"variant": name, "env": kv}
         results.append(res)
