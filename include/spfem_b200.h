@@ -210,6 +210,8 @@ typedef struct SpfemPlanIn {
                                  jumps; the largest tile sizes every CTA's shared memory) */
     int ne_budget;            /* > 0: split tiles with more than ne_budget elements
                                  (absolute form of the same rule; never below the median) */
+    int owner_rule;           /* owner of a CSR row: 0 the lowest tile touching it, 1 the
+                                 tile holding most of its elements (ties: the lowest)     */
 } SpfemPlanIn;
 
 typedef struct SpfemPlanBatch {

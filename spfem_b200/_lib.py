@@ -72,7 +72,7 @@ class SpfemPlanIn(C.Structure):
         ("alias", C.c_void_p), ("nuniq", C.c_int),
         ("E", C.c_int), ("with_el", C.c_int), ("sort_slots", C.c_int), ("compact", C.c_int),
         ("row_mask", C.c_void_p), ("index_bytes", C.c_int), ("batch_cap", C.c_longlong),
-        ("split_factor", C.c_double), ("ne_budget", C.c_int),
+        ("split_factor", C.c_double), ("ne_budget", C.c_int), ("owner_rule", C.c_int),
     ]
 
 

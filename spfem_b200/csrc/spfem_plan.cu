@@ -383,13 +383,55 @@ int build(const SpfemPlanIn &in, SpfemPlanOut &out, Ctx &c)
         }
         drop(c, tstart);
         fill<int>(c, owner, NR, INF);
-        par_for(c, n * nbv, [=] __host__ __device__(i64 w) {
-            const int i = (int)(w / n);
-            const i64 e = w - (i64)i * n;
-            const int R = g.row(i, e);
-            if (row_mask && !row_mask[(i64)R * bsv]) return;
-            amin(&owner[R], etile[e]);
-        });
+        if (in.owner_rule == 0) {
+            // lowest tile touching the row
+            par_for(c, n * nbv, [=] __host__ __device__(i64 w) {
+                const int i = (int)(w / n);
+                const i64 e = w - (i64)i * n;
+                const int R = g.row(i, e);
+                if (row_mask && !row_mask[(i64)R * bsv]) return;
+                amin(&owner[R], etile[e]);
+            });
+        } else {
+            // the tile holding MOST of the row's elements (ties: the lowest): fewer halo
+            // elements, and above all balanced tiles -- with "lowest tile" the first tile
+            // of a neighbourhood owns every shared row (TetP2: up to 184 rows against a
+            // mean of 90), and the largest tile sizes the shared memory of every CTA
+            const i64 nW = n * nbv;
+            const u64 nt64 = (u64)ntiles;
+            u64 *rk = scratch<u64>(c, nW, "own:rk"), *rk2 = scratch<u64>(c, nW, "own:rk2");
+            par_for(c, nW, [=] __host__ __device__(i64 w) {
+                const int i = (int)(w / n);
+                const i64 e = w - (i64)i * n;
+                const int R = g.row(i, e);
+                const bool off = row_mask && !row_mask[(i64)R * bsv];
+                rk[w] = off ? ~(u64)0 : (u64)R * nt64 + (u64)etile[e];
+            });
+            sort_keys(c, rk, rk2, nW, 64);
+            drop(c, rk2);
+            u64 *best = scratch<u64>(c, NR, "own:best");
+            fill<u64>(c, best, NR, (u64)0);
+            {
+                const u64 *k = rk;
+                par_for(c, nW, [=] __host__ __device__(i64 w) {
+                    const u64 key = k[w];
+                    if (key == ~(u64)0 || (w > 0 && k[w - 1] == key)) return;     // heads of runs only
+                    i64 lo = w, hi = nW;                                            // first index with k > key
+                    while (lo < hi) { const i64 m = (lo + hi) >> 1; if (k[m] <= key) lo = m + 1; else hi = m; }
+                    const u64 R = key / nt64, T = key - R * nt64;
+                    const u64 packed = ((u64)(lo - w) << 32) | (u64)(u32)(nt64 - 1 - T);
+#ifdef __CUDA_ARCH__
+                    atomicMax((unsigned long long *)&best[R], (unsigned long long)packed);
+#else
+                    if (packed > best[R]) best[R] = packed;
+#endif
+                });
+            }
+            par_for(c, NR, [=] __host__ __device__(i64 R) {
+                if (best[R] != 0) owner[R] = (int)(nt64 - 1 - (best[R] & 0xffffffffull));
+            });
+            drop(c, rk); drop(c, best);
+        }
         i64 *cnt = scratch<i64>(c, n + 1, "cnt");
         par_for(c, n, [=] __host__ __device__(i64 e) {
             int seen[MAXLOC];

@@ -791,7 +791,8 @@ class Engine(object):
         ckey = (plan.bilinear, spec.n_unique, tuple(spec.alias), spec.needs_el,
                 env("SPFEM_TILE_MODE", "auto"), env("SPFEM_TILE_E", "0"),
                 env("SPFEM_TILE_SORT", "auto"), env("SPFEM_TILE_BLOCKS", "1"),
-                env("SPFEM_TILE_SPLIT", "0"), env("SPFEM_TILE_BUDGET", "1"))
+                env("SPFEM_TILE_SPLIT", "0"), env("SPFEM_TILE_BUDGET", "1"),
+                env("SPFEM_TILE_OWNER", "1"))
         if ckey in self._tile_cache:
             return self._tile_cache[ckey]
         force = env("SPFEM_FUSED", "1") == "force"
@@ -852,7 +853,8 @@ class Engine(object):
                                    index_bytes=8 if idt == np.int64 else 4,
                                    batch_cap=int(env("SPFEM_TILE_BATCH", "0")),
                                    split_factor=float(env("SPFEM_TILE_SPLIT", "0")),
-                                   ne_budget=ne_budget)
+                                   ne_budget=ne_budget,
+                                   owner_rule=int(env("SPFEM_TILE_OWNER", "1")))
         tp = None
         for E in cands:
             if E_env <= 0 and not compact and E > 64 and 8 * nuniq * (1.3 * E + 32) > prefer:

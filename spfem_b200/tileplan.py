@@ -4,8 +4,9 @@ of the native builder ``spfem_tileplan_build`` (csrc/spfem_plan.cu, declared in
 include/spfem_b200.h).
 
 The elements (already in Morton order) are cut into tiles of ``E`` consecutive
-elements.  Every CSR row is *owned* by the lowest tile that contains one of its
-elements; a tile's CTA computes the local matrices of all elements that touch a
+elements.  Every CSR row is *owned* by the tile that contains most of its
+elements (ties: the lowest tile; ``owner_rule = 0``: simply the lowest tile); a
+tile's CTA computes the local matrices of all elements that touch a
 row it owns (its own elements plus a thin halo that neighbouring tiles compute
 as well) into shared memory and then produces every CSR value of its rows
 exactly once, summing the contributions in a fixed order.  No floating point
@@ -102,7 +103,7 @@ class _Arena(object):
 def build_tile_plan(torch, rowdof, coldof, vt, nrows, ncols, E, alias, nuniq,
                     dim, bsv=1, bsu=1, with_el=False, sort_slots=0, compact=False,
                     row_mask=None, index_bytes=4, batch_cap=0, split_factor=0.0,
-                    ne_budget=0, stream=None):
+                    ne_budget=0, owner_rule=1, stream=None):
     """Pattern + tile plan for the DOF tables ``rowdof`` (nloc_v, n) /
     ``coldof`` (nloc_u, n) or ``None`` (int32, one device, element order of the
     kernel) and the vertex table ``vt`` (nve, n).  Returns a dict; raises
@@ -136,6 +137,7 @@ def build_tile_plan(torch, rowdof, coldof, vt, nrows, ncols, E, alias, nuniq,
     pin.batch_cap = int(batch_cap)
     pin.split_factor = float(split_factor)
     pin.ne_budget = int(ne_budget)
+    pin.owner_rule = int(owner_rule)
     pout = _lib.SpfemPlanOut()
     arena = _Arena(torch, dev)
     if stream is None and on_dev:

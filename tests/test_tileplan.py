@@ -68,7 +68,7 @@ def _build(asm, plan, tv, tu, vt, E, **kw):
     return tp
 
 
-VARIANTS = [dict(), dict(sort_slots=1), dict(sort_slots=2), dict(compact=True),
+VARIANTS = [dict(), dict(owner_rule=0), dict(owner_rule=0, compact=True, sort_slots=1), dict(sort_slots=1), dict(sort_slots=2), dict(compact=True),
             dict(compact=True, sort_slots=1), dict(batch_cap=3000),
             dict(batch_cap=1500, sort_slots=1), dict(split_factor=1.05),
             dict(split_factor=1.1, compact=True, sort_slots=1)]
