@@ -1301,9 +1301,13 @@ def _generate_interior_source(spec, name, looped):
             alias[idx] = groups[gkey][0]
         # threads per element in the tile kernel's phase A (distinct values dealt
         # round-robin to the parts)
+        # Measured (profiles/r02_owner_rule_sweep.jsonl): one thread per element for
+        # forms with aliased entries (vector-P2 elasticity 63 of 144 values: 0.458 ->
+        # 0.481, TetP2 49 of 100: 0.169 -> 0.183 with one part), two threads for large
+        # local matrices without aliases (Stokes B, 36 of 36: 0.339 -> 0.364 with two)
         npart = int(os.environ.get("SPFEM_TILE_NPART", "0"))
         if npart <= 0:
-            npart = 1 if len(order_u) <= 24 else 2
+            npart = 2 if (len(order_u) > 24 and len(order_u) == len(entries)) else 1
         spec.npart = npart
         for gkey in order_u:
             u, expr, idxs = groups[gkey]

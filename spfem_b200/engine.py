@@ -827,7 +827,7 @@ class Engine(object):
         nuniq = spec.n_unique
         nsidx = (spec.n_rows // spec.bsv) * (spec.n_cols // spec.bsu)
         minb = int(env("SPFEM_TILE_MINB", str(getattr(spec, "minb", 3 if dim == 2 else 2))))
-        prefer = (110 if minb <= 2 and not compact else 96 if compact else 56) * 1024
+        prefer = (110 if minb <= 2 or compact else 56) * 1024     # two / three-four CTAs per SM
         limit = 220 * 1024
         E_env = int(env("SPFEM_TILE_E", "0"))
         if E_env > 0:
@@ -837,7 +837,7 @@ class Engine(object):
         else:
             # measured (profiles/r01_configs.json): three to four CTAs per SM
             # (<= 56 KB each) but at least 64 elements per tile
-            cands = [384, 256, 160, 96, 64, 48, 32, 16]
+            cands = [384, 256, 160, 96, 72, 64, 48, 32, 16]
         bilinear = plan.bilinear
         n_entries = spec.n_entries * self.nt
         idt = scipy_index_dtype(n_entries, asm.dofnum_v.N, asm.dofnum_u.N if bilinear else 1)
@@ -859,7 +859,7 @@ class Engine(object):
         for E in cands:
             if E_env <= 0 and not compact and E > 64 and 8 * nuniq * (1.3 * E + 32) > prefer:
                 continue                # cannot fit the preferred footprint
-            if E_env <= 0 and compact and E > 64:
+            if E_env <= 0 and compact and E > 72:
                 continue
             # quadrature-loop bodies are long: one pass of phase A over the CTA's threads
             # (NPART threads per tile element) beats a second, half-empty pass

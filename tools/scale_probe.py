@@ -54,6 +54,10 @@ def run(kind, size):
         p, t = meshgen.grid_tri(size)
         m = sp.MeshTri(p, t, validate=False)
         elem, form, C = sp.ElementTriP2(), cases.lap2, 6
+    elif kind == "tetp1":
+        p, t = meshgen.grid_tet(size)
+        m = sp.MeshTet(p, t, validate=False)
+        elem, form, C = sp.ElementTetP1(), cases.lap3, 4
     elif kind == "tetp2":
         p, t = meshgen.grid_tet(size)
         m = sp.MeshTet(p, t, validate=False)
