@@ -297,8 +297,26 @@ class AssemblerElement(Assembler):
         return [phi] + [dphi[:, l, :] for l in range(dim)]
 
     def plan_fasm(self, form, interior=False, intorder=None, normals=True,
-                  interp=None):
-        """Trace ``form`` and generate the facet kernel (no device work)."""
+                  interp=None, find=None):
+        """Trace ``form`` and generate the facet kernel (no device work).  Like
+        :meth:`plan_iasm`, a form that applies opaque callables to ``x``, ``h`` or
+        ``n`` is traced a second time on the reference's own ``(facets, points)``
+        arrays (spfem/assembly.py:1046-1075) for the facets ``find``."""
+        try:
+            return self._plan_fasm(form, interior, intorder, normals, interp, None)
+        except TraceError as exc:
+            if os.environ.get("SPFEM_FIELDS", "1") == "0":
+                raise
+            if find is None:
+                find = (self.mesh.interior_facets() if interior
+                        else self.mesh.boundary_facets())
+            try:
+                return self._plan_fasm(form, interior, intorder, normals, interp,
+                                       np.asarray(find))
+            except Exception as exc2:
+                raise exc from exc2
+
+    def _plan_fasm(self, form, interior, intorder, normals, interp, field_find):
         mesh = self.mesh
         if intorder is None:
             intorder = self.elem_u.maxdeg + self.elem_v.maxdeg
@@ -331,8 +349,24 @@ class AssemblerElement(Assembler):
              for s, key in enumerate(wkeys)}
         dw = {key: {a: Form.coef(Coef.sym("dw%d_%d" % (s, a), True))
                     for a in range(dim)} for s, key in enumerate(wkeys)}
+        fctx = None
+        if field_find is not None:
+            if wkeys:
+                raise TraceError("field mode: interpolated fields in facet forms")
+            if mesh.refdom == "quad":
+                raise TraceError("field mode: facet forms on quadrilaterals")
+            # x, h, n as the reference evaluates them   (spfem/assembly.py:1046-1075)
+            mp = self.mapping
+            nq = X.shape[1]
+            x = mp.G(X, field_find)
+            detB = np.tile(mp.detB[field_find][:, None], (1, nq))
+            h = np.abs(detB) ** (1.0 / (dim - 1.0))
+            n = (mp.normals(X, mesh.f2t[0, field_find], field_find, mesh.t2f)
+                 if normals else {})
+            fctx = _tracer.FieldContext((len(field_find), nq))
         sides = [(1, 1), (2, 2), (2, 1), (1, 2)] if interior else [(1, 1)]
         blocks = []
+        _tracer._FIELDS = fctx
         for (su, sv) in sides:
             blk = {}
             for cu in range(ncu if bilinear else 1):
@@ -354,14 +388,28 @@ class AssemblerElement(Assembler):
                         if bilinear:
                             u, du = basis_args(ncu, cu, 0, dim, inv[1])
                             avail.update({'u': u, 'du': du})
-                    blk[(cu, cv)] = call_form(form, names, avail)
+                    try:
+                        blk[(cu, cv)] = call_form(form, names, avail)
+                    except TraceError:
+                        _tracer._FIELDS = None
+                        raise
+                    except (TypeError, ValueError, AttributeError, NotImplementedError) as exc:
+                        _tracer._FIELDS = None
+                        if field_find is not None:
+                            raise
+                        raise TraceError("the form could not be traced symbolically (%s: %s)"
+                                         % (type(exc).__name__, exc))
             blocks.append(blk)
+        _tracer._FIELDS = None
         spec = codegen.FacetSpec(mesh.refdom, dim, bilinear, interior,
                                  bu.nbfun_ref(), bv.nbfun_ref(), ncu, ncv,
                                  blocks, sides, X, W, bu.polys(), bv.polys(),
-                                 normals=normals, nw=len(wkeys))
+                                 normals=normals, nw=len(wkeys),
+                                 nfld=len(fctx.arrays) if fctx is not None else 0)
         src = codegen.generate_facet(spec, "spfem_facet")
-        return _Plan("facet", spec, src, "spfem_facet", bilinear, wkeys)
+        plan = _Plan("facet", spec, src, "spfem_facet", bilinear, wkeys)
+        plan.fields = fctx.arrays if fctx is not None else []
+        return plan
 
     # ------------------------------------------------------------------
     # index tables shared by the device path and the tests
@@ -549,7 +597,7 @@ class AssemblerElement(Assembler):
             find = (self.mesh.interior_facets() if interior
                     else self.mesh.boundary_facets())
         plan = self.plan_fasm(form, interior=interior, intorder=intorder,
-                              normals=normals, interp=interp)
+                              normals=normals, interp=interp, find=find)
         return self._get_engine().prepare_facet(plan, np.asarray(find), interior, interp)
 
     # ------------------------------------------------------------------
@@ -720,6 +768,6 @@ class AssemblerElement(Assembler):
             find = (self.mesh.interior_facets() if interior
                     else self.mesh.boundary_facets())
         plan = self.plan_fasm(form, interior=interior, intorder=intorder,
-                              normals=normals, interp=interp)
+                              normals=normals, interp=interp, find=find)
         return self._get_engine().run_facet(plan, np.asarray(find), interior,
                                             interp)

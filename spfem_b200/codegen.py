@@ -1459,7 +1459,7 @@ class FacetSpec(object):
 
     def __init__(self, refdom, dim, bilinear, interior, nbu, nbv, ncu, ncv,
                  blocks, sides, X, W, polys_u, polys_v, normals=True, nw=0,
-                 functional=False):
+                 functional=False, nfld=0):
         # functional: one value per facet (fnorm) -- no test functions, and the
         # interpolated fields exist on both sides of an interior facet
         self.functional = functional
@@ -1469,6 +1469,7 @@ class FacetSpec(object):
         self.blocks, self.sides, self.X, self.W = blocks, sides, X, W
         self.polys_u, self.polys_v = polys_u, polys_v
         self.normals, self.nw = normals, nw
+        self.nfld = nfld            # host-evaluated coefficient fields, [q * ldf + facet]
 
     @property
     def n_rows(self):
@@ -1581,6 +1582,8 @@ def generate_facet(spec, name="spfem_facet"):
             acc = _add(acc, _mul("B_%d%d" % (i, j), "XQ[%d][q]" % j))
         A("  const double x%d = %s;" % (i, _add(acc, "c_%d" % i)))
     A("  const double wdet = WQ[q] * absdetB;")
+    for i in range(getattr(spec, "nfld", 0)):
+        A("  const double fld%d = P.fields[%d][(long long)q * P.ldf + k];" % (i, i))
     for s in range(1, nsides + 1):
         # Y = invF(x)                         (spfem/mapping.py:350-387)
         if quad:

@@ -652,14 +652,15 @@ class Engine(object):
             out.append(self._dev(np.asarray(interp[key]), np.float64))
         return out
 
-    def _field_tensors(self, plan):
-        """Device copies ``(nq, nt)`` (device element order) of the plan's
-        host-evaluated coefficient fields, and their leading dimension."""
+    def _field_tensors(self, plan, permute=True):
+        """Device copies ``(nq, n)`` of the plan's host-evaluated coefficient
+        fields (interior forms: in the device element order; facet forms: in the
+        order of the facet set)."""
         torch = self.torch
         out = []
         for f in getattr(plan, "fields", ()) or ():
             t = torch.from_numpy(np.ascontiguousarray(f.T)).to(self.device)
-            if self.perm is not None:
+            if permute and self.perm is not None:
                 t = t.index_select(1, self.perm_l).contiguous()
             out.append(t)
         return out
@@ -837,7 +838,7 @@ class Engine(object):
         else:
             # measured (profiles/r01_configs.json): three to four CTAs per SM
             # (<= 56 KB each) but at least 64 elements per tile
-            cands = [384, 256, 160, 96, 72, 64, 48, 32, 16]
+            cands = [384, 256, 160, 128, 96, 72, 64, 48, 32, 16]
         bilinear = plan.bilinear
         n_entries = spec.n_entries * self.nt
         idt = scipy_index_dtype(n_entries, asm.dofnum_v.N, asm.dofnum_u.N if bilinear else 1)
@@ -857,7 +858,7 @@ class Engine(object):
                                    owner_rule=int(env("SPFEM_TILE_OWNER", "1")))
         tp = None
         for E in cands:
-            if E_env <= 0 and not compact and E > 64 and 8 * nuniq * (1.3 * E + 32) > prefer:
+            if E_env <= 0 and not compact and E > 64 and 8 * nuniq * (1.25 * E + 24) > prefer:
                 continue                # cannot fit the preferred footprint
             if E_env <= 0 and compact and E > 72:
                 continue
@@ -993,11 +994,14 @@ class Engine(object):
         pat, fv_d, e1_d, e2_d, lf_d = hit
         local = self._empty(max(spec.n_entries * nblk * n, 1), torch.float64)
         wt = self._interp_tensors(plan, interp)
+        ft = self._field_tensors(plan, permute=False)
+        wt = (wt, ft)
         a = _lib.SpfemArgs()
         a.set_params(plan)
+        self._set_fields(a, ft)
         a.n, a.ldo, a.ldk = n, nblk * n, 1
         a.tdof_u, a.ldd = self.tdof_u.data_ptr(), self.tdof_u.shape[1]
-        for s, w in enumerate(wt):
+        for s, w in enumerate(wt[0]):
             a.interp[s] = w.data_ptr()
         a.fv, a.e1, a.e2, a.lf1 = (fv_d.data_ptr(), e1_d.data_ptr(),
                                    e2_d.data_ptr(), lf_d.data_ptr())

@@ -109,7 +109,7 @@ def fasm(asm, form, find=None, interior=False, intorder=None, normals=True,
     if find is None:
         find = mesh.interior_facets() if interior else mesh.boundary_facets()
     plan = asm.plan_fasm(form, interior=interior, intorder=intorder,
-                         normals=normals, interp=interp)
+                         normals=normals, interp=interp, find=find)
     fv, e1, e2, lf1 = asm.facet_tables(find)
     n = len(find)
     nblk = len(plan.spec.blocks)
@@ -133,6 +133,11 @@ def fasm(asm, form, find=None, interior=False, intorder=None, normals=True,
         keep.append(arr)
         a.interp[s] = arr.ctypes.data
     a.fv, a.e1, a.e2, a.lf1 = _ptr(fv), _ptr(e1), _ptr(e2), _ptr(lf1)
+    for i_, f in enumerate(getattr(plan, "fields", ()) or ()):
+        arr = np.ascontiguousarray(f.T, dtype=np.float64)      # (nq, nfacets), order of `find`
+        keep.append(arr)
+        a.fields[i_] = arr.ctypes.data
+        a.ldf = arr.shape[1]
     a.out = _ptr(out)
     compile_host(plan)(C.byref(a))
     rows, cols = asm.facet_dofs(find, interior)

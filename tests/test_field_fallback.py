@@ -128,3 +128,56 @@ def test_same_kernel_for_different_opaque_functions():
     p2 = a.plan_iasm(lambda v, x: np.interp(x[1], XP, FP[::-1]) * v)
     assert p1.source == p2.source
     assert not np.array_equal(p1.fields[0], p2.fields[0])
+
+
+# ---------------------------------------------------------------------------
+# facet forms (fasm): opaque functions of x, h, n
+# ---------------------------------------------------------------------------
+def bnd_interp(u, v, x, h):
+    return np.interp(x[1], XP, FP) / h * u * v
+
+
+def bnd_load_table(v, x, n):
+    g = np.where(x[0] > 0.5, 2.0, -1.0) * n[0] + np.interp(x[1], XP, FP) * n[1]
+    return g * v
+
+
+def jump_opaque(u1, u2, v1, v2, x, h):
+    # (not a pure jump: on a continuous element (u1 - u2)(v1 - v2) assembles to round-off)
+    k = np.interp(x[0] + x[1], [0.0, 1.0, 2.0], [1.0, 4.0, 2.0])
+    return k / h * (u1 * v1 + 2.0 * u2 * v2) - k * u1 * v2
+
+
+FCASES = {
+    "bnd_interp_p2": (bnd_interp, "MeshTri", 2, "TriP2", False),
+    "bnd_load_table_p1": (bnd_load_table, "MeshTri", 3, "TriP1", False),
+    "bnd_interp_tet": (bnd_interp, "MeshTet", 1, "TetP1", False),
+    "jump_opaque_p1": (jump_opaque, "MeshTri", 2, "TriP1", True),
+}
+
+
+def _fsetup(name):
+    form, mesh, refine, ename, interior = FCASES[name]
+    m = getattr(sp, mesh)()
+    m.refine(refine)
+    a = AssemblerElement(m, util.element(ename, 1))
+    ref = asm_oracle.fasm(m, ename, form, interior=interior)
+    return a, form, interior, ref
+
+
+@pytest.mark.parametrize("name", sorted(FCASES))
+def test_opaque_facet_form_host(name):
+    a, form, interior, ref = _fsetup(name)
+    plan = a.plan_fasm(form, interior=interior)
+    assert len(plan.fields) >= 1
+    util.check(hostemu.fasm(a, form, interior=interior), ref)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", sorted(FCASES))
+def test_opaque_facet_form_cuda(name):
+    a, form, interior, ref = _fsetup(name)
+    util.check(a.fasm(form, interior=interior), ref)
+    if name == "bnd_interp_p2":          # a facet subset gets its own fields
+        find = a.mesh.boundary_facets()[::2]
+        util.check(a.fasm(form, find=find), asm_oracle.fasm(a.mesh, "TriP2", form, find=find))
