@@ -828,7 +828,9 @@ class Engine(object):
         nuniq = spec.n_unique
         nsidx = (spec.n_rows // spec.bsv) * (spec.n_cols // spec.bsu)
         minb = int(env("SPFEM_TILE_MINB", str(getattr(spec, "minb", 3 if dim == 2 else 2))))
-        prefer = (110 if minb <= 2 or compact else 56) * 1024     # two / three-four CTAs per SM
+        # two CTAs per SM (3-D, Q2), else four for scalar plans (TriP2: 48 registers) and
+        # three for the block plans of vector elements (80 registers)
+        prefer = (110 if minb <= 2 or compact else 58 if nb > 1 else 55) * 1024
         limit = 220 * 1024
         E_env = int(env("SPFEM_TILE_E", "0"))
         if E_env > 0:
