@@ -197,7 +197,7 @@ extern "C" __global__ void __launch_bounds__(@THREADS@, @MINB@) @NAME@_tile(cons
     unsigned char *sB = sA + T.max_a;
     unsigned long long *bars = (unsigned long long *)(sB + T.max_b);
     const int *d = T.desc + 16 * (size_t)blockIdx.x;
-    const int bytes_a = d[1], bytes_b = d[2], ne = d[3], ne_pad = d[4], ns = d[5], nr = d[9];
+    const int bytes_a = d[1], bytes_b = d[2], ne = d[3], ne_pad = d[4], ns = d[5];
     if (ne == 0 || ns == 0) return;
 #if SPFEM_NB > 1
     int *sUT = (int *)(bars + 2);             /* id * ldl, one row of NB ints per entry */
@@ -267,36 +267,31 @@ extern "C" __global__ void __launch_bounds__(@THREADS@, @MINB@) @NAME@_tile(cons
        added in list order => bitwise reproducible.                              */
     spfem_mbar_wait(&bars[1], 0);
     __syncthreads();
-    const long long *rbase = (const long long *)sB;
-    const unsigned *rinfo = (const unsigned *)(sB + (((size_t)8 * nr + 15) & ~(size_t)15));
+    /* every slot carries the 32-bit offset of its (first) CSR value from the tile's
+       lowest position: one look-up, no slot -> row -> row base chain               */
+    const unsigned *spos = (const unsigned *)(sB + 16);
     const unsigned short *soff = (const unsigned short *)(sB + d[6]);
-    const unsigned short *srow = (const unsigned short *)(sB + d[7]);
-    const unsigned short *spos = (const unsigned short *)(sB + d[7] + (((size_t)2 * ns + 15) & ~(size_t)15));
     const unsigned short *cb = (const unsigned short *)(sB + d[8]);
-    double *__restrict__ vals = T.values;
-    const bool srt = T.sorted != 0;
+    double *__restrict__ vals = T.values + *reinterpret_cast<const long long *>(sB);
 #if SPFEM_NB == 1
 #pragma unroll @BUNROLL@
     for (int s = threadIdx.x; s < ns; s += blockDim.x) {
         const unsigned k0 = soff[s], k1 = soff[s + 1];
         const unsigned c0 = cb[k0], c1 = cb[k0 + 1];
-        const unsigned r = srow[s];
-        const unsigned info = rinfo[r];
-        const unsigned k = srt ? (unsigned)spos[s] : (unsigned)s - (info & 0xffffu);
+        const unsigned pos = spos[s];
         double acc = sL[c0];
         if (k0 + 1 < k1) acc += sL[c1];
 #pragma unroll @TUNROLL@
         for (unsigned kk = k0 + 2; kk < k1; ++kk) acc += sL[cb[kk]];
-        vals[rbase[r] + (long long)k] = acc;
+        vals[pos] = acc;
     }
 #else
     const unsigned elm = (1u << T.els) - 1u;
+    const unsigned short *slen = (const unsigned short *)(sB + d[7]);
     for (int s = threadIdx.x; s < ns; s += blockDim.x) {
         const unsigned k0 = soff[s], k1 = soff[s + 1];
-        const unsigned r = srow[s];
-        const unsigned info = rinfo[r];
-        const unsigned L = info >> 16;
-        const unsigned k = srt ? (unsigned)spos[s] : (unsigned)s - (info & 0xffffu);
+        const unsigned pos = spos[s];
+        const unsigned L = slen[s];
         double acc[SPFEM_NB];
         {
             const unsigned c = cb[k0];
@@ -315,7 +310,7 @@ extern "C" __global__ void __launch_bounds__(@THREADS@, @MINB@) @NAME@_tile(cons
 #pragma unroll
             for (int ab = 0; ab < SPFEM_NB; ++ab) acc[ab] += col[ut[ab]];
         }
-        double *__restrict__ o = vals + rbase[r] + (long long)(SPFEM_BSU * k);
+        double *__restrict__ o = vals + pos;
 #pragma unroll
         for (int a = 0; a < SPFEM_BSV; ++a) {
 #if SPFEM_BSU == 2

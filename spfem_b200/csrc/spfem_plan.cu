@@ -151,6 +151,15 @@ __host__ __device__ inline void amin(int *p, int v)
 #endif
 }
 
+__host__ __device__ inline void amin64(long long *p, long long v)
+{
+#ifdef __CUDA_ARCH__
+    atomicMin(p, v);
+#else
+    if (v < *p) *p = v;
+#endif
+}
+
 __host__ __device__ inline void amax(int *p, int v)
 {
 #ifdef __CUDA_ARCH__
@@ -647,6 +656,7 @@ int build(const SpfemPlanIn &in, SpfemPlanOut &out, Ctx &c)
 
     struct Pending {             // kept until indptr is known
         int *cols; i64 nS; i64 *rowfirst; i64 nRb; i64 Ta; i64 *blob_off; i64 *bytes_a;
+        i64 *ts_ptr; int *srow;
     };
     std::vector<Pending> pend;
 
@@ -808,17 +818,19 @@ int build(const SpfemPlanIn &in, SpfemPlanOut &out, Ctx &c)
             i64 off_base = 0;
             if (compact) { off_base = ba; ba = pad16(off_base + (1 + W) * 4 * ne_pad); }
             ba = pad16(ba);
-            const i64 off_rinfo = pad16(8 * nr);
-            const i64 off_soff = off_rinfo + pad16(4 * nr);
-            const i64 off_srow = off_soff + pad16(2 * (ns + 1));
-            const i64 off_spos = off_srow + pad16(2 * ns);
-            const i64 off_contrib = off_spos + (sorted ? pad16(2 * ns) : 0);
+            // section B: base position of the tile (int64), per slot the 32-bit offset of
+            // its (first) CSR value from it [+ the length of its scalar row for block
+            // plans], the start of every slot's contributions, the contribution lists
+            const i64 off_pos = 16;
+            const i64 off_slen = off_pos + pad16(4 * ns);
+            const i64 off_soff = off_slen + (nb > 1 ? pad16(2 * ns) : 0);
+            const i64 off_contrib = off_soff + pad16(2 * (ns + 1));
             const i64 bb = off_contrib + pad16(2 * (nc + 1));
             bytes_a[t] = ba;
             tbytes[t] = ba + bb;
             int *d = desc + 16 * t;
             d[1] = (int)ba; d[2] = (int)bb; d[3] = (int)ne; d[4] = (int)ne_pad; d[5] = (int)ns;
-            d[6] = (int)off_soff; d[7] = (int)off_srow; d[8] = (int)off_contrib; d[9] = (int)nr;
+            d[6] = (int)off_soff; d[7] = (int)off_slen; d[8] = (int)off_contrib; d[9] = (int)nr;
             d[10] = (int)nc; d[11] = (int)nvt_pad; d[12] = (int)off_pc;
             d[13] = with_el ? (int)off_el : -1; d[14] = (int)nvt; d[15] = (int)off_base;
             amax(&mx[3], (int)(ns > INT_MAX ? INT_MAX : ns));
@@ -864,20 +876,8 @@ int build(const SpfemPlanIn &in, SpfemPlanOut &out, Ctx &c)
             }
         });
         drop(c, uv);
-        // -- section B: rows, slots, contributions
-        par_for(c, nRb, [=] __host__ __device__(i64 r) {
-            // tile of the row: binary search in tr_ptr
-            i64 lo = Ta, hi = Tb;
-            while (hi - lo > 1) { const i64 m = (lo + hi) >> 1; if (tr_ptr[m] - ra <= r) lo = m; else hi = m; }
-            const i64 t = lo - Ta;
-            const i64 rr = r - (tr_ptr[lo] - ra);
-            const int *d = desc + 16 * t;
-            unsigned char *Bs = blob + blob_off[t] + d[1];
-            const i64 L = rowfirst[r + 1] - rowfirst[r];
-            const i64 sfirst = rowfirst[r] - ts_ptr[t];
-            int *rinfo = (int *)(Bs + pad16(8 * (i64)d[9]));
-            rinfo[rr] = (int)(u32)((u64)(sfirst & 0xffff) | ((u64)L << 16));
-        });
+        // -- section B: slots, contributions (CSR positions are patched in step 6)
+        int *srow_keep = scratch<int>(c, nS > 0 ? nS : 1, "srow_keep");
         par_for(c, nS, [=] __host__ __device__(i64 s) {
             const i64 so = order ? order[s] : s;
             const i64 t = (i64)(skey[so] >> (rbits + cbits));
@@ -887,27 +887,22 @@ int build(const SpfemPlanIn &in, SpfemPlanOut &out, Ctx &c)
             const i64 ns = d[5];
             const u64 rmask = ((u64)1 << rbits) - 1;
             const i64 rr = (i64)((skey[so] >> cbits) & rmask);
+            const i64 rb = tr_ptr[Ta + t] - ra + rr;
             u16 *soff = (u16 *)(Bs + d[6]);
-            u16 *srow = (u16 *)(Bs + d[7]);
             const i64 k0 = kofs[s] - kofs[ts_ptr[t]];
             soff[sl] = (u16)k0;
             if (sl == ns - 1) soff[ns] = (u16)d[10];
-            srow[sl] = (u16)rr;
-            if (sorted) {
-                u16 *spos = (u16 *)(Bs + d[7] + pad16(2 * ns));
-                const i64 rb = tr_ptr[Ta + t] - ra + rr;
-                spos[sl] = (u16)(so - rowfirst[rb]);
-            }
+            srow_keep[s] = (int)rb;
+            ((u32 *)(Bs + 16))[sl] = (u32)(so - rowfirst[rb]);       // position inside the row, for now
             u16 *cb = (u16 *)(Bs + d[8]);
             const i64 c0 = sfc[so], c1 = sfc[so + 1];
             for (i64 k = c0; k < c1; ++k) cb[k0 + (k - c0)] = (u16)cv[k];
         });
         drop(c, cv); drop(c, skey); drop(c, sfc); drop(c, kofs);
         if (order) drop(c, order);
-        drop(c, ts_ptr);
         B.desc = desc; B.blob = blob; B.vid = vid; B.vptr = vptr;
         B.blob_bytes = blob_bytes; B.nvid = nU; B.first_tile = Ta; B.nslots = nS;
-        pend.push_back(Pending{cols, nS, rowfirst, nRb, Ta, blob_off, bytes_a});
+        pend.push_back(Pending{cols, nS, rowfirst, nRb, Ta, blob_off, bytes_a, ts_ptr, srow_keep});
     }
 
     // ---- 6. indptr, indices, row positions in the blobs ---------------------------
@@ -941,15 +936,47 @@ int build(const SpfemPlanIn &in, SpfemPlanOut &out, Ctx &c)
         const i64 *rowfirst = pd.rowfirst, *blob_off = pd.blob_off;
         const int *cols = pd.cols;
         const i64 nRb = pd.nRb;
+        // base position of every tile = the lowest CSR position of its rows; the slots
+        // hold 32-bit offsets from it (one look-up per slot instead of slot -> row ->
+        // row base / row info)
+        const i64 nT = B.ntiles, nS = pd.nS;
+        const i64 *ts_ptr = pd.ts_ptr;
+        const int *srow_keep = pd.srow;
+        i64 *tmin = scratch<i64>(c, nT + 1, "tmin");
+        fill<i64>(c, tmin, nT + 1, LLONG_MAX);
         par_for(c, nRb, [=] __host__ __device__(i64 r) {
             i64 lo = Ta, hi = Tb;
             while (hi - lo > 1) { const i64 m = (lo + hi) >> 1; if (tr_ptr[m] - ra <= r) lo = m; else hi = m; }
-            const i64 t = lo - Ta;
-            const i64 rr = r - (tr_ptr[lo] - ra);
+            amin64(&tmin[lo - Ta], nb * iptr[rows_sorted[ra + r]]);
+        });
+        par_for(c, nT, [=] __host__ __device__(i64 t) {
+            if (desc[16 * t + 5] > 0)
+                *(i64 *)(blob + blob_off[t] + desc[16 * t + 1]) = tmin[t];
+        });
+        par_for(c, nS, [=] __host__ __device__(i64 s) {
+            i64 lo = 0, hi = nT;
+            while (hi - lo > 1) { const i64 m = (lo + hi) >> 1; if (ts_ptr[m] <= s) lo = m; else hi = m; }
+            const int *d = desc + 16 * lo;
+            unsigned char *Bs = blob + blob_off[lo] + d[1];
+            const i64 sl = s - ts_ptr[lo];
+            const int R = rows_sorted[ra + srow_keep[s]];
+            u32 *pos = (u32 *)(Bs + 16);
+            const i64 g = nb * iptr[R] + (i64)bsu * pos[sl] - tmin[lo];
+            if (g > (i64)UINT_MAX) amax(&mx[2], INT_MAX);
+            pos[sl] = (u32)g;
+            if (nb > 1) {
+                if (rowlen[R] > 65535) amax(&mx[2], INT_MAX);
+                ((u16 *)(Bs + d[7]))[sl] = (u16)rowlen[R];
+            }
+        });
+        if (get(c, mx + 2) == INT_MAX)
+            throw Err{1, "tile plan: the rows of one tile span more than 2^32 CSR positions (or a row has more than 65535 blocks)"};
+        drop(c, tmin);
+        par_for(c, nRb, [=] __host__ __device__(i64 r) {
+            i64 lo = Ta, hi = Tb;
+            while (hi - lo > 1) { const i64 m = (lo + hi) >> 1; if (tr_ptr[m] - ra <= r) lo = m; else hi = m; }
             const int R = rows_sorted[ra + r];
             const i64 base = nb * iptr[R];
-            i64 *rbase = (i64 *)(blob + blob_off[t] + desc[16 * t + 1]);
-            rbase[rr] = base;
             if (!indices) return;
             const i64 L = rowfirst[r + 1] - rowfirst[r];
             for (i64 k = 0; k < L; ++k) {

@@ -31,19 +31,18 @@ Blob of one tile (all sections 16-byte aligned; descriptor = 16 int32):
                                   of the element's packed values + bit mask of the
                                   distinct local values that are read at all)
   section B (TMA copy 2, needed to sum and store)
-    rbase  int64  [nr]     CSR position of the first value of the owned row
-                           (block plans: of row bsv*R, component 0)
-    rinfo  uint32 [nr]     tile slot index of the row's first slot | length << 16
+    pbase  int64           lowest CSR position of the tile's rows (+ 8 bytes pad)
+    spos   uint32 [ns]     CSR position of the slot's (first) value minus pbase
+    slen   uint16 [ns]     block plans only: length of the slot's scalar row (the
+                           bsv sub-rows of a block are bsu * length apart)
     soff   uint16 [ns+1]   start of every slot's contributions in ``contrib``
-    srow   uint16 [ns]     owned-row index of the slot
-    spos   uint16 [ns]     position of the slot inside its row (sorted plans only;
-                           otherwise slots are in CSR order and the position is
-                           slot index - first slot of the row)
     contrib uint16 [nc+1]  scalar plans: shared-memory cell ``u*ldl + el`` (compact:
                            packed position); block plans: ``(j*nbv+i) << els | el``
+  The slots of a tile are in CSR order (``sort_slots = 0``) or ordered by their
+  number of contributions (1: exactly, 2: coarse classes, CSR order inside a class).
 
 Descriptor: 0 blob offset / 16, 1 bytes A, 2 bytes B, 3 ne, 4 ne_pad, 5 ns,
-6 / 7 / 8 byte offsets of soff / srow / contrib in B, 9 nr, 10 nc, 11 nvt_pad,
+6 / 7 / 8 byte offsets of soff / slen / contrib in B, 9 nr, 10 nc, 11 nvt_pad,
 12 / 13 byte offsets of pc / el in A (13 = -1: no element ids), 14 nvt,
 15 byte offset of sbase in A.
 """
@@ -222,7 +221,6 @@ def emulate(plan, local, ut=None):
     ldl, els = plan["ldl"], plan["els"]
     bsv, bsu = plan["bsv"], plan["bsu"]
     nb = bsv * bsu
-    srt = plan["sort_slots"] != 0
     values = np.full(nnz, np.nan)
     written = np.zeros(nnz, dtype=np.int64)
     nuniq = local.shape[0]
@@ -251,19 +249,16 @@ def emulate(plan, local, ut=None):
                 sL = np.full(nuniq * ldl + 16, np.nan)
                 for u in range(nuniq):
                     sL[u * ldl: u * ldl + ne] = local[u, elems]
-            rbase = S[:8 * nr].view(np.int64)
-            rinfo = S[_pad16(8 * nr): _pad16(8 * nr) + 4 * nr].view(np.uint32).astype(np.int64)
+            pbase = int(S[:8].view(np.int64)[0])
+            spos = S[16: 16 + 4 * ns].view(np.uint32).astype(np.int64)
+            slen = (S[o_srow: o_srow + 2 * ns].view(np.uint16).astype(np.int64)
+                    if nb > 1 else None)
             soff = S[o_soff: o_soff + 2 * (ns + 1)].view(np.uint16).astype(np.int64)
-            srow = S[o_srow: o_srow + 2 * ns].view(np.uint16).astype(np.int64)
-            o_spos = o_srow + _pad16(2 * ns)
-            spos = S[o_spos: o_spos + 2 * ns].view(np.uint16).astype(np.int64) if srt else None
             cb = S[o_cb: o_cb + 2 * (nc + 1)].view(np.uint16).astype(np.int64)
             assert soff[ns] == nc
             for s in range(ns):
-                r = srow[s]
-                L = rinfo[r] >> 16
-                k = spos[s] if srt else s - (rinfo[r] & 0xffff)
-                g = rbase[r] + bsu * k
+                g = pbase + spos[s]
+                L = slen[s] if nb > 1 else 0
                 acc = np.zeros(nb)
                 for kk in range(soff[s], soff[s + 1]):
                     c = cb[kk]
