@@ -69,7 +69,8 @@ typedef struct SpfemTileArgs {
     int store;                   /* doubles of shared memory for the local values:
                                     nuniq * ldl, or max_store + 2 (compact)           */
     int prefetch;                /* L2 prefetch distance in tiles (0 = off)           */
-    int sorted;                  /* SpfemPlanIn.sort_slots != 0                       */
+    int sorted;                  /* SpfemPlanIn.sort_slots != 0 (informational: every slot
+                                    carries its CSR position)                         */
     int els;                     /* SpfemPlanOut.els                                  */
 } SpfemTileArgs;
 
