@@ -162,8 +162,8 @@ int spfem_morton_order(const double *d_p, long long ldp, int dim,
  * (spfem/assembly.py:985-986: sorted unique columns per row, explicit zeros
  * kept) and (ii) the per-tile blobs the generated kernel `<name>_tile` reads
  * (codegen.TILE_KERNEL): tiles of E consecutive elements, every row owned by
- * the lowest tile touching it, a tile's element list = its elements + the halo
- * elements touching its rows.  The work is done in batches of tiles with at
+ * the tile holding most of its elements (SpfemPlanIn.owner_rule), a tile's
+ * element list = its elements + the halo elements touching its rows.  The work is done in batches of tiles with at
  * most `batch_cap` contributions each, so the memory in use is bounded by the
  * batch, not by the mesh (no 2^31 limit on Nu*Nv*nt).  One SpfemPlanBatch = one
  * launch of the tile kernel.

@@ -9,8 +9,9 @@
 // tile-local and batched, so memory is bounded by the batch size, not by the
 // mesh:
 //
-//   1. every CSR row gets an owner tile (lowest tile of E Morton-consecutive
-//      elements touching it): integer atomicMin,
+//   1. every CSR row gets an owner tile: the tile of E Morton-consecutive elements
+//      that holds most of the row's elements (one radix sort of (row, tile) keys),
+//      or simply the lowest tile touching it (integer atomicMin),
 //   2. tile element lists = own elements + halo (elements touching an owned
 //      row): (tile, element) pairs, one radix sort,
 //   3. batches of tiles with <= batch_cap contributions: the contributions
