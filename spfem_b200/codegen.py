@@ -35,6 +35,7 @@ against the oracle without a GPU.
 """
 import hashlib
 import os
+import re
 import numpy as np
 from .tracer import NONE
 
@@ -1051,23 +1052,52 @@ def looped_quad_body(spec, syms, em):
     if npart <= 0:
         npart = 1 if n_unique <= 24 else 2
     spec.npart = npart
+    # The distinct entries are dealt to the NPART threads of an element BY TRIAL
+    # FUNCTION (greedy balance): a thread then needs the H vectors of its own trial
+    # functions only, not all of them.
+    part_of_u = {}
+    if npart > 1:
+        by_j = {}
+        for gkey in order_u:
+            u, idx, _ = groups[gkey]
+            jj = eterms[idx][0][1] if eterms[idx] else 0
+            by_j.setdefault(jj, []).append(u)
+        load = [0] * npart
+        for jj in sorted(by_j, key=lambda k: -len(by_j[k])):
+            tgt = load.index(min(load))
+            load[tgt] += len(by_j[jj])
+            for u in by_j[jj]:
+                part_of_u[u] = tgt
     for gkey in order_u:
         u = groups[gkey][0]
+        part_of_u.setdefault(u, 0 if npart == 1 else u % npart)
         body.append("double acc_%d = 0.0;" % u)
 
     # ---- the loop over the quadrature points --------------------------------------
+    # Parallelograms (every element of a uniform grid) have a constant Jacobian: if the
+    # form's point data is geometry only (no x, w, fields), the Jacobian and the
+    # coefficient DAG are evaluated at the first point only.  The test is exact
+    # (P0 - P1 + P2 - P3 == 0); anything else takes the general path.
+    geom_only = not any(nm[0] in "xwf" for nm in syms if nm not in ("hq",))
+    pre = []
+    if geom_only and os.environ.get("SPFEM_QAFFINE", "1") != "0":
+        pre.append("const bool spfem_affine = (Q0_0 - Q0_1 + Q0_2 - Q0_3 == 0.0) && "
+                   "(Q1_0 - Q1_1 + Q1_2 - Q1_3 == 0.0);")
     L = ["for (int q = 0; q < %d; ++q) {" % nq]
+    G = []          # per-point geometry + coefficients (hoisted for parallelograms)
+    L_ = L
+    L = G
     L.append("const double omy = SPFEM_QT[0][q], opy = SPFEM_QT[1][q], omx = SPFEM_QT[2][q], "
              "opx = SPFEM_QT[3][q];")
+    # (plain products / sums: the compiler may contract them into FMAs -- unlike the
+    # coordinates x, which masks compare with ==, the Jacobian needs no bit-exactness)
     for i in range(2):
         P = ["Q%d_%d" % (i, k) for k in range(4)]
-        e0 = _sub(_add(_add(_mul(_neg(P[0]), "omy"), _mul(P[1], "omy")), _mul(P[2], "opy")),
-                  _mul(P[3], "opy"))
-        e1 = _add(_add(_sub(_mul(_neg(P[0]), "omx"), _mul(P[1], "opx")), _mul(P[2], "opx")),
-                  _mul(P[3], "omx"))
-        L.append("const double J%d0_L = %s;" % (i, _mul("0.25", e0)))
-        L.append("const double J%d1_L = %s;" % (i, _mul("0.25", e1)))
-    L.append("const double detJ_L = %s;" % _sub(_mul("J00_L", "J11_L"), _mul("J01_L", "J10_L")))
+        L.append("const double J%d0_L = 0.25 * ((%s - %s) * omy + (%s - %s) * opy);"
+                 % (i, P[1], P[0], P[2], P[3]))
+        L.append("const double J%d1_L = 0.25 * ((%s - %s) * omx + (%s - %s) * opx);"
+                 % (i, P[3], P[0], P[2], P[1]))
+    L.append("const double detJ_L = J00_L * J11_L - J01_L * J10_L;")
     # one division per point: adj * (1 / det) instead of adj / det (<= 1 ulp apart,
     # like the affine path; on axis-aligned meshes J01 = J10 = 0 exactly and a
     # zero numerator would send every one of those divisions down the slow path)
@@ -1105,6 +1135,23 @@ def looped_quad_body(spec, syms, em):
             if coef.uid not in cname:
                 cname[coef.uid] = em.name(coef, "L", symname)
     L += [ln.strip() for ln in em.lines]
+    L = L_
+    if pre:
+        # declarations outside the loop, assignments under the parallelogram test
+        decl, asg = [], []
+        for ln in G:
+            m_ = re.match(r"const double (.*)$", ln)
+            if m_ is None:
+                raise AssertionError("unexpected geometry line: " + ln)
+            asg.append(m_.group(1))
+            for part in re.split(r",\s*(?=[A-Za-z_]\w*\s*=)", m_.group(1).rstrip(";")):
+                decl.append(part.split("=")[0].strip())
+        body += pre + ["double %s;" % ", ".join(decl)]
+        L.append("if (q == 0 || !spfem_affine) {")
+        L += asg
+        L.append("}")
+    else:
+        L += G
     # H^b_j per (block, trial function, b) that some distinct entry needs
     reps = [groups[g][1] for g in order_u]
     need_h, hterms = [], {}
@@ -1123,28 +1170,37 @@ def looped_quad_body(spec, syms, em):
                     hterms[hk].append("%s * %s" % (cname[coef.uid], fac))
     n_terms = 0
     hname = {}
+    # which parts need which H vector
+    h_parts = {}
+    for gkey in order_u:
+        u, idx, idxs = groups[gkey]
+        for a, j, b, i, coef, cu, cv in eterms[idx]:
+            h_parts.setdefault((cu, cv, j, b), set()).add(part_of_u[u])
     for hk in need_h:
         cu, cv, j, b = hk
         hname[hk] = "H_%d_%d_%d_%s" % (cu, cv, j, "n" if b == NONE else str(b))
-        L.append("const double %s = %s;" % (hname[hk], " + ".join(hterms[hk]) or "0.0"))
+        cond = " || ".join("PART == %d" % pp for pp in sorted(h_parts.get(hk, {0})))
+        L.append("double %s = 0.0; if (PART < 0 || %s) %s = %s;"
+                 % (hname[hk], cond, hname[hk], " + ".join(hterms[hk]) or "0.0"))
         n_terms += len(hterms[hk])
     for gkey in order_u:
         u, idx, idxs = groups[gkey]
         by_b = {}
         for a, j, b, i, coef, cu, cv in eterms[idx]:
             by_b.setdefault((cu, cv, j, b), i)
-        parts = []
+        stmts = []
         for (cu, cv, j, b), i in by_b.items():
-            parts.append(hname[(cu, cv, j, b)] if b == NONE
-                         else "%s * SPFEM_TV[%d][%d][q]" % (hname[(cu, cv, j, b)], b, i))
-        n_terms += len(parts)
-        if parts:
-            L.append("if (PART < 0 || PART == %d) acc_%d += %s;" % (u % npart, u, " + ".join(parts)))
+            # one statement per product: each contracts into a single FMA
+            stmts.append("acc_%d += %s;" % (u, hname[(cu, cv, j, b)] if b == NONE
+                         else "%s * SPFEM_TV[%d][%d][q]" % (hname[(cu, cv, j, b)], b, i)))
+        n_terms += len(stmts)
+        if stmts:
+            L.append("if (PART < 0 || PART == %d) { %s }" % (part_of_u[u], " ".join(stmts)))
     L.append("}")
     body += L
     for gkey in order_u:
         u, idx, idxs = groups[gkey]
-        body.append("if (PART < 0 || PART == %d) { const double val = acc_%d;" % (u % npart, u))
+        body.append("if (PART < 0 || PART == %d) { const double val = acc_%d;" % (part_of_u[u], u))
         body.append("  if (TILED) { out[(long long)%d * ldo + k] = val; } else {" % u)
         for ii in idxs:
             body.append("    SPFEM_PUT(%d, val);" % ii)

@@ -49,6 +49,8 @@ CASES = {
     "vecq1_elasticity": (f_vec, "Q1", 2, False),
     "q2_nonsym": (f_nonsym, "Q2", 1, False),
     "q1_opaque": (f_opaque, "Q1", 1, False),
+    "q2_laplace": (cases.lap2, "Q2", 1, False),
+    "q2_convection": (lambda u, dv, h: (0.3 + h) * u * dv[0] - 2.0 * u * dv[1], "Q2", 1, False),
 }
 
 
@@ -84,6 +86,31 @@ def test_quadrature_loop_cuda(name):
     util.check(a.iasm(form, interp=interp), ref)                      # tile kernel
     tind = np.arange(a.mesh.t.shape[1])
     util.check(a.iasm(form, interp=interp, tind=tind), ref)           # two-kernel route
+
+
+@pytest.mark.parametrize("name", ["q2_laplace", "q2_convection", "vecq1_elasticity", "q2_x"])
+def test_parallelogram_shortcut_host(name):
+    """Uniform grid: every element is a parallelogram, the Jacobian and the
+    coefficients are evaluated at the first point only (forms without x / w)."""
+    a, form, interp, ref = _setup(name, jiggle=False)
+    plan = a.plan_iasm(form, interp=interp)
+    assert ("spfem_affine" in plan.source) == (name != "q2_x")
+    util.check(hostemu.iasm(a, form, interp=interp), ref)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["q2_laplace", "q2_convection", "vecq1_elasticity"])
+def test_parallelogram_shortcut_cuda(name):
+    a, form, interp, ref = _setup(name, jiggle=False)
+    util.check(a.iasm(form, interp=interp), ref)
+    # a mesh that mixes parallelograms and general quadrilaterals in one warp
+    m = sp.MeshQuad()
+    m.refine(3)
+    I = m.interior_nodes()[::3]
+    m.p[:, I] += 0.01 * np.random.default_rng(4).standard_normal((2, len(I)))
+    ename, ncomp = CASES[name][1], CASES[name][2]
+    a2 = AssemblerElement(m, util.element(ename, ncomp))
+    util.check(a2.iasm(form), asm_oracle.iasm(m, ename, form, ncomp_u=ncomp, ncomp_v=ncomp))
 
 
 def test_symmetric_entries_are_aliased_in_the_loop():
