@@ -35,7 +35,6 @@ against the oracle without a GPU.
 """
 import hashlib
 import os
-import re
 import numpy as np
 from .tracer import NONE
 
@@ -1075,16 +1074,16 @@ def looped_quad_body(spec, syms, em):
 
     # ---- the loop over the quadrature points --------------------------------------
     # Parallelograms (every element of a uniform grid) have a constant Jacobian: if the
-    # form's point data is geometry only (no x, w, fields), the Jacobian and the
-    # coefficient DAG are evaluated at the first point only.  The test is exact
-    # (P0 - P1 + P2 - P3 == 0); anything else takes the general path.
+    # form's point data is geometry only (no x, w, fields), such an element takes a
+    # loop-free branch with the reference integrals folded into literals (below).
+    # The test is exact (P0 - P1 + P2 - P3 == 0); anything else takes the loop.
     geom_only = not any(nm[0] in "xwf" for nm in syms if nm not in ("hq",))
     pre = []
     if geom_only and os.environ.get("SPFEM_QAFFINE", "1") != "0":
         pre.append("const bool spfem_affine = (Q0_0 - Q0_1 + Q0_2 - Q0_3 == 0.0) && "
                    "(Q1_0 - Q1_1 + Q1_2 - Q1_3 == 0.0);")
     L = ["for (int q = 0; q < %d; ++q) {" % nq]
-    G = []          # per-point geometry + coefficients (hoisted for parallelograms)
+    G = []          # per-point geometry + coefficients
     L_ = L
     L = G
     L.append("const double omy = SPFEM_QT[0][q], opy = SPFEM_QT[1][q], omx = SPFEM_QT[2][q], "
@@ -1136,22 +1135,37 @@ def looped_quad_body(spec, syms, em):
                 cname[coef.uid] = em.name(coef, "L", symname)
     L += [ln.strip() for ln in em.lines]
     L = L_
+    L += G
+    affine = []
     if pre:
-        # declarations outside the loop, assignments under the parallelogram test
-        decl, asg = [], []
-        for ln in G:
-            m_ = re.match(r"const double (.*)$", ln)
-            if m_ is None:
-                raise AssertionError("unexpected geometry line: " + ln)
-            asg.append(m_.group(1))
-            for part in re.split(r",\s*(?=[A-Za-z_]\w*\s*=)", m_.group(1).rstrip(";")):
-                decl.append(part.split("=")[0].strip())
-        body += pre + ["double %s;" % ", ".join(decl)]
-        L.append("if (q == 0 || !spfem_affine) {")
-        L += asg
-        L.append("}")
-    else:
-        L += G
+        # Parallelogram: the coefficients are constants of the element, so an entry is
+        #     sum_terms c * (sum_q W_q psi^a_j(X_q) psi^b_i(X_q))
+        # with the reference integrals folded into literals (math.fsum), exactly what
+        # the straight-line generator does for affine simplices: no loop, no tables.
+        import math
+        affine.append("if (spfem_affine) {")
+        affine.append("const int q = 0;")
+        affine += G
+        folded, fmag = {}, 0.0
+        for gkey in order_u:
+            u, idx, _ = groups[gkey]
+            merged, order = {}, []
+            for a, j, b, i, coef, cu, cv in eterms[idx]:
+                prod = [spec.W[q] * ((1.0 if a == NONE else tu[a][j][q])
+                                     * (1.0 if b == NONE else tv[b][i][q])) for q in range(nq)]
+                fmag = max(fmag, math.fsum(abs(x) for x in prod))
+                if coef.uid not in merged:
+                    merged[coef.uid] = 0.0
+                    order.append(coef.uid)
+                merged[coef.uid] = math.fsum([merged[coef.uid]] + prod)
+            folded[u] = [(merged[c], c) for c in order]
+        for gkey in order_u:
+            u = groups[gkey][0]
+            terms = ["%s * %s" % (lit(K), cname[c]) for K, c in folded[u] if abs(K) > 1e-15 * fmag]
+            if terms:
+                affine.append("if (PART < 0 || PART == %d) acc_%d = %s;"
+                              % (part_of_u[u], u, " + ".join(terms)))
+        affine.append("} else")
     # H^b_j per (block, trial function, b) that some distinct entry needs
     reps = [groups[g][1] for g in order_u]
     need_h, hterms = [], {}
@@ -1197,7 +1211,7 @@ def looped_quad_body(spec, syms, em):
         if stmts:
             L.append("if (PART < 0 || PART == %d) { %s }" % (part_of_u[u], " ".join(stmts)))
     L.append("}")
-    body += L
+    body += pre + affine + L
     for gkey in order_u:
         u, idx, idxs = groups[gkey]
         body.append("if (PART < 0 || PART == %d) { const double val = acc_%d;" % (part_of_u[u], u))
