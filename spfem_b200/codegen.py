@@ -267,18 +267,33 @@ extern "C" __global__ void __launch_bounds__(@THREADS@, @MINB@) @NAME@_tile(cons
        added in list order => bitwise reproducible.                              */
     spfem_mbar_wait(&bars[1], 0);
     __syncthreads();
-    /* every slot carries the 32-bit offset of its (first) CSR value from the tile's
-       lowest position: one look-up, no slot -> row -> row base chain               */
+    /* Where a slot's (first) CSR value goes, as a 32-bit offset from the tile's lowest
+       position.  Slots ordered by contribution count carry it themselves (`spos`, and
+       `slen` = length of the scalar row for block plans).  Slots in CSR order: one
+       header per 32 slots (bit l = slot l starts a new row, row of slot 0) and one
+       record per row (offset, first slot, length) -- a quarter byte of plan per slot
+       instead of 4 or 6, and the kernels are bound by HBM traffic.                 */
     const unsigned *spos = (const unsigned *)(sB + 16);
+    const uint2 *rrec = (const uint2 *)(sB + 16);
+    const uint2 *shdr = (const uint2 *)(sB + d[7]);
+#define SPFEM_SLOT_PLACE(s, pos, L) \
+    unsigned pos, L; \
+    if (T.sorted) { pos = spos[s]; L = SPFEM_NB > 1 ? (unsigned)slen[s] : 0u; } \
+    else { \
+        const uint2 h_ = shdr[(s) >> 5]; \
+        const uint2 r_ = rrec[h_.y + __popc(h_.x & (0xffffffffu >> (31 - ((s) & 31))))]; \
+        pos = r_.x + SPFEM_BSU * ((unsigned)(s) - (r_.y & 0xffffu)); L = r_.y >> 16; \
+    }
     const unsigned short *soff = (const unsigned short *)(sB + d[6]);
     const unsigned short *cb = (const unsigned short *)(sB + d[8]);
     double *__restrict__ vals = T.values + *reinterpret_cast<const long long *>(sB);
+    const unsigned short *slen = (const unsigned short *)(sB + d[7]);
 #if SPFEM_NB == 1
 #pragma unroll @BUNROLL@
     for (int s = threadIdx.x; s < ns; s += blockDim.x) {
         const unsigned k0 = soff[s], k1 = soff[s + 1];
         const unsigned c0 = cb[k0], c1 = cb[k0 + 1];
-        const unsigned pos = spos[s];
+        SPFEM_SLOT_PLACE(s, pos, L_);
         double acc = sL[c0];
         if (k0 + 1 < k1) acc += sL[c1];
 #pragma unroll @TUNROLL@
@@ -287,11 +302,9 @@ extern "C" __global__ void __launch_bounds__(@THREADS@, @MINB@) @NAME@_tile(cons
     }
 #else
     const unsigned elm = (1u << T.els) - 1u;
-    const unsigned short *slen = (const unsigned short *)(sB + d[7]);
     for (int s = threadIdx.x; s < ns; s += blockDim.x) {
         const unsigned k0 = soff[s], k1 = soff[s + 1];
-        const unsigned pos = spos[s];
-        const unsigned L = slen[s];
+        SPFEM_SLOT_PLACE(s, pos, L);
         double acc[SPFEM_NB];
         {
             const unsigned c = cb[k0];

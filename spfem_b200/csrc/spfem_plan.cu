@@ -819,12 +819,18 @@ int build(const SpfemPlanIn &in, SpfemPlanOut &out, Ctx &c)
             i64 off_base = 0;
             if (compact) { off_base = ba; ba = pad16(off_base + (1 + W) * 4 * ne_pad); }
             ba = pad16(ba);
-            // section B: base position of the tile (int64), per slot the 32-bit offset of
-            // its (first) CSR value from it [+ the length of its scalar row for block
-            // plans], the start of every slot's contributions, the contribution lists
+            // section B: base position of the tile (int64); then
+            //   slots ordered by contribution count: per slot the 32-bit offset of its
+            //   (first) CSR value from the base [+ the length of its scalar row for block
+            //   plans];
+            //   slots in CSR order: one 8-byte record per ROW (offset of the row, first
+            //   slot, length) and one 8-byte header per 32 slots (bit l: slot l starts a
+            //   new row; row of slot 0) -- 0.25 bytes per slot instead of 4 or 6;
+            // the start of every slot's contributions, the contribution lists
             const i64 off_pos = 16;
-            const i64 off_slen = off_pos + pad16(4 * ns);
-            const i64 off_soff = off_slen + (nb > 1 ? pad16(2 * ns) : 0);
+            const i64 off_slen = off_pos + (sorted ? pad16(4 * ns) : pad16(8 * nr));
+            const i64 off_soff = off_slen + (sorted ? (nb > 1 ? pad16(2 * ns) : 0)
+                                                    : pad16(8 * ((ns + 31) / 32)));
             const i64 off_contrib = off_soff + pad16(2 * (ns + 1));
             const i64 bb = off_contrib + pad16(2 * (nc + 1));
             bytes_a[t] = ba;
@@ -894,7 +900,7 @@ int build(const SpfemPlanIn &in, SpfemPlanOut &out, Ctx &c)
             soff[sl] = (u16)k0;
             if (sl == ns - 1) soff[ns] = (u16)d[10];
             srow_keep[s] = (int)rb;
-            ((u32 *)(Bs + 16))[sl] = (u32)(so - rowfirst[rb]);       // position inside the row, for now
+            if (sorted) ((u32 *)(Bs + 16))[sl] = (u32)(so - rowfirst[rb]);   // position inside the row, for now
             u16 *cb = (u16 *)(Bs + d[8]);
             const i64 c0 = sfc[so], c1 = sfc[so + 1];
             for (i64 k = c0; k < c1; ++k) cb[k0 + (k - c0)] = (u16)cv[k];
@@ -954,7 +960,40 @@ int build(const SpfemPlanIn &in, SpfemPlanOut &out, Ctx &c)
             if (desc[16 * t + 5] > 0)
                 *(i64 *)(blob + blob_off[t] + desc[16 * t + 1]) = tmin[t];
         });
-        par_for(c, nS, [=] __host__ __device__(i64 s) {
+        if (!sorted) {
+            // row records and chunk headers (slots of a tile: row after row, CSR order)
+            par_for(c, nRb, [=] __host__ __device__(i64 r) {
+                i64 lo = Ta, hi = Tb;
+                while (hi - lo > 1) { const i64 m = (lo + hi) >> 1; if (tr_ptr[m] - ra <= r) lo = m; else hi = m; }
+                const i64 t = lo - Ta;
+                const int *d = desc + 16 * t;
+                if (d[5] <= 0) return;
+                const int R = rows_sorted[ra + r];
+                const i64 g = nb * iptr[R] - tmin[t];
+                if (g > (i64)UINT_MAX || rowlen[R] > 65535) amax(&mx[2], INT_MAX);
+                u32 *rec = (u32 *)(blob + blob_off[t] + d[1] + 16) + 2 * (r - (tr_ptr[lo] - ra));
+                rec[0] = (u32)g;
+                rec[1] = (u32)(rowfirst[r] - ts_ptr[t]) | ((u32)rowlen[R] << 16);
+            });
+            par_for(c, nS, [=] __host__ __device__(i64 s) {
+                i64 lo = 0, hi = nT;
+                while (hi - lo > 1) { const i64 m = (lo + hi) >> 1; if (ts_ptr[m] <= s) lo = m; else hi = m; }
+                const i64 sl = s - ts_ptr[lo];
+                if (sl & 31) return;
+                const int *d = desc + 16 * lo;
+                u32 *hd = (u32 *)(blob + blob_off[lo] + d[1] + d[7]) + 2 * (sl >> 5);
+                const i64 send = ts_ptr[lo + 1];
+                u32 m = 0;
+                for (int l = 1; l < 32 && s + l < send; ++l) {
+                    const int step = srow_keep[s + l] - srow_keep[s + l - 1];
+                    if (step) m |= (u32)1 << l;
+                    if (step > 1 || step < 0) amax(&mx[2], INT_MAX - 1);      // (cannot happen: every row has a slot)
+                }
+                hd[0] = m;
+                hd[1] = (u32)(srow_keep[s] - (tr_ptr[Ta + lo] - ra));
+            });
+        }
+        else par_for(c, nS, [=] __host__ __device__(i64 s) {
             i64 lo = 0, hi = nT;
             while (hi - lo > 1) { const i64 m = (lo + hi) >> 1; if (ts_ptr[m] <= s) lo = m; else hi = m; }
             const int *d = desc + 16 * lo;
@@ -970,6 +1009,7 @@ int build(const SpfemPlanIn &in, SpfemPlanOut &out, Ctx &c)
                 ((u16 *)(Bs + d[7]))[sl] = (u16)rowlen[R];
             }
         });
+        if (get(c, mx + 2) == INT_MAX - 1) throw Err{1, "tile plan: a row of a tile has no slot"};
         if (get(c, mx + 2) == INT_MAX)
             throw Err{1, "tile plan: the rows of one tile span more than 2^32 CSR positions (or a row has more than 65535 blocks)"};
         drop(c, tmin);

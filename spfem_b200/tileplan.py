@@ -32,9 +32,16 @@ Blob of one tile (all sections 16-byte aligned; descriptor = 16 int32):
                                   distinct local values that are read at all)
   section B (TMA copy 2, needed to sum and store)
     pbase  int64           lowest CSR position of the tile's rows (+ 8 bytes pad)
-    spos   uint32 [ns]     CSR position of the slot's (first) value minus pbase
-    slen   uint16 [ns]     block plans only: length of the slot's scalar row (the
+    slots ordered by contribution count (``sort_slots != 0``):
+      spos uint32 [ns]     CSR position of the slot's (first) value minus pbase
+      slen uint16 [ns]     block plans only: length of the slot's scalar row (the
                            bsv sub-rows of a block are bsu * length apart)
+    slots in CSR order (``sort_slots = 0``; the tile's rows one after the other):
+      rrec {uint32 pos, uint16 first, uint16 len} [nr]   per ROW: position of its
+                           first value minus pbase, its first slot, its length
+      shdr {uint32 mask, uint32 row0} [ceil(ns/32)]      per 32 slots: bit l set =
+                           slot l starts a new row; row of slot 0.  The row of slot
+                           l is row0 + popcount(mask & bits 0..l)
     soff   uint16 [ns+1]   start of every slot's contributions in ``contrib``
     contrib uint16 [nc+1]  scalar plans: shared-memory cell ``u*ldl + el`` (compact:
                            packed position); block plans: ``(j*nbv+i) << els | el``
@@ -42,7 +49,7 @@ Blob of one tile (all sections 16-byte aligned; descriptor = 16 int32):
   number of contributions (1: exactly, 2: coarse classes, CSR order inside a class).
 
 Descriptor: 0 blob offset / 16, 1 bytes A, 2 bytes B, 3 ne, 4 ne_pad, 5 ns,
-6 / 7 / 8 byte offsets of soff / slen / contrib in B, 9 nr, 10 nc, 11 nvt_pad,
+6 / 7 / 8 byte offsets of soff / slen (or shdr) / contrib in B, 9 nr, 10 nc, 11 nvt_pad,
 12 / 13 byte offsets of pc / el in A (13 = -1: no element ids), 14 nvt,
 15 byte offset of sbase in A.
 """
@@ -250,15 +257,27 @@ def emulate(plan, local, ut=None):
                 for u in range(nuniq):
                     sL[u * ldl: u * ldl + ne] = local[u, elems]
             pbase = int(S[:8].view(np.int64)[0])
-            spos = S[16: 16 + 4 * ns].view(np.uint32).astype(np.int64)
-            slen = (S[o_srow: o_srow + 2 * ns].view(np.uint16).astype(np.int64)
-                    if nb > 1 else None)
+            if plan["sort_slots"]:
+                spos = S[16: 16 + 4 * ns].view(np.uint32).astype(np.int64)
+                slen = (S[o_srow: o_srow + 2 * ns].view(np.uint16).astype(np.int64)
+                        if nb > 1 else np.zeros(ns, dtype=np.int64))
+            else:
+                rrec = S[16: 16 + 8 * nr].view(np.uint32).astype(np.int64).reshape(nr, 2)
+                nch = (ns + 31) // 32
+                shdr = S[o_srow: o_srow + 8 * nch].view(np.uint32).astype(np.int64).reshape(nch, 2)
+                spos, slen = np.zeros(ns, dtype=np.int64), np.zeros(ns, dtype=np.int64)
+                for s in range(ns):
+                    mask, row0 = shdr[s >> 5]
+                    row = row0 + bin(int(mask) & (0xffffffff >> (31 - (s & 31)))).count("1")
+                    pos, fl = rrec[row]
+                    spos[s] = pos + bsu * (s - (fl & 0xffff))
+                    slen[s] = fl >> 16
             soff = S[o_soff: o_soff + 2 * (ns + 1)].view(np.uint16).astype(np.int64)
             cb = S[o_cb: o_cb + 2 * (nc + 1)].view(np.uint16).astype(np.int64)
             assert soff[ns] == nc
             for s in range(ns):
                 g = pbase + spos[s]
-                L = slen[s] if nb > 1 else 0
+                L = slen[s]
                 acc = np.zeros(nb)
                 for kk in range(soff[s], soff[s + 1]):
                     c = cb[kk]
