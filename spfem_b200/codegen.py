@@ -1093,8 +1093,14 @@ def looped_quad_body(spec, syms, em):
     geom_only = not any(nm[0] in "xwf" for nm in syms if nm not in ("hq",))
     pre = []
     if geom_only and os.environ.get("SPFEM_QAFFINE", "1") != "0":
+        # (SPFEM_PARALLELOGRAMS: the engine found every element of the mesh to be one --
+        # the kernel variant without the loop branch needs half the registers)
+        pre.append("#ifdef SPFEM_PARALLELOGRAMS")
+        pre.append("const bool spfem_affine = true;")
+        pre.append("#else")
         pre.append("const bool spfem_affine = (Q0_0 - Q0_1 + Q0_2 - Q0_3 == 0.0) && "
                    "(Q1_0 - Q1_1 + Q1_2 - Q1_3 == 0.0);")
+        pre.append("#endif")
     L = ["for (int q = 0; q < %d; ++q) {" % nq]
     G = []          # per-point geometry + coefficients
     L_ = L
@@ -1178,7 +1184,9 @@ def looped_quad_body(spec, syms, em):
             if terms:
                 affine.append("if (PART < 0 || PART == %d) acc_%d = %s;"
                               % (part_of_u[u], u, " + ".join(terms)))
-        affine.append("} else")
+        affine.append("}")
+        affine.append("#ifndef SPFEM_PARALLELOGRAMS")
+        affine.append("else")
     # H^b_j per (block, trial function, b) that some distinct entry needs
     reps = [groups[g][1] for g in order_u]
     need_h, hterms = [], {}
@@ -1224,6 +1232,9 @@ def looped_quad_body(spec, syms, em):
         if stmts:
             L.append("if (PART < 0 || PART == %d) { %s }" % (part_of_u[u], " ".join(stmts)))
     L.append("}")
+    if affine:
+        L.append("#endif")
+    spec.affine_variant = bool(affine)
     body += pre + affine + L
     for gkey in order_u:
         u, idx, idxs = groups[gkey]
@@ -1413,6 +1424,9 @@ def _generate_interior_source(spec, name, looped):
     spec.minb = 3 if dim == 2 else 2          # CTAs of the tile kernel per SM (register cap)
     if looped and spec.n_unique > 24:
         spec.minb = 2
+    # CTAs per SM of the variant for meshes of parallelograms only (no loop branch)
+    spec.minb_affine = 3 if spec.n_unique > 24 else 4
+    spec.affine_variant = bool(looped and getattr(spec, "affine_variant", False))
     src = [PRELUDE, DEVICE_HELPERS]
     if os.environ.get("SPFEM_RCP", "0") == "0":      # measured: the Newton reciprocal is not faster
         src.insert(0, "#define SPFEM_IEEE_RCP 1")
@@ -1430,6 +1444,9 @@ def _generate_interior_source(spec, name, looped):
                "#define SPFEM_CONST %s\n#endif" % space)
     src += tables
     src.append("#define SPFEM_NENTRIES %d" % spec.n_entries)
+    src.append("#ifdef SPFEM_PARALLELOGRAMS\n#define SPFEM_TILE_MINB %s\n#else\n#define SPFEM_TILE_MINB %s\n#endif"
+               % (os.environ.get("SPFEM_TILE_MINB_AFFINE", str(spec.minb_affine)),
+                  os.environ.get("SPFEM_TILE_MINB", str(spec.minb))))
     src.append("#define SPFEM_NUNIQUE %d" % spec.n_unique)
     src.append("#define SPFEM_NPART %d" % spec.npart)
     src.append("#define SPFEM_NMASK %d" % ((spec.n_unique + 31) // 32))
@@ -1514,7 +1531,7 @@ def _generate_interior_source(spec, name, looped):
                    # registers; measured +19 % for vector-P2), two on 3-D meshes
                    # (the quadrature loop of the larger quadrilateral elements keeps ~25
                    # accumulators + the H vectors live: 128 registers, two CTAs)
-                   .replace("@MINB@", os.environ.get("SPFEM_TILE_MINB", str(spec.minb))))
+                   .replace("@MINB@", "SPFEM_TILE_MINB"))
     src.append("#else")
     src.append('extern "C" void %s_host(const SpfemArgs *P)\n{' % name)
     src.append("    for (long long k = 0; k < P->n; ++k) {")

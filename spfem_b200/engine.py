@@ -396,6 +396,9 @@ class TiledPrepared(Prepared):
     def __init__(self, engine, plan, kernel, tile_kernel, args, pattern, tp, keep=()):
         Prepared.__init__(self, engine, plan, kernel, args, 128, None, pattern, keep)
         self.tile_kernel, self.tp = tile_kernel, tp
+        self._kernel_version = None
+        if tile_kernel is None:
+            self._select_kernel()
         spec = plan.spec
         nb = tp["bsv"] * tp["bsu"]
         nsidx = (spec.n_rows // tp["bsv"]) * (spec.n_cols // tp["bsu"])
@@ -421,8 +424,23 @@ class TiledPrepared(Prepared):
             self.threads = min(int(os.environ["SPFEM_TILE_THREADS"]), codegen_tile_threads())
         self.n_launches = len(self.targs)
 
+    def _select_kernel(self):
+        """``<name>_tile`` of the plan's module -- for quadrilateral forms with a
+        parallelogram branch (``spec.affine_variant``) the variant compiled without
+        the quadrature loop while every element of the mesh is a parallelogram
+        (re-checked when the coordinates change)."""
+        e, plan = self.engine, self.plan
+        source = plan.source
+        if getattr(plan.spec, "affine_variant", False) and e.all_parallelograms():
+            source = "#define SPFEM_PARALLELOGRAMS 1\n" + source
+            pin_module(source, self)
+        self.tile_kernel = get_kernel(source, plan.name + "_tile")
+        self._kernel_version = e.p_version
+
     def launch(self):
         e = self.engine
+        if self._kernel_version is not None and self._kernel_version != e.p_version:
+            self._select_kernel()
         a = self.args
         a.t, a.ldt = e.t.data_ptr(), e.t.shape[1]
         a.p, a.ldp = e.p.data_ptr(), e.p.shape[1]
@@ -718,8 +736,7 @@ class Engine(object):
                 hit = self.tile_plan(plan)
                 if hit is not None:
                     pat, tp = hit
-                    tk = get_kernel(plan.source, plan.name + "_tile")
-                    return TiledPrepared(self, plan, kernel, tk, a, pat, tp, keep=(wt,))
+                    return TiledPrepared(self, plan, kernel, None, a, pat, tp, keep=(wt,))
             if spec.n_entries * n > 2 ** 31 - 1:
                 raise NotImplementedError(
                     "this form needs the two-kernel route, which is limited to 2^31-1 "
@@ -741,6 +758,20 @@ class Engine(object):
         local = self._empty(max(spec.n_entries * n, 1), torch.float64)
         a.out = local.data_ptr()
         return Prepared(self, plan, kernel, a, 128, local, pat, keep=(sel, wt))
+
+    def all_parallelograms(self):
+        """Every element of a quadrilateral mesh is a parallelogram -- the exact test
+        of the generated kernels (``codegen.looped_quad_body``), once per coordinate
+        upload."""
+        if getattr(self, "_para_version", None) != self.p_version:
+            self._para = False
+            if self.t.shape[0] == 4 and self.p.shape[0] == 2 and \
+                    os.environ.get("SPFEM_QPARA", "1") != "0":
+                t, p = self.t.long(), self.p
+                d = p[:, t[0]] - p[:, t[1]] + p[:, t[2]] - p[:, t[3]]
+                self._para = bool((d == 0).all())
+            self._para_version = self.p_version
+        return self._para
 
     def fan_plan(self, pat, rows=128):
         """Plan of the vertex-fan kernel for ``pat`` with ``rows`` rows per tile
@@ -828,6 +859,8 @@ class Engine(object):
         nuniq = spec.n_unique
         nsidx = (spec.n_rows // spec.bsv) * (spec.n_cols // spec.bsu)
         minb = int(env("SPFEM_TILE_MINB", str(getattr(spec, "minb", 3 if dim == 2 else 2))))
+        if getattr(spec, "affine_variant", False) and self.all_parallelograms():
+            minb = int(env("SPFEM_TILE_MINB_AFFINE", str(spec.minb_affine)))
         # two CTAs per SM (3-D, Q2), else four for scalar plans (TriP2: 48 registers) and
         # three for the block plans of vector elements (80 registers)
         prefer = (110 if minb <= 2 or compact else 58 if nb > 1 else 55) * 1024

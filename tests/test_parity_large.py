@@ -165,3 +165,102 @@ def test_more_than_2_31_local_entries_int64_device_resident():
     # trace of the stiffness matrix is positive and every diagonal entry is stored
     diag = A.values[(pat.indices == rows)]
     assert diag.numel() == N and float(diag.min()) > 0.0
+
+
+def test_config4_full_size_tetp2_energy_identities():
+    """BASELINE config 4 at full size: ElementTetP2 Laplace on the Kuhn 203^3 grid
+    (50 193 162 tetrahedra, ~2e9 nonzeros, 5e9 local entries => int64 indices).
+    Size-independent properties of the assembled matrix, with the P2 interpolants of
+    1, x and y^2 (P2 reproduces them exactly): A 1 = 0, x^T A x = |grad x|^2 |cube| = 1,
+    (y^2)^T A (y^2) = int (2y)^2 = 4/3, x^T A y^2 = 0."""
+    import torch
+    import spfem_b200 as sp
+    from spfem_b200 import meshgen
+    from spfem_b200.assembly import AssemblerElement
+    if torch.cuda.get_device_properties(0).total_memory < 150 * 2 ** 30:
+        pytest.skip("needs ~120 GB of device memory")
+    p, t = meshgen.grid_tet(203)
+    m = sp.MeshTet(p, t, validate=False)
+    assert m.t.shape[1] == 6 * 203 ** 3
+    a = AssemblerElement(m, sp.ElementTetP2())
+    A = a.iasm_device(cases.lap3)
+    pat = A.pattern
+    N = a.dofnum_u.N
+    assert pat.indptr.dtype == torch.int64 and A.shape == (N, N)
+    assert int(pat.indptr[-1]) == pat.nnz == A.values.numel()
+    dev = A.values.device
+    # coordinates of the DOFs: vertices, then edge midpoints (spfem/assembly.py:1499-1512)
+    X = np.empty((3, N))
+    X[:, a.dofnum_u.n_dof[0]] = m.p
+    X[:, a.dofnum_u.e_dof[0]] = 0.5 * (m.p[:, m.edges[0]] + m.p[:, m.edges[1]])
+    one = torch.ones(N, dtype=torch.float64, device=dev)
+    ux = torch.from_numpy(X[0]).to(dev)
+    uy2 = torch.from_numpy(X[1] ** 2).to(dev)
+    lens = pat.indptr[1:] - pat.indptr[:-1]
+
+    def matvec(u):                           # row blocks: bounded scratch memory
+        y = torch.empty(N, dtype=torch.float64, device=dev)
+        step = 1 << 22
+        for r0 in range(0, N, step):
+            r1 = min(N, r0 + step)
+            k0, k1 = int(pat.indptr[r0]), int(pat.indptr[r1])
+            rows = torch.repeat_interleave(torch.arange(r1 - r0, device=dev), lens[r0:r1])
+            part = torch.zeros(r1 - r0, dtype=torch.float64, device=dev)
+            part.index_add_(0, rows, A.values[k0:k1] * u[pat.indices[k0:k1]])
+            y[r0:r1] = part
+        return y
+    scale = float(A.values.abs().max())
+    assert float(matvec(one).abs().max()) <= 1e-10 * scale
+    Ax = matvec(ux)
+    assert abs(float(ux @ Ax) - 1.0) <= 1e-9
+    Ay2 = matvec(uy2)
+    assert abs(float(uy2 @ Ay2) - 4.0 / 3.0) <= 1e-9
+    assert abs(float(ux @ Ay2)) <= 1e-9
+    assert abs(float(uy2 @ Ax)) <= 1e-9
+
+
+def test_config5_full_size_divergence_block_identities():
+    """BASELINE config 5 at full size: the Taylor-Hood divergence block B (rows P1,
+    columns vector-P2, ``(du[0][0]+du[1][1])*v``, learning/Example 1 - Stokes
+    equations.ipynb cell 9) on the 3162^2 grid.  With the P2 interpolant of a velocity
+    field U, (B U)_i = int div(U) phi_i: div (x, y) = 2 => sum_i (B U)_i = 2 |square| = 2 and
+    B U = 2 M 1 >= 0; the rotation (-y, x) is divergence free => B U = 0."""
+    import torch
+    import spfem_b200 as sp
+    from spfem_b200 import meshgen
+    from spfem_b200.assembly import AssemblerElement
+    if torch.cuda.get_device_properties(0).total_memory < 100 * 2 ** 30:
+        pytest.skip("needs ~40 GB of device memory")
+    p, t = meshgen.grid_tri(3162)
+    m = sp.MeshTri(p, t, validate=False)
+    a = AssemblerElement(m, sp.ElementH1Vec(sp.ElementTriP2()), sp.ElementTriP1())
+    B = a.iasm_device(cases.stokes_b)
+    pat = B.pattern
+    Nv, Nu = a.dofnum_v.N, a.dofnum_u.N
+    assert B.shape == (Nv, Nu) and Nv == m.p.shape[1]
+    dev = B.values.device
+    # DOF coordinates of the vector-P2 space: components interleaved at vertices, then at
+    # facet (edge) midpoints (spfem/assembly.py:1499-1521, element.py:505-507)
+    dn = a.dofnum_u
+    X = np.empty((2, Nu))
+    mid = 0.5 * (m.p[:, m.facets[0]] + m.p[:, m.facets[1]])
+    for c in range(2):
+        X[:, dn.n_dof[c]] = m.p
+        X[:, dn.f_dof[c]] = mid
+    comp = np.empty(Nu, dtype=np.int64)
+    for c in range(2):
+        comp[dn.n_dof[c]] = c
+        comp[dn.f_dof[c]] = c
+    radial = torch.from_numpy(np.where(comp == 0, X[0], X[1])).to(dev)
+    rot = torch.from_numpy(np.where(comp == 0, -X[1], X[0])).to(dev)
+    rows = torch.repeat_interleave(torch.arange(Nv, device=dev), pat.indptr[1:] - pat.indptr[:-1])
+
+    def matvec(u):
+        y = torch.zeros(Nv, dtype=torch.float64, device=dev)
+        y.index_add_(0, rows, B.values * u[pat.indices])
+        return y
+    y = matvec(radial)
+    assert abs(float(y.sum()) - 2.0) <= 1e-10
+    assert float(y.min()) > 0.0
+    scale = float(y.max())
+    assert float(matvec(rot).abs().max()) <= 1e-9 * scale

@@ -95,7 +95,14 @@ def test_parallelogram_shortcut_host(name):
     a, form, interp, ref = _setup(name, jiggle=False)
     plan = a.plan_iasm(form, interp=interp)
     assert ("spfem_affine" in plan.source) == (name != "q2_x")
+    assert bool(plan.spec.affine_variant) == (name != "q2_x")
     util.check(hostemu.iasm(a, form, interp=interp), ref)
+    if plan.spec.affine_variant:
+        # the kernel variant for meshes of parallelograms only (no loop branch compiled)
+        import copy
+        pv = copy.copy(plan)
+        pv.source = "#define SPFEM_PARALLELOGRAMS 1\n" + plan.source
+        assert np.array_equal(hostemu.run_interior(a, pv), hostemu.run_interior(a, plan))
 
 
 @pytest.mark.gpu
@@ -111,6 +118,29 @@ def test_parallelogram_shortcut_cuda(name):
     ename, ncomp = CASES[name][1], CASES[name][2]
     a2 = AssemblerElement(m, util.element(ename, ncomp))
     util.check(a2.iasm(form), asm_oracle.iasm(m, ename, form, ncomp_u=ncomp, ncomp_v=ncomp))
+
+
+@pytest.mark.gpu
+def test_parallelogram_variant_follows_the_mesh():
+    """Uniform mesh: the engine launches the variant compiled without the quadrature
+    loop; after the coordinates change (``upload_mesh``) the general kernel."""
+    m = sp.MeshQuad()
+    m.refine(3)
+    a = AssemblerElement(m, sp.ElementQ2())
+    prep = a.prepare_iasm(cases.lap2)
+    eng = a._get_engine()
+    assert type(prep).__name__ == "TiledPrepared" and eng.all_parallelograms()
+    k0 = prep.tile_kernel.value
+    prep.launch()
+    util.check(prep.result(), asm_oracle.iasm(m, "Q2", cases.lap2))
+    I = m.interior_nodes()[::3]
+    m.p[:, I] += 0.01 * np.random.default_rng(5).standard_normal((2, len(I)))
+    eng.upload_mesh()
+    assert not eng.all_parallelograms()
+    prep.launch()
+    assert prep.tile_kernel.value != k0
+    util.check(prep.result(), asm_oracle.iasm(m, "Q2", cases.lap2))
+    util.check(a.iasm(cases.lap2), asm_oracle.iasm(m, "Q2", cases.lap2))
 
 
 def test_symmetric_entries_are_aliased_in_the_loop():
