@@ -69,8 +69,9 @@ typedef struct SpfemTileArgs {
     int store;                   /* doubles of shared memory for the local values:
                                     nuniq * ldl, or max_store + 2 (compact)           */
     int prefetch;                /* L2 prefetch distance in tiles (0 = off)           */
-    int sorted;                  /* SpfemPlanIn.sort_slots != 0 (informational: every slot
-                                    carries its CSR position)                         */
+    int sorted;                  /* SpfemPlanIn.sort_slots != 0: every slot carries its CSR
+                                    position; 0: slots in CSR order, positions from the
+                                    row records + 32-slot headers of section B         */
     int els;                     /* SpfemPlanOut.els                                  */
 } SpfemTileArgs;
 
@@ -201,7 +202,9 @@ typedef struct SpfemPlanIn {
     int nuniq;                /*   local value (scalar plans only), their number       */
     int E;                    /* elements per tile                                     */
     int with_el;              /* keep element ids in the blobs (interp gathers)        */
-    int sort_slots;           /* 0: CSR order, 1: by contribution count, 2: coarse classes */
+    int sort_slots;           /* 0: CSR order (section B: row records + 32-slot headers),
+                                 1: by contribution count, 2: coarse classes (section B:
+                                 per-slot positions); layout in spfem_b200/tileplan.py */
     int compact;              /* shared memory holds only the local values that are read */
     const unsigned char *row_mask; /* optional [nrows]: 0 = row is not assembled here  */
     int index_bytes;          /* 4 or 8: width of indptr / indices                     */
