@@ -149,3 +149,74 @@ def test_symmetric_entries_are_aliased_in_the_loop():
     assert spec.n_unique == 45 and len(set(spec.alias)) == 45          # 81 entries, 45 distinct
     spec = a.plan_iasm(f_nonsym).spec
     assert spec.n_unique == 81
+
+
+# ---------------------------------------------------------------------------
+# randomly composed geometry-only forms (constants and the element size h) on
+# uniform, sheared (parallelograms that are not rectangles) and mixed meshes:
+# the loop-free parallelogram branch against the oracle
+# ---------------------------------------------------------------------------
+def _geom_form(rng, bilinear):
+    terms = []
+    for _ in range(int(rng.integers(1, 4))):
+        a = float(np.round(rng.uniform(0.5, 2.0), 3))
+        kind = int(rng.integers(3))
+        terms.append((a, kind, int(rng.integers(3)), int(rng.integers(3))))
+
+    def coef(a, kind, h):
+        return a if kind == 0 else (a / h if kind == 1 else a + h * h)
+
+    def pick(val, grad, t):
+        return val if t == 0 else grad[t - 1]
+    if bilinear:
+        def form(u, v, du, dv, h):
+            return sum(coef(a, k, h) * pick(u, du, tu) * pick(v, dv, tv) for a, k, tu, tv in terms)
+    else:
+        def form(v, dv, h):
+            return sum(coef(a, k, h) * pick(v, dv, tv) for a, k, tu, tv in terms)
+    return form
+
+
+def _geom_mesh(kind):
+    m = sp.MeshQuad()
+    m.refine(2)
+    if kind in ("sheared", "mixed"):
+        m.p[0] += 0.25 * m.p[1]                    # dyadic shear: still exact parallelograms
+        m.p[1] *= 1.5
+    if kind == "mixed":
+        I = m.interior_nodes()[::4]
+        m.p[:, I] += 0.02 * np.random.default_rng(9).standard_normal((2, len(I)))
+    return m
+
+
+def _geom_cases():
+    rng = np.random.default_rng(777)
+    return [(e, mk, k, bool(k % 2 == 0), int(rng.integers(1 << 30)))
+            for e in ("Q1", "Q2") for mk in ("uniform", "sheared", "mixed") for k in range(2)]
+
+
+def _geom_run(ename, mkind, bilinear, seed, device):
+    m = _geom_mesh(mkind)
+    form = _geom_form(np.random.default_rng(seed), bilinear)
+    a = AssemblerElement(m, util.element(ename, 1))
+    plan = a.plan_iasm(form)
+    assert plan.spec.affine_variant
+    ref = asm_oracle.iasm(m, ename, form)
+    got = a.iasm(form) if device else hostemu.iasm(a, form)
+    if bilinear:
+        cases.compare_csr(got, ref)
+    else:
+        cases.compare_vec(got, ref)
+    if device:
+        assert a._get_engine().all_parallelograms() == (mkind != "mixed")
+
+
+@pytest.mark.parametrize("ename,mkind,k,bilinear,seed", _geom_cases())
+def test_random_geometry_only_form_host(ename, mkind, k, bilinear, seed):
+    _geom_run(ename, mkind, bilinear, seed, False)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("ename,mkind,k,bilinear,seed", _geom_cases())
+def test_random_geometry_only_form_cuda(ename, mkind, k, bilinear, seed):
+    _geom_run(ename, mkind, bilinear, seed, True)
