@@ -997,6 +997,11 @@ def looped_quad_body(spec, syms, em):
         H^b_j = sum_a G^{ab} (W_q psi^a_j)        (per trial function and b)
         A[j, i] += sum_b H^b_j psi^b_i            (distinct entries only)
 
+    Elements that are parallelograms take a loop-free branch (constant Jacobian:
+    reference integrals folded into literals) when the form's point data is
+    geometry only; ``SPFEM_PARALLELOGRAMS`` compiles the body without the loop
+    for meshes that consist of parallelograms only (``spec.affine_variant``).
+
     Returns ``(tables, body, alias, n_unique, n_terms)``."""
     dim, nq = spec.dim, len(spec.W)
     nbu = spec.nbu if spec.bilinear else 1
